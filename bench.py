@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: A-scans/sec of batched PAUT signal-model inference on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model msc]
+
+A step = one pass of forward + post-processing over one resident synthetic volume
+(default: BASELINE.json configs[1], MultiSignalClassifier over 1 000 200 A-scans = 3334 sets x 300 x 320,
+bf16 in HBM).  N > 1 is launched by torchrun, one rank per GPU; every rank owns its own shard of the same
+size (sets are independent: no data-path collective, weak scaling) and the time is the max over ranks.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of each key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SETS = {"msc": (3334, 300), "msc_n": (3334, 300), "conv1d_msc": (3334, 300),
+        "ssd": (20000, 50), "enhanced": (20000, 50), "two_stage": (20000, 50)}
+S = 320
+
+# algorithmic work per A-scan of each kernel (DESIGN.md "Kernels"): (FLOPs, HBM bytes)
+KERNEL_WORK = {}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    sm_max=d.get("sm_max_mhz"), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, sm_max=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_volume(kind, n_sets, n_per_set, seed):
+    from oracle import synth
+    x = synth.synth_paut_sets(n_sets, n_per_set, S, seed=seed, defect_frac=0.01)     # [sets, N, S] fp32 in [0,1]
+    if kind == "conv1d_msc":
+        x = np.ascontiguousarray(x.transpose(0, 2, 1))
+    return torch.from_numpy(x)
+
+
+def oracle_forward(kind, sd, x, threshold=0.5):
+    from oracle import models as om
+    from oracle import postprocess as opp
+    with torch.no_grad():
+        out = om.FORWARD[kind](sd, x)
+    return opp.postprocess(kind, out, threshold, S)
+
+
+def cpu_reference_rate(kind, sd, x_host_f32, budget_s, n_per_set):
+    """Oracle (the CPU port of the reference path, torch fp32 on all host threads) on a bounded sample."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    chunk = 8
+    n_sets = x_host_f32.shape[0]
+    oracle_forward(kind, sd, x_host_f32[:chunk])                       # warm-up
+    done, t0, i = 0, time.perf_counter(), 0
+    while True:
+        lo = (i * chunk) % max(n_sets - chunk, 1)
+        oracle_forward(kind, sd, x_host_f32[lo:lo + chunk])
+        done += chunk * n_per_set
+        i += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return done / el, done, el
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="msc", choices=sorted(SETS))
+    ap.add_argument("--sets", type=int, default=0, help="sets per GPU (default: the BASELINE config)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kind = args.model
+    n_sets, n_per = SETS[kind]
+    if args.sets:
+        n_sets = args.sets
+    from oracle import synth
+    sd = synth.synth_state_dict(kind, seed=0)
+    workload = f"{kind} over {n_sets * n_per} A-scans per GPU ({n_sets} sets x {n_per} x {S}), synthetic PAUT volume"
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_sets = 64
+        x = make_volume(kind, sample_sets, n_per, seed=42)
+        per_step = max(2.0, min(20.0, 90.0 / max(args.steps + args.warmup, 1)))
+        for _ in range(args.warmup):
+            cpu_reference_rate(kind, sd, x, 0.5, n_per)
+        t0, done = time.perf_counter(), 0
+        for _ in range(args.steps):
+            _, d, _ = cpu_reference_rate(kind, sd, x, per_step, n_per)
+            done += d
+        el = time.perf_counter() - t0
+        rate = done / el
+        cores = torch.get_num_threads()
+        print(json.dumps({
+            "impl": "reference", "metric": "A-scans/sec", "value": rate, "unit": "A-scans/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "l2": "sample larger than L2 is not relevant on the CPU arm"},
+            "cpu_baseline": {"value": rate, "unit": "A-scans/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample_sets} sets x {n_per} A-scans cycled for {per_step:.0f} s per step, "
+                                       "oracle port of the reference forward + predict post-processing, fp32"},
+            "e2e": {"value": rate, "unit": "A-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import defectdetection_viaobjectdetection_b200 as paut
+    from defectdetection_viaobjectdetection_b200 import runtime
+    from tests.test_abi import MODELS
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    model = MODELS[kind](dict(signal_length=S))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    model.precision = args.precision
+    in_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
+
+    x_host = make_volume(kind, n_sets, n_per, seed=42 + rank).to(in_dtype).pin_memory()
+    x_dev = x_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    ctx = paut.get_context(dev)
+    n_ascans = n_sets * n_per
+
+    def step_resident():
+        native, (outs, struct, (B, N, S_)) = model._run(x_dev)
+        return native.postprocess(struct, B, N, S_, 0.5, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ctx.launch_count
+    ctx.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        det, count = step_resident()
+    e1.record()
+    barrier()
+    prof = ctx.profile_end()
+    launches = ctx.launch_count - launches0
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    n_found = int(count.item())
+
+    # ---- end to end through the public API with host buffers: H2D + forward + post-process + D2H records
+    x_stage = torch.empty_like(x_dev)
+
+    def step_e2e():
+        x_stage.copy_(x_host, non_blocking=True)
+        native, (outs, struct, (B, N, S_)) = model._run(x_stage)
+        det, count = native.postprocess(struct, B, N, S_, 0.5, dev)
+        return runtime.records_to_numpy(det, count)
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rec = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        value = world * n_ascans * args.steps / (ms * 1e-3)
+        e2e = world * n_ascans * args.steps / e2e_s
+        # dominant kernel and its roofline
+        total_ms = sum(v[1] for v in prof.values()) or 1.0
+        top = max(prof.items(), key=lambda kv: kv[1][1])
+        name, (n_launch, k_ms) = top
+        work = KERNEL_WORK.get(name)
+        roof = {"kernel": name, "share_of_step": k_ms / total_ms, "launches": n_launch,
+                "avg_launch_ms": k_ms / n_launch, "peak_source": pk["source"]}
+        if work:
+            flops, nbytes, bound = work
+            per_launch_ascans = n_ascans * args.steps / n_launch
+            t = (k_ms / n_launch) * 1e-3
+            if bound == "tensor":
+                ach = flops * per_launch_ascans / t / 1e12
+                roof.update(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"])
+            else:
+                ach = nbytes * per_launch_ascans / t / 1e9
+                roof.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"])
+        else:
+            roof.update(bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None)
+        roof["traffic"] = None
+        line = {
+            "metric": "A-scans/sec", "value": value, "unit": "A-scans/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": workload, "l2": "input volume (%.0f MB) larger than the 126 MB L2" %
+                       (x_dev.numel() * x_dev.element_size() / 1e6), "sharding": f"dp{world} by scan position",
+                       "threshold": 0.5, "detections_last_step": n_found},
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": "A-scans/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
+                    "d2h_bytes_per_step": 4 + 48 * len(rec)},
+            "roofline": roof,
+            "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        }
+        if world == 1:
+            x_cpu = x_host[:64].float()
+            rate, done, el = cpu_reference_rate(kind, sd, x_cpu, args.cpu_seconds, n_per)
+            line["cpu_baseline"] = {"value": rate, "unit": "A-scans/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{done} A-scans (64 sets cycled) in {el:.1f} s, oracle port of the "
+                                              "reference forward + predict post-processing, fp32, all host threads"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+// Internal declarations shared by the translation units of libpaut.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/paut.h"
+
+namespace paut {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PAUT_CUDA(expr)                                                                            \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw ::paut::Error(PAUT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+#define PAUT_CHECK(cond, code, msg)                                                                \
+  do {                                                                                             \
+    if (!(cond)) throw ::paut::Error(code, std::string(msg));                                      \
+  } while (0)
+
+// One context = one GPU = one stream.  Owns the activation workspace (bump arena).
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  char* ws = nullptr;
+  size_t ws_cap = 0, ws_off = 0;
+  size_t ws_limit = size_t(2) << 30;
+  int64_t launches = 0;
+  int num_sms = 148;
+  int smem_optin = 0;
+  size_t att_smem_configured = 0;
+  bool profiling = false;                // per-kernel CUDA-event timing (paut_ctx_profile_*)
+  std::vector<std::pair<std::string, cudaEvent_t>> prof_events;
+  bool dry = false;                      // allocation-only pass used to size chunks: ops do nothing
+
+  void reserve(size_t bytes);            // grow workspace (synchronises only when growing)
+  void* alloc(size_t bytes);             // bump allocation, 256-byte aligned
+  float* allocf(size_t n) { return static_cast<float*>(alloc(n * sizeof(float))); }
+  void reset() { ws_off = 0; }
+  void launched(const char* what);       // counts the launch and checks cudaGetLastError
+};
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SOFTPLUS = 4, ACT_TANH_HALF = 5 };
+
+// ---------------------------------------------------------------------------------------------
+// fp32 CUDA-core operators (ops_f32.cu).  Activations are channels-last: [rows, C], C contiguous.
+// ---------------------------------------------------------------------------------------------
+// [B,S,N] -> [B,N,S] (DefectDetectionModel's permute, MSC_Conv1D_training.py:81), any input dtype -> fp32
+void op_transpose_sn(Ctx& c, const void* x, int x_dtype, float* out, int64_t B, int S, int N);
+// any dtype -> fp32 copy
+void op_to_f32(Ctx& c, const void* x, int x_dtype, float* out, int64_t n);
+
+// Conv1d with C_in = 1 (+ folded BN, optional ReLU): x [A,S] -> out [A,S,Cout].  w is [k][Cout].
+void op_stem_conv(Ctx& c, const float* x, int64_t A, int S, const float* w, const float* shift, int k,
+                  int Cout, bool relu, float* out);
+
+struct ConvArgs {
+  const float* in = nullptr;   // [A, Lin, Cin]
+  int64_t A = 0;
+  int Lin = 0, Cin = 0;
+  const float* w = nullptr;    // [taps][Cin][Cout], BN scale folded
+  const float* shift = nullptr;
+  int Cout = 0, taps = 1, dil = 1, stride = 1, pad = 0, Lout = 0;
+  bool relu = false;
+  const float* res = nullptr;  // [A, Lout, ldr], added before the ReLU
+  int ldr = 0;
+  float* out = nullptr;        // [A, Lout, ldc] written at column offset coff (nullable)
+  int ldc = 0, coff = 0;
+  float* pool = nullptr;       // [A, ldp]: mean over Lout written at column offset poff (nullable)
+  int ldp = 0, poff = 0;
+};
+void op_conv(Ctx& c, const ConvArgs& a);
+
+struct LinArgs {
+  const float* A = nullptr;    // [M, lda]
+  int lda = 0;
+  const float* Wt = nullptr;   // [K][N]  (transposed nn.Linear weight)
+  const float* W = nullptr;    // [N][K]  (original layout, used when N is tiny)
+  const float* bias = nullptr;
+  int64_t M = 0;
+  int K = 0, N = 0;
+  float* C = nullptr;          // [M, ldc] written at column offset coff
+  int ldc = 0, coff = 0;
+  int act = ACT_NONE;
+  float act_eps = 0.f;         // added after the activation (two-stage softplus + 1e-6)
+  const float* res = nullptr;  // [M, ldr] added after the activation
+  int ldr = 0;
+  const float* table = nullptr;  // [table_mod, N] row (m % table_mod) added after the activation
+  int table_mod = 1;
+};
+void op_linear(Ctx& c, const LinArgs& a);
+
+// out = act(LN(x + res)) row-wise; res nullable; in-place allowed.
+void op_layernorm(Ctx& c, const float* x, const float* res, const float* gamma, const float* beta, float* out,
+                  int64_t M, int D, int act);
+
+// Multi-head attention core (softmax(QK^T/sqrt(hd)) V) for B sets.  q/k/v may be column slices of a
+// packed buffer (leading dimensions ldq/ldk/ldv).  kv_shift: key/value row j reads row min(j+1, Nk-1)
+// (the MSC cross-attention, NN_models.py:35).  avgw (nullable) [B,Nq,Nk] gets the head-averaged weights.
+void op_attention(Ctx& c, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
+                  int ldo, int64_t B, int Nq, int Nk, int H, int hd, bool kv_shift, float* avgw);
+
+// depthwise conv along the set axis (LocalAttention_N, NN_models.py:159-167): x [B,N,D], w [D][k]
+void op_dwconv_seq(Ctx& c, const float* x, const float* w, const float* bias, float* out, int64_t B, int N,
+                   int D, int k);
+
+// Bidirectional recurrent layer.  gi [B,T,2*G*H] holds x W_ih^T + b_ih for both directions (forward
+// first); whh_t [2][H][G*H]; bhh [2][G*H]; out [B,T,2H].  G = 3 (GRU, gates r|z|n) or 4 (LSTM, i|f|g|o).
+void op_rnn_bidir(Ctx& c, const float* gi, const float* whh_t, const float* bhh, float* out, int64_t B, int T,
+                  int H, int G);
+
+// softmax over the sequence axis: x [B,N] (row stride N) -> out [B,N]
+void op_softmax_seq(Ctx& c, const float* x, float* out, int64_t B, int N);
+// out[m,:] = a[m,:] * s[m] + b[m,:]   (b nullable)
+void op_rowscale_add(Ctx& c, const float* a, const float* s, const float* b, float* out, int64_t M, int D);
+// out[m] = sum_c x[m,c] * q[c]
+void op_rowdot(Ctx& c, const float* x, const float* q, float* out, int64_t M, int D);
+// out[m,:] = x[m,:] + table[m % mod, :]   (positional encodings)
+void op_add_table(Ctx& c, const float* x, const float* table, int mod, float* out, int64_t M, int D);
+// dst[m, coff:coff+D] = src[m, :]
+void op_copy_cols(Ctx& c, const float* src, int lds, float* dst, int ldd, int coff, int64_t M, int D);
+
+// MSC front end (NN_models.py:111-115 / :227-234): per A-scan conv 1->8 k3 ReLU, 8->16 k3 ReLU,
+// optional depthwise k11 background subtraction, mean over channels -> f [A,S].
+void op_msc_front(Ctx& c, const float* x, int64_t A, int S, const float* w1, const float* b1, const float* w2,
+                  const float* b2, const float* wbg, const float* bbg, float* f);
+// MSC head (NN_models.py:123-127): o [M,3] -> sigmoid / tanh*0.5+0.5 into three arrays
+void op_msc_head(Ctx& c, const float* o, int64_t M, float* prob, float* start, float* end);
+// logits[:, 1:] += anomaly (model.py:332, enhanced_model.py:550)
+void op_add_anomaly(Ctx& c, float* logits, const float* anomaly, int64_t M, int C);
+// two-stage finalisation (two_stage_model.py:294-301): probs = softmax(logits); pos *= probs[:,1]
+void op_two_stage_final(Ctx& c, const float* logits, float* probs, float* pos, int64_t M);
+
+// ---------------------------------------------------------------------------------------------
+// post-processing and windowing (ops_post.cu)
+// ---------------------------------------------------------------------------------------------
+struct PostArgs {
+  int kind = 0;
+  const float* score_src = nullptr;   // class logits [M,C] (SSD/ENHANCED), defect_probs [M,2], or prob [M]
+  const float* unc = nullptr;         // class_uncertainty [M,C] / defect_uncertainty [M,2]
+  const float* pos = nullptr;         // position_preds [M,2] (or nullptr for MSC kinds)
+  const float* start = nullptr;       // MSC: defect_start [M]
+  const float* end = nullptr;         // MSC: defect_end [M]
+  const float* anomaly = nullptr;     // [M]
+  int C = 2;
+  int64_t B = 0;
+  int N = 0, S = 0;
+  double threshold = 0.5;
+};
+void op_postprocess(Ctx& c, const PostArgs& a, paut_detection* det, int32_t* count_dev);
+void op_window_gather(Ctx& c, const void* volume, int src_dtype, int64_t G, int64_t n, int S,
+                      const int32_t* table, int64_t W, int L, void* sets, int dst_dtype);
+
+}  // namespace paut

@@ -1,0 +1,878 @@
+// state_dict contract, weight packing (BatchNorm folding, kernel layouts) and the forward graphs.
+#include "model.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <utility>
+#include <cstring>
+
+namespace paut {
+
+// ------------------------------------------------------------------------------------------ contract
+namespace {
+struct SpecBuilder {
+  std::vector<KeySpec>& s;
+  void add(const std::string& k, std::vector<int64_t> shape) { s.push_back({k, std::move(shape)}); }
+  void lin(const std::string& n, int out, int in) { add(n + ".weight", {out, in}); add(n + ".bias", {out}); }
+  void conv(const std::string& n, int co, int ci, int k) { add(n + ".weight", {co, ci, k}); add(n + ".bias", {co}); }
+  void bn(const std::string& n, int c) {
+    add(n + ".weight", {c}); add(n + ".bias", {c}); add(n + ".running_mean", {c}); add(n + ".running_var", {c});
+    add(n + ".num_batches_tracked", {});
+  }
+  void ln(const std::string& n, int c) { add(n + ".weight", {c}); add(n + ".bias", {c}); }
+  void mha(const std::string& n, int d) {
+    add(n + ".in_proj_weight", {3 * d, d}); add(n + ".in_proj_bias", {3 * d});
+    add(n + ".out_proj.weight", {d, d}); add(n + ".out_proj.bias", {d});
+  }
+  void tel(const std::string& n, int d, int dff) {
+    mha(n + ".self_attn", d); lin(n + ".linear1", dff, d); lin(n + ".linear2", d, dff);
+    ln(n + ".norm1", d); ln(n + ".norm2", d);
+  }
+  void rnn(const std::string& n, int gates, int in0, int hidden) {
+    for (int layer = 0; layer < 2; ++layer) {
+      const int in_f = layer == 0 ? in0 : 2 * hidden;
+      for (const char* suf : {"", "_reverse"}) {
+        const std::string l = "_l" + std::to_string(layer) + suf;
+        add(n + ".weight_ih" + l, {gates * hidden, in_f});
+        add(n + ".weight_hh" + l, {gates * hidden, hidden});
+        add(n + ".bias_ih" + l, {gates * hidden});
+        add(n + ".bias_hh" + l, {gates * hidden});
+      }
+    }
+  }
+};
+std::string istr(int i) { return std::to_string(i); }
+}  // namespace
+
+void Model::build_spec() {
+  spec.clear();
+  SpecBuilder b{spec};
+  const int S = cfg.signal_length, d = cfg.d_model, C = cfg.num_classes;
+  switch (kind) {
+    case PAUT_MODEL_MSC:
+    case PAUT_MODEL_MSC_N: {
+      const int h0 = cfg.hidden_sizes[0], h1 = cfg.hidden_sizes[1], h2 = cfg.hidden_sizes[2];
+      b.conv("conv1d.0", 8, 1, 3);
+      b.conv("conv1d.2", 16, 8, 3);
+      if (kind == PAUT_MODEL_MSC_N) b.conv("background_extractor", 16, 1, 11);
+      b.lin("shared_layer.0", h0, S);
+      b.lin("shared_layer.2", h1, h0);
+      b.add("position_encoding.encoding", {300, h1});
+      b.mha("transformer_encoder.self_attn", h1);
+      if (kind == PAUT_MODEL_MSC) b.mha("transformer_encoder.cross_attn", h1);
+      else b.conv("transformer_encoder.local_attn.local_conv", h1, 1, 5);
+      b.lin("transformer_encoder.ffn.0", h2, h1);
+      b.lin("transformer_encoder.ffn.2", h1, h2);
+      for (int i = 1; i <= 3; ++i) b.ln("transformer_encoder.norm" + istr(i), h1);
+      b.lin("classifier", 3, h1);
+      break;
+    }
+    case PAUT_MODEL_CONV1D_MSC:
+      b.conv("feature_extractor.0", 64, 1, 3);
+      b.conv("feature_extractor.2", 128, 64, 3);
+      b.conv("feature_extractor.4", 128, 128, 1);
+      for (int i = 0; i < 4; ++i) b.tel("transformer_encoder.layers." + istr(i), 128, 2048);
+      b.lin("classifier.0", 64, 128);
+      b.lin("classifier.2", 1, 64);
+      break;
+    case PAUT_MODEL_SSD:
+      b.conv("signal_encoder.conv1", 64, 1, 7);  b.bn("signal_encoder.bn1", 64);
+      b.conv("signal_encoder.conv2", 128, 64, 5); b.bn("signal_encoder.bn2", 128);
+      b.conv("signal_encoder.conv3", 256, 128, 3); b.bn("signal_encoder.bn3", 256);
+      b.lin("signal_encoder.fc", d, 256);
+      b.add("sequence_transformer.pos_encoder.pe", {1, 5000, d});
+      for (int i = 0; i < cfg.num_layers; ++i)
+        b.tel("sequence_transformer.transformer_encoder.layers." + istr(i), d, cfg.dim_feedforward);
+      b.rnn("context_aggregator.gru", 3, d, d / 2);
+      b.lin("context_aggregator.projection", d, d);
+      b.lin("anomaly_detector.anomaly_net.0", 64, 2 * d);
+      b.lin("anomaly_detector.anomaly_net.3", 32, 64);
+      b.lin("anomaly_detector.anomaly_net.5", 1, 32);
+      b.lin("detection_head.class_head.0", d / 2, d);
+      b.lin("detection_head.class_head.3", C, d / 2);
+      b.lin("detection_head.position_head.0", d / 2, d);
+      b.lin("detection_head.position_head.3", 2, d / 2);
+      b.lin("health_extractor.0", d / 2, d);
+      b.lin("health_extractor.2", d / 4, d / 2);
+      b.lin("health_extractor.4", d, d / 4);
+      b.lin("attention.0", d / 4, d);
+      b.lin("attention.2", 1, d / 4);
+      break;
+    case PAUT_MODEL_ENHANCED: {
+      const int hd = 128;
+      const std::string e = "signal_encoder.";
+      b.conv(e + "conv_init.0", 64, 1, 7); b.bn(e + "conv_init.1", 64);
+      for (int i = 1; i <= 4; ++i) b.conv(e + "multi_scale.branch" + istr(i), 32, 64, 3);
+      b.conv(e + "multi_scale.combine.0", 128, 128, 1); b.bn(e + "multi_scale.combine.1", 128);
+      for (int r = 0; r < 3; ++r) {
+        const std::string q = e + "res_blocks." + istr(r) + ".conv_block.";
+        b.conv(q + "0", 128, 128, 3); b.bn(q + "1", 128); b.conv(q + "3", 128, 128, 3); b.bn(q + "4", 128);
+      }
+      b.conv(e + "pyramid_1", 256, 128, 3); b.bn(e + "pyramid_bn1", 256);
+      b.conv(e + "pyramid_2", 256, 256, 3); b.bn(e + "pyramid_bn2", 256);
+      b.lin(e + "fc.0", d, 640); b.ln(e + "fc.1", d);
+      b.add("sequence_transformer.pos_encoder.pe", {1, 5000, d});
+      for (int i = 0; i < cfg.num_layers; ++i) b.tel("sequence_transformer.layers." + istr(i), d, cfg.dim_feedforward);
+      b.ln("sequence_transformer.norm", d);
+      b.add("context_aggregator.attention_query", {d});
+      b.rnn("context_aggregator.lstm", 4, d, d / 2);
+      b.lin("context_aggregator.attention_keys", d, d);
+      b.lin("context_aggregator.attention_values", d, d);
+      b.lin("context_aggregator.projection.0", d, 2 * d); b.ln("context_aggregator.projection.1", d);
+      const std::string a = "anomaly_detector.";
+      b.lin(a + "health_extractor.0", hd, d); b.ln(a + "health_extractor.1", hd);
+      b.lin(a + "health_extractor.4", hd / 2, hd); b.ln(a + "health_extractor.5", hd / 2);
+      b.lin(a + "health_extractor.7", d, hd / 2);
+      b.lin(a + "anomaly_net.0", hd, 2 * d); b.ln(a + "anomaly_net.1", hd);
+      b.lin(a + "anomaly_net.4", hd / 2, hd); b.ln(a + "anomaly_net.5", hd / 2);
+      b.lin(a + "anomaly_net.7", 1, hd / 2);
+      b.lin(a + "uncertainty_net.0", hd, 2 * d); b.ln(a + "uncertainty_net.1", hd);
+      b.lin(a + "uncertainty_net.4", 1, hd);
+      const std::string h = "detection_head.";
+      const char* heads[2] = {"class_head", "position_head"};
+      const char* uncs[2] = {"class_uncertainty", "position_uncertainty"};
+      const int nouts[2] = {C, 2};
+      for (int i = 0; i < 2; ++i) {
+        b.lin(h + heads[i] + ".0", d / 2, d); b.ln(h + heads[i] + ".1", d / 2);
+        b.lin(h + heads[i] + ".4", d / 4, d / 2); b.ln(h + heads[i] + ".5", d / 4);
+        b.lin(h + heads[i] + ".7", nouts[i], d / 4);
+        b.lin(h + uncs[i] + ".0", d / 4, d); b.ln(h + uncs[i] + ".1", d / 4);
+        b.lin(h + uncs[i] + ".3", nouts[i], d / 4);
+      }
+      b.mha("cross_attention", d);
+      b.ln("cross_norm", d);
+      b.lin("sequence_integration.0", d, 2 * d); b.ln("sequence_integration.1", d);
+      break;
+    }
+    case PAUT_MODEL_TWO_STAGE: {
+      const int q = d / 4;
+      const char* names[4] = {"small", "medium", "large", "xlarge"};
+      const int ks[4] = {3, 5, 7, 11};
+      for (int i = 0; i < 4; ++i) {
+        const std::string p = std::string("signal_encoder.conv_") + names[i] + ".";
+        b.conv(p + "0", q, 1, ks[i]); b.bn(p + "1", q); b.conv(p + "3", q, q, ks[i]); b.bn(p + "4", q);
+      }
+      b.lin("signal_encoder.projection.0", d, d); b.ln("signal_encoder.projection.1", d);
+      b.add("sequence_transformer.pos_encoder.pe", {1, 5000, d});
+      for (int i = 0; i < 4; ++i) b.tel("sequence_transformer.transformer_encoder.layers." + istr(i), d, 512);
+      b.ln("sequence_transformer.norm", d);
+      const char* mods[4] = {"defect_classifier.classifier", "defect_classifier.uncertainty",
+                             "position_predictor.position_predictor", "position_predictor.uncertainty"};
+      for (const char* m : mods) {
+        b.lin(std::string(m) + ".0", 64, d); b.ln(std::string(m) + ".1", 64); b.lin(std::string(m) + ".4", 2, 64);
+      }
+      break;
+    }
+    default:
+      throw Error(PAUT_ERR_INVALID, "unknown model kind");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tensors
+Model::~Model() {
+  for (void* p : dev_allocs) cudaFree(p);
+}
+
+void Model::set_tensor(const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim) {
+  PAUT_CHECK(key && ptr, PAUT_ERR_INVALID, "set_tensor: null key or pointer");
+  const KeySpec* ks = nullptr;
+  for (const auto& k : spec)
+    if (k.key == key) { ks = &k; break; }
+  PAUT_CHECK(ks, PAUT_ERR_INVALID, std::string("set_tensor: unexpected key '") + key + "'");
+  PAUT_CHECK(ndim == (int)ks->shape.size(), PAUT_ERR_INVALID, std::string("set_tensor: rank mismatch for ") + key);
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    PAUT_CHECK(shape[i] == ks->shape[i], PAUT_ERR_INVALID, std::string("set_tensor: shape mismatch for ") + key);
+    n *= shape[i];
+  }
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.resize(n);
+  if (dtype == PAUT_F32) {
+    PAUT_CUDA(cudaMemcpy(t.data.data(), ptr, n * sizeof(float), cudaMemcpyDefault));
+  } else if (dtype == PAUT_I64) {
+    std::vector<int64_t> tmp(n);
+    PAUT_CUDA(cudaMemcpy(tmp.data(), ptr, n * sizeof(int64_t), cudaMemcpyDefault));
+    for (int64_t i = 0; i < n; ++i) t.data[i] = (float)tmp[i];
+  } else if (dtype == PAUT_BF16) {
+    std::vector<uint16_t> tmp(n);
+    PAUT_CUDA(cudaMemcpy(tmp.data(), ptr, n * sizeof(uint16_t), cudaMemcpyDefault));
+    for (int64_t i = 0; i < n; ++i) {
+      uint32_t u = (uint32_t)tmp[i] << 16;
+      std::memcpy(&t.data[i], &u, 4);
+    }
+  } else {
+    throw Error(PAUT_ERR_INVALID, "set_tensor: dtype must be F32, BF16 or I64");
+  }
+  host[key] = std::move(t);
+  finalized = false;
+}
+
+const HostTensor& Model::H(const std::string& key) const {
+  auto it = host.find(key);
+  if (it == host.end()) throw Error(PAUT_ERR_MISSING, "state_dict tensor not set: " + key);
+  return it->second;
+}
+
+const float* Model::upload(const std::vector<float>& v) {
+  void* p = nullptr;
+  PAUT_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 4) * sizeof(float)));
+  dev_allocs.push_back(p);
+  PAUT_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return static_cast<const float*>(p);
+}
+
+Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int row0, int rows) {
+  const HostTensor& w = H(wkey);
+  const HostTensor& b = H(bkey);
+  const int K = (int)w.shape[1];
+  std::vector<float> W((size_t)rows * K), Wt((size_t)rows * K), bias(rows);
+  for (int n = 0; n < rows; ++n) {
+    bias[n] = b.data[row0 + n];
+    for (int k = 0; k < K; ++k) {
+      const float v = w.data[(size_t)(row0 + n) * K + k];
+      W[(size_t)n * K + k] = v;
+      Wt[(size_t)k * rows + n] = v;
+    }
+  }
+  Lin l;
+  l.K = K;
+  l.N = rows;
+  l.W = upload(W);
+  l.Wt = upload(Wt);
+  l.b = upload(bias);
+  return l;
+}
+
+Lin Model::pack_lin(const std::string& name) {
+  return pack_lin_rows(name + ".weight", name + ".bias", 0, (int)H(name + ".weight").shape[0]);
+}
+
+// Conv1d (+ optional eval BatchNorm folded in): y = conv(x) * scale + shift,
+// scale = gamma / sqrt(var + eps), shift = (bias - mean) * scale + beta.
+ConvW Model::pack_conv(const std::string& cn, const std::string& bn) {
+  const HostTensor& w = H(cn + ".weight");
+  const HostTensor& b = H(cn + ".bias");
+  const int Cout = (int)w.shape[0], Cin = (int)w.shape[1], taps = (int)w.shape[2];
+  std::vector<float> scale(Cout, 1.f), shift(Cout);
+  for (int c = 0; c < Cout; ++c) shift[c] = b.data[c];
+  if (!bn.empty()) {
+    const HostTensor& g = H(bn + ".weight");
+    const HostTensor& be = H(bn + ".bias");
+    const HostTensor& mu = H(bn + ".running_mean");
+    const HostTensor& var = H(bn + ".running_var");
+    for (int c = 0; c < Cout; ++c) {
+      const double sc = (double)g.data[c] / std::sqrt((double)var.data[c] + 1e-5);
+      scale[c] = (float)sc;
+      shift[c] = (float)(((double)b.data[c] - (double)mu.data[c]) * sc + (double)be.data[c]);
+    }
+  }
+  std::vector<float> p((size_t)taps * Cin * Cout);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int t = 0; t < taps; ++t)
+        p[((size_t)t * Cin + ci) * Cout + co] = w.data[((size_t)co * Cin + ci) * taps + t] * scale[co];
+  ConvW cw;
+  cw.Cin = Cin;
+  cw.Cout = Cout;
+  cw.taps = taps;
+  cw.w = upload(p);
+  cw.shift = upload(shift);
+  return cw;
+}
+
+LNW Model::pack_ln(const std::string& name) {
+  LNW l;
+  l.D = (int)H(name + ".weight").shape[0];
+  l.g = upload(H(name + ".weight").data);
+  l.b = upload(H(name + ".bias").data);
+  return l;
+}
+
+MHAW Model::pack_mha(const std::string& name, int heads) {
+  MHAW m;
+  m.D = (int)H(name + ".in_proj_weight").shape[1];
+  m.H = heads;
+  PAUT_CHECK(heads > 0 && m.D % heads == 0, PAUT_ERR_INVALID, "embed_dim must be divisible by num_heads");
+  PAUT_CHECK(m.D / heads <= 64, PAUT_ERR_UNSUPPORTED, "attention head_dim must be <= 64");
+  m.in_proj = pack_lin_rows(name + ".in_proj_weight", name + ".in_proj_bias", 0, 3 * m.D);
+  m.out_proj = pack_lin(name + ".out_proj");
+  return m;
+}
+
+TELW Model::pack_tel(const std::string& name, int heads) {
+  TELW t;
+  t.attn = pack_mha(name + ".self_attn", heads);
+  t.l1 = pack_lin(name + ".linear1");
+  t.l2 = pack_lin(name + ".linear2");
+  t.n1 = pack_ln(name + ".norm1");
+  t.n2 = pack_ln(name + ".norm2");
+  return t;
+}
+
+RNNW Model::pack_rnn(const std::string& name, int layer, int G, int Hh) {
+  RNNW r;
+  r.G = G;
+  r.H = Hh;
+  const int GH = G * Hh;
+  const std::string l = "_l" + std::to_string(layer);
+  const HostTensor& wf = H(name + ".weight_ih" + l);
+  const HostTensor& wr = H(name + ".weight_ih" + l + "_reverse");
+  const int K = (int)wf.shape[1];
+  std::vector<float> W((size_t)2 * GH * K), Wt((size_t)2 * GH * K), bias(2 * GH);
+  for (int dir = 0; dir < 2; ++dir) {
+    const HostTensor& w = dir == 0 ? wf : wr;
+    const HostTensor& b = H(name + ".bias_ih" + l + (dir ? "_reverse" : ""));
+    for (int n = 0; n < GH; ++n) {
+      bias[dir * GH + n] = b.data[n];
+      for (int k = 0; k < K; ++k) {
+        const float v = w.data[(size_t)n * K + k];
+        W[(size_t)(dir * GH + n) * K + k] = v;
+        Wt[(size_t)k * 2 * GH + dir * GH + n] = v;
+      }
+    }
+  }
+  r.ih.K = K;
+  r.ih.N = 2 * GH;
+  r.ih.W = upload(W);
+  r.ih.Wt = upload(Wt);
+  r.ih.b = upload(bias);
+  std::vector<float> whh((size_t)2 * Hh * GH), bhh(2 * GH);
+  for (int dir = 0; dir < 2; ++dir) {
+    const HostTensor& w = H(name + ".weight_hh" + l + (dir ? "_reverse" : ""));
+    const HostTensor& b = H(name + ".bias_hh" + l + (dir ? "_reverse" : ""));
+    for (int n = 0; n < GH; ++n) {
+      bhh[dir * GH + n] = b.data[n];
+      for (int k = 0; k < Hh; ++k) whh[((size_t)dir * Hh + k) * GH + n] = w.data[(size_t)n * Hh + k];
+    }
+  }
+  r.whh_t = upload(whh);
+  r.bhh = upload(bhh);
+  return r;
+}
+
+void Model::finalize() {
+  for (const auto& k : spec)
+    if (!host.count(k.key)) throw Error(PAUT_ERR_MISSING, "state_dict tensor not set: " + k.key);
+  for (void* p : dev_allocs) cudaFree(p);
+  dev_allocs.clear();
+  lin.clear(); conv.clear(); ln.clear(); mha.clear(); tel.clear(); rnn.clear(); raw.clear();
+  PAUT_CUDA(cudaSetDevice(ctx->device));
+
+  auto L = [&](const std::string& n) { lin[n] = pack_lin(n); };
+  auto N_ = [&](const std::string& n) { ln[n] = pack_ln(n); };
+  auto C_ = [&](const std::string& n, const std::string& bn) { conv[n] = pack_conv(n, bn); };
+  auto R = [&](const std::string& n) { raw[n] = upload(H(n).data); };
+  const int d = cfg.d_model;
+
+  switch (kind) {
+    case PAUT_MODEL_MSC:
+    case PAUT_MODEL_MSC_N: {
+      PAUT_CHECK(cfg.hidden_sizes[1] % cfg.num_heads == 0, PAUT_ERR_INVALID,
+                 "embed_dim must be divisible by num_heads");
+      for (const char* n : {"conv1d.0.weight", "conv1d.0.bias", "conv1d.2.weight", "conv1d.2.bias"}) R(n);
+      if (kind == PAUT_MODEL_MSC_N) {
+        R("background_extractor.weight"); R("background_extractor.bias");
+        R("transformer_encoder.local_attn.local_conv.weight"); R("transformer_encoder.local_attn.local_conv.bias");
+      }
+      L("shared_layer.0"); L("shared_layer.2");
+      R("position_encoding.encoding");
+      mha["self"] = pack_mha("transformer_encoder.self_attn", cfg.num_heads);
+      if (kind == PAUT_MODEL_MSC) mha["cross"] = pack_mha("transformer_encoder.cross_attn", cfg.num_heads);
+      L("transformer_encoder.ffn.0"); L("transformer_encoder.ffn.2");
+      for (int i = 1; i <= 3; ++i) N_("transformer_encoder.norm" + istr(i));
+      L("classifier");
+      break;
+    }
+    case PAUT_MODEL_CONV1D_MSC:
+      C_("feature_extractor.0", ""); C_("feature_extractor.2", ""); C_("feature_extractor.4", "");
+      for (int i = 0; i < 4; ++i) tel.push_back(pack_tel("transformer_encoder.layers." + istr(i), 4));
+      L("classifier.0"); L("classifier.2");
+      break;
+    case PAUT_MODEL_SSD:
+      C_("signal_encoder.conv1", "signal_encoder.bn1");
+      C_("signal_encoder.conv2", "signal_encoder.bn2");
+      C_("signal_encoder.conv3", "signal_encoder.bn3");
+      L("signal_encoder.fc");
+      R("sequence_transformer.pos_encoder.pe");
+      for (int i = 0; i < cfg.num_layers; ++i)
+        tel.push_back(pack_tel("sequence_transformer.transformer_encoder.layers." + istr(i), cfg.num_heads));
+      for (int l = 0; l < 2; ++l) rnn.push_back(pack_rnn("context_aggregator.gru", l, 3, d / 2));
+      for (const char* n : {"context_aggregator.projection", "anomaly_detector.anomaly_net.0",
+                            "anomaly_detector.anomaly_net.3", "anomaly_detector.anomaly_net.5",
+                            "detection_head.class_head.0", "detection_head.class_head.3",
+                            "detection_head.position_head.0", "detection_head.position_head.3", "health_extractor.0",
+                            "health_extractor.2", "health_extractor.4", "attention.0", "attention.2"})
+        L(n);
+      break;
+    case PAUT_MODEL_ENHANCED: {
+      const std::string e = "signal_encoder.";
+      C_(e + "conv_init.0", e + "conv_init.1");
+      for (int i = 1; i <= 4; ++i) C_(e + "multi_scale.branch" + istr(i), "");
+      C_(e + "multi_scale.combine.0", e + "multi_scale.combine.1");
+      for (int r = 0; r < 3; ++r) {
+        const std::string q = e + "res_blocks." + istr(r) + ".conv_block.";
+        C_(q + "0", q + "1"); C_(q + "3", q + "4");
+      }
+      C_(e + "pyramid_1", e + "pyramid_bn1"); C_(e + "pyramid_2", e + "pyramid_bn2");
+      L(e + "fc.0"); N_(e + "fc.1");
+      R("sequence_transformer.pos_encoder.pe");
+      for (int i = 0; i < cfg.num_layers; ++i)
+        tel.push_back(pack_tel("sequence_transformer.layers." + istr(i), cfg.num_heads));
+      N_("sequence_transformer.norm");
+      R("context_aggregator.attention_query");
+      for (int l = 0; l < 2; ++l) rnn.push_back(pack_rnn("context_aggregator.lstm", l, 4, d / 2));
+      L("context_aggregator.attention_keys"); L("context_aggregator.attention_values");
+      L("context_aggregator.projection.0"); N_("context_aggregator.projection.1");
+      const std::string a = "anomaly_detector.";
+      for (const char* n : {"health_extractor.0", "health_extractor.4", "health_extractor.7", "anomaly_net.0",
+                            "anomaly_net.4", "anomaly_net.7", "uncertainty_net.0", "uncertainty_net.4"})
+        L(a + n);
+      for (const char* n : {"health_extractor.1", "health_extractor.5", "anomaly_net.1", "anomaly_net.5",
+                            "uncertainty_net.1"})
+        N_(a + n);
+      const std::string h = "detection_head.";
+      for (const char* n : {"class_head", "position_head"}) {
+        L(h + n + ".0"); N_(h + n + ".1"); L(h + n + ".4"); N_(h + n + ".5"); L(h + n + ".7");
+      }
+      for (const char* n : {"class_uncertainty", "position_uncertainty"}) {
+        L(h + n + ".0"); N_(h + n + ".1"); L(h + n + ".3");
+      }
+      PAUT_CHECK(d % 8 == 0, PAUT_ERR_INVALID, "cross_attention: d_model must be divisible by 8");
+      lin["cross.q"] = pack_lin_rows("cross_attention.in_proj_weight", "cross_attention.in_proj_bias", 0, d);
+      lin["cross.kv"] = pack_lin_rows("cross_attention.in_proj_weight", "cross_attention.in_proj_bias", d, 2 * d);
+      L("cross_attention.out_proj");
+      N_("cross_norm");
+      L("sequence_integration.0"); N_("sequence_integration.1");
+      break;
+    }
+    case PAUT_MODEL_TWO_STAGE: {
+      for (const char* n : {"small", "medium", "large", "xlarge"}) {
+        const std::string p = std::string("signal_encoder.conv_") + n + ".";
+        C_(p + "0", p + "1"); C_(p + "3", p + "4");
+      }
+      L("signal_encoder.projection.0"); N_("signal_encoder.projection.1");
+      R("sequence_transformer.pos_encoder.pe");
+      for (int i = 0; i < 4; ++i)
+        tel.push_back(pack_tel("sequence_transformer.transformer_encoder.layers." + istr(i), 8));
+      N_("sequence_transformer.norm");
+      for (const char* m : {"defect_classifier.classifier", "defect_classifier.uncertainty",
+                            "position_predictor.position_predictor", "position_predictor.uncertainty"}) {
+        L(std::string(m) + ".0"); N_(std::string(m) + ".1"); L(std::string(m) + ".4");
+      }
+      break;
+    }
+  }
+  PAUT_CUDA(cudaDeviceSynchronize());
+  finalized = true;
+}
+
+// ------------------------------------------------------------------------------------------ graph helpers
+namespace {
+struct G {
+  Ctx& c;
+  float* linear(const float* A, int lda, const Lin& L, int64_t M, int act = ACT_NONE, const float* res = nullptr,
+                int ldr = 0, float* out = nullptr, int ldc = 0, int coff = 0, float eps = 0.f,
+                const float* table = nullptr, int mod = 1) {
+    LinArgs a;
+    a.A = A; a.lda = lda; a.Wt = L.Wt; a.W = L.W; a.bias = L.b; a.M = M; a.K = L.K; a.N = L.N;
+    if (!out) { out = c.allocf((size_t)M * L.N); ldc = L.N; coff = 0; }
+    a.C = out; a.ldc = ldc; a.coff = coff; a.act = act; a.act_eps = eps; a.res = res; a.ldr = ldr;
+    a.table = table; a.table_mod = mod;
+    op_linear(c, a);
+    return out;
+  }
+  float* norm(const float* x, const float* res, const LNW& n, int64_t M, int act = ACT_NONE, float* out = nullptr) {
+    if (!out) out = c.allocf((size_t)M * n.D);
+    op_layernorm(c, x, res, n.g, n.b, out, M, n.D, act);
+    return out;
+  }
+  // x [B*N, D] -> self attention block output (before residual/norm): att_out = out_proj(attn(qkv)) + res
+  float* self_attention(const float* x, const MHAW& m, int64_t B, int N, const float* res, bool kv_shift = false,
+                        float* avgw = nullptr) {
+    const int64_t M = B * N;
+    const int D = m.D;
+    float* qkv = linear(x, D, m.in_proj, M);
+    float* att = c.allocf((size_t)M * D);
+    op_attention(c, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, att, D, B, N, N, m.H, D / m.H, kv_shift, avgw);
+    return linear(att, D, m.out_proj, M, ACT_NONE, res, D);
+  }
+  // post-norm encoder layer (nn.TransformerEncoderLayer / SelfAttentionBlock)
+  float* encoder_layer(const float* x, const TELW& t, int64_t B, int N, int act, float* avgw = nullptr) {
+    const int64_t M = B * N;
+    float* y = self_attention(x, t.attn, B, N, x, false, avgw);
+    float* x1 = norm(y, nullptr, t.n1, M);
+    float* h = linear(x1, t.attn.D, t.l1, M, act);
+    float* y2 = linear(h, t.l1.N, t.l2, M, ACT_NONE, x1, t.attn.D);
+    return norm(y2, nullptr, t.n2, M);
+  }
+  float* conv(const float* in, int64_t A, int Lin_, const ConvW& w, int dil, int stride, int pad, bool relu,
+              const float* res, float* out, int ldc, int coff, float* pool, int ldp, int poff, int* Lout_ = nullptr) {
+    ConvArgs a;
+    a.in = in; a.A = A; a.Lin = Lin_; a.Cin = w.Cin; a.w = w.w; a.shift = w.shift; a.Cout = w.Cout; a.taps = w.taps;
+    a.dil = dil; a.stride = stride; a.pad = pad;
+    a.Lout = (Lin_ + 2 * pad - dil * (w.taps - 1) - 1) / stride + 1;
+    a.relu = relu; a.res = res; a.ldr = w.Cout; a.out = out; a.ldc = ldc; a.coff = coff;
+    a.pool = pool; a.ldp = ldp; a.poff = poff;
+    if (Lout_) *Lout_ = a.Lout;
+    op_conv(c, a);
+    return out;
+  }
+};
+template <typename T>
+T* slot_at(const paut_outputs& o, int i, int64_t elem_off) {
+  return o.slot[i] ? static_cast<T*>(o.slot[i]) + elem_off : nullptr;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ MSC / MSC_N
+void Model::fwd_msc(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+  Ctx& c = *ctx;
+  G g{c};
+  const int64_t A = B * N;
+  const bool isn = kind == PAUT_MODEL_MSC_N;
+  float* f = c.allocf((size_t)A * S);
+  op_msc_front(c, x, A, S, raw["conv1d.0.weight"], raw["conv1d.0.bias"], raw["conv1d.2.weight"],
+               raw["conv1d.2.bias"], isn ? raw["background_extractor.weight"] : nullptr,
+               isn ? raw["background_extractor.bias"] : nullptr, f);
+  float* h0 = g.linear(f, S, lin["shared_layer.0"], A, ACT_RELU);
+  const Lin& l2 = lin["shared_layer.2"];
+  const int D = l2.N;
+  float* h = g.linear(h0, l2.K, l2, A, ACT_RELU, nullptr, 0, nullptr, 0, 0, 0.f, raw["position_encoding.encoding"], N);
+  float* y = g.self_attention(h, mha["self"], B, N, h);
+  h = g.norm(y, nullptr, ln["transformer_encoder.norm1"], A);
+  if (!isn) {
+    y = g.self_attention(h, mha["cross"], B, N, h, /*kv_shift=*/true);        // NN_models.py:35-36
+    h = g.norm(y, nullptr, ln["transformer_encoder.norm2"], A);
+  } else {
+    float* loc = c.allocf((size_t)A * D);
+    op_dwconv_seq(c, h, raw["transformer_encoder.local_attn.local_conv.weight"],
+                  raw["transformer_encoder.local_attn.local_conv.bias"], loc, B, N, D, 5);
+    h = g.norm(h, loc, ln["transformer_encoder.norm2"], A);
+  }
+  float* f1 = g.linear(h, D, lin["transformer_encoder.ffn.0"], A, ACT_RELU);
+  y = g.linear(f1, lin["transformer_encoder.ffn.0"].N, lin["transformer_encoder.ffn.2"], A, ACT_NONE, h, D);
+  h = g.norm(y, nullptr, ln["transformer_encoder.norm3"], A);
+  float* o = g.linear(h, D, lin["classifier"], A);
+  op_msc_head(c, o, A, slot_at<float>(out, 0, b0 * N), slot_at<float>(out, 1, b0 * N), slot_at<float>(out, 2, b0 * N));
+}
+
+// ------------------------------------------------------------------------------------------ MSC Conv1D
+void Model::fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+  Ctx& c = *ctx;
+  G g{c};
+  const int64_t A = B * N;
+  float* xt = c.allocf((size_t)A * S);
+  op_transpose_sn(c, x, x_dtype, xt, B, S, N);                                  // MSC_Conv1D_training.py:81
+  const ConvW& c0 = conv["feature_extractor.0"];
+  float* a0 = c.allocf((size_t)A * S * 64);
+  op_stem_conv(c, xt, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
+  float* a1 = c.allocf((size_t)A * S * 128);
+  g.conv(a0, A, S, conv["feature_extractor.2"], 1, 1, 1, true, nullptr, a1, 128, 0, nullptr, 0, 0);
+  float* feat = c.allocf((size_t)A * 128);
+  g.conv(a1, A, S, conv["feature_extractor.4"], 1, 1, 0, true, nullptr, nullptr, 0, 0, feat, 128, 0);   // mean over L
+  float* h = feat;
+  for (const TELW& t : tel) h = g.encoder_layer(h, t, B, N, ACT_RELU);
+  float* h1 = g.linear(h, 128, lin["classifier.0"], A, ACT_RELU);
+  if (out.slot[0]) g.linear(h1, 64, lin["classifier.2"], A, ACT_SIGMOID, nullptr, 0, slot_at<float>(out, 0, b0 * N), 1, 0);
+}
+
+// ------------------------------------------------------------------------------------------ SignalSequenceDetector
+void Model::fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t) {
+  Ctx& c = *ctx;
+  G g{c};
+  const int64_t A = B * N;
+  const int d = cfg.d_model, C = cfg.num_classes;
+  const ConvW& c1 = conv["signal_encoder.conv1"];
+  float* a0 = c.allocf((size_t)A * S * 64);
+  op_stem_conv(c, x, A, S, c1.w, c1.shift, c1.taps, c1.Cout, true, a0);
+  float* a1 = c.allocf((size_t)A * S * 128);
+  g.conv(a0, A, S, conv["signal_encoder.conv2"], 1, 1, 2, true, nullptr, a1, 128, 0, nullptr, 0, 0);
+  float* feat = c.allocf((size_t)A * 256);
+  g.conv(a1, A, S, conv["signal_encoder.conv3"], 1, 1, 1, true, nullptr, nullptr, 0, 0, feat, 256, 0);
+  float* seq = g.linear(feat, 256, lin["signal_encoder.fc"], A, ACT_NONE, nullptr, 0, nullptr, 0, 0, 0.f,
+                        raw["sequence_transformer.pos_encoder.pe"], N);          // + pe[:, :N]
+  for (const TELW& t : tel) seq = g.encoder_layer(seq, t, B, N, ACT_RELU);
+  // ContextAggregator: 2-layer bidirectional GRU + projection (model.py:179-192)
+  const float* rin = seq;
+  int rin_ld = d;
+  float* ro = nullptr;
+  for (const RNNW& r : rnn) {
+    float* gi = g.linear(rin, rin_ld, r.ih, A);
+    ro = c.allocf((size_t)A * 2 * r.H);
+    op_rnn_bidir(c, gi, r.whh_t, r.bhh, ro, B, N, r.H, r.G);
+    rin = ro;
+    rin_ld = 2 * r.H;
+  }
+  float* ctxf = g.linear(ro, d, lin["context_aggregator.projection"], A);
+  // health features go straight into the right half of the concat buffer
+  float* comb = c.allocf((size_t)A * 2 * d);
+  float* hf = g.linear(seq, d, lin["health_extractor.0"], A, ACT_RELU);
+  hf = g.linear(hf, d / 2, lin["health_extractor.2"], A, ACT_RELU);
+  g.linear(hf, d / 4, lin["health_extractor.4"], A, ACT_NONE, nullptr, 0, comb, 2 * d, d);
+  // attention over the sequence (model.py:313-314)
+  float* at = g.linear(seq, d, lin["attention.0"], A, ACT_RELU);
+  float* sc = g.linear(at, d / 4, lin["attention.2"], A);
+  float* attw = slot_at<float>(out, 3, b0 * N);
+  if (!attw) attw = c.allocf((size_t)A);
+  op_softmax_seq(c, sc, attw, B, N);
+  float* enh = c.allocf((size_t)A * d);
+  op_rowscale_add(c, seq, attw, ctxf, enh, A, d);                               // model.py:317
+  op_copy_cols(c, enh, d, comb, 2 * d, 0, A, d);
+  float* an = g.linear(comb, 2 * d, lin["anomaly_detector.anomaly_net.0"], A, ACT_RELU);
+  an = g.linear(an, 64, lin["anomaly_detector.anomaly_net.3"], A, ACT_RELU);
+  float* anomaly = slot_at<float>(out, 2, b0 * N);
+  if (!anomaly) anomaly = c.allocf((size_t)A);
+  g.linear(an, 32, lin["anomaly_detector.anomaly_net.5"], A, ACT_SIGMOID, nullptr, 0, anomaly, 1, 0);
+  if (out.slot[0]) {
+    float* ch = g.linear(enh, d, lin["detection_head.class_head.0"], A, ACT_RELU);
+    float* logits = slot_at<float>(out, 0, b0 * N * C);
+    g.linear(ch, d / 2, lin["detection_head.class_head.3"], A, ACT_NONE, nullptr, 0, logits, C, 0);
+    op_add_anomaly(c, logits, anomaly, A, C);                                   // model.py:327-334
+  }
+  if (out.slot[1]) {
+    float* ph = g.linear(enh, d, lin["detection_head.position_head.0"], A, ACT_RELU);
+    g.linear(ph, d / 2, lin["detection_head.position_head.3"], A, ACT_SIGMOID, nullptr, 0,
+             slot_at<float>(out, 1, b0 * N * 2), 2, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ TwoStageDefectDetector
+void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+  Ctx& c = *ctx;
+  G g{c};
+  const int64_t A = B * N;
+  const int d = cfg.d_model, q = d / 4;
+  float* feat = c.allocf((size_t)A * d);
+  float* a0 = c.allocf((size_t)A * S * q);
+  const char* names[4] = {"small", "medium", "large", "xlarge"};
+  for (int i = 0; i < 4; ++i) {                                                  // two_stage_model.py:102-114
+    const std::string p = std::string("signal_encoder.conv_") + names[i] + ".";
+    const ConvW& s = conv[p + "0"];
+    op_stem_conv(c, x, A, S, s.w, s.shift, s.taps, s.Cout, true, a0);
+    const ConvW& w = conv[p + "3"];
+    g.conv(a0, A, S, w, 1, 1, w.taps / 2, true, nullptr, nullptr, 0, 0, feat, d, q * i);
+  }
+  float* pr = g.linear(feat, d, lin["signal_encoder.projection.0"], A);
+  float* seq = g.norm(pr, nullptr, ln["signal_encoder.projection.1"], A);
+  {
+    // + pe[:, :N]: reuse the row-table epilogue through an identity-free path
+    float* seq2 = c.allocf((size_t)A * d);
+    op_add_table(c, seq, raw["sequence_transformer.pos_encoder.pe"], N, seq2, A, d);
+    seq = seq2;
+  }
+  for (const TELW& t : tel) seq = g.encoder_layer(seq, t, B, N, ACT_RELU);
+  seq = g.norm(seq, nullptr, ln["sequence_transformer.norm"], A);
+  auto head = [&](const std::string& m, int act, float eps, float* dst) {
+    float* h = g.linear(seq, d, lin[m + ".0"], A);
+    h = g.norm(h, nullptr, ln[m + ".1"], A, ACT_RELU);
+    if (!dst) dst = c.allocf((size_t)A * 2);
+    g.linear(h, 64, lin[m + ".4"], A, act, nullptr, 0, dst, 2, 0, eps);
+    return dst;
+  };
+  float* logits = head("defect_classifier.classifier", ACT_NONE, 0.f, slot_at<float>(out, 0, b0 * N * 2));
+  if (out.slot[2]) head("defect_classifier.uncertainty", ACT_SOFTPLUS, 1e-6f, slot_at<float>(out, 2, b0 * N * 2));
+  float* pos = nullptr;
+  if (out.slot[3]) pos = head("position_predictor.position_predictor", ACT_SIGMOID, 0.f, slot_at<float>(out, 3, b0 * N * 2));
+  if (out.slot[4]) head("position_predictor.uncertainty", ACT_SOFTPLUS, 1e-6f, slot_at<float>(out, 4, b0 * N * 2));
+  op_two_stage_final(c, logits, slot_at<float>(out, 1, b0 * N * 2), pos, A);
+}
+
+// ------------------------------------------------------------------------------------------ EnhancedSignalSequenceDetector
+void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot) {
+  Ctx& c = *ctx;
+  G g{c};
+  const int64_t A = B * N;
+  const int d = cfg.d_model, C = cfg.num_classes;
+  const std::string e = "signal_encoder.";
+  // ---- EnhancedSignalEncoder (enhanced_model.py:135-175); three rotating [A,S,128] buffers
+  const ConvW& ci = conv[e + "conv_init.0"];
+  float* s0 = c.allocf((size_t)A * S * 64);
+  op_stem_conv(c, x, A, S, ci.w, ci.shift, ci.taps, ci.Cout, true, s0);
+  float* bufA = c.allocf((size_t)A * S * 128);
+  float* bufB = c.allocf((size_t)A * S * 128);
+  float* bufC = c.allocf((size_t)A * S * 128);
+  float* feat = c.allocf((size_t)A * 640);
+  for (int b = 0; b < 4; ++b)
+    g.conv(s0, A, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, 1, 1 << b, false, nullptr, bufA, 128, 32 * b,
+           nullptr, 0, 0);
+  g.conv(bufA, A, S, conv[e + "multi_scale.combine.0"], 1, 1, 0, true, nullptr, bufB, 128, 0, nullptr, 0, 0);
+  float* h = bufB;
+  float* spare = bufC;
+  for (int r = 0; r < 3; ++r) {
+    const int dil = 1 << r;
+    const std::string qn = e + "res_blocks." + istr(r) + ".conv_block.";
+    g.conv(h, A, S, conv[qn + "0"], dil, 1, dil, true, nullptr, bufA, 128, 0, nullptr, 0, 0);
+    g.conv(bufA, A, S, conv[qn + "3"], dil, 1, dil, true, h, spare, 128, 0, r == 2 ? feat : nullptr, 640, 0);
+    std::swap(h, spare);
+  }
+  int L1 = 0, L2 = 0;
+  g.conv(h, A, S, conv[e + "pyramid_1"], 1, 2, 1, true, nullptr, bufA, 256, 0, feat, 640, 128, &L1);
+  g.conv(bufA, A, L1, conv[e + "pyramid_2"], 1, 2, 1, true, nullptr, nullptr, 0, 0, feat, 640, 384, &L2);
+  float* fc = g.linear(feat, 640, lin[e + "fc.0"], A);
+  float* sf = g.norm(fc, nullptr, ln[e + "fc.1"], A, ACT_RELU);
+  // ---- EnhancedSequenceTransformer (:230-251)
+  float* seq = c.allocf((size_t)A * d);
+  op_add_table(c, sf, raw["sequence_transformer.pos_encoder.pe"], N, seq, A, d);
+  for (size_t l = 0; l < tel.size(); ++l) {
+    float* aw = out.slot[6] ? static_cast<float*>(out.slot[6]) + ((int64_t)l * Btot + b0) * N * N : nullptr;
+    seq = g.encoder_layer(seq, tel[l], B, N, ACT_GELU, aw);
+  }
+  seq = g.norm(seq, nullptr, ln["sequence_transformer.norm"], A);
+  // ---- EnhancedContextAggregator (:283-313)
+  const float* rin = seq;
+  int rin_ld = d;
+  float* lo = nullptr;
+  for (const RNNW& r : rnn) {
+    float* gi = g.linear(rin, rin_ld, r.ih, A);
+    lo = c.allocf((size_t)A * 2 * r.H);
+    op_rnn_bidir(c, gi, r.whh_t, r.bhh, lo, B, N, r.H, r.G);
+    rin = lo;
+    rin_ld = 2 * r.H;
+  }
+  float* keys = g.linear(lo, d, lin["context_aggregator.attention_keys"], A);
+  float* sc = c.allocf((size_t)A);
+  op_rowdot(c, keys, raw["context_aggregator.attention_query"], sc, A, d);
+  float* cw = slot_at<float>(out, 7, b0 * N);
+  if (!cw) cw = c.allocf((size_t)A);
+  op_softmax_seq(c, sc, cw, B, N);
+  float* cat = c.allocf((size_t)A * 2 * d);
+  float* vals = g.linear(lo, d, lin["context_aggregator.attention_values"], A);
+  op_rowscale_add(c, vals, cw, nullptr, vals, A, d);
+  op_copy_cols(c, lo, d, cat, 2 * d, 0, A, d);
+  op_copy_cols(c, vals, d, cat, 2 * d, d, A, d);
+  float* cp = g.linear(cat, 2 * d, lin["context_aggregator.projection.0"], A);
+  float* ctxf = g.norm(cp, nullptr, ln["context_aggregator.projection.1"], A);
+  // ---- cross attention (:525-528): Q = encoder features, K = V = context; always 8 heads (:491)
+  float* qb = g.linear(sf, d, lin["cross.q"], A);
+  float* kv = g.linear(ctxf, d, lin["cross.kv"], A);
+  float* att = c.allocf((size_t)A * d);
+  op_attention(c, qb, d, kv, 2 * d, kv + d, 2 * d, att, d, B, N, N, 8, d / 8, false,
+               slot_at<float>(out, 8, b0 * N * N));
+  float* co = g.linear(att, d, lin["cross_attention.out_proj"], A, ACT_NONE, sf, d);
+  float* cf = g.norm(co, nullptr, ln["cross_norm"], A);
+  // ---- sequence integration (:531-533)
+  float* cat2 = c.allocf((size_t)A * 2 * d);
+  op_copy_cols(c, cf, d, cat2, 2 * d, 0, A, d);
+  op_copy_cols(c, seq, d, cat2, 2 * d, d, A, d);
+  float* ig = g.linear(cat2, 2 * d, lin["sequence_integration.0"], A);
+  float* integ = g.norm(ig, nullptr, ln["sequence_integration.1"], A, ACT_GELU);
+  // ---- EnhancedAnomalyDetector (:358-380)
+  const std::string a = "anomaly_detector.";
+  float* comb = c.allocf((size_t)A * 2 * d);
+  op_copy_cols(c, integ, d, comb, 2 * d, 0, A, d);
+  float* hl = g.norm(g.linear(seq, d, lin[a + "health_extractor.0"], A), nullptr, ln[a + "health_extractor.1"], A, ACT_GELU);
+  hl = g.norm(g.linear(hl, 128, lin[a + "health_extractor.4"], A), nullptr, ln[a + "health_extractor.5"], A, ACT_GELU);
+  g.linear(hl, 64, lin[a + "health_extractor.7"], A, ACT_NONE, nullptr, 0, comb, 2 * d, d);
+  float* an = g.norm(g.linear(comb, 2 * d, lin[a + "anomaly_net.0"], A), nullptr, ln[a + "anomaly_net.1"], A, ACT_GELU);
+  an = g.norm(g.linear(an, 128, lin[a + "anomaly_net.4"], A), nullptr, ln[a + "anomaly_net.5"], A, ACT_GELU);
+  float* anomaly = slot_at<float>(out, 4, b0 * N);
+  if (!anomaly) anomaly = c.allocf((size_t)A);
+  g.linear(an, 64, lin[a + "anomaly_net.7"], A, ACT_SIGMOID, nullptr, 0, anomaly, 1, 0);
+  if (out.slot[5]) {
+    float* un = g.norm(g.linear(comb, 2 * d, lin[a + "uncertainty_net.0"], A), nullptr, ln[a + "uncertainty_net.1"], A, ACT_GELU);
+    g.linear(un, 128, lin[a + "uncertainty_net.4"], A, ACT_SOFTPLUS, nullptr, 0, slot_at<float>(out, 5, b0 * N), 1, 0);
+  }
+  // ---- EnhancedDefectDetectionHead (:433-448)
+  const std::string hd = "detection_head.";
+  auto deep = [&](const std::string& n, int nout, int act, float* dst) {
+    float* t = g.norm(g.linear(integ, d, lin[hd + n + ".0"], A), nullptr, ln[hd + n + ".1"], A, ACT_GELU);
+    t = g.norm(g.linear(t, d / 2, lin[hd + n + ".4"], A), nullptr, ln[hd + n + ".5"], A, ACT_GELU);
+    g.linear(t, d / 4, lin[hd + n + ".7"], A, act, nullptr, 0, dst, nout, 0);
+  };
+  auto shallow = [&](const std::string& n, int nout, float* dst) {
+    float* t = g.norm(g.linear(integ, d, lin[hd + n + ".0"], A), nullptr, ln[hd + n + ".1"], A, ACT_GELU);
+    g.linear(t, d / 4, lin[hd + n + ".3"], A, ACT_SOFTPLUS, nullptr, 0, dst, nout, 0);
+  };
+  if (out.slot[0]) {
+    float* logits = slot_at<float>(out, 0, b0 * N * C);
+    deep("class_head", C, ACT_NONE, logits);
+    op_add_anomaly(c, logits, anomaly, A, C);                                   // :545-552
+  }
+  if (out.slot[1]) shallow("class_uncertainty", C, slot_at<float>(out, 1, b0 * N * C));
+  if (out.slot[2]) deep("position_head", 2, ACT_SIGMOID, slot_at<float>(out, 2, b0 * N * 2));
+  if (out.slot[3]) shallow("position_uncertainty", 2, slot_at<float>(out, 3, b0 * N * 2));
+}
+
+// ------------------------------------------------------------------------------------------ driver
+void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S, const paut_outputs& out) {
+  PAUT_CHECK(finalized, PAUT_ERR_STATE, "forward before paut_model_finalize");
+  PAUT_CHECK(x != nullptr, PAUT_ERR_INVALID, "forward: x is null");
+  PAUT_CHECK(B > 0 && N > 0 && S > 0, PAUT_ERR_INVALID, "forward: B, N, S must be positive");
+  PAUT_CHECK(x_dtype == PAUT_F32 || x_dtype == PAUT_BF16, PAUT_ERR_INVALID, "forward: x dtype must be F32 or BF16");
+  PAUT_CHECK(N <= 4096 && S <= 8192, PAUT_ERR_UNSUPPORTED, "forward: N or S too large");
+  if (kind == PAUT_MODEL_MSC || kind == PAUT_MODEL_MSC_N) {
+    PAUT_CHECK(S == cfg.signal_length, PAUT_ERR_INVALID,
+               "forward: signal length differs from the model's signal_length (shared_layer.0 in_features)");
+    PAUT_CHECK(N <= 300, PAUT_ERR_INVALID, "forward: more than 300 signals per set (position table has 300 rows)");
+  } else if (kind != PAUT_MODEL_CONV1D_MSC) {
+    PAUT_CHECK(N <= 5000, PAUT_ERR_INVALID, "forward: sequence longer than the positional-encoding table");
+  }
+  PAUT_CHECK(S % 4 == 0, PAUT_ERR_UNSUPPORTED, "forward: signal length must be a multiple of 4");
+  PAUT_CUDA(cudaSetDevice(ctx->device));
+  Ctx& c = *ctx;
+  const size_t esz = x_dtype == PAUT_BF16 ? 2 : 4;
+  auto run = [&](int64_t b0, int64_t nb) {
+    const char* xc = static_cast<const char*>(x) + (size_t)b0 * N * S * esz;
+    if (kind == PAUT_MODEL_CONV1D_MSC) {
+      fwd_conv1d_msc(xc, x_dtype, nb, (int)N, (int)S, out, b0);
+      return;
+    }
+    const float* xf = reinterpret_cast<const float*>(xc);
+    if (x_dtype != PAUT_F32) {
+      float* t = c.allocf((size_t)nb * N * S);
+      op_to_f32(c, xc, x_dtype, t, nb * N * S);
+      xf = t;
+    }
+    switch (kind) {
+      case PAUT_MODEL_MSC:
+      case PAUT_MODEL_MSC_N: fwd_msc(xf, nb, (int)N, (int)S, out, b0); break;
+      case PAUT_MODEL_SSD: fwd_ssd(xf, nb, (int)N, (int)S, out, b0, B); break;
+      case PAUT_MODEL_ENHANCED: fwd_enhanced(xf, nb, (int)N, (int)S, out, b0, B); break;
+      case PAUT_MODEL_TWO_STAGE: fwd_two_stage(xf, nb, (int)N, (int)S, out, b0); break;
+      default: throw Error(PAUT_ERR_INVALID, "unknown model kind");
+    }
+  };
+  // size the chunk with two dry runs (allocation only): footprint(nb) = fixed + per_set * nb
+  c.dry = true;
+  c.reset(); run(0, 1); const size_t s1 = c.ws_off;
+  c.reset(); run(0, 2); const size_t s2 = c.ws_off;
+  c.dry = false;
+  c.reset();
+  const size_t per_set = s2 > s1 ? s2 - s1 : 1;
+  const size_t slack = size_t(1) << 20;
+  int64_t chunk = c.ws_limit > s1 + slack ? (int64_t)((c.ws_limit - s1 - slack) / per_set) + 1 : 1;
+  if (chunk < 1) chunk = 1;
+  if (chunk > B) chunk = B;
+  c.reserve(s1 + per_set * (size_t)(chunk - 1) + slack);
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    c.reset();
+    run(b0, std::min<int64_t>(chunk, B - b0));
+  }
+}
+
+void Model::postprocess(const paut_outputs& o, int64_t B, int64_t N, int64_t S, double thr, paut_detection* det,
+                        int32_t* count_dev) {
+  PAUT_CHECK(det && count_dev, PAUT_ERR_INVALID, "postprocess: null output");
+  PAUT_CUDA(cudaSetDevice(ctx->device));
+  PostArgs a;
+  a.kind = kind; a.B = B; a.N = (int)N; a.S = (int)S; a.threshold = thr; a.C = cfg.num_classes;
+  auto need = [&](int i) {
+    PAUT_CHECK(o.slot[i] != nullptr, PAUT_ERR_INVALID, "postprocess: required forward output slot is null");
+    return static_cast<const float*>(o.slot[i]);
+  };
+  switch (kind) {
+    case PAUT_MODEL_MSC:
+    case PAUT_MODEL_MSC_N: a.score_src = need(0); a.start = need(1); a.end = need(2); break;
+    case PAUT_MODEL_CONV1D_MSC: a.score_src = need(0); break;
+    case PAUT_MODEL_SSD: a.score_src = need(0); a.pos = need(1); a.anomaly = need(2); break;
+    case PAUT_MODEL_ENHANCED: a.score_src = need(0); a.unc = need(1); a.pos = need(2); a.anomaly = need(4); break;
+    case PAUT_MODEL_TWO_STAGE: a.score_src = need(1); a.unc = need(2); a.pos = need(3); break;
+    default: throw Error(PAUT_ERR_INVALID, "unknown model kind");
+  }
+  ctx->reset();
+  ctx->reserve(sizeof(int32_t) * 2 * (size_t)B + 1024);
+  op_postprocess(*ctx, a, det, count_dev);
+}
+
+}  // namespace paut

@@ -1,0 +1,95 @@
+// Model object of libpaut.so: state_dict contract, packed weights, forward graphs.
+#pragma once
+#include "common.cuh"
+
+namespace paut {
+
+struct KeySpec {
+  std::string key;
+  std::vector<int64_t> shape;
+};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+// Packed parameter views (device pointers owned by Model::dev_allocs)
+struct Lin {
+  const float* Wt = nullptr;  // [K][N]
+  const float* W = nullptr;   // [N][K]
+  const float* b = nullptr;
+  int K = 0, N = 0;
+};
+struct ConvW {
+  const float* w = nullptr;      // [taps][Cin][Cout] (BN scale folded); Cin == 1 -> [taps][Cout]
+  const float* shift = nullptr;  // folded bias
+  int Cin = 0, Cout = 0, taps = 0;
+};
+struct LNW {
+  const float* g = nullptr;
+  const float* b = nullptr;
+  int D = 0;
+};
+struct MHAW {
+  Lin in_proj, out_proj;
+  int D = 0, H = 0;
+};
+struct TELW {  // post-norm transformer encoder layer
+  MHAW attn;
+  Lin l1, l2;
+  LNW n1, n2;
+};
+struct RNNW {  // one bidirectional layer
+  Lin ih;                        // N = 2*G*H (forward rows first), bias = b_ih
+  const float* whh_t = nullptr;  // [2][H][G*H]
+  const float* bhh = nullptr;    // [2][G*H]
+  int H = 0, G = 0;
+};
+
+struct Model {
+  Ctx* ctx = nullptr;
+  int kind = 0;
+  paut_model_cfg cfg{};
+  std::vector<KeySpec> spec;
+  std::map<std::string, HostTensor> host;
+  bool finalized = false;
+  std::vector<void*> dev_allocs;
+
+  // ---- packed parameters (filled by finalize) ----
+  std::map<std::string, Lin> lin;
+  std::map<std::string, ConvW> conv;
+  std::map<std::string, LNW> ln;
+  std::map<std::string, MHAW> mha;
+  std::vector<TELW> tel;
+  std::vector<RNNW> rnn;
+  std::map<std::string, const float*> raw;   // tensors uploaded as they are
+
+  ~Model();
+  void build_spec();
+  void set_tensor(const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim);
+  void finalize();
+  void forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S, const paut_outputs& out);
+  void postprocess(const paut_outputs& outs, int64_t B, int64_t N, int64_t S, double thr, paut_detection* det,
+                   int32_t* count_dev);
+
+  // helpers used by finalize
+  const HostTensor& H(const std::string& key) const;
+  const float* upload(const std::vector<float>& v);
+  Lin pack_lin(const std::string& name);
+  Lin pack_lin_rows(const std::string& wkey, const std::string& bkey, int row0, int rows);
+  ConvW pack_conv(const std::string& conv_name, const std::string& bn_name);
+  LNW pack_ln(const std::string& name);
+  MHAW pack_mha(const std::string& name, int heads);
+  TELW pack_tel(const std::string& name, int heads);
+  RNNW pack_rnn(const std::string& name, int layer, int G, int Hh);
+
+  // forward graphs (one chunk of whole sets)
+  void fwd_msc(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
+  void fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
+  void fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+};
+
+}  // namespace paut

@@ -1,0 +1,233 @@
+"""Thin host layer over the C ABI: one library context per (GPU, CUDA stream), native model handles.
+
+PyTorch is used for device memory and streams only; every computation is a libpaut kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DETECTION, KINDS, PRECISION, ModelCfg, Outputs, check
+
+_contexts = {}
+_contexts_lock = threading.Lock()
+
+# (name, trailing shape as a function of (N, C, L)) per output slot -- include/paut.h "Output slots"
+OUTPUT_SLOTS = {
+    "msc": [("defect_prob", "N"), ("defect_start", "N"), ("defect_end", "N")],
+    "msc_n": [("defect_prob", "N"), ("defect_start", "N"), ("defect_end", "N")],
+    "conv1d_msc": [("defect_prob", "N")],
+    "ssd": [("class_preds", "NC"), ("position_preds", "N2"), ("anomaly_scores", "N1"), ("attention_weights", "N1")],
+    "enhanced": [("class_preds", "NC"), ("class_uncertainty", "NC"), ("position_preds", "N2"),
+                 ("position_uncertainty", "N2"), ("anomaly_scores", "N1"), ("anomaly_uncertainty", "N1"),
+                 ("attention_weights", "LNN"), ("context_attention", "N"), ("cross_attention", "NN")],
+    "two_stage": [("defect_logits", "N2"), ("defect_probs", "N2"), ("defect_uncertainty", "N2"),
+                  ("position_preds", "N2"), ("position_uncertainty", "N2")],
+}
+
+
+class Context:
+    """paut_ctx bound to a device and a CUDA stream."""
+
+    def __init__(self, device_index, stream_handle):
+        self.lib = _lib.load()
+        self.device_index = device_index
+        self.stream_handle = stream_handle
+        h = C.c_void_p()
+        check(self.lib.paut_ctx_create(device_index, C.c_void_p(stream_handle), C.byref(h)))
+        self.handle = h
+
+    def set_workspace_limit(self, nbytes):
+        check(self.lib.paut_ctx_set_workspace_limit(self.handle, int(nbytes)), self.handle)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.paut_ctx_launch_count(self.handle))
+
+    def profile_begin(self):
+        check(self.lib.paut_ctx_profile_begin(self.handle), self.handle)
+
+    def profile_end(self):
+        """{kernel name: (launches, total_ms)} measured with CUDA events on the ctx stream."""
+        buf = C.create_string_buffer(1 << 16)
+        check(self.lib.paut_ctx_profile_end(self.handle, buf, len(buf)), self.handle)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out
+
+    def close(self):
+        if self.handle:
+            self.lib.paut_ctx_destroy(self.handle)
+            self.handle = None
+
+
+def get_context(device=None):
+    """Context for `device` and torch's current stream on it (created on first use)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("libpaut needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"libpaut runs on CUDA devices only, got {dev}")
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(index).cuda_stream
+    key = (index, stream)
+    with _contexts_lock:
+        ctx = _contexts.get(key)
+        if ctx is None:
+            ctx = Context(index, stream)
+            _contexts[key] = ctx
+    return ctx
+
+
+def total_launches():
+    return sum(c.launch_count for c in _contexts.values())
+
+
+class NativeModel:
+    """paut_model handle: weights packed once, forward / postprocess on device buffers."""
+
+    def __init__(self, ctx, kind, cfg, precision="fp32"):
+        self.ctx, self.kind, self.precision = ctx, kind, precision
+        self.lib = ctx.lib
+        c = ModelCfg()
+        c.signal_length = int(cfg.get("signal_length", 0) or 0)
+        hs = cfg.get("hidden_sizes") or (0, 0, 0)
+        for i in range(3):
+            c.hidden_sizes[i] = int(hs[i])
+        c.num_heads = int(cfg.get("num_heads", 0) or 0)
+        c.d_model = int(cfg.get("d_model", 0) or 0)
+        c.num_classes = int(cfg.get("num_classes", 0) or 0)
+        c.num_layers = int(cfg.get("num_layers", 0) or 0)
+        c.dim_feedforward = int(cfg.get("dim_feedforward", 0) or 0)
+        c.precision = PRECISION[precision]
+        self.num_classes = c.num_classes or 2
+        self.num_layers = c.num_layers
+        h = C.c_void_p()
+        check(self.lib.paut_model_create(ctx.handle, KINDS[kind], C.byref(c), C.byref(h)), ctx.handle)
+        self.handle = h
+
+    def keys(self):
+        out = []
+        key, shape, ndim = C.c_char_p(), (C.c_int64 * 4)(), C.c_int()
+        for i in range(self.lib.paut_model_num_keys(self.handle)):
+            check(self.lib.paut_model_key(self.handle, i, C.byref(key), shape, C.byref(ndim)), self.ctx.handle)
+            out.append((key.value.decode(), tuple(shape[j] for j in range(ndim.value))))
+        return out
+
+    def load_state_dict(self, state_dict):
+        for key, _ in self.keys():
+            if key not in state_dict:
+                raise KeyError(f"state_dict is missing {key!r}")
+            t = state_dict[key].detach()
+            if t.dtype == torch.int64:
+                t, dt = t.contiguous(), _lib.I64
+            else:
+                t, dt = t.to(torch.float32).contiguous(), _lib.F32
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            check(self.lib.paut_model_set_tensor(self.handle, key.encode(), C.c_void_p(t.data_ptr()), dt, shape,
+                                                 t.dim()), self.ctx.handle)
+        check(self.lib.paut_model_finalize(self.handle), self.ctx.handle)
+
+    def _alloc_outputs(self, B, N, device, wanted=None, num_layers=1):
+        outs, struct = {}, Outputs()
+        shapes = {"N": (B, N), "NC": (B, N, self.num_classes), "N2": (B, N, 2), "N1": (B, N, 1),
+                  "NN": (B, N, N), "LNN": (num_layers, B, N, N)}
+        for i, (name, code) in enumerate(OUTPUT_SLOTS[self.kind]):
+            if wanted is not None and name not in wanted:
+                continue
+            t = torch.empty(shapes[code], dtype=torch.float32, device=device)
+            outs[name] = t
+            struct.slot[i] = t.data_ptr()
+        return outs, struct
+
+    def forward(self, x, wanted=None, num_layers=1):
+        """x: CUDA tensor [B,N,S] (conv1d_msc: [B,S,N]), fp32 or bf16, contiguous."""
+        if not x.is_cuda:
+            raise RuntimeError("libpaut forward needs a CUDA tensor (no CPU fallback)")
+        if x.dim() != 3:
+            raise ValueError("expected a 3-D input [batch, signals, samples]")
+        if not x.is_contiguous():
+            # the reference's x.view(...) raises on non-contiguous input (NN_models.py:111)
+            raise RuntimeError("input must be contiguous")
+        if x.dtype == torch.float32:
+            dt = _lib.F32
+        elif x.dtype == torch.bfloat16:
+            dt = _lib.BF16
+        else:
+            raise TypeError(f"unsupported input dtype {x.dtype}")
+        if self.kind == "conv1d_msc":
+            B, S, N = x.shape
+        else:
+            B, N, S = x.shape
+        outs, struct = self._alloc_outputs(B, N, x.device, wanted, num_layers)
+        check(self.lib.paut_forward(self.handle, C.c_void_p(x.data_ptr()), dt, B, N, S, C.byref(struct)),
+              self.ctx.handle)
+        return outs, struct, (B, N, S)
+
+    def postprocess(self, struct, B, N, S, threshold, device):
+        """Device post-processing; returns (records tensor [B*N*48] uint8 on device, count tensor int32)."""
+        det = torch.empty(B * N * DETECTION.itemsize, dtype=torch.uint8, device=device)
+        count = torch.zeros(1, dtype=torch.int32, device=device)
+        check(self.lib.paut_postprocess(self.handle, C.byref(struct), B, N, S, float(threshold),
+                                        C.c_void_p(det.data_ptr()), C.c_void_p(count.data_ptr())), self.ctx.handle)
+        return det, count
+
+    def close(self):
+        if self.handle:
+            self.lib.paut_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def records_to_numpy(det, count):
+    """D2H of the kept records only -> numpy structured array (dtype DETECTION)."""
+    n = int(count.item())
+    if n == 0:
+        return np.zeros(0, dtype=DETECTION)
+    raw = det[: n * DETECTION.itemsize].cpu().numpy()
+    return raw.view(DETECTION).copy()
+
+
+def window_table(rule, n, seq_length=50):
+    """(start, valid_len) pairs of the reference windowing rules; rule 'msc' or 'ssd' (host arithmetic)."""
+    lib = _lib.load()
+    r = {"msc": 0, "ssd": 1}[rule]
+    cnt = lib.paut_window_table_host(r, n, seq_length, None, 0)
+    if cnt < 0:
+        raise ValueError("bad window arguments")
+    buf = (C.c_int32 * (2 * max(cnt, 1)))()
+    lib.paut_window_table_host(r, n, seq_length, buf, cnt)
+    return [(buf[2 * i], buf[2 * i + 1]) for i in range(cnt)]
+
+
+def gather_windows(volume, rule, seq_length=50, out_dtype=None, keep_groups=None):
+    """Device windowing: volume [G, n, S] (CUDA, fp32/bf16) -> (sets [W, L, S], table int32 [W,3] on host).
+    keep_groups: optional bool mask [G] (e.g. the all-zero-run drop of dataset_preparation.py:205)."""
+    if not volume.is_cuda or not volume.is_contiguous():
+        raise RuntimeError("volume must be a contiguous CUDA tensor")
+    G, n, S = volume.shape
+    wins = window_table(rule, n, seq_length)
+    groups = range(G) if keep_groups is None else [g for g in range(G) if bool(keep_groups[g])]
+    table = np.array([(g, s, v) for g in groups for (s, v) in wins], dtype=np.int32).reshape(-1, 3)
+    out_dtype = out_dtype or volume.dtype
+    sets = torch.empty((len(table), seq_length, S), dtype=out_dtype, device=volume.device)
+    if len(table) == 0:
+        return sets, table
+    ctx = get_context(volume.device)
+    dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+    table_dev = torch.from_numpy(table).to(volume.device)
+    check(ctx.lib.paut_window_gather(ctx.handle, C.c_void_p(volume.data_ptr()), dt[volume.dtype], G, n, S,
+                                     C.c_void_p(table_dev.data_ptr()), len(table), seq_length,
+                                     C.c_void_p(sets.data_ptr()), dt[out_dtype]), ctx.handle)
+    return sets, table

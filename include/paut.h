@@ -1,0 +1,181 @@
+/*
+ * paut.h -- C ABI of libpaut.so: B200 (sm_100a) batched inference of the PAUT
+ * A-scan signal models of CSMaus/DefectDetection_viaObjectDetection.
+ *
+ * The reference has no FFI layer: its boundary for this path is the Python
+ * nn.Module surface.  This header is the boundary a
+ * Python (ctypes), C or C++ caller binds instead; each entry point names the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer
+ *     unless the name ends in _host;
+ *   - one paut_ctx <-> one GPU <-> one CUDA stream; calls on a ctx are
+ *     asynchronous on that stream and never synchronise, except
+ *     paut_model_finalize (one-time weight packing), paut_ctx_destroy and the
+ *     *_host convenience calls;
+ *   - a ctx is not thread-safe; different ctxs may be used from different
+ *     threads concurrently;
+ *   - the library never allocates caller-visible memory: outputs are written
+ *     to caller-owned buffers; its private workspace grows on demand;
+ *   - every function returns PAUT_OK (0) or a negative paut_status;
+ *     paut_last_error() gives the message of the last failure on that ctx.
+ *   - there is NO CPU fallback: without a CUDA device every compute call
+ *     fails with PAUT_ERR_CUDA.
+ */
+#ifndef PAUT_H_
+#define PAUT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAUT_ABI_VERSION 1
+
+typedef enum {
+  PAUT_OK = 0,
+  PAUT_ERR_INVALID = -1,     /* bad argument / shape / unknown key            */
+  PAUT_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail)    */
+  PAUT_ERR_STATE = -3,       /* call order (forward before finalize, ...)      */
+  PAUT_ERR_MISSING = -4,     /* finalize: a state_dict tensor was never set    */
+  PAUT_ERR_UNSUPPORTED = -5  /* configuration outside what the kernels cover   */
+} paut_status;
+
+/* Model kinds = the reference classes on the hot path. */
+typedef enum {
+  PAUT_MODEL_MSC = 0,        /* signals/multisignalNN/NN_models.py:45-128   MultiSignalClassifier   */
+  PAUT_MODEL_MSC_N = 1,      /* signals/multisignalNN/NN_models.py:198-246  MultiSignalClassifier_N */
+  PAUT_MODEL_CONV1D_MSC = 2, /* signals/MSC_Conv1D_training.py:50-89        DefectDetectionModel    */
+  PAUT_MODEL_SSD = 3,        /* SignalSequenceDetection/model.py:230-343    SignalSequenceDetector  */
+  PAUT_MODEL_ENHANCED = 4,   /* SignalSequenceDetection/enhanced_model.py:449-566                   */
+  PAUT_MODEL_TWO_STAGE = 5   /* SignalSequenceDetection/two_stage_model.py:254-312                  */
+} paut_model_kind;
+
+typedef enum { PAUT_F32 = 0, PAUT_BF16 = 1, PAUT_I64 = 2 } paut_dtype;
+
+/* Arithmetic mode of the encoder (the per-A-scan conv/MLP stack).
+ * FP32: fp32 CUDA-core math everywhere (logits within 1e-4 of the reference).
+ * BF16: bf16 operands on the tcgen05 tensor cores, fp32 accumulate (within 1e-2). */
+typedef enum { PAUT_PRECISION_FP32 = 0, PAUT_PRECISION_BF16 = 1 } paut_precision;
+
+/* Constructor arguments of the reference classes (unused ones are ignored per kind):
+ *   MSC / MSC_N : (signal_length, hidden_sizes[3], num_heads)        NN_models.py:46,199
+ *   CONV1D_MSC  : (signal_length, num_signals_per_set) -- both unused by the layers; nhead fixed 4
+ *   SSD         : (signal_length, d_model, num_classes, nhead, num_layers, dim_feedforward) model.py:234-243
+ *   ENHANCED    : same six, enhanced_model.py:453-462 (cross-attention heads fixed at 8, :491)
+ *   TWO_STAGE   : (signal_length, d_model, num_classes)  two_stage_model.py:258 (nhead 8, 4 layers, ff 512)
+ * A zero field selects the reference default. */
+typedef struct {
+  int32_t signal_length;
+  int32_t hidden_sizes[3];
+  int32_t num_heads;
+  int32_t d_model;
+  int32_t num_classes;
+  int32_t num_layers;
+  int32_t dim_feedforward;
+  int32_t precision;       /* paut_precision */
+  int32_t reserved[6];
+} paut_model_cfg;
+
+/* Output slots of paut_forward, per model kind.  Every slot is fp32, contiguous,
+ * caller-owned; a NULL slot is skipped (not computed if it is a pure by-product).
+ *   MSC, MSC_N  : 0 defect_prob[B,N]  1 defect_start[B,N]  2 defect_end[B,N]        NN_models.py:125-128
+ *   CONV1D_MSC  : 0 defect_prob[B,N]                                            MSC_Conv1D_training.py:87
+ *   SSD         : 0 class_preds[B,N,C] 1 position_preds[B,N,2] 2 anomaly_scores[B,N,1]
+ *                 3 attention_weights[B,N,1]                                        model.py:337-343
+ *   ENHANCED    : 0 class_preds[B,N,C] 1 class_uncertainty[B,N,C] 2 position_preds[B,N,2]
+ *                 3 position_uncertainty[B,N,2] 4 anomaly_scores[B,N,1] 5 anomaly_uncertainty[B,N,1]
+ *                 6 attention_weights[L,B,N,N] (layer-major) 7 context_attention[B,N]
+ *                 8 cross_attention[B,N,N]                                   enhanced_model.py:556-566
+ *   TWO_STAGE   : 0 defect_logits[B,N,2] 1 defect_probs[B,N,2] 2 defect_uncertainty[B,N,2]
+ *                 3 position_preds[B,N,2] 4 position_uncertainty[B,N,2]      two_stage_model.py:305-312 */
+#define PAUT_MAX_OUTPUTS 12
+typedef struct {
+  void* slot[PAUT_MAX_OUTPUTS];
+} paut_outputs;
+
+/* One kept prediction; replaces the dict the reference predict() appends
+ * (model.py:465-471, enhanced_model.py:793-803, two_stage_model.py:490-497) plus the integer
+ * sample indices of predict.py:111-113 / signal_visualizer.py:409-410. */
+typedef struct {
+  int32_t set_index;    /* b                                                    */
+  int32_t position;     /* i, index of the A-scan inside its set                */
+  int32_t cls;          /* pred_class (1 for the two-stage and MSC rules)       */
+  int32_t start_index;  /* trunc(RN_fp32(start * S))                            */
+  int32_t end_index;    /* trunc(RN_fp32(end * S))                              */
+  float start, end;     /* defect_position (fp32, as returned by forward)       */
+  float score;          /* class_score / defect_prob                            */
+  float uncertainty;    /* class_unc[pred_class] / defect_unc[...,1]; else 0    */
+  float anomaly;        /* anomaly score (SSD, ENHANCED); else 0                */
+  double confidence;    /* fp64 value compared with the threshold               */
+} paut_detection;       /* 48 bytes */
+
+typedef struct paut_ctx paut_ctx;
+typedef struct paut_model paut_model;
+
+int paut_abi_version(void);
+
+/* Context: replaces the reference's device selection idiom (predict.py:215, training_01.py:125).
+ * cuda_stream is a cudaStream_t (NULL = the legacy default stream). */
+int paut_ctx_create(int device, void* cuda_stream, paut_ctx** out);
+void paut_ctx_destroy(paut_ctx* ctx);
+const char* paut_last_error(const paut_ctx* ctx); /* ctx may be NULL: last create failure */
+/* Upper bound (bytes) of the private activation workspace a forward may use; default 2 GiB.
+ * Larger batches are processed in resident chunks of whole sets. */
+int paut_ctx_set_workspace_limit(paut_ctx* ctx, uint64_t bytes);
+
+/* Model lifetime: replaces  Model(**ctor).to(device); load_state_dict(sd); eval()
+ * (predict.py:14-49, model_pred.py:11-13). */
+int paut_model_create(paut_ctx* ctx, int model_kind, const paut_model_cfg* cfg, paut_model** out);
+void paut_model_destroy(paut_model* m);
+/* One state_dict entry (key exactly as in the reference state_dict).  ptr may be host or device
+ * memory; the tensor is copied.  dtype F32 (or I64 for num_batches_tracked, ignored). */
+int paut_model_set_tensor(paut_model* m, const char* key, const void* ptr, int dtype,
+                          const int64_t* shape, int ndim);
+/* Folds BatchNorm, packs weights into kernel layouts.  Fails with PAUT_ERR_MISSING (and the
+ * key name in paut_last_error) if a tensor of the contract was not set. */
+int paut_model_finalize(paut_model* m);
+/* Number of state_dict keys of this kind/cfg, and the i-th key + shape (contract introspection). */
+int paut_model_num_keys(const paut_model* m);
+int paut_model_key(const paut_model* m, int i, const char** key, int64_t* shape4, int* ndim);
+
+/* forward(x): replaces Model.forward in eval mode under no_grad
+ * (NN_models.py:108, :225; MSC_Conv1D_training.py:78; model.py:287; enhanced_model.py:502;
+ * two_stage_model.py:273).  x is [B,N,S] contiguous (CONV1D_MSC: [B,S,N], as the reference),
+ * x_dtype F32 or BF16.  Asynchronous on the ctx stream. */
+int paut_forward(paut_model* m, const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
+                 const paut_outputs* out);
+
+/* predict() post-processing: replaces the Python loops model.py:446-473, enhanced_model.py:766-805,
+ * two_stage_model.py:477-499, the MSC threshold of model_pred.py:82-85, and the index conversion
+ * predict.py:111-113.  `outs` holds the forward outputs (same slots).  Records are written in the
+ * reference's (b, i) order to det[0..count) (capacity B*N), *count_dev receives the count.
+ * Confidence arithmetic is fp64, indices are trunc(fp32 product) -- bit-exact with the reference
+ * given identical forward outputs. */
+int paut_postprocess(paut_model* m, const paut_outputs* outs, int64_t B, int64_t N, int64_t S,
+                     double threshold, paut_detection* det, int32_t* count_dev);
+
+/* Windowing + cast (a0): gathers fixed-length sets from a resident volume [G, n, S]
+ * (json_dataset.py:84-103, dataset_preparation.py:222-282, cast json_dataset.py:112-116).
+ * table_dev is int32 [W,3] = (group, start, valid_len) rows; rows >= valid_len are zero.
+ * sets_dev is [W, L, S] in dst_dtype. */
+int paut_window_gather(paut_ctx* ctx, const void* volume, int src_dtype, int64_t G, int64_t n, int64_t S,
+                       const int32_t* table_dev, int64_t W, int64_t L, void* sets_dev, int dst_dtype);
+/* Host-side window tables for the two reference rules (rule 0 = signals/ json_dataset rule,
+ * 1 = SignalSequenceDetection rule).  Writes up to cap (start, valid_len) pairs, returns the count. */
+int paut_window_table_host(int rule, int64_t n, int64_t L, int32_t* pairs_host, int cap);
+
+/* Instrumentation: number of kernels this ctx launched since creation (bench.py's gpu_launches). */
+int64_t paut_ctx_launch_count(const paut_ctx* ctx);
+/* Per-kernel device timing: between begin and end every launch on the ctx is followed by a CUDA event
+ * on the ctx stream; end synchronises and writes one line per kernel name, "name launches total_ms\n",
+ * into buf (bench.py's roofline numbers come from here, not from a profiler). */
+int paut_ctx_profile_begin(paut_ctx* ctx);
+int paut_ctx_profile_end(paut_ctx* ctx, char* buf, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAUT_H_ */
