@@ -285,6 +285,54 @@ int paut_window_gather(paut_ctx* ctx, const void* volume, int src_dtype, int64_t
   });
 }
 
+// One fused linear layer on device buffers (unit tests / stand-alone GEMM).  Weights are packed per call.
+int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float* W, const float* bias, int N,
+                   float* C, int act, int impl) {
+  if (!ctx) return PAUT_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    Ctx& c = ctx->c;
+    PAUT_CHECK(A && W && C && M > 0 && K > 0 && N > 0, PAUT_ERR_INVALID, "op_linear: bad arguments");
+    PAUT_CUDA(cudaSetDevice(c.device));
+    std::vector<float> w((size_t)N * K), wt((size_t)N * K), b(N, 0.f);
+    PAUT_CUDA(cudaMemcpy(w.data(), W, w.size() * sizeof(float), cudaMemcpyDefault));
+    if (bias) PAUT_CUDA(cudaMemcpy(b.data(), bias, N * sizeof(float), cudaMemcpyDefault));
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) wt[(size_t)k * N + n] = w[(size_t)n * K + k];
+    std::vector<void*> tmp;
+    auto up = [&](const void* src, size_t bytes) {
+      void* p = nullptr;
+      PAUT_CUDA(cudaMalloc(&p, bytes));
+      tmp.push_back(p);
+      PAUT_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+      return p;
+    };
+    paut::LinArgs a;
+    a.A = A; a.lda = K; a.M = M; a.K = K; a.N = N; a.C = C; a.ldc = N; a.act = act;
+    a.W = static_cast<const float*>(up(w.data(), w.size() * 4));
+    a.Wt = static_cast<const float*>(up(wt.data(), wt.size() * 4));
+    a.bias = static_cast<const float*>(up(b.data(), b.size() * 4));
+    try {
+      if (impl == 1) {
+        const int nt = paut::tc_pick_ntile(N);
+        PAUT_CHECK(nt > 0, PAUT_ERR_UNSUPPORTED, "op_linear: tcgen05 path needs N to be a multiple of 16");
+        std::vector<uint16_t> packed;
+        int Kp = 0;
+        paut::tc_pack_weight(w.data(), N, K, nt, packed, &Kp);
+        a.Wp = up(packed.data(), packed.size() * 2);
+        a.NT = nt;
+        paut::op_linear_tc(c, a);
+      } else {
+        paut::op_linear(c, a);
+      }
+      PAUT_CUDA(cudaStreamSynchronize(c.stream));
+    } catch (...) {
+      for (void* p : tmp) cudaFree(p);
+      throw;
+    }
+    for (void* p : tmp) cudaFree(p);
+  });
+}
+
 // Window tables: rule 0 = json_dataset.py:84-103 (end-anchored last window, short runs skipped),
 // rule 1 = dataset_preparation.py:222-282 (zero-pad short runs, overlapping windows + tail).
 int paut_window_table_host(int rule, int64_t n, int64_t L, int32_t* pairs, int cap) {

@@ -43,6 +43,7 @@ struct Ctx {
   int num_sms = 148;
   int smem_optin = 0;
   size_t att_smem_configured = 0;
+  size_t gemm_tc_smem_configured = 0;
   bool profiling = false;                // per-kernel CUDA-event timing (paut_ctx_profile_*)
   std::vector<std::pair<std::string, cudaEvent_t>> prof_events;
   bool dry = false;                      // allocation-only pass used to size chunks: ops do nothing
@@ -90,6 +91,8 @@ struct LinArgs {
   int lda = 0;
   const float* Wt = nullptr;   // [K][N]  (transposed nn.Linear weight)
   const float* W = nullptr;    // [N][K]  (original layout, used when N is tiny)
+  const void* Wp = nullptr;    // bf16, packed for tcgen05 (ops_tc.cu); null in fp32 mode
+  int NT = 0;                  // N tile of the packed weight
   const float* bias = nullptr;
   int64_t M = 0;
   int K = 0, N = 0;
@@ -103,6 +106,11 @@ struct LinArgs {
   int table_mod = 1;
 };
 void op_linear(Ctx& c, const LinArgs& a);
+// tcgen05 path (ops_tc.cu): bf16 operands, fp32 accumulation in TMEM
+int tc_pick_ntile(int N);
+void tc_pack_weight(const float* W, int N, int K, int NT, std::vector<uint16_t>& out, int* Kp_out);
+bool linear_tc_supported(const LinArgs& a);
+void op_linear_tc(Ctx& c, const LinArgs& a);
 
 // out = act(LN(x + res)) row-wise; res nullable; in-place allowed.
 void op_layernorm(Ctx& c, const float* x, const float* res, const float* gamma, const float* beta, float* out,
@@ -113,6 +121,11 @@ void op_layernorm(Ctx& c, const float* x, const float* res, const float* gamma, 
 // (the MSC cross-attention, NN_models.py:35).  avgw (nullable) [B,Nq,Nk] gets the head-averaged weights.
 void op_attention(Ctx& c, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
                   int ldo, int64_t B, int Nq, int Nk, int H, int hd, bool kv_shift, float* avgw);
+
+// bf16-mode attention (ops_attn.cu): same contract, bf16 operands on the tensor cores (mma.sync), fp32 softmax.
+bool attention_bf16_supported(int Nq, int Nk, int hd, bool want_weights);
+void op_attention_bf16(Ctx& c, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out,
+                       int ldo, int64_t B, int Nq, int Nk, int H, int hd, bool kv_shift, float* avgw);
 
 // depthwise conv along the set axis (LocalAttention_N, NN_models.py:159-167): x [B,N,D], w [D][k]
 void op_dwconv_seq(Ctx& c, const float* x, const float* w, const float* bias, float* out, int64_t B, int N,

@@ -241,7 +241,24 @@ Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int r
   l.W = upload(W);
   l.Wt = upload(Wt);
   l.b = upload(bias);
+  pack_tc(l, W);
   return l;
+}
+
+// bf16 mode: additionally pack the weight for the tcgen05 GEMM (chunked K-major bf16)
+void Model::pack_tc(Lin& l, const std::vector<float>& W) {
+  if (cfg.precision != PAUT_PRECISION_BF16) return;
+  const int nt = tc_pick_ntile(l.N);
+  if (nt == 0) return;
+  std::vector<uint16_t> packed;
+  int Kp = 0;
+  tc_pack_weight(W.data(), l.N, l.K, nt, packed, &Kp);
+  void* p = nullptr;
+  PAUT_CUDA(cudaMalloc(&p, packed.size() * sizeof(uint16_t)));
+  dev_allocs.push_back(p);
+  PAUT_CUDA(cudaMemcpy(p, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  l.Wp = p;
+  l.NT = nt;
 }
 
 Lin Model::pack_lin(const std::string& name) {
@@ -337,6 +354,7 @@ RNNW Model::pack_rnn(const std::string& name, int layer, int G, int Hh) {
   r.ih.W = upload(W);
   r.ih.Wt = upload(Wt);
   r.ih.b = upload(bias);
+  pack_tc(r.ih, W);
   std::vector<float> whh((size_t)2 * Hh * GH), bhh(2 * GH);
   for (int dir = 0; dir < 2; ++dir) {
     const HostTensor& w = H(name + ".weight_hh" + l + (dir ? "_reverse" : ""));
@@ -471,6 +489,14 @@ void Model::finalize() {
 namespace {
 struct G {
   Ctx& c;
+  bool bf16 = false;     // PAUT_PRECISION_BF16: tensor-core kernels where they exist
+  void attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* out, int ldo,
+                 int64_t B, int Nq, int Nk, int H, int hd, bool kv_shift, float* avgw) {
+    if (bf16 && attention_bf16_supported(Nq, Nk, hd, avgw != nullptr))
+      op_attention_bf16(c, q, ldq, k, ldk, v, ldv, out, ldo, B, Nq, Nk, H, hd, kv_shift, avgw);
+    else
+      op_attention(c, q, ldq, k, ldk, v, ldv, out, ldo, B, Nq, Nk, H, hd, kv_shift, avgw);
+  }
   float* linear(const float* A, int lda, const Lin& L, int64_t M, int act = ACT_NONE, const float* res = nullptr,
                 int ldr = 0, float* out = nullptr, int ldc = 0, int coff = 0, float eps = 0.f,
                 const float* table = nullptr, int mod = 1) {
@@ -479,7 +505,9 @@ struct G {
     if (!out) { out = c.allocf((size_t)M * L.N); ldc = L.N; coff = 0; }
     a.C = out; a.ldc = ldc; a.coff = coff; a.act = act; a.act_eps = eps; a.res = res; a.ldr = ldr;
     a.table = table; a.table_mod = mod;
-    op_linear(c, a);
+    a.Wp = L.Wp; a.NT = L.NT;
+    if (bf16 && linear_tc_supported(a)) op_linear_tc(c, a);
+    else op_linear(c, a);
     return out;
   }
   float* norm(const float* x, const float* res, const LNW& n, int64_t M, int act = ACT_NONE, float* out = nullptr) {
@@ -494,7 +522,7 @@ struct G {
     const int D = m.D;
     float* qkv = linear(x, D, m.in_proj, M);
     float* att = c.allocf((size_t)M * D);
-    op_attention(c, qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, att, D, B, N, N, m.H, D / m.H, kv_shift, avgw);
+    attention(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, att, D, B, N, N, m.H, D / m.H, kv_shift, avgw);
     return linear(att, D, m.out_proj, M, ACT_NONE, res, D);
   }
   // post-norm encoder layer (nn.TransformerEncoderLayer / SelfAttentionBlock)
@@ -528,7 +556,7 @@ T* slot_at(const paut_outputs& o, int i, int64_t elem_off) {
 // ------------------------------------------------------------------------------------------ MSC / MSC_N
 void Model::fwd_msc(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
-  G g{c};
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
   const bool isn = kind == PAUT_MODEL_MSC_N;
   float* f = c.allocf((size_t)A * S);
@@ -560,7 +588,7 @@ void Model::fwd_msc(const float* x, int64_t B, int N, int S, const paut_outputs&
 // ------------------------------------------------------------------------------------------ MSC Conv1D
 void Model::fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
-  G g{c};
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
   float* xt = c.allocf((size_t)A * S);
   op_transpose_sn(c, x, x_dtype, xt, B, S, N);                                  // MSC_Conv1D_training.py:81
@@ -580,7 +608,7 @@ void Model::fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, 
 // ------------------------------------------------------------------------------------------ SignalSequenceDetector
 void Model::fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t) {
   Ctx& c = *ctx;
-  G g{c};
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
   const int d = cfg.d_model, C = cfg.num_classes;
   const ConvW& c1 = conv["signal_encoder.conv1"];
@@ -640,7 +668,7 @@ void Model::fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs&
 // ------------------------------------------------------------------------------------------ TwoStageDefectDetector
 void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
-  G g{c};
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
   const int d = cfg.d_model, q = d / 4;
   float* feat = c.allocf((size_t)A * d);
@@ -681,7 +709,7 @@ void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_ou
 // ------------------------------------------------------------------------------------------ EnhancedSignalSequenceDetector
 void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot) {
   Ctx& c = *ctx;
-  G g{c};
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
   const int d = cfg.d_model, C = cfg.num_classes;
   const std::string e = "signal_encoder.";
@@ -747,7 +775,7 @@ void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_out
   float* qb = g.linear(sf, d, lin["cross.q"], A);
   float* kv = g.linear(ctxf, d, lin["cross.kv"], A);
   float* att = c.allocf((size_t)A * d);
-  op_attention(c, qb, d, kv, 2 * d, kv + d, 2 * d, att, d, B, N, N, 8, d / 8, false,
+  g.attention(qb, d, kv, 2 * d, kv + d, 2 * d, att, d, B, N, N, 8, d / 8, false,
                slot_at<float>(out, 8, b0 * N * N));
   float* co = g.linear(att, d, lin["cross_attention.out_proj"], A, ACT_NONE, sf, d);
   float* cf = g.norm(co, nullptr, ln["cross_norm"], A);

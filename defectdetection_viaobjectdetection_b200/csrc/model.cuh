@@ -19,6 +19,8 @@ struct Lin {
   const float* Wt = nullptr;  // [K][N]
   const float* W = nullptr;   // [N][K]
   const float* b = nullptr;
+  const void* Wp = nullptr;   // bf16 packed for tcgen05 (bf16 mode only)
+  int NT = 0;
   int K = 0, N = 0;
 };
 struct ConvW {
@@ -77,6 +79,7 @@ struct Model {
   const HostTensor& H(const std::string& key) const;
   const float* upload(const std::vector<float>& v);
   Lin pack_lin(const std::string& name);
+  void pack_tc(Lin& l, const std::vector<float>& W);
   Lin pack_lin_rows(const std::string& wkey, const std::string& bkey, int row0, int rows);
   ConvW pack_conv(const std::string& conv_name, const std::string& bn_name);
   LNW pack_ln(const std::string& name);

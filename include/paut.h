@@ -167,6 +167,13 @@ int paut_window_gather(paut_ctx* ctx, const void* volume, int src_dtype, int64_t
  * 1 = SignalSequenceDetection rule).  Writes up to cap (start, valid_len) pairs, returns the count. */
 int paut_window_table_host(int rule, int64_t n, int64_t L, int32_t* pairs_host, int cap);
 
+/* One fused linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) on device buffers A, C (fp32, contiguous);
+ * W and bias may be host or device memory and are packed on every call (a unit-test / stand-alone entry,
+ * not a hot path; synchronises).  act: 0 none, 1 ReLU, 2 GELU(erf), 3 sigmoid, 4 softplus.
+ * impl: 0 = fp32 CUDA cores (F.linear within fp32 rounding), 1 = bf16 operands on tcgen05, fp32 accumulate. */
+int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float* W, const float* bias, int N,
+                   float* C, int act, int impl);
+
 /* Instrumentation: number of kernels this ctx launched since creation (bench.py's gpu_launches). */
 int64_t paut_ctx_launch_count(const paut_ctx* ctx);
 /* Per-kernel device timing: between begin and end every launch on the ctx is followed by a CUDA event
