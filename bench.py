@@ -272,7 +272,7 @@ def main():
             "roofline": roof,
             "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
         }
-        if world == 1:
+        if world == 1 and args.cpu_seconds > 0:
             x_cpu = x_host[:64].float()
             rate, done, el = cpu_reference_rate(kind, sd, x_cpu, args.cpu_seconds, n_per)
             line["cpu_baseline"] = {"value": rate, "unit": "A-scans/s", "cores": torch.get_num_threads(), "kind": "port",

@@ -151,6 +151,12 @@ void op_copy_cols(Ctx& c, const float* src, int lds, float* dst, int ldd, int co
 // optional depthwise k11 background subtraction, mean over channels -> f [A,S].
 void op_msc_front(Ctx& c, const float* x, int64_t A, int S, const float* w1, const float* b1, const float* w2,
                   const float* b2, const float* wbg, const float* bbg, float* f);
+// Fused tcgen05 encoder of MultiSignalClassifier (ops_msc_tc.cu): x -> h [A,64] (bf16 mode)
+bool msc_encoder_tc_supported(int S, int h0, int h1);
+void msc_pack_conv2(const float* w2, const float* b2, std::vector<uint16_t>& out);
+void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1, const float* b1,
+                       const void* Bc, const void* W1p, const float* bl1, const void* W2p, const float* bl2,
+                       const float* pos, float* h);
 // MSC head (NN_models.py:123-127): o [M,3] -> sigmoid / tanh*0.5+0.5 into three arrays
 void op_msc_head(Ctx& c, const float* o, int64_t M, float* prob, float* start, float* end);
 // logits[:, 1:] += anomaly (model.py:332, enhanced_model.py:550)

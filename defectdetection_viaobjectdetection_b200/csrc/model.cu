@@ -395,6 +395,29 @@ void Model::finalize() {
       }
       L("shared_layer.0"); L("shared_layer.2");
       R("position_encoding.encoding");
+      enc_tc = EncTc{};
+      if (cfg.precision == PAUT_PRECISION_BF16 && kind == PAUT_MODEL_MSC &&
+          msc_encoder_tc_supported(cfg.signal_length, cfg.hidden_sizes[0], cfg.hidden_sizes[1])) {
+        auto up16 = [&](const std::vector<uint16_t>& v) {
+          void* p = nullptr;
+          PAUT_CUDA(cudaMalloc(&p, v.size() * sizeof(uint16_t)));
+          dev_allocs.push_back(p);
+          PAUT_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          return p;
+        };
+        std::vector<uint16_t> packed;
+        msc_pack_conv2(H("conv1d.2.weight").data.data(), H("conv1d.2.bias").data.data(), packed);
+        enc_tc.Bc = up16(packed);
+        std::vector<float> w1 = H("shared_layer.0.weight").data;
+        for (float& v : w1) v *= (1.f / 32.f);        // (1/2 from relu = (y+|y|)/2) * (1/16 channel mean)
+        int Kp = 0;
+        tc_pack_weight(w1.data(), cfg.hidden_sizes[0], cfg.signal_length, cfg.hidden_sizes[0], packed, &Kp);
+        enc_tc.W1p = up16(packed);
+        tc_pack_weight(H("shared_layer.2.weight").data.data(), cfg.hidden_sizes[1], cfg.hidden_sizes[0],
+                       cfg.hidden_sizes[1], packed, &Kp);
+        enc_tc.W2p = up16(packed);
+        enc_tc.ready = true;
+      }
       mha["self"] = pack_mha("transformer_encoder.self_attn", cfg.num_heads);
       if (kind == PAUT_MODEL_MSC) mha["cross"] = pack_mha("transformer_encoder.cross_attn", cfg.num_heads);
       L("transformer_encoder.ffn.0"); L("transformer_encoder.ffn.2");
@@ -554,19 +577,33 @@ T* slot_at(const paut_outputs& o, int i, int64_t elem_off) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ MSC / MSC_N
-void Model::fwd_msc(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
   G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
   const bool isn = kind == PAUT_MODEL_MSC_N;
-  float* f = c.allocf((size_t)A * S);
-  op_msc_front(c, x, A, S, raw["conv1d.0.weight"], raw["conv1d.0.bias"], raw["conv1d.2.weight"],
-               raw["conv1d.2.bias"], isn ? raw["background_extractor.weight"] : nullptr,
-               isn ? raw["background_extractor.bias"] : nullptr, f);
-  float* h0 = g.linear(f, S, lin["shared_layer.0"], A, ACT_RELU);
   const Lin& l2 = lin["shared_layer.2"];
   const int D = l2.N;
-  float* h = g.linear(h0, l2.K, l2, A, ACT_RELU, nullptr, 0, nullptr, 0, 0, 0.f, raw["position_encoding.encoding"], N);
+  float* h = nullptr;
+  if (enc_tc.ready) {
+    // bf16 mode: conv1 -> conv2 -> channel mean -> MLP -> + position table in one tcgen05 kernel
+    h = c.allocf((size_t)A * D);
+    op_msc_encoder_tc(c, xin, x_dtype, A, S, N, raw["conv1d.0.weight"], raw["conv1d.0.bias"], enc_tc.Bc, enc_tc.W1p,
+                      lin["shared_layer.0"].b, enc_tc.W2p, l2.b, raw["position_encoding.encoding"], h);
+  } else {
+    const float* x = static_cast<const float*>(xin);
+    if (x_dtype != PAUT_F32) {
+      float* t = c.allocf((size_t)A * S);
+      op_to_f32(c, xin, x_dtype, t, A * S);
+      x = t;
+    }
+    float* f = c.allocf((size_t)A * S);
+    op_msc_front(c, x, A, S, raw["conv1d.0.weight"], raw["conv1d.0.bias"], raw["conv1d.2.weight"],
+                 raw["conv1d.2.bias"], isn ? raw["background_extractor.weight"] : nullptr,
+                 isn ? raw["background_extractor.bias"] : nullptr, f);
+    float* h0 = g.linear(f, S, lin["shared_layer.0"], A, ACT_RELU);
+    h = g.linear(h0, l2.K, l2, A, ACT_RELU, nullptr, 0, nullptr, 0, 0, 0.f, raw["position_encoding.encoding"], N);
+  }
   float* y = g.self_attention(h, mha["self"], B, N, h);
   h = g.norm(y, nullptr, ln["transformer_encoder.norm1"], A);
   if (!isn) {
@@ -846,6 +883,10 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
       fwd_conv1d_msc(xc, x_dtype, nb, (int)N, (int)S, out, b0);
       return;
     }
+    if (kind == PAUT_MODEL_MSC || kind == PAUT_MODEL_MSC_N) {
+      fwd_msc(xc, x_dtype, nb, (int)N, (int)S, out, b0);
+      return;
+    }
     const float* xf = reinterpret_cast<const float*>(xc);
     if (x_dtype != PAUT_F32) {
       float* t = c.allocf((size_t)nb * N * S);
@@ -853,8 +894,6 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
       xf = t;
     }
     switch (kind) {
-      case PAUT_MODEL_MSC:
-      case PAUT_MODEL_MSC_N: fwd_msc(xf, nb, (int)N, (int)S, out, b0); break;
       case PAUT_MODEL_SSD: fwd_ssd(xf, nb, (int)N, (int)S, out, b0, B); break;
       case PAUT_MODEL_ENHANCED: fwd_enhanced(xf, nb, (int)N, (int)S, out, b0, B); break;
       case PAUT_MODEL_TWO_STAGE: fwd_two_stage(xf, nb, (int)N, (int)S, out, b0); break;

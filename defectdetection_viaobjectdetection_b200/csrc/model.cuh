@@ -66,6 +66,12 @@ struct Model {
   std::vector<TELW> tel;
   std::vector<RNNW> rnn;
   std::map<std::string, const float*> raw;   // tensors uploaded as they are
+  struct EncTc {                               // operands of the fused tcgen05 MSC encoder (bf16 mode)
+    const void* Bc = nullptr;
+    const void* W1p = nullptr;
+    const void* W2p = nullptr;
+    bool ready = false;
+  } enc_tc;
 
   ~Model();
   void build_spec();
@@ -88,7 +94,7 @@ struct Model {
   RNNW pack_rnn(const std::string& name, int layer, int G, int Hh);
 
   // forward graphs (one chunk of whole sets)
-  void fwd_msc(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_msc(const void* x, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
   void fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
   void fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
   void fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);

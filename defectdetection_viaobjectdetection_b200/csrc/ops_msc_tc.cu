@@ -1,0 +1,362 @@
+// Fused per-A-scan encoder of MultiSignalClassifier on tcgen05 (bf16 mode):
+//   x[S] -> Conv1d 1->8 k3 + ReLU -> Conv1d 8->16 k3 + ReLU -> mean over channels -> Linear S->128 + ReLU
+//        -> Linear 128->64 + ReLU -> + position table            (NN_models.py:111-121, :11-14)
+// One CTA = 128 A-scans; nothing but x and the 64-wide result touches HBM.
+//
+//  conv1 (C_in = 1, 24 MACs/position) runs on the CUDA cores straight into an im2col operand in shared
+//  memory: row = position, K = 3 taps x 8 channels (+ a constant chunk [1,1,0..] that carries the bias as
+//  a bf16 hi+lo pair), so conv2 is a plain [128 x 32] x [32 x 32] tcgen05.mma per 128 positions.
+//  Its 32 output columns are the 16 channels (bias included) plus hi/lo halves of their sum, which turns
+//  ReLU + channel-mean into   sum_c relu(y_c) = (sum_c y_c + sum_c |y_c|) / 2   -- 18 FADDs per position in
+//  the epilogue instead of bias + max + add per channel.  The factor 1/32 is folded into the S->128 weights.
+//  The epilogue writes f (bf16) directly in the canonical K-major operand layout of the next GEMM, so the
+//  two Linear layers are tcgen05.mma on operands that never left shared memory; their accumulators live
+//  in TMEM next to the double-buffered conv accumulators (2 x 160 + 128 + 64 = 512 columns).
+//
+//  Pipeline per group of 2 A-scans (= 5 M tiles): conv1(g) on all warps -> one thread issues the 10 MMAs of
+//  group g and commits them to an mbarrier -> all warps run the epilogue of group g-1 while those MMAs
+//  execute (im2col buffers and TMEM accumulators are double-buffered).
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace paut {
+
+using namespace tc;
+
+namespace {
+
+constexpr int H0 = 128, H1 = 64;
+constexpr int ENC_THREADS = 256;
+constexpr int D1_COL = 320, D2_COL = 448;
+constexpr int XS_PAD = 16;
+
+struct MscEncArgs {
+  const void* x;
+  int x_dtype;
+  int64_t A;
+  int S, Nset;
+  const float* w1;                 // conv1d.0.weight [8][3]
+  const float* b1;                 // conv1d.0.bias   [8]
+  const __nv_bfloat16* Bc;         // conv2 operand [4 chunks][32 rows][8]
+  const __nv_bfloat16* W1p;        // shared_layer.0 / 32, packed [S/8][128][8]
+  const float* bl1;
+  const __nv_bfloat16* W2p;        // shared_layer.2 packed [16][64][8]
+  const float* bl2;
+  const float* pos;                // [300][64]
+  float* h;                        // [A][64]
+};
+
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  a = __uint_as_float(r0);
+  b = __uint_as_float(r1);
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_conv[2], bar_w[2], bar_l2;
+  __shared__ uint32_t tmem_slot;
+
+  const int S = p.S;
+  const int rows = 2 * S;                          // im2col rows of one group (2 A-scans)
+  const int tiles = rows / 128;
+  const uint32_t im_chunk = (uint32_t)rows * 16;
+  const uint32_t im_bytes = 4 * im_chunk;
+  unsigned char* IM = smem;                        // [2][4 chunks][rows][16 B]
+  unsigned char* A2 = smem + 2 * im_bytes;         // [S/8 chunks][128 rows][16 B]
+  unsigned char* WR = A2 + (size_t)256 * S;        // [2][8 chunks][128 rows][16 B]
+  unsigned char* BC = WR + 2 * 16384;              // [4 chunks][32 rows][16 B]
+  __nv_bfloat16* XS = reinterpret_cast<__nv_bfloat16*>(BC + 2048);   // [2][2][S + 16]
+  const int xs_stride = S + XS_PAD;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t a0 = (int64_t)blockIdx.x * 128;
+
+  // ---- one-time setup
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bar_conv[0], 1); mbar_init(&bar_conv[1], 1);
+    mbar_init(&bar_w[0], 1); mbar_init(&bar_w[1], 1);
+    mbar_init(&bar_l2, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 128; i += ENC_THREADS) reinterpret_cast<uint4*>(BC)[i] = reinterpret_cast<const uint4*>(p.Bc)[i];
+  {
+    // constant chunk 3 (K = 24..31) = [1, 1, 0, 0, 0, 0, 0, 0]; zero rows of tap 0 / tap 2 at the A-scan edges
+    const uint4 ones = make_uint4(0x3F803F80u, 0u, 0u, 0u);
+    for (int b = 0; b < 2; ++b) {
+      unsigned char* im = IM + b * im_bytes;
+      for (int r = tid; r < rows; r += ENC_THREADS) *reinterpret_cast<uint4*>(im + 3 * im_chunk + r * 16) = ones;
+      if (tid < 2) {
+        *reinterpret_cast<uint4*>(im + 0 * im_chunk + (tid * S) * 16) = make_uint4(0, 0, 0, 0);           // act1[-1]
+        *reinterpret_cast<uint4*>(im + 2 * im_chunk + (tid * S + S - 1) * 16) = make_uint4(0, 0, 0, 0);   // act1[S]
+      }
+    }
+    for (int i = tid; i < 2 * 2 * xs_stride; i += ENC_THREADS) XS[i] = __float2bfloat16_rn(0.f);
+  }
+  // per-thread conv1 weights: this thread always computes channels 4*hf .. 4*hf+3
+  const int hf = tid & 1;
+  float cw[4][3], cb[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    cb[c] = p.b1[hf * 4 + c];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) cw[c][t] = p.w1[(hf * 4 + c) * 3 + t];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc_conv = make_idesc_bf16(128, 32);
+
+  // x prefetch registers: thread t < S/4 owns 8 samples of one of the two A-scans of the group
+  const int xparts = S / 8;
+  const bool xloader = tid < 2 * xparts;
+  const int x_al = tid / xparts, x_part = tid % xparts;
+  uint4 xr = make_uint4(0, 0, 0, 0);
+  auto prefetch_x = [&](int g) {
+    xr = make_uint4(0, 0, 0, 0);
+    if (!xloader) return;
+    const int64_t a = a0 + 2 * g + x_al;
+    if (a >= p.A) return;
+    if (p.x_dtype == PAUT_BF16) {
+      xr = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.x) + a * S + x_part * 8));
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + a * S + x_part * 8);
+      const float4 u = __ldg(src), v = __ldg(src + 1);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(u.x, u.y), h1 = __floats2bfloat162_rn(u.z, u.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y), h3 = __floats2bfloat162_rn(v.z, v.w);
+      xr.x = *reinterpret_cast<uint32_t*>(&h0); xr.y = *reinterpret_cast<uint32_t*>(&h1);
+      xr.z = *reinterpret_cast<uint32_t*>(&h2); xr.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+  };
+
+  // epilogue of one conv group: TMEM -> f = y16 + y17 + sum|y_c| -> bf16 -> A2[row = A-scan][k = position]
+  auto conv_epilogue = [&](int g) {
+    const int buf = g & 1;
+    mbar_wait(&bar_conv[buf], (g >> 1) & 1);
+    tc_fence_after();
+    const int q = warp & 3;
+    for (int T = warp >> 2; T < tiles; T += 2) {
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + T * 32;
+      float y[16], s0, s1;
+      tmem_ld16(taddr, y);
+      tmem_ld2(taddr + 16, s0, s1);
+      float f = s0 + s1;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) f += fabsf(y[c]);
+      const int r = T * 128 + q * 32 + lane;        // row inside the group
+      const int al = r >= S ? 1 : 0;
+      const int pos = r - al * S;
+      const int arow = 2 * g + al;                  // A-scan row inside the CTA tile
+      *reinterpret_cast<__nv_bfloat16*>(A2 + (size_t)(pos >> 3) * 2048 + arow * 16 + (pos & 7) * 2) =
+          __float2bfloat16_rn(f);
+    }
+  };
+
+  prefetch_x(0);
+  const int ngroups = 64;
+  for (int g = 0; g < ngroups; ++g) {
+    const int buf = g & 1;
+    __nv_bfloat16* xs = XS + buf * 2 * xs_stride;
+    if (xloader) *reinterpret_cast<uint4*>(xs + x_al * xs_stride + 8 + x_part * 8) = xr;
+    __syncthreads();
+    if (g + 1 < ngroups) prefetch_x(g + 1);
+    // ---- conv1 + ReLU -> im2col operand (3 shifted copies of the 8-channel vector of each position)
+    unsigned char* im = IM + buf * im_bytes;
+    for (int item = tid; item < 2 * rows; item += ENC_THREADS) {
+      const int pp = item >> 1;
+      const int al = pp >= S ? 1 : 0;
+      const int pos = pp - al * S;
+      const __nv_bfloat16* xp = xs + al * xs_stride + 8 + pos;
+      const float x0 = __bfloat162float(xp[-1]), x1 = __bfloat162float(xp[0]), x2 = __bfloat162float(xp[1]);
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+      const uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+      // A[row, tap t] = act1[row + t - 1]  =>  act1[pos] lands in row pos + 1 - t of tap t
+      unsigned char* dst = im + (size_t)pp * 16 + hf * 8;
+      if (pos + 1 < S) *reinterpret_cast<uint2*>(dst + 16) = pk;                       // tap 0, row pos + 1
+      *reinterpret_cast<uint2*>(dst + im_chunk) = pk;                                  // tap 1, row pos
+      if (pos > 0) *reinterpret_cast<uint2*>(dst + 2 * im_chunk - 16) = pk;            // tap 2, row pos - 1
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t im_addr = smem_u32(im), bc_addr = smem_u32(BC);
+      for (int T = 0; T < tiles; ++T) {
+        const uint32_t d = tmem + buf * (tiles * 32) + T * 32;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          mma_bf16_ss(d, make_desc(im_addr + ks * 2 * im_chunk + T * 2048, im_chunk, 128),
+                      make_desc(bc_addr + ks * 2 * 512, 512, 128), idesc_conv, ks);
+      }
+      mma_commit(&bar_conv[buf]);
+    }
+    if (g > 0) conv_epilogue(g - 1);
+  }
+  conv_epilogue(ngroups - 1);
+
+  // ---- Linear S -> 128 (+ReLU): A = A2 (resident), B streamed from L2 through a 2-stage ring
+  // W2p (16 KB) is parked in the second im2col buffer meanwhile (its MMAs are complete: epilogue waited)
+  for (int i = tid; i < 1024; i += ENC_THREADS)
+    reinterpret_cast<uint4*>(IM + im_bytes)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2p) + i);
+  const int nkb = S / 64;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb & 1;
+    if (kb >= 2) mbar_wait(&bar_w[s], ((kb >> 1) - 1) & 1);
+    const uint4* src = reinterpret_cast<const uint4*>(p.W1p) + (size_t)kb * 1024;
+    uint4* dst = reinterpret_cast<uint4*>(WR + s * 16384);
+    for (int i = tid; i < 1024; i += ENC_THREADS) dst[i] = __ldg(src + i);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(A2) + kb * 8 * 2048, b_addr = smem_u32(WR + s * 16384);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_bf16_ss(tmem + D1_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
+                    make_desc(b_addr + ks * 2 * 2048, 2048, 128), make_idesc_bf16(128, H0), (kb | ks) ? 1u : 0u);
+      mma_commit(&bar_w[s]);
+    }
+  }
+  mbar_wait(&bar_w[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
+  tc_fence_after();
+  // ---- epilogue 1: relu(D1 + b) -> bf16 -> A3 (aliases the first im2col buffer), K-major for the next GEMM
+  {
+    unsigned char* A3 = IM;
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      const int n = half * 64 + c0;
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D1_COL + n, v);
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(v[2 * j] + __ldg(p.bl1 + n + 2 * j), 0.f),
+                                                  fmaxf(v[2 * j + 1] + __ldg(p.bl1 + n + 2 * j + 1), 0.f));
+        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(A3 + (size_t)(n >> 3) * 2048 + r * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(A3 + (size_t)((n >> 3) + 1) * 2048 + r * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  // ---- Linear 128 -> 64
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(IM), b_addr = smem_u32(IM + im_bytes);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+      mma_bf16_ss(tmem + D2_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
+                  make_desc(b_addr + ks * 2 * 1024, 1024, 128), make_idesc_bf16(128, H1), ks ? 1u : 0u);
+    mma_commit(&bar_l2);
+  }
+  mbar_wait(&bar_l2, 0);
+  tc_fence_after();
+  // ---- epilogue 2: relu(D2 + b) + position table -> h (fp32)
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t a = a0 + q * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      const int n = half * 32 + c0;
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D2_COL + n, v);
+      if (a < p.A) {
+        const float* pr = p.pos + (a % p.Nset) * H1 + n;
+        float4* dst = reinterpret_cast<float4*>(p.h + a * H1 + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bl2 + n) + j);
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(pr) + j);
+          dst[j] = make_float4(fmaxf(v[4 * j] + b4.x, 0.f) + t4.x, fmaxf(v[4 * j + 1] + b4.y, 0.f) + t4.y,
+                               fmaxf(v[4 * j + 2] + b4.z, 0.f) + t4.z, fmaxf(v[4 * j + 3] + b4.w, 0.f) + t4.w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)((u + r) >> 16);
+}
+float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+}  // namespace
+
+bool msc_encoder_tc_supported(int S, int h0, int h1) { return h0 == H0 && h1 == H1 && S % 64 == 0 && S >= 64 && S <= 320; }
+
+// conv2 operand [4 chunks][32 rows][8]: rows 0..15 = channels (taps 0..2 in chunks 0..2, bias hi/lo in chunk 3),
+// row 16 / 17 = hi / lo halves of the column sums (so that y16 + y17 = sum_c y_c), rows 18..31 = 0.
+void msc_pack_conv2(const float* w2 /*[16][8][3]*/, const float* b2 /*[16]*/, std::vector<uint16_t>& out) {
+  out.assign(4 * 32 * 8, 0);
+  auto at = [&](int chunk, int row, int e) -> uint16_t& { return out[((size_t)chunk * 32 + row) * 8 + e]; };
+  float wsum[3][8] = {}, bsum = 0.f;
+  for (int n = 0; n < 16; ++n) {
+    for (int t = 0; t < 3; ++t)
+      for (int ci = 0; ci < 8; ++ci) {
+        const uint16_t h = f2bf(w2[(n * 8 + ci) * 3 + t]);
+        at(t, n, ci) = h;
+        wsum[t][ci] += bf2f(h);
+      }
+    const uint16_t hi = f2bf(b2[n]);
+    const uint16_t lo = f2bf(b2[n] - bf2f(hi));
+    at(3, n, 0) = hi;
+    at(3, n, 1) = lo;
+    bsum += bf2f(hi) + bf2f(lo);
+  }
+  for (int t = 0; t < 3; ++t)
+    for (int ci = 0; ci < 8; ++ci) {
+      const uint16_t hi = f2bf(wsum[t][ci]);
+      at(t, 16, ci) = hi;
+      at(t, 17, ci) = f2bf(wsum[t][ci] - bf2f(hi));
+    }
+  const uint16_t bhi = f2bf(bsum);
+  at(3, 16, 0) = bhi;
+  at(3, 16, 1) = f2bf(bsum - bf2f(bhi));
+}
+
+void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1, const float* b1,
+                       const void* Bc, const void* W1p, const float* bl1, const void* W2p, const float* bl2,
+                       const float* pos, float* h) {
+  if (c.dry) return;
+  PAUT_CHECK(msc_encoder_tc_supported(S, H0, H1), PAUT_ERR_UNSUPPORTED, "msc encoder: unsupported signal length");
+  MscEncArgs p;
+  p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset; p.w1 = w1; p.b1 = b1;
+  p.Bc = static_cast<const __nv_bfloat16*>(Bc); p.W1p = static_cast<const __nv_bfloat16*>(W1p); p.bl1 = bl1;
+  p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
+  const size_t smem = (size_t)2 * 4 * (2 * S) * 16 + (size_t)256 * S + 2 * 16384 + 2048 + (size_t)2 * 2 * (S + XS_PAD) * 2;
+  PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
+  PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = (A + 127) / 128;
+  PAUT_CHECK(grid < (int64_t(1) << 31), PAUT_ERR_INVALID, "msc encoder: too many A-scans");
+  k_msc_encoder_tc<<<(unsigned)grid, ENC_THREADS, smem, c.stream>>>(p);
+  c.launched("msc_encoder_tc");
+}
+
+}  // namespace paut

@@ -1,0 +1,116 @@
+"""Whole-volume inference from HOST memory: the end-to-end call of this package.
+
+The reference feeds the model one window at a time (batch 1, one H2D per window, one D2H sync per scalar:
+model_tester.py:37-117, predict.py:169-197).  ``VolumeScanner`` streams a host-resident stack of sets through
+the drop-in module in resident chunks on two CUDA streams, so the host->device copy of chunk i+1 and the
+device->host copy of the kept detections of chunk i-1 overlap the kernels of chunk i.  Each stream has its
+own library context (one paut_ctx <-> one stream); results come back as one structured array in the
+reference's (set, position) order, or as the reference's ``list[list[dict]]`` via ``to_predictions``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .runtime import DETECTION
+
+
+class _Lane:
+    def __init__(self, device, shape, dtype, capacity):
+        self.stream = torch.cuda.Stream(device=device)
+        self.x = torch.empty(shape, dtype=dtype, device=device)
+        self.host = torch.empty(capacity * DETECTION.itemsize, dtype=torch.uint8).pin_memory()
+        self.count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.done = torch.cuda.Event()
+        self.pending = None          # (first_set, n_sets, det, count) of the chunk in flight
+
+
+class VolumeScanner:
+    """scanner = VolumeScanner(model, chunk_sets=256); records = scanner.scan(x_host, threshold=0.5)
+
+    ``x_host``: CPU tensor [sets, N, S] (``DefectDetectionModel``: [sets, S, N]), fp32 or bf16; pinned memory
+    makes the copies asynchronous.  Returns a numpy structured array (dtype ``DETECTION``) whose
+    ``set_index`` is the index into ``x_host``."""
+
+    def __init__(self, model, chunk_sets=256, device=None):
+        self.model = model
+        self.chunk_sets = int(chunk_sets)
+        self.device = torch.device(device) if device is not None else next(iter(model.state_dict().values())).device
+        if self.device.type != "cuda":
+            raise RuntimeError("VolumeScanner needs the model on a CUDA device (no CPU fallback)")
+        self._lanes = None
+        self._key = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _ensure_lanes(self, x_host):
+        shape = (self.chunk_sets,) + tuple(x_host.shape[1:])
+        key = (shape, x_host.dtype)
+        if self._key != key:
+            n_per = x_host.shape[2] if self.model._kind == "conv1d_msc" else x_host.shape[1]
+            self._lanes = [_Lane(self.device, shape, x_host.dtype, self.chunk_sets * n_per) for _ in range(2)]
+            self._key = key
+
+    def _harvest(self, lane, out):
+        if lane.pending is None:
+            return
+        first, n_sets, det, count = lane.pending
+        lane.done.synchronize()
+        n = int(lane.count_host[0])
+        if n:
+            nbytes = n * DETECTION.itemsize
+            with torch.cuda.stream(lane.stream):
+                lane.host[:nbytes].copy_(det[:nbytes], non_blocking=True)
+            lane.stream.synchronize()
+            rec = lane.host[:nbytes].numpy().view(DETECTION).copy()
+            rec["set_index"] += first
+            out.append(rec)
+            self.d2h_bytes += nbytes
+        self.d2h_bytes += 4
+        lane.pending = None
+
+    @torch.no_grad()
+    def scan(self, x_host, threshold=0.5):
+        if x_host.is_cuda:
+            raise ValueError("scan() takes a host tensor; call the module directly for device-resident data")
+        if not x_host.is_contiguous():
+            raise RuntimeError("input must be contiguous")
+        self._ensure_lanes(x_host)
+        self.h2d_bytes = self.d2h_bytes = 0
+        out = []
+        n_total = x_host.shape[0]
+        main = torch.cuda.current_stream(self.device)
+        for lane in self._lanes:
+            lane.stream.wait_stream(main)
+        for i, first in enumerate(range(0, n_total, self.chunk_sets)):
+            lane = self._lanes[i & 1]
+            self._harvest(lane, out)
+            n_sets = min(self.chunk_sets, n_total - first)
+            with torch.cuda.stream(lane.stream):
+                xd = lane.x[:n_sets]
+                xd.copy_(x_host[first:first + n_sets], non_blocking=True)
+                native, (outs, struct, (B, N, S)) = self.model._run(xd)
+                det, count = native.postprocess(struct, B, N, S, threshold, self.device)
+                lane.count_host.copy_(count, non_blocking=True)
+                lane.done.record(lane.stream)
+            lane.pending = (first, n_sets, det, count)
+            self.h2d_bytes += xd.numel() * xd.element_size()
+        for lane in self._lanes:
+            self._harvest(lane, out)
+        for lane in self._lanes:
+            main.wait_stream(lane.stream)
+        return np.concatenate(out) if out else np.zeros(0, dtype=DETECTION)
+
+
+def to_predictions(records, n_sets):
+    """Structured records -> the reference's ``list[list[dict]]`` (two_stage_model.py:490-497 field names
+    where they exist; every record also carries the integer sample indices)."""
+    out = [[] for _ in range(n_sets)]
+    for r in records:
+        out[int(r["set_index"])].append({
+            "position": int(r["position"]), "class": int(r["cls"]), "score": float(r["score"]),
+            "defect_position": np.array([r["start"], r["end"]], dtype=np.float32),
+            "start_index": int(r["start_index"]), "end_index": int(r["end_index"]),
+            "adjusted_confidence": float(r["confidence"]),
+        })
+    return out
