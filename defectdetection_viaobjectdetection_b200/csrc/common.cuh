@@ -44,6 +44,7 @@ struct Ctx {
   int smem_optin = 0;
   size_t att_smem_configured = 0;
   size_t gemm_tc_smem_configured = 0;
+  size_t conv_tc_smem_configured = 0;
   bool profiling = false;                // per-kernel CUDA-event timing (paut_ctx_profile_*)
   std::vector<std::pair<std::string, cudaEvent_t>> prof_events;
   bool dry = false;                      // allocation-only pass used to size chunks: ops do nothing
@@ -157,6 +158,33 @@ void msc_pack_conv2(const float* w2, const float* b2, std::vector<uint16_t>& out
 void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1, const float* b1,
                        const void* Bc, const void* W1p, const float* bl1, const void* W2p, const float* bl2,
                        const float* pos, float* h);
+// ---- tcgen05 implicit-GEMM Conv1d on "flat rows" (ops_conv_tc.cu), bf16 mode
+constexpr int CONV_HALO = 8;                       // zero rows between A-scans; covers pad*dilation <= 8
+struct ConvTcLaunch {
+  const void* in = nullptr;      // bf16 flat rows [R, Cin]
+  int64_t A = 0;
+  int L = 0, halo = CONV_HALO, Cin = 0, Cout = 0;
+  const void* Wp = nullptr;      // conv_tc_pack() layout
+  const float* shift = nullptr;
+  int taps = 1, dil = 1, pad = 0;  // pad in taps (PyTorch padding = pad * dil)
+  bool relu = false;
+  const void* res = nullptr;     // bf16 flat rows [R, ldr], added before the ReLU
+  int ldr = 0;
+  void* out = nullptr;           // bf16 flat rows [R, ldc] at column offset coff (nullable)
+  int ldc = 0, coff = 0;
+  float* pool_partial = nullptr; // scratch [ceil(R/128)][2][Cout]
+  float* pool_out = nullptr;     // [A, ldp] mean over L at column offset poff
+  int ldp = 0, poff = 0;
+};
+int conv_tc_cb(int Cin);
+int conv_tc_nt(int Cout);
+void conv_tc_pack(const float* w, int taps, int Cin, int Cout, std::vector<uint16_t>& out);
+size_t flat_rows(int64_t A, int L, int halo);
+void op_conv_tc(Ctx& c, const ConvTcLaunch& a);
+void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const float* w, const float* shift, int k,
+                  int Cout, bool relu, void* out, int ldc, int coff, int halo);
+// bf16 flat rows [R, C] -> dense fp32 [A, L, C]
+void op_unflatten(Ctx& c, const void* flat, int64_t A, int L, int halo, int C, float* out);
 // MSC head (NN_models.py:123-127): o [M,3] -> sigmoid / tanh*0.5+0.5 into three arrays
 void op_msc_head(Ctx& c, const float* o, int64_t M, float* prob, float* start, float* end);
 // logits[:, 1:] += anomaly (model.py:332, enhanced_model.py:550)

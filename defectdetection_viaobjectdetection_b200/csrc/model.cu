@@ -295,6 +295,15 @@ ConvW Model::pack_conv(const std::string& cn, const std::string& bn) {
   cw.taps = taps;
   cw.w = upload(p);
   cw.shift = upload(shift);
+  if (cfg.precision == PAUT_PRECISION_BF16 && Cin % 16 == 0 && Cout % 16 == 0) {
+    std::vector<uint16_t> packed;
+    conv_tc_pack(p.data(), taps, Cin, Cout, packed);
+    void* d = nullptr;
+    PAUT_CUDA(cudaMalloc(&d, packed.size() * sizeof(uint16_t)));
+    dev_allocs.push_back(d);
+    PAUT_CUDA(cudaMemcpy(d, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    cw.Wp = d;
+  }
   return cw;
 }
 
@@ -569,6 +578,27 @@ struct G {
     op_conv(c, a);
     return out;
   }
+  // ---- bf16 mode: tcgen05 conv on flat rows
+  bool tc_convs(int S) const { return bf16 && S % 8 == 0 && S + CONV_HALO >= 128; }
+  __nv_bfloat16* alloc_flat(int64_t A, int L, int C) {
+    return static_cast<__nv_bfloat16*>(c.alloc(flat_rows(A, L, CONV_HALO) * (size_t)C * sizeof(__nv_bfloat16)));
+  }
+  void stem_flat(const float* x, int64_t A, int S, const ConvW& w, __nv_bfloat16* out, int ldc, int coff) {
+    op_stem_flat(c, x, PAUT_F32, A, S, w.w, w.shift, w.taps, w.Cout, true, out, ldc, coff, CONV_HALO);
+  }
+  void convtc(const __nv_bfloat16* in, int64_t A, int L, const ConvW& w, int dil, bool relu, const __nv_bfloat16* res,
+              int ldr, __nv_bfloat16* out, int ldc, int coff, float* pool_out, int ldp, int poff) {
+    ConvTcLaunch a;
+    a.in = in; a.A = A; a.L = L; a.Cin = w.Cin; a.Cout = w.Cout; a.Wp = w.Wp; a.shift = w.shift; a.taps = w.taps;
+    a.dil = dil; a.pad = w.taps / 2; a.relu = relu; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.coff = coff;
+    if (pool_out) {
+      const size_t tiles = (flat_rows(A, L, CONV_HALO) + 127) / 128;
+      a.pool_partial = c.allocf(tiles * 2 * (size_t)w.Cout);
+      a.pool_out = pool_out; a.ldp = ldp; a.poff = poff;
+    }
+    PAUT_CHECK(w.Wp != nullptr, PAUT_ERR_STATE, "conv_tc: weights were not packed for the tensor-core path");
+    op_conv_tc(c, a);
+  }
 };
 template <typename T>
 T* slot_at(const paut_outputs& o, int i, int64_t elem_off) {
@@ -630,12 +660,20 @@ void Model::fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, 
   float* xt = c.allocf((size_t)A * S);
   op_transpose_sn(c, x, x_dtype, xt, B, S, N);                                  // MSC_Conv1D_training.py:81
   const ConvW& c0 = conv["feature_extractor.0"];
-  float* a0 = c.allocf((size_t)A * S * 64);
-  op_stem_conv(c, xt, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
-  float* a1 = c.allocf((size_t)A * S * 128);
-  g.conv(a0, A, S, conv["feature_extractor.2"], 1, 1, 1, true, nullptr, a1, 128, 0, nullptr, 0, 0);
   float* feat = c.allocf((size_t)A * 128);
-  g.conv(a1, A, S, conv["feature_extractor.4"], 1, 1, 0, true, nullptr, nullptr, 0, 0, feat, 128, 0);   // mean over L
+  if (g.tc_convs(S)) {
+    __nv_bfloat16* a0 = g.alloc_flat(A, S, 64);
+    g.stem_flat(xt, A, S, c0, a0, 64, 0);
+    __nv_bfloat16* a1 = g.alloc_flat(A, S, 128);
+    g.convtc(a0, A, S, conv["feature_extractor.2"], 1, true, nullptr, 0, a1, 128, 0, nullptr, 0, 0);
+    g.convtc(a1, A, S, conv["feature_extractor.4"], 1, true, nullptr, 0, nullptr, 0, 0, feat, 128, 0);
+  } else {
+    float* a0 = c.allocf((size_t)A * S * 64);
+    op_stem_conv(c, xt, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
+    float* a1 = c.allocf((size_t)A * S * 128);
+    g.conv(a0, A, S, conv["feature_extractor.2"], 1, 1, 1, true, nullptr, a1, 128, 0, nullptr, 0, 0);
+    g.conv(a1, A, S, conv["feature_extractor.4"], 1, 1, 0, true, nullptr, nullptr, 0, 0, feat, 128, 0);   // mean over L
+  }
   float* h = feat;
   for (const TELW& t : tel) h = g.encoder_layer(h, t, B, N, ACT_RELU);
   float* h1 = g.linear(h, 128, lin["classifier.0"], A, ACT_RELU);
@@ -649,12 +687,20 @@ void Model::fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs&
   const int64_t A = B * N;
   const int d = cfg.d_model, C = cfg.num_classes;
   const ConvW& c1 = conv["signal_encoder.conv1"];
-  float* a0 = c.allocf((size_t)A * S * 64);
-  op_stem_conv(c, x, A, S, c1.w, c1.shift, c1.taps, c1.Cout, true, a0);
-  float* a1 = c.allocf((size_t)A * S * 128);
-  g.conv(a0, A, S, conv["signal_encoder.conv2"], 1, 1, 2, true, nullptr, a1, 128, 0, nullptr, 0, 0);
   float* feat = c.allocf((size_t)A * 256);
-  g.conv(a1, A, S, conv["signal_encoder.conv3"], 1, 1, 1, true, nullptr, nullptr, 0, 0, feat, 256, 0);
+  if (g.tc_convs(S)) {
+    __nv_bfloat16* a0 = g.alloc_flat(A, S, 64);
+    g.stem_flat(x, A, S, c1, a0, 64, 0);
+    __nv_bfloat16* a1 = g.alloc_flat(A, S, 128);
+    g.convtc(a0, A, S, conv["signal_encoder.conv2"], 1, true, nullptr, 0, a1, 128, 0, nullptr, 0, 0);
+    g.convtc(a1, A, S, conv["signal_encoder.conv3"], 1, true, nullptr, 0, nullptr, 0, 0, feat, 256, 0);
+  } else {
+    float* a0 = c.allocf((size_t)A * S * 64);
+    op_stem_conv(c, x, A, S, c1.w, c1.shift, c1.taps, c1.Cout, true, a0);
+    float* a1 = c.allocf((size_t)A * S * 128);
+    g.conv(a0, A, S, conv["signal_encoder.conv2"], 1, 1, 2, true, nullptr, a1, 128, 0, nullptr, 0, 0);
+    g.conv(a1, A, S, conv["signal_encoder.conv3"], 1, 1, 1, true, nullptr, nullptr, 0, 0, feat, 256, 0);
+  }
   float* seq = g.linear(feat, 256, lin["signal_encoder.fc"], A, ACT_NONE, nullptr, 0, nullptr, 0, 0, 0.f,
                         raw["sequence_transformer.pos_encoder.pe"], N);          // + pe[:, :N]
   for (const TELW& t : tel) seq = g.encoder_layer(seq, t, B, N, ACT_RELU);
@@ -709,14 +755,21 @@ void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_ou
   const int64_t A = B * N;
   const int d = cfg.d_model, q = d / 4;
   float* feat = c.allocf((size_t)A * d);
-  float* a0 = c.allocf((size_t)A * S * q);
   const char* names[4] = {"small", "medium", "large", "xlarge"};
+  const bool tcc = g.tc_convs(S) && q % 16 == 0;
+  float* a0 = tcc ? nullptr : c.allocf((size_t)A * S * q);
+  __nv_bfloat16* a0h = tcc ? g.alloc_flat(A, S, q) : nullptr;
   for (int i = 0; i < 4; ++i) {                                                  // two_stage_model.py:102-114
     const std::string p = std::string("signal_encoder.conv_") + names[i] + ".";
     const ConvW& s = conv[p + "0"];
-    op_stem_conv(c, x, A, S, s.w, s.shift, s.taps, s.Cout, true, a0);
     const ConvW& w = conv[p + "3"];
-    g.conv(a0, A, S, w, 1, 1, w.taps / 2, true, nullptr, nullptr, 0, 0, feat, d, q * i);
+    if (tcc) {
+      g.stem_flat(x, A, S, s, a0h, q, 0);
+      g.convtc(a0h, A, S, w, 1, true, nullptr, 0, nullptr, 0, 0, feat, d, q * i);
+    } else {
+      op_stem_conv(c, x, A, S, s.w, s.shift, s.taps, s.Cout, true, a0);
+      g.conv(a0, A, S, w, 1, 1, w.taps / 2, true, nullptr, nullptr, 0, 0, feat, d, q * i);
+    }
   }
   float* pr = g.linear(feat, d, lin["signal_encoder.projection.0"], A);
   float* seq = g.norm(pr, nullptr, ln["signal_encoder.projection.1"], A);
@@ -752,28 +805,56 @@ void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_out
   const std::string e = "signal_encoder.";
   // ---- EnhancedSignalEncoder (enhanced_model.py:135-175); three rotating [A,S,128] buffers
   const ConvW& ci = conv[e + "conv_init.0"];
-  float* s0 = c.allocf((size_t)A * S * 64);
-  op_stem_conv(c, x, A, S, ci.w, ci.shift, ci.taps, ci.Cout, true, s0);
-  float* bufA = c.allocf((size_t)A * S * 128);
-  float* bufB = c.allocf((size_t)A * S * 128);
-  float* bufC = c.allocf((size_t)A * S * 128);
   float* feat = c.allocf((size_t)A * 640);
-  for (int b = 0; b < 4; ++b)
-    g.conv(s0, A, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, 1, 1 << b, false, nullptr, bufA, 128, 32 * b,
-           nullptr, 0, 0);
-  g.conv(bufA, A, S, conv[e + "multi_scale.combine.0"], 1, 1, 0, true, nullptr, bufB, 128, 0, nullptr, 0, 0);
-  float* h = bufB;
-  float* spare = bufC;
-  for (int r = 0; r < 3; ++r) {
-    const int dil = 1 << r;
-    const std::string qn = e + "res_blocks." + istr(r) + ".conv_block.";
-    g.conv(h, A, S, conv[qn + "0"], dil, 1, dil, true, nullptr, bufA, 128, 0, nullptr, 0, 0);
-    g.conv(bufA, A, S, conv[qn + "3"], dil, 1, dil, true, h, spare, 128, 0, r == 2 ? feat : nullptr, 640, 0);
-    std::swap(h, spare);
-  }
   int L1 = 0, L2 = 0;
-  g.conv(h, A, S, conv[e + "pyramid_1"], 1, 2, 1, true, nullptr, bufA, 256, 0, feat, 640, 128, &L1);
-  g.conv(bufA, A, L1, conv[e + "pyramid_2"], 1, 2, 1, true, nullptr, nullptr, 0, 0, feat, 640, 384, &L2);
+  if (g.tc_convs(S)) {
+    // bf16 mode: every stride-1 conv of the encoder is a tcgen05 implicit GEMM on flat bf16 rows
+    __nv_bfloat16* s0 = g.alloc_flat(A, S, 64);
+    g.stem_flat(x, A, S, ci, s0, 64, 0);
+    __nv_bfloat16* bufA = g.alloc_flat(A, S, 128);
+    __nv_bfloat16* bufB = g.alloc_flat(A, S, 128);
+    __nv_bfloat16* bufC = g.alloc_flat(A, S, 128);
+    for (int b = 0; b < 4; ++b)
+      g.convtc(s0, A, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, false, nullptr, 0, bufA, 128, 32 * b,
+               nullptr, 0, 0);
+    g.convtc(bufA, A, S, conv[e + "multi_scale.combine.0"], 1, true, nullptr, 0, bufB, 128, 0, nullptr, 0, 0);
+    __nv_bfloat16* h = bufB;
+    __nv_bfloat16* spare = bufC;
+    for (int r = 0; r < 3; ++r) {
+      const int dil = 1 << r;
+      const std::string qn = e + "res_blocks." + istr(r) + ".conv_block.";
+      g.convtc(h, A, S, conv[qn + "0"], dil, true, nullptr, 0, bufA, 128, 0, nullptr, 0, 0);
+      g.convtc(bufA, A, S, conv[qn + "3"], dil, true, h, 128, spare, 128, 0, r == 2 ? feat : nullptr, 640, 0);
+      std::swap(h, spare);
+    }
+    // the two stride-2 pyramid convs still run on the fp32 CUDA-core kernel
+    float* hd = c.allocf((size_t)A * S * 128);
+    op_unflatten(c, h, A, S, CONV_HALO, 128, hd);
+    float* x1 = c.allocf((size_t)A * ((S + 1) / 2) * 256);
+    g.conv(hd, A, S, conv[e + "pyramid_1"], 1, 2, 1, true, nullptr, x1, 256, 0, feat, 640, 128, &L1);
+    g.conv(x1, A, L1, conv[e + "pyramid_2"], 1, 2, 1, true, nullptr, nullptr, 0, 0, feat, 640, 384, &L2);
+  } else {
+    float* s0 = c.allocf((size_t)A * S * 64);
+    op_stem_conv(c, x, A, S, ci.w, ci.shift, ci.taps, ci.Cout, true, s0);
+    float* bufA = c.allocf((size_t)A * S * 128);
+    float* bufB = c.allocf((size_t)A * S * 128);
+    float* bufC = c.allocf((size_t)A * S * 128);
+    for (int b = 0; b < 4; ++b)
+      g.conv(s0, A, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, 1, 1 << b, false, nullptr, bufA, 128, 32 * b,
+             nullptr, 0, 0);
+    g.conv(bufA, A, S, conv[e + "multi_scale.combine.0"], 1, 1, 0, true, nullptr, bufB, 128, 0, nullptr, 0, 0);
+    float* h = bufB;
+    float* spare = bufC;
+    for (int r = 0; r < 3; ++r) {
+      const int dil = 1 << r;
+      const std::string qn = e + "res_blocks." + istr(r) + ".conv_block.";
+      g.conv(h, A, S, conv[qn + "0"], dil, 1, dil, true, nullptr, bufA, 128, 0, nullptr, 0, 0);
+      g.conv(bufA, A, S, conv[qn + "3"], dil, 1, dil, true, h, spare, 128, 0, r == 2 ? feat : nullptr, 640, 0);
+      std::swap(h, spare);
+    }
+    g.conv(h, A, S, conv[e + "pyramid_1"], 1, 2, 1, true, nullptr, bufA, 256, 0, feat, 640, 128, &L1);
+    g.conv(bufA, A, L1, conv[e + "pyramid_2"], 1, 2, 1, true, nullptr, nullptr, 0, 0, feat, 640, 384, &L2);
+  }
   float* fc = g.linear(feat, 640, lin[e + "fc.0"], A);
   float* sf = g.norm(fc, nullptr, ln[e + "fc.1"], A, ACT_RELU);
   // ---- EnhancedSequenceTransformer (:230-251)

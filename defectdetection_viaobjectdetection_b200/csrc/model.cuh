@@ -26,6 +26,7 @@ struct Lin {
 struct ConvW {
   const float* w = nullptr;      // [taps][Cin][Cout] (BN scale folded); Cin == 1 -> [taps][Cout]
   const float* shift = nullptr;  // folded bias
+  const void* Wp = nullptr;      // bf16 blocks for the tcgen05 conv (bf16 mode, Cin and Cout multiples of 16)
   int Cin = 0, Cout = 0, taps = 0;
 };
 struct LNW {

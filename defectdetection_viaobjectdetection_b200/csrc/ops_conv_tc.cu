@@ -1,0 +1,425 @@
+// tcgen05 implicit-GEMM Conv1d (+ folded BatchNorm shift, residual, ReLU, pooled mean) for the bf16 mode.
+//
+// Activation layout ("flat rows"): every A-scan owns L rows of C channels (bf16, channels-last) followed by
+// HALO zero rows; HALO more zero rows precede the first A-scan:  row(a, l) = HALO + a*(L+HALO) + l.
+// Because the halo rows are zero and at least pad*dilation wide, a convolution is a plain 1-D convolution
+// over the whole flat row axis: no per-A-scan edge handling, and an M tile is simply 128 consecutive rows.
+//
+// K loop: for each block of 64 input channels, the window rows [r0 - pad*dil, r0 + 128 + pad*dil) are
+// staged once in shared memory in the canonical K-major layout ([8 chunks][window rows][16 B]); tap t of
+// the kernel is the SAME window addressed through a descriptor whose start address is advanced by
+// t*dil rows (rows are uniformly 16 B apart inside a chunk), so no im2col copy exists anywhere.
+// The matching weight blocks ([tap][8 chunks][NT rows][16 B]) ride in the same pipeline stage.
+//
+// Warp roles (256 threads): warps 0-3 stage operands (ld.global -> st.shared) into a 3-deep ring and their
+// thread 0 issues the tcgen05.mma of each stage (commit -> stage-free barrier; last stage of a tile also
+// commits -> accumulator-full barrier); warps 4-7 are the epilogue: TMEM -> registers -> shift, residual,
+// ReLU -> bf16 rows in HBM (halo rows are written as zeros to keep the layout invariant) and/or per-tile
+// column sums for the pooled mean.  Two TMEM accumulators let tile i+1's MMAs overlap tile i's epilogue.
+// CTAs are persistent over (row tile, N tile) pairs.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace paut {
+
+using namespace tc;
+
+namespace {
+
+constexpr int CT_STAGES = 3;
+constexpr int CT_THREADS = 256;
+
+struct ConvTcArgs {
+  const __nv_bfloat16* in;      // flat rows [R, Cin]
+  int64_t R;                    // total flat rows (multiple of 8 not required)
+  int Cin, Cout;
+  const __nv_bfloat16* Wp;      // [Cout/NT][Cin/CB blocks][taps][CB/8 chunks][NT rows][8]
+  const float* shift;           // [Cout]
+  int taps, dil, pad;           // stride 1
+  int NT, CB;                   // N tile (<= 128), input-channel block (<= 64, multiple of 16)
+  int relu;
+  const __nv_bfloat16* res;     // flat rows [R, ldr] (nullable), same row geometry
+  int ldr;
+  __nv_bfloat16* out;           // flat rows [R, ldc] at column offset coff (nullable)
+  int ldc, coff;
+  float* pool;                  // per-tile column sums [tiles][2 segments][Cout] (nullable)
+  int L, Lp, H0;                // geometry: valid rows per A-scan, period, leading halo
+  int64_t A;
+  int wrows;                    // window rows = 128 + (taps-1)*dil
+  int a_stage_bytes, b_stage_bytes;
+  int64_t num_tiles;            // row tiles
+};
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t stage_free[CT_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float pool_s[4][2][16];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NT = p.NT;
+  const int ntn = p.Cout / NT;
+  const int ncb = p.Cin / p.CB;
+  const int chunks = p.CB / 8;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int64_t work_total = p.num_tiles * ntn;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) {
+    for (int s = 0; s < CT_STAGES; ++s) mbar_init(&stage_free[s], 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = make_idesc_bf16(128, NT);
+
+  if (warp < 4) {
+    // ================= loader / MMA group =================
+    int stage = 0;
+    uint32_t stage_use = 0;                 // number of times the ring wrapped (phase tracking)
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x, ++it) {
+      const int64_t tile = w / ntn;
+      const int nt = (int)(w - tile * ntn);
+      const int64_t r0 = tile * 128;
+      const int acc = it & 1;
+      for (int cb = 0; cb < ncb; ++cb) {
+        // wait until the MMAs that last read this stage have completed
+        if (stage_use > 0) mbar_wait(&stage_free[stage], (stage_use - 1) & 1);
+        unsigned char* As = smem + (size_t)stage * stage_bytes;
+        unsigned char* Bs = As + p.a_stage_bytes;
+        // ---- A window: rows [r0 - pad*dil, +wrows) x CB channels of this block -> [chunk][row][16 B]
+        const int64_t wr0 = r0 - (int64_t)p.pad * p.dil;
+        for (int i = tid; i < chunks * p.wrows; i += 128) {
+          const int ch = i / p.wrows, r = i - ch * p.wrows;
+          const int64_t row = wr0 + r;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (row >= 0 && row < p.R)
+            v = __ldg(reinterpret_cast<const uint4*>(p.in + row * p.Cin + cb * p.CB + ch * 8));
+          *reinterpret_cast<uint4*>(As + (size_t)ch * p.wrows * 16 + r * 16) = v;
+        }
+        // ---- B block: all taps of (nt, cb): contiguous taps*chunks*NT*16 bytes
+        {
+          const int n16 = p.taps * chunks * NT;
+          const uint4* src = reinterpret_cast<const uint4*>(p.Wp) + ((size_t)nt * ncb + cb) * n16;
+          uint4* dst = reinterpret_cast<uint4*>(Bs);
+          for (int i = tid; i < n16; i += 128) dst[i] = __ldg(src + i);
+        }
+        fence_async_smem();
+        named_sync(1, 128);
+        if (tid == 0) {
+          if (cb == 0 && it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+          const uint32_t d = tmem + acc * 128;
+          for (int t = 0; t < p.taps; ++t)
+            for (int ks = 0; ks < chunks / 2; ++ks) {
+              const uint64_t ad = make_desc(a_addr + (uint32_t)(ks * 2 * p.wrows + t * p.dil) * 16, p.wrows * 16, 128);
+              const uint64_t bd = make_desc(b_addr + (uint32_t)((t * chunks + ks * 2) * NT) * 16, NT * 16, 128);
+              mma_bf16_ss(d, ad, bd, idesc, (cb | t | ks) ? 1u : 0u);
+            }
+          mma_commit(&stage_free[stage]);
+          if (cb == ncb - 1) mma_commit(&acc_full[acc]);
+        }
+        if (++stage == CT_STAGES) { stage = 0; ++stage_use; }
+      }
+    }
+  } else {
+    // ================= epilogue group =================
+    const int q = warp - 4;                 // TMEM lane quarter (warp % 4)
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x, ++it) {
+      const int64_t tile = w / ntn;
+      const int nt = (int)(w - tile * ntn);
+      const int acc = it & 1;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = tile * 128 + q * 32 + lane;
+      // geometry of this row: which A-scan, valid or halo
+      const int64_t rel = row - p.H0;
+      const int64_t a_of_row = rel >= 0 ? rel / p.Lp : -1;
+      const int l_of_row = rel >= 0 ? (int)(rel - a_of_row * p.Lp) : p.L;
+      const bool valid = rel >= 0 && a_of_row < p.A && l_of_row < p.L && row < p.R;
+      // first A-scan touched by the tile (segment 0); rows of the next one are segment 1
+      const int64_t rel0 = tile * 128 - p.H0;
+      const int64_t a_first = rel0 >= 0 ? rel0 / p.Lp : 0;
+      const int seg = (int)(a_of_row - a_first);
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, v);
+        const int n = nt * NT + c0;
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __ldg(p.shift + n + j);
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + row * p.ldr + n);
+            const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
+            const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+              v[2 * j] += __low2float(h2);
+              v[2 * j + 1] += __high2float(h2);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (p.out && row < p.R) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.ldc + p.coff + n);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        if (p.pool) {
+          // column sums of the tile per segment, reduced in a fixed order: lanes (butterfly) -> 4 warps
+#pragma unroll
+          for (int sgm = 0; sgm < 2; ++sgm) {
+            float u[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = (valid && seg == sgm) ? v[j] : 0.f;
+            // transpose-reduce: after the 4 halving steps lane l holds the sum of column (l & 15) over a
+            // 16-lane half; one more shuffle folds the two halves.
+#pragma unroll
+            for (int step = 0; step < 4; ++step) {
+              const int half = 8 >> step;                    // values kept per lane after this step
+              const bool upper = (lane >> (3 - step)) & 1;   // lane bit 3,2,1,0
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (j < half) {
+                  const float send = upper ? u[j] : u[j + half];
+                  const float keep = upper ? u[j + half] : u[j];
+                  u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8 >> step);
+                }
+              }
+            }
+            float tot = u[0] + __shfl_xor_sync(0xffffffffu, u[0], 16);
+            // lane l (< 16) now holds a column; which one: bits of l select the kept halves
+            if (lane < 16) {
+              const int col = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+              pool_s[q][sgm][col] = tot;
+            }
+          }
+          named_sync(2, 128);
+          if (tid - 128 < 32) {
+            const int t = tid - 128;
+            const int sgm = t >> 4, col = t & 15;
+            const float s = pool_s[0][sgm][col] + pool_s[1][sgm][col] + pool_s[2][sgm][col] + pool_s[3][sgm][col];
+            p.pool[((size_t)tile * 2 + sgm) * p.Cout + n + col] = s;
+          }
+          named_sync(2, 128);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// pooled mean from the per-tile partial sums, in a fixed order: out[a, poff + c] = sum / L
+__global__ void k_pool_finish(const float* __restrict__ partial, float* __restrict__ out, int ldp, int poff,
+                              int64_t A, int C, int L, int Lp, int H0) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= A * C) return;
+  const int64_t a = idx / C;
+  const int c = (int)(idx - a * C);
+  const int64_t first = H0 + a * Lp, last = first + L - 1;
+  float s = 0.f;
+  for (int64_t t = first / 128; t <= last / 128; ++t) {
+    const int64_t rel0 = t * 128 - H0;
+    const int64_t a_first = rel0 >= 0 ? rel0 / Lp : 0;
+    const int seg = (int)(a - a_first);
+    if (seg >= 0 && seg < 2) s += partial[((size_t)t * 2 + seg) * C + c];
+  }
+  out[a * ldp + poff + c] = s / (float)L;
+}
+
+// x [A, S] (fp32 or bf16) -> Conv1d 1->Cout (+folded BN, ReLU) -> flat rows bf16 (halo rows zeroed)
+__global__ void k_stem_flat(const void* __restrict__ x, int x_dtype, int64_t A, int S, const float* __restrict__ w,
+                            const float* __restrict__ shift, int k, int Cout, int relu, __nv_bfloat16* __restrict__ out,
+                            int ldc, int coff, int Lp, int H0, int64_t R) {
+  const int c8n = Cout >> 3;
+  const int64_t total = R * c8n;
+  const int half = k >> 1;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % c8n);
+    const int64_t row = idx / c8n;
+    const int64_t rel = row - H0;
+    const int64_t a = rel >= 0 ? rel / Lp : -1;
+    const int l = rel >= 0 ? (int)(rel - a * Lp) : S;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (a >= 0 && a < A && l < S) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = shift[c8 * 8 + j];
+      for (int t = 0; t < k; ++t) {
+        const int li = l + t - half;
+        if (li >= 0 && li < S) {
+          const float xv = x_dtype == PAUT_BF16
+                               ? __bfloat162float(static_cast<const __nv_bfloat16*>(x)[a * S + li])
+                               : static_cast<const float*>(x)[a * S + li];
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * Cout + c8 * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + t * Cout + c8 * 8 + 4));
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(out + row * ldc + coff + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+__global__ void k_unflatten(const __nv_bfloat16* __restrict__ flat, int64_t A, int L, int Lp, int H0, int C,
+                            float* __restrict__ out) {
+  const int c8n = C >> 3;
+  const int64_t total = A * L * c8n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % c8n);
+    const int64_t al = idx / c8n;
+    const int64_t a = al / L;
+    const int l = (int)(al - a * L);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(flat + (H0 + a * Lp + l) * C + c8 * 8));
+    const uint32_t rr[4] = {v.x, v.y, v.z, v.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+      o[2 * j] = __low2float(h2);
+      o[2 * j + 1] = __high2float(h2);
+    }
+    float4* dst = reinterpret_cast<float4*>(out + al * C + c8 * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+uint16_t f2bf_(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)((u + r) >> 16);
+}
+
+}  // namespace
+
+int conv_tc_cb(int Cin) { return Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : (Cin % 16 == 0 ? 16 : 0)); }
+int conv_tc_nt(int Cout) {
+  if (Cout % 16 != 0) return 0;
+  for (int nt = 128; nt >= 16; nt -= 16)
+    if (Cout % nt == 0) return nt;
+  return 0;
+}
+
+// weights [taps][Cin][Cout] fp32 (BN scale folded, as packed for the fp32 path) -> bf16 blocks
+// [Cout/NT][Cin/CB][taps][CB/8][NT][8]
+void conv_tc_pack(const float* w, int taps, int Cin, int Cout, std::vector<uint16_t>& out) {
+  const int NT = conv_tc_nt(Cout), CB = conv_tc_cb(Cin);
+  const int ncb = Cin / CB, chunks = CB / 8;
+  out.assign((size_t)taps * Cin * Cout, 0);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const int nt = co / NT, r = co % NT, cb = ci / CB, ch = (ci % CB) / 8, e = ci % 8;
+        const size_t idx = (((((size_t)nt * ncb + cb) * taps + t) * chunks + ch) * NT + r) * 8 + e;
+        out[idx] = f2bf_(w[((size_t)t * Cin + ci) * Cout + co]);
+      }
+}
+
+size_t flat_rows(int64_t A, int L, int halo) { return (size_t)halo + (size_t)A * (L + halo); }
+
+void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
+  if (c.dry) return;
+  ConvTcArgs p;
+  p.in = static_cast<const __nv_bfloat16*>(a.in); p.Cin = a.Cin; p.Cout = a.Cout;
+  p.Wp = static_cast<const __nv_bfloat16*>(a.Wp); p.shift = a.shift; p.taps = a.taps; p.dil = a.dil; p.pad = a.pad;
+  p.NT = conv_tc_nt(a.Cout); p.CB = conv_tc_cb(a.Cin);
+  PAUT_CHECK(p.NT > 0 && p.CB > 0, PAUT_ERR_UNSUPPORTED, "conv_tc: channel counts must be multiples of 16");
+  PAUT_CHECK(a.pad * a.dil <= a.halo && (a.taps - 1) * a.dil == 2 * a.pad * a.dil, PAUT_ERR_UNSUPPORTED,
+             "conv_tc: needs 'same' padding no wider than the halo");
+  p.relu = a.relu ? 1 : 0; p.res = static_cast<const __nv_bfloat16*>(a.res); p.ldr = a.ldr;
+  p.out = static_cast<__nv_bfloat16*>(a.out); p.ldc = a.ldc; p.coff = a.coff; p.pool = a.pool_partial;
+  p.L = a.L; p.Lp = a.L + a.halo; p.H0 = a.halo; p.A = a.A;
+  p.R = (int64_t)flat_rows(a.A, a.L, a.halo);
+  p.wrows = 128 + (a.taps - 1) * a.dil;
+  p.a_stage_bytes = ((p.CB / 8) * p.wrows * 16 + 127) & ~127;
+  p.b_stage_bytes = a.taps * (p.CB / 8) * p.NT * 16;
+  p.num_tiles = (p.R + 127) / 128;
+  const size_t smem = (size_t)CT_STAGES * (p.a_stage_bytes + p.b_stage_bytes);
+  PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory");
+  if (smem > c.conv_tc_smem_configured) {
+    PAUT_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c.conv_tc_smem_configured = smem;
+  }
+  const int64_t work = p.num_tiles * (a.Cout / p.NT);
+  const int grid = (int)std::min<int64_t>(work, c.num_sms);
+  k_conv_tc<<<grid, CT_THREADS, smem, c.stream>>>(p);
+  c.launched("conv_tc");
+  if (a.pool_partial && a.pool_out) {
+    const int64_t n = a.A * a.Cout;
+    k_pool_finish<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(a.pool_partial, a.pool_out, a.ldp, a.poff, a.A,
+                                                                    a.Cout, a.L, a.L + a.halo, a.halo);
+    c.launched("pool_finish");
+  }
+}
+
+void op_unflatten(Ctx& c, const void* flat, int64_t A, int L, int halo, int C, float* out) {
+  if (c.dry) return;
+  PAUT_CHECK(C % 8 == 0, PAUT_ERR_UNSUPPORTED, "unflatten: C must be a multiple of 8");
+  int64_t blocks = (A * L * (C / 8) + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_unflatten<<<(unsigned)blocks, 256, 0, c.stream>>>(static_cast<const __nv_bfloat16*>(flat), A, L, L + halo, halo, C, out);
+  c.launched("unflatten");
+}
+
+void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const float* w, const float* shift, int k,
+                  int Cout, bool relu, void* out, int ldc, int coff, int halo) {
+  if (c.dry) return;
+  PAUT_CHECK(Cout % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0, PAUT_ERR_UNSUPPORTED, "stem_flat: channels must be multiples of 8");
+  const int64_t R = (int64_t)flat_rows(A, S, halo);
+  const int64_t total = R * (Cout / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_stem_flat<<<(unsigned)blocks, 256, 0, c.stream>>>(x, x_dtype, A, S, w, shift, k, Cout, relu ? 1 : 0,
+                                                      static_cast<__nv_bfloat16*>(out), ldc, coff, S + halo, halo, R);
+  c.launched("stem_flat");
+}
+
+}  // namespace paut

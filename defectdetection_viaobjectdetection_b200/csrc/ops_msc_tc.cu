@@ -28,7 +28,8 @@ using namespace tc;
 namespace {
 
 constexpr int H0 = 128, H1 = 64;
-constexpr int ENC_THREADS = 256;
+constexpr int ENC_THREADS = 640;        // 20 warps: 2 conv1 items per thread, 1 epilogue unit (tile, quarter) per warp
+constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
 constexpr int D1_COL = 320, D2_COL = 448;
 constexpr int XS_PAD = 16;
 
@@ -48,12 +49,27 @@ struct MscEncArgs {
   float* h;                        // [A][64]
 };
 
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
-  uint32_t r0, r1;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  a = __uint_as_float(r0);
-  b = __uint_as_float(r1);
+// 18 accumulator columns of one row (16 channels + hi/lo of their sum) with a single wait; the wait names the
+// destination registers so that no use can be scheduled ahead of it
+__device__ __forceinline__ void tmem_ld18(uint32_t taddr, float (&y)[16], float& s0, float& s1) {
+  uint32_t r[18];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r[16]), "=r"(r[17]) : "r"(taddr + 16) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(r[i]);
+  s0 = __uint_as_float(r[16]);
+  s1 = __uint_as_float(r[17]);
 }
 
 __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
@@ -68,7 +84,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   const uint32_t im_bytes = 4 * im_chunk;
   unsigned char* IM = smem;                        // [2][4 chunks][rows][16 B]
   unsigned char* A2 = smem + 2 * im_bytes;         // [S/8 chunks][128 rows][16 B]
-  unsigned char* WR = A2 + (size_t)256 * S;        // [2][8 chunks][128 rows][16 B]
+  unsigned char* WR = A2 + (size_t)(S / 8) * A2_LBO;   // [2][8 chunks][128 rows][16 B]
   unsigned char* BC = WR + 2 * 16384;              // [4 chunks][32 rows][16 B]
   __nv_bfloat16* XS = reinterpret_cast<__nv_bfloat16*>(BC + 2048);   // [2][2][S + 16]
   const int xs_stride = S + XS_PAD;
@@ -141,11 +157,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     mbar_wait(&bar_conv[buf], (g >> 1) & 1);
     tc_fence_after();
     const int q = warp & 3;
-    for (int T = warp >> 2; T < tiles; T += 2) {
+    for (int T = warp >> 2; T < tiles; T += ENC_THREADS / 128) {
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + T * 32;
       float y[16], s0, s1;
-      tmem_ld16(taddr, y);
-      tmem_ld2(taddr + 16, s0, s1);
+      tmem_ld18(taddr, y, s0, s1);
       float f = s0 + s1;
 #pragma unroll
       for (int c = 0; c < 16; ++c) f += fabsf(y[c]);
@@ -153,19 +168,25 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       const int al = r >= S ? 1 : 0;
       const int pos = r - al * S;
       const int arow = 2 * g + al;                  // A-scan row inside the CTA tile
-      *reinterpret_cast<__nv_bfloat16*>(A2 + (size_t)(pos >> 3) * 2048 + arow * 16 + (pos & 7) * 2) =
+      *reinterpret_cast<__nv_bfloat16*>(A2 + (size_t)(pos >> 3) * A2_LBO + arow * 16 + (pos & 7) * 2) =
           __float2bfloat16_rn(f);
     }
   };
 
-  prefetch_x(0);
   const int ngroups = 64;
+  prefetch_x(0);
+  if (xloader) *reinterpret_cast<uint4*>(XS + x_al * xs_stride + 8 + x_part * 8) = xr;
+  prefetch_x(1);
+  __syncthreads();
   for (int g = 0; g < ngroups; ++g) {
     const int buf = g & 1;
-    __nv_bfloat16* xs = XS + buf * 2 * xs_stride;
-    if (xloader) *reinterpret_cast<uint4*>(xs + x_al * xs_stride + 8 + x_part * 8) = xr;
-    __syncthreads();
-    if (g + 1 < ngroups) prefetch_x(g + 1);
+    const __nv_bfloat16* xs = XS + buf * 2 * xs_stride;
+    // x of group g+1 goes to the other staging buffer (its last reader, conv1 of group g-1, finished before
+    // the previous block barrier); x of group g+2 starts its trip from HBM
+    if (g + 1 < ngroups) {
+      if (xloader) *reinterpret_cast<uint4*>(XS + (buf ^ 1) * 2 * xs_stride + x_al * xs_stride + 8 + x_part * 8) = xr;
+      if (g + 2 < ngroups) prefetch_x(g + 2);
+    }
     // ---- conv1 + ReLU -> im2col operand (3 shifted copies of the 8-channel vector of each position)
     unsigned char* im = IM + buf * im_bytes;
     for (int item = tid; item < 2 * rows; item += ENC_THREADS) {
@@ -221,10 +242,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(A2) + kb * 8 * 2048, b_addr = smem_u32(WR + s * 16384);
+      const uint32_t a_addr = smem_u32(A2) + kb * 8 * A2_LBO, b_addr = smem_u32(WR + s * 16384);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        mma_bf16_ss(tmem + D1_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
+        mma_bf16_ss(tmem + D1_COL, make_desc(a_addr + ks * 2 * A2_LBO, A2_LBO, 128),
                     make_desc(b_addr + ks * 2 * 2048, 2048, 128), make_idesc_bf16(128, H0), (kb | ks) ? 1u : 0u);
       mma_commit(&bar_w[s]);
     }
@@ -234,11 +255,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   // ---- epilogue 1: relu(D1 + b) -> bf16 -> A3 (aliases the first im2col buffer), K-major for the next GEMM
   {
     unsigned char* A3 = IM;
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3;
     const int r = q * 32 + lane;
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      const int n = half * 64 + c0;
+    for (int n = (warp >> 2) * 16; n < H0; n += (ENC_THREADS / 128) * 16) {
       float v[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D1_COL + n, v);
       uint32_t pk[8];
@@ -269,11 +288,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   tc_fence_after();
   // ---- epilogue 2: relu(D2 + b) + position table -> h (fp32)
   {
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3;
     const int64_t a = a0 + q * 32 + lane;
-#pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 16) {
-      const int n = half * 32 + c0;
+    for (int n = (warp >> 2) * 16; n < H1; n += (ENC_THREADS / 128) * 16) {
       float v[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D2_COL + n, v);
       if (a < p.A) {
@@ -350,7 +367,7 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
   p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset; p.w1 = w1; p.b1 = b1;
   p.Bc = static_cast<const __nv_bfloat16*>(Bc); p.W1p = static_cast<const __nv_bfloat16*>(W1p); p.bl1 = bl1;
   p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
-  const size_t smem = (size_t)2 * 4 * (2 * S) * 16 + (size_t)256 * S + 2 * 16384 + 2048 + (size_t)2 * 2 * (S + XS_PAD) * 2;
+  const size_t smem = (size_t)2 * 4 * (2 * S) * 16 + (size_t)(S / 8) * A2_LBO + 2 * 16384 + 2048 + (size_t)2 * 2 * (S + XS_PAD) * 2;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
   PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (A + 127) / 128;

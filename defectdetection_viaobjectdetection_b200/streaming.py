@@ -2,7 +2,7 @@
 
 The reference feeds the model one window at a time (batch 1, one H2D per window, one D2H sync per scalar:
 model_tester.py:37-117, predict.py:169-197).  ``VolumeScanner`` streams a host-resident stack of sets through
-the drop-in module in resident chunks on two CUDA streams, so the host->device copy of chunk i+1 and the
+the drop-in module in resident chunks on a few CUDA streams, so the host->device copy of chunk i+1 and the
 device->host copy of the kept detections of chunk i-1 overlap the kernels of chunk i.  Each stream has its
 own library context (one paut_ctx <-> one stream); results come back as one structured array in the
 reference's (set, position) order, or as the reference's ``list[list[dict]]`` via ``to_predictions``.
@@ -32,9 +32,10 @@ class VolumeScanner:
     makes the copies asynchronous.  Returns a numpy structured array (dtype ``DETECTION``) whose
     ``set_index`` is the index into ``x_host``."""
 
-    def __init__(self, model, chunk_sets=256, device=None):
+    def __init__(self, model, chunk_sets=256, device=None, lanes=4):
         self.model = model
         self.chunk_sets = int(chunk_sets)
+        self.num_lanes = max(2, int(lanes))
         self.device = torch.device(device) if device is not None else next(iter(model.state_dict().values())).device
         if self.device.type != "cuda":
             raise RuntimeError("VolumeScanner needs the model on a CUDA device (no CPU fallback)")
@@ -48,25 +49,28 @@ class VolumeScanner:
         key = (shape, x_host.dtype)
         if self._key != key:
             n_per = x_host.shape[2] if self.model._kind == "conv1d_msc" else x_host.shape[1]
-            self._lanes = [_Lane(self.device, shape, x_host.dtype, self.chunk_sets * n_per) for _ in range(2)]
+            self._lanes = [_Lane(self.device, shape, x_host.dtype, self.chunk_sets * n_per)
+                           for _ in range(self.num_lanes)]
             self._key = key
 
     def _harvest(self, lane, out):
         if lane.pending is None:
             return
-        first, n_sets, det, count = lane.pending
+        first, n_sets, det, count, copied = lane.pending
         lane.done.synchronize()
         n = int(lane.count_host[0])
         if n:
             nbytes = n * DETECTION.itemsize
-            with torch.cuda.stream(lane.stream):
-                lane.host[:nbytes].copy_(det[:nbytes], non_blocking=True)
-            lane.stream.synchronize()
+            if nbytes > copied:                      # more records than the speculative copy covered
+                with torch.cuda.stream(lane.stream):
+                    lane.host[copied:nbytes].copy_(det[copied:nbytes], non_blocking=True)
+                lane.stream.synchronize()
+                self.d2h_bytes += nbytes - copied
             rec = lane.host[:nbytes].numpy().view(DETECTION).copy()
             rec["set_index"] += first
-            out.append(rec)
-            self.d2h_bytes += nbytes
-        self.d2h_bytes += 4
+            out.append((first, rec))
+            self._spec_bytes = max(self._spec_bytes, int(nbytes * 1.25) // 48 * 48 + 48)
+        self.d2h_bytes += 4 + copied
         lane.pending = None
 
     @torch.no_grad()
@@ -77,13 +81,14 @@ class VolumeScanner:
             raise RuntimeError("input must be contiguous")
         self._ensure_lanes(x_host)
         self.h2d_bytes = self.d2h_bytes = 0
+        self._spec_bytes = getattr(self, "_spec_bytes", 1 << 20)
         out = []
         n_total = x_host.shape[0]
         main = torch.cuda.current_stream(self.device)
         for lane in self._lanes:
             lane.stream.wait_stream(main)
         for i, first in enumerate(range(0, n_total, self.chunk_sets)):
-            lane = self._lanes[i & 1]
+            lane = self._lanes[i % self.num_lanes]
             self._harvest(lane, out)
             n_sets = min(self.chunk_sets, n_total - first)
             with torch.cuda.stream(lane.stream):
@@ -92,14 +97,19 @@ class VolumeScanner:
                 native, (outs, struct, (B, N, S)) = self.model._run(xd)
                 det, count = native.postprocess(struct, B, N, S, threshold, self.device)
                 lane.count_host.copy_(count, non_blocking=True)
+                # speculative copy of the record buffer in the same stream (no second round trip): as many
+                # bytes as the previous chunks needed, plus head-room; the rare overflow is fetched at harvest
+                copied = min(det.numel(), self._spec_bytes)
+                lane.host[:copied].copy_(det[:copied], non_blocking=True)
                 lane.done.record(lane.stream)
-            lane.pending = (first, n_sets, det, count)
+            lane.pending = (first, n_sets, det, count, copied)
             self.h2d_bytes += xd.numel() * xd.element_size()
         for lane in self._lanes:
             self._harvest(lane, out)
         for lane in self._lanes:
             main.wait_stream(lane.stream)
-        return np.concatenate(out) if out else np.zeros(0, dtype=DETECTION)
+        out.sort(key=lambda fr: fr[0])                       # chunks back in volume order
+        return np.concatenate([r for _, r in out]) if out else np.zeros(0, dtype=DETECTION)
 
 
 def to_predictions(records, n_sets):

@@ -186,3 +186,27 @@ def test_error_behaviour_matches_reference():
         m(torch.rand(1, 301, 320, device="cuda"))
     with pytest.raises(NotImplementedError):
         build("two_stage", dict(signal_length=320))(torch.rand(1, 50, 320, device="cuda"), targets=[{}])
+
+
+@pytest.mark.parametrize("kind,precision", [("two_stage", "fp32"), ("msc", "bf16")])
+def test_volume_scanner_equals_resident_run(kind, precision):
+    """Streaming from host memory in chunks on two streams returns exactly the records of one resident call."""
+    from defectdetection_viaobjectdetection_b200.streaming import VolumeScanner, to_predictions
+    N = 300 if kind == "msc" else 50
+    B = 37
+    x = torch.from_numpy(synth.synth_paut_sets(B, N, 320, seed=8, defect_frac=0.1))
+    if precision == "bf16":
+        x = x.to(torch.bfloat16)
+    m = build(kind, dict(signal_length=320), precision=precision)
+    everything = m.predict_records(x.cuda(), threshold=-1.0)
+    thr = float(np.median(everything["confidence"]))          # keeps about half of the A-scans
+    whole = m.predict_records(x.cuda(), threshold=thr)
+    scanner = VolumeScanner(m, chunk_sets=8)
+    for host in (x.pin_memory(), x):
+        got = scanner.scan(host, threshold=thr)
+        assert len(got) == len(whole) > 0
+        for f in whole.dtype.names:
+            np.testing.assert_array_equal(got[f], whole[f], err_msg=f)
+    assert scanner.h2d_bytes == x.numel() * x.element_size()
+    preds = to_predictions(got, B)
+    assert sum(len(p) for p in preds) == len(got)
