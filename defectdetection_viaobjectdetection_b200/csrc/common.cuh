@@ -176,7 +176,7 @@ struct ConvTcLaunch {
   float* pool_out = nullptr;     // [A, ldp] mean over L at column offset poff
   int ldp = 0, poff = 0;
 };
-int conv_tc_cb(int Cin);
+int conv_tc_cb(int Cin, int taps, int Cout);
 int conv_tc_nt(int Cout);
 void conv_tc_pack(const float* w, int taps, int Cin, int Cout, std::vector<uint16_t>& out);
 size_t flat_rows(int64_t A, int L, int halo);

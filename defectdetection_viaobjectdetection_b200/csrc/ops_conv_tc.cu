@@ -340,7 +340,6 @@ uint16_t f2bf_(float f) {
 
 }  // namespace
 
-int conv_tc_cb(int Cin) { return Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : (Cin % 16 == 0 ? 16 : 0)); }
 int conv_tc_nt(int Cout) {
   if (Cout % 16 != 0) return 0;
   for (int nt = 128; nt >= 16; nt -= 16)
@@ -348,10 +347,21 @@ int conv_tc_nt(int Cout) {
   return 0;
 }
 
+// input-channel block: the largest of 64/32/16 dividing Cin whose 3-stage ring fits ~200 KB of shared memory
+int conv_tc_cb(int Cin, int taps, int Cout) {
+  const int NT = conv_tc_nt(Cout);
+  for (int cb : {64, 32, 16}) {
+    if (Cin % cb != 0) continue;
+    const size_t a = (size_t)(cb / 8) * (128 + (taps - 1) * 8) * 16 + 128;     // worst-case dilation 8
+    const size_t b = (size_t)taps * (cb / 8) * NT * 16;
+    if (CT_STAGES * (a + b) <= 200 * 1024) return cb;
+  }
+  return 0;
+}
 // weights [taps][Cin][Cout] fp32 (BN scale folded, as packed for the fp32 path) -> bf16 blocks
 // [Cout/NT][Cin/CB][taps][CB/8][NT][8]
 void conv_tc_pack(const float* w, int taps, int Cin, int Cout, std::vector<uint16_t>& out) {
-  const int NT = conv_tc_nt(Cout), CB = conv_tc_cb(Cin);
+  const int NT = conv_tc_nt(Cout), CB = conv_tc_cb(Cin, taps, Cout);
   const int ncb = Cin / CB, chunks = CB / 8;
   out.assign((size_t)taps * Cin * Cout, 0);
   for (int co = 0; co < Cout; ++co)
@@ -370,7 +380,7 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   ConvTcArgs p;
   p.in = static_cast<const __nv_bfloat16*>(a.in); p.Cin = a.Cin; p.Cout = a.Cout;
   p.Wp = static_cast<const __nv_bfloat16*>(a.Wp); p.shift = a.shift; p.taps = a.taps; p.dil = a.dil; p.pad = a.pad;
-  p.NT = conv_tc_nt(a.Cout); p.CB = conv_tc_cb(a.Cin);
+  p.NT = conv_tc_nt(a.Cout); p.CB = conv_tc_cb(a.Cin, a.taps, a.Cout);
   PAUT_CHECK(p.NT > 0 && p.CB > 0, PAUT_ERR_UNSUPPORTED, "conv_tc: channel counts must be multiples of 16");
   PAUT_CHECK(a.pad * a.dil <= a.halo && (a.taps - 1) * a.dil == 2 * a.pad * a.dil, PAUT_ERR_UNSUPPORTED,
              "conv_tc: needs 'same' padding no wider than the halo");

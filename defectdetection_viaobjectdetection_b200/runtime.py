@@ -195,8 +195,8 @@ def records_to_numpy(det, count):
     n = int(count.item())
     if n == 0:
         return np.zeros(0, dtype=DETECTION)
-    raw = det[: n * DETECTION.itemsize].cpu().numpy()
-    return raw.view(DETECTION).copy()
+    raw = det[: n * DETECTION.itemsize].cpu().numpy()          # fresh host array: view it, no second copy
+    return raw.view(DETECTION)
 
 
 def window_table(rule, n, seq_length=50):

@@ -9,6 +9,8 @@ reference's (set, position) order, or as the reference's ``list[list[dict]]`` vi
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 import torch
 
@@ -57,7 +59,10 @@ class VolumeScanner:
         if lane.pending is None:
             return
         first, n_sets, det, count, copied = lane.pending
+        t0 = time.perf_counter()
         lane.done.synchronize()
+        t1 = time.perf_counter()
+        self.stats["wait_s"] += t1 - t0
         n = int(lane.count_host[0])
         if n:
             nbytes = n * DETECTION.itemsize
@@ -66,12 +71,14 @@ class VolumeScanner:
                     lane.host[copied:nbytes].copy_(det[copied:nbytes], non_blocking=True)
                 lane.stream.synchronize()
                 self.d2h_bytes += nbytes - copied
-            rec = lane.host[:nbytes].numpy().view(DETECTION).copy()
-            rec["set_index"] += first
-            out.append((first, rec))
+            # raw byte memcpy out of the pinned buffer (a structured-dtype copy would go field by field)
+            self._raw[self._off:self._off + nbytes] = lane.host[:nbytes].numpy()
+            self._chunks.append((self._off // DETECTION.itemsize, n, first))
+            self._off += nbytes
             self._spec_bytes = max(self._spec_bytes, int(nbytes * 1.25) // 48 * 48 + 48)
         self.d2h_bytes += 4 + copied
         lane.pending = None
+        self.stats["unpack_s"] += time.perf_counter() - t1
 
     @torch.no_grad()
     def scan(self, x_host, threshold=0.5):
@@ -81,9 +88,13 @@ class VolumeScanner:
             raise RuntimeError("input must be contiguous")
         self._ensure_lanes(x_host)
         self.h2d_bytes = self.d2h_bytes = 0
+        self.stats = {"wait_s": 0.0, "unpack_s": 0.0, "launch_s": 0.0}
         self._spec_bytes = getattr(self, "_spec_bytes", 1 << 20)
-        out = []
+        out = None
         n_total = x_host.shape[0]
+        n_per = x_host.shape[2] if self.model._kind == "conv1d_msc" else x_host.shape[1]
+        self._raw = np.empty(n_total * n_per * DETECTION.itemsize, dtype=np.uint8)   # worst case, touched lazily
+        self._off, self._chunks = 0, []
         main = torch.cuda.current_stream(self.device)
         for lane in self._lanes:
             lane.stream.wait_stream(main)
@@ -91,6 +102,7 @@ class VolumeScanner:
             lane = self._lanes[i % self.num_lanes]
             self._harvest(lane, out)
             n_sets = min(self.chunk_sets, n_total - first)
+            t_launch = time.perf_counter()
             with torch.cuda.stream(lane.stream):
                 xd = lane.x[:n_sets]
                 xd.copy_(x_host[first:first + n_sets], non_blocking=True)
@@ -103,13 +115,18 @@ class VolumeScanner:
                 lane.host[:copied].copy_(det[:copied], non_blocking=True)
                 lane.done.record(lane.stream)
             lane.pending = (first, n_sets, det, count, copied)
+            self.stats["launch_s"] += time.perf_counter() - t_launch
             self.h2d_bytes += xd.numel() * xd.element_size()
-        for lane in self._lanes:
-            self._harvest(lane, out)
+        n_chunks = (n_total + self.chunk_sets - 1) // self.chunk_sets
+        for j in range(self.num_lanes):                        # flush the chunks in flight, oldest first
+            self._harvest(self._lanes[(n_chunks + j) % self.num_lanes], out)
         for lane in self._lanes:
             main.wait_stream(lane.stream)
-        out.sort(key=lambda fr: fr[0])                       # chunks back in volume order
-        return np.concatenate([r for _, r in out]) if out else np.zeros(0, dtype=DETECTION)
+        rec = self._raw[:self._off].view(DETECTION)
+        for start, n, first in self._chunks:                   # chunk-local set indices -> volume indices
+            rec["set_index"][start:start + n] += first
+        self._raw = None
+        return rec
 
 
 def to_predictions(records, n_sets):

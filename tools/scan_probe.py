@@ -23,6 +23,7 @@ for chunk in (128, 256, 512, 1024, 3334):
         t0 = time.perf_counter(); _o(lane, out); acc["harvest"] += time.perf_counter() - t0
     sc._harvest = timed_h
     torch.cuda.synchronize(); t = time.perf_counter(); r = sc.scan(x); torch.cuda.synchronize(); dt = time.perf_counter() - t
+    print({k: round(v * 1e3, 2) for k, v in sc.stats.items()})
     print(f"chunk {chunk}: total {dt*1e3:.1f} ms  harvest {acc['harvest']*1e3:.1f} ms  rate {n_sets*300/dt/1e6:.1f} M/s  records {len(r)}")
 # per-chunk device time without host copies
 for chunk in (256, 1024):
