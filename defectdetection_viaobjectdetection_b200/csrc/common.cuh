@@ -185,6 +185,13 @@ void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const fl
                   int Cout, bool relu, void* out, int ldc, int coff, int halo);
 // bf16 flat rows [R, C] -> dense fp32 [A, L, C]
 void op_unflatten(Ctx& c, const void* flat, int64_t A, int L, int halo, int C, float* out);
+// Fused per-set stage of MSC / MSC_N (ops_set_tc.cu, bf16 mode): attention block and FFN + head
+bool msc_set_tc_supported(int N, int d, int heads, int ff);
+void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bqkv, const void* Wo, const float* bo,
+                       const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift);
+void op_msc_ffn_head(Ctx& c, const float* x, const float* pre, const float* pre_g, const float* pre_b, const void* W1,
+                     const float* b1, const void* W2, const float* b2, const float* ln_g, const float* ln_b,
+                     const void* Wc, const float* bc, float* prob, float* start, float* end, int64_t M);
 // MSC head (NN_models.py:123-127): o [M,3] -> sigmoid / tanh*0.5+0.5 into three arrays
 void op_msc_head(Ctx& c, const float* o, int64_t M, float* prob, float* start, float* end);
 // logits[:, 1:] += anomaly (model.py:332, enhanced_model.py:550)

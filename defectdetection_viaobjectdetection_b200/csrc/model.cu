@@ -432,6 +432,35 @@ void Model::finalize() {
       L("transformer_encoder.ffn.0"); L("transformer_encoder.ffn.2");
       for (int i = 1; i <= 3; ++i) N_("transformer_encoder.norm" + istr(i));
       L("classifier");
+      set_tc = SetTc{};
+      if (cfg.precision == PAUT_PRECISION_BF16 &&
+          msc_set_tc_supported(1, cfg.hidden_sizes[1], cfg.num_heads, cfg.hidden_sizes[2])) {
+        auto bf = [](float f) -> uint16_t {
+          uint32_t u;
+          std::memcpy(&u, &f, 4);
+          return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+        };
+        auto up_bf16 = [&](const std::vector<float>& w, size_t pad_to = 0) {
+          std::vector<uint16_t> hb(std::max(w.size(), pad_to), 0);
+          for (size_t i = 0; i < w.size(); ++i) hb[i] = bf(w[i]);
+          void* p = nullptr;
+          PAUT_CUDA(cudaMalloc(&p, hb.size() * sizeof(uint16_t)));
+          dev_allocs.push_back(p);
+          PAUT_CUDA(cudaMemcpy(p, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          return p;
+        };
+        const std::string te = "transformer_encoder.";
+        set_tc.Wqkv_self = up_bf16(H(te + "self_attn.in_proj_weight").data);
+        set_tc.Wo_self = up_bf16(H(te + "self_attn.out_proj.weight").data);
+        if (kind == PAUT_MODEL_MSC) {
+          set_tc.Wqkv_cross = up_bf16(H(te + "cross_attn.in_proj_weight").data);
+          set_tc.Wo_cross = up_bf16(H(te + "cross_attn.out_proj.weight").data);
+        }
+        set_tc.W1 = up_bf16(H(te + "ffn.0.weight").data);
+        set_tc.W2 = up_bf16(H(te + "ffn.2.weight").data);
+        set_tc.Wc = up_bf16(H("classifier.weight").data, 8 * 64);        // rows 3..7 zero
+        set_tc.ready = true;
+      }
       break;
     }
     case PAUT_MODEL_CONV1D_MSC:
@@ -633,6 +662,32 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
                  isn ? raw["background_extractor.bias"] : nullptr, f);
     float* h0 = g.linear(f, S, lin["shared_layer.0"], A, ACT_RELU);
     h = g.linear(h0, l2.K, l2, A, ACT_RELU, nullptr, 0, nullptr, 0, 0, 0.f, raw["position_encoding.encoding"], N);
+  }
+  if (set_tc.ready && msc_set_tc_supported(N, D, cfg.num_heads, cfg.hidden_sizes[2])) {
+    // bf16 mode: the whole per-set stage in three fused mma.sync kernels
+    const std::string te = "transformer_encoder.";
+    const MHAW& sa = mha["self"];
+    float* x1 = c.allocf((size_t)A * D);
+    op_msc_attn_block(c, h, set_tc.Wqkv_self, sa.in_proj.b, set_tc.Wo_self, sa.out_proj.b, ln[te + "norm1"].g,
+                      ln[te + "norm1"].b, x1, B, N, false);
+    const float* pre = nullptr;
+    const float* pre_g = nullptr;
+    const float* pre_b = nullptr;
+    float* x2 = x1;
+    if (!isn) {
+      const MHAW& ca = mha["cross"];
+      x2 = c.allocf((size_t)A * D);
+      op_msc_attn_block(c, x1, set_tc.Wqkv_cross, ca.in_proj.b, set_tc.Wo_cross, ca.out_proj.b, ln[te + "norm2"].g,
+                        ln[te + "norm2"].b, x2, B, N, true);                     // NN_models.py:35-37
+    } else {
+      float* loc = c.allocf((size_t)A * D);
+      op_dwconv_seq(c, x1, raw[te + "local_attn.local_conv.weight"], raw[te + "local_attn.local_conv.bias"], loc, B, N, D, 5);
+      pre = loc; pre_g = ln[te + "norm2"].g; pre_b = ln[te + "norm2"].b;        // x2 = LN2(x1 + local(x1))
+    }
+    op_msc_ffn_head(c, x2, pre, pre_g, pre_b, set_tc.W1, lin[te + "ffn.0"].b, set_tc.W2, lin[te + "ffn.2"].b,
+                    ln[te + "norm3"].g, ln[te + "norm3"].b, set_tc.Wc, lin["classifier"].b,
+                    slot_at<float>(out, 0, b0 * N), slot_at<float>(out, 1, b0 * N), slot_at<float>(out, 2, b0 * N), A);
+    return;
   }
   float* y = g.self_attention(h, mha["self"], B, N, h);
   h = g.norm(y, nullptr, ln["transformer_encoder.norm1"], A);

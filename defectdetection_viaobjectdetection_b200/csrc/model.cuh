@@ -73,6 +73,12 @@ struct Model {
     const void* W2p = nullptr;
     bool ready = false;
   } enc_tc;
+  struct SetTc {                               // plain bf16 [N][K] weights of the fused set-stage kernels
+    const void* Wqkv_self = nullptr; const void* Wo_self = nullptr;
+    const void* Wqkv_cross = nullptr; const void* Wo_cross = nullptr;
+    const void* W1 = nullptr; const void* W2 = nullptr; const void* Wc = nullptr;
+    bool ready = false;
+  } set_tc;
 
   ~Model();
   void build_spec();

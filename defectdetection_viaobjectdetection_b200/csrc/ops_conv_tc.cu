@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   __shared__ uint32_t tmem_slot;
   __shared__ float pool_s[4][2][16];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
   const int NT = p.NT;
   const int ntn = p.Cout / NT;
   const int ncb = p.Cin / p.CB;
@@ -117,10 +117,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
         }
         fence_async_smem();
         named_sync(1, 128);
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
           if (cb == 0 && it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+          const uint32_t a_addr = smem_u32(smem) + stage * stage_bytes, b_addr = a_addr + p.a_stage_bytes;
           const uint32_t d = tmem + acc * 128;
           for (int t = 0; t < p.taps; ++t)
             for (int ks = 0; ks < chunks / 2; ++ks) {

@@ -16,6 +16,8 @@
 //  Pipeline per group of 2 A-scans (= 5 M tiles): conv1(g) on all warps -> one thread issues the 10 MMAs of
 //  group g and commits them to an mbarrier -> all warps run the epilogue of group g-1 while those MMAs
 //  execute (im2col buffers and TMEM accumulators are double-buffered).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,7 +30,8 @@ using namespace tc;
 namespace {
 
 constexpr int H0 = 128, H1 = 64;
-constexpr int ENC_THREADS = 640;        // 20 warps: 2 conv1 items per thread, 1 epilogue unit (tile, quarter) per warp
+constexpr int ENC_COMPUTE = 640;        // 20 compute warps: 2 conv1 items per thread, 1 epilogue unit (tile, quarter) per warp
+constexpr int ENC_THREADS = ENC_COMPUTE + 32;   // + 1 issuer warp (tcgen05.mma for the conv groups)
 constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
 constexpr int D1_COL = 320, D2_COL = 448;
 constexpr int XS_PAD = 16;
@@ -47,6 +50,7 @@ struct MscEncArgs {
   const float* bl2;
   const float* pos;                // [300][64]
   float* h;                        // [A][64]
+  unsigned long long* dbg;         // optional cycle probe (PAUT_ENC_DEBUG=1): [warps][8] sums for CTA 0
 };
 
 // 18 accumulator columns of one row (16 channels + hi/lo of their sum) with a single wait; the wait names the
@@ -72,9 +76,13 @@ __device__ __forceinline__ void tmem_ld18(uint32_t taddr, float (&y)[16], float&
   s1 = __uint_as_float(r[17]);
 }
 
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_conv[2], bar_w[2], bar_l2;
+  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_w[2], bar_l2;
   __shared__ uint32_t tmem_slot;
 
   const int S = p.S;
@@ -89,13 +97,14 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   __nv_bfloat16* XS = reinterpret_cast<__nv_bfloat16*>(BC + 2048);   // [2][2][S + 16]
   const int xs_stride = S + XS_PAD;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
   const int64_t a0 = (int64_t)blockIdx.x * 128;
 
   // ---- one-time setup
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&bar_conv[0], 1); mbar_init(&bar_conv[1], 1);
+    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
     mbar_init(&bar_w[0], 1); mbar_init(&bar_w[1], 1);
     mbar_init(&bar_l2, 1);
     fence_mbar_init();
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     mbar_wait(&bar_conv[buf], (g >> 1) & 1);
     tc_fence_after();
     const int q = warp & 3;
-    for (int T = warp >> 2; T < tiles; T += ENC_THREADS / 128) {
+    for (int T = warp >> 2; T < tiles; T += ENC_COMPUTE / 128) {
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + T * 32;
       float y[16], s0, s1;
       tmem_ld18(taddr, y, s0, s1);
@@ -174,58 +183,87 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   };
 
   const int ngroups = 64;
-  prefetch_x(0);
-  if (xloader) *reinterpret_cast<uint4*>(XS + x_al * xs_stride + 8 + x_part * 8) = xr;
-  prefetch_x(1);
-  __syncthreads();
-  for (int g = 0; g < ngroups; ++g) {
-    const int buf = g & 1;
-    const __nv_bfloat16* xs = XS + buf * 2 * xs_stride;
-    // x of group g+1 goes to the other staging buffer (its last reader, conv1 of group g-1, finished before
-    // the previous block barrier); x of group g+2 starts its trip from HBM
-    if (g + 1 < ngroups) {
-      if (xloader) *reinterpret_cast<uint4*>(XS + (buf ^ 1) * 2 * xs_stride + x_al * xs_stride + 8 + x_part * 8) = xr;
-      if (g + 2 < ngroups) prefetch_x(g + 2);
-    }
-    // ---- conv1 + ReLU -> im2col operand (3 shifted copies of the 8-channel vector of each position)
-    unsigned char* im = IM + buf * im_bytes;
-    for (int item = tid; item < 2 * rows; item += ENC_THREADS) {
-      const int pp = item >> 1;
-      const int al = pp >= S ? 1 : 0;
-      const int pos = pp - al * S;
-      const __nv_bfloat16* xp = xs + al * xs_stride + 8 + pos;
-      const float x0 = __bfloat162float(xp[-1]), x1 = __bfloat162float(xp[0]), x2 = __bfloat162float(xp[1]);
-      float v[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-      const uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
-      // A[row, tap t] = act1[row + t - 1]  =>  act1[pos] lands in row pos + 1 - t of tap t
-      unsigned char* dst = im + (size_t)pp * 16 + hf * 8;
-      if (pos + 1 < S) *reinterpret_cast<uint2*>(dst + 16) = pk;                       // tap 0, row pos + 1
-      *reinterpret_cast<uint2*>(dst + im_chunk) = pk;                                  // tap 1, row pos
-      if (pos > 0) *reinterpret_cast<uint2*>(dst + 2 * im_chunk - 16) = pk;            // tap 2, row pos - 1
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t im_addr = smem_u32(im), bc_addr = smem_u32(BC);
-      for (int T = 0; T < tiles; ++T) {
-        const uint32_t d = tmem + buf * (tiles * 32) + T * 32;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          mma_bf16_ss(d, make_desc(im_addr + ks * 2 * im_chunk + T * 2048, im_chunk, 128),
-                      make_desc(bc_addr + ks * 2 * 512, 512, 128), idesc_conv, ks);
+  unsigned long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+  if (warp == ENC_COMPUTE / 32) {
+    // ================= issuer warp: conv2 MMAs of every group, decoupled from the compute warps =================
+    for (int g = 0; g < ngroups; ++g) {
+      const int buf = g & 1;
+      mbar_wait(&bar_full[buf], (g >> 1) & 1);          // im2col operand of group g is complete
+      if (elect_one()) {
+        tc_fence_after();
+        // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4)
+        const uint64_t ad0 = make_desc(smem_u32(IM) + buf * im_bytes, im_chunk, 128);
+        const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
+        const uint64_t a_ks = (uint64_t)((2 * im_chunk) >> 4), b_ks = (uint64_t)((2 * 512) >> 4);
+        for (int T = 0; T < tiles; ++T) {
+          const uint32_t d = tmem + buf * (tiles * 32) + T * 32;
+          const uint64_t ad = ad0 + (uint64_t)(T * (2048 >> 4));
+          mma_bf16_ss(d, ad, bd0, idesc_conv, 0u);
+          mma_bf16_ss(d, ad + a_ks, bd0 + b_ks, idesc_conv, 1u);
+        }
+        mma_commit(&bar_conv[buf]);
       }
-      mma_commit(&bar_conv[buf]);
+      __syncwarp();
     }
-    if (g > 0) conv_epilogue(g - 1);
+  } else {
+    // ================= compute warps =================
+    prefetch_x(0);
+    if (xloader) *reinterpret_cast<uint4*>(XS + x_al * xs_stride + 8 + x_part * 8) = xr;
+    prefetch_x(1);
+    named_sync(1, ENC_COMPUTE);
+    for (int g = 0; g < ngroups; ++g) {
+      const int buf = g & 1;
+      const __nv_bfloat16* xs = XS + buf * 2 * xs_stride;
+      const long long c0 = probe ? clock64() : 0;
+      // x of group g+1 goes to the other staging buffer (its last reader, conv1 of group g-1, finished before
+      // the previous compute-warp barrier); x of group g+2 starts its trip from HBM
+      if (g + 1 < ngroups) {
+        if (xloader) *reinterpret_cast<uint4*>(XS + (buf ^ 1) * 2 * xs_stride + x_al * xs_stride + 8 + x_part * 8) = xr;
+        if (g + 2 < ngroups) prefetch_x(g + 2);
+      }
+      // ---- conv1 + ReLU -> im2col operand (3 shifted copies of the 8-channel vector of each position).
+      // The buffer is free: the MMAs of group g-2 completed before the epilogue of group g-2 ran.
+      unsigned char* im = IM + buf * im_bytes;
+      for (int item = tid; item < 2 * rows; item += ENC_COMPUTE) {
+        const int pp = item >> 1;
+        const int al = pp >= S ? 1 : 0;
+        const int pos = pp - al * S;
+        const __nv_bfloat16* xp = xs + al * xs_stride + 8 + pos;
+        const float x0 = __bfloat162float(xp[-1]), x1 = __bfloat162float(xp[0]), x2 = __bfloat162float(xp[1]);
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        const uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+        // A[row, tap t] = act1[row + t - 1]  =>  act1[pos] lands in row pos + 1 - t of tap t
+        unsigned char* dst = im + (size_t)pp * 16 + hf * 8;
+        if (pos + 1 < S) *reinterpret_cast<uint2*>(dst + 16) = pk;                       // tap 0, row pos + 1
+        *reinterpret_cast<uint2*>(dst + im_chunk) = pk;                                  // tap 1, row pos
+        if (pos > 0) *reinterpret_cast<uint2*>(dst + 2 * im_chunk - 16) = pk;            // tap 2, row pos - 1
+      }
+      const long long c1 = probe ? clock64() : 0;
+      fence_async_smem();
+      tc_fence_before();
+      named_sync(1, ENC_COMPUTE);                         // all compute warps: operand written, TMEM buffer drained
+      if (tid == 0) mbar_arrive(&bar_full[buf]);          // hand the group to the issuer warp
+      const long long c2 = probe ? clock64() : 0;
+      if (g > 0) conv_epilogue(g - 1);
+      if (probe) {
+        const long long c4 = clock64();
+        tsum[0] += c1 - c0;    // x staging + conv1
+        tsum[2] += c2 - c1;    // fence + compute-warp barrier (issue time)
+        tsum[4] += c4 - c2;    // barrier release + epilogue of the previous group (incl. mbarrier wait)
+      }
+    }
+    if (probe) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) p.dbg[warp * 8 + i] = tsum[i];
+    }
+    conv_epilogue(ngroups - 1);
   }
-  conv_epilogue(ngroups - 1);
-
+  __syncthreads();
   // ---- Linear S -> 128 (+ReLU): A = A2 (resident), B streamed from L2 through a 2-stage ring
   // W2p (16 KB) is parked in the second im2col buffer meanwhile (its MMAs are complete: epilogue waited)
   for (int i = tid; i < 1024; i += ENC_THREADS)
@@ -240,14 +278,17 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a_addr = smem_u32(A2) + kb * 8 * A2_LBO, b_addr = smem_u32(WR + s * 16384);
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(A2) + kb * 8 * A2_LBO, b_addr = smem_u32(WR) + s * 16384;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        mma_bf16_ss(tmem + D1_COL, make_desc(a_addr + ks * 2 * A2_LBO, A2_LBO, 128),
-                    make_desc(b_addr + ks * 2 * 2048, 2048, 128), make_idesc_bf16(128, H0), (kb | ks) ? 1u : 0u);
-      mma_commit(&bar_w[s]);
+        for (int ks = 0; ks < 4; ++ks)
+          mma_bf16_ss(tmem + D1_COL, make_desc(a_addr + ks * 2 * A2_LBO, A2_LBO, 128),
+                      make_desc(b_addr + ks * 2 * 2048, 2048, 128), make_idesc_bf16(128, H0), (kb | ks) ? 1u : 0u);
+        mma_commit(&bar_w[s]);
+      }
+      __syncwarp();
     }
   }
   mbar_wait(&bar_w[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
@@ -257,7 +298,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     unsigned char* A3 = IM;
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    for (int n = (warp >> 2) * 16; n < H0; n += (ENC_THREADS / 128) * 16) {
+    for (int n = (warp >> 2) * 16; n < H0 && warp < ENC_COMPUTE / 32; n += (ENC_COMPUTE / 128) * 16) {
       float v[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D1_COL + n, v);
       uint32_t pk[8];
@@ -275,14 +316,17 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   tc_fence_before();
   __syncthreads();
   // ---- Linear 128 -> 64
-  if (tid == 0) {
-    tc_fence_after();
-    const uint32_t a_addr = smem_u32(IM), b_addr = smem_u32(IM + im_bytes);
+  if (warp == 0) {
+    if (elect_one()) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(IM), b_addr = smem_u32(IM) + im_bytes;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks)
-      mma_bf16_ss(tmem + D2_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
-                  make_desc(b_addr + ks * 2 * 1024, 1024, 128), make_idesc_bf16(128, H1), ks ? 1u : 0u);
-    mma_commit(&bar_l2);
+      for (int ks = 0; ks < 8; ++ks)
+        mma_bf16_ss(tmem + D2_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
+                    make_desc(b_addr + ks * 2 * 1024, 1024, 128), make_idesc_bf16(128, H1), ks ? 1u : 0u);
+      mma_commit(&bar_l2);
+    }
+    __syncwarp();
   }
   mbar_wait(&bar_l2, 0);
   tc_fence_after();
@@ -290,7 +334,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   {
     const int q = warp & 3;
     const int64_t a = a0 + q * 32 + lane;
-    for (int n = (warp >> 2) * 16; n < H1; n += (ENC_THREADS / 128) * 16) {
+    for (int n = (warp >> 2) * 16; n < H1 && warp < ENC_COMPUTE / 32; n += (ENC_COMPUTE / 128) * 16) {
       float v[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D2_COL + n, v);
       if (a < p.A) {
@@ -372,8 +416,20 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
   PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (A + 127) / 128;
   PAUT_CHECK(grid < (int64_t(1) << 31), PAUT_ERR_INVALID, "msc encoder: too many A-scans");
+  static const bool debug = std::getenv("PAUT_ENC_DEBUG") != nullptr;
+  p.dbg = nullptr;
+  if (debug) PAUT_CUDA(cudaMalloc(&p.dbg, sizeof(unsigned long long) * 8 * (ENC_THREADS / 32)));
   k_msc_encoder_tc<<<(unsigned)grid, ENC_THREADS, smem, c.stream>>>(p);
   c.launched("msc_encoder_tc");
+  if (debug) {
+    std::vector<unsigned long long> hbuf(8 * (ENC_THREADS / 32));
+    PAUT_CUDA(cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    fprintf(stderr, "[enc probe] per-group cycles (CTA 0): warp  conv1  fence  barrier  mma_issue  epilogue\n");
+    for (int w = 0; w < ENC_THREADS / 32; w += 3)
+      fprintf(stderr, "[enc probe] %4d %6llu %6llu %8llu %9llu %9llu\n", w, hbuf[w * 8] / 64, hbuf[w * 8 + 1] / 64,
+              hbuf[w * 8 + 2] / 64, hbuf[w * 8 + 3] / 64, hbuf[w * 8 + 4] / 64);
+  }
 }
 
 }  // namespace paut

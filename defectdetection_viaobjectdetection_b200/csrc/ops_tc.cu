@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs p) {
   __shared__ __align__(8) uint64_t mma_done[STAGES];
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int ntile = blockIdx.y;
   const int NT = p.NT;
@@ -125,10 +125,10 @@ __global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs p) {
     }
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(As + s * a_stage_bytes);
-      const uint32_t b_addr = smem_u32(Bs + s * b_stage_bytes);
+      const uint32_t a_addr = smem_u32(As) + s * a_stage_bytes;
+      const uint32_t b_addr = smem_u32(Bs) + s * b_stage_bytes;
       for (int ks = 0; ks < nchunks / 2; ++ks) {
         const uint64_t ad = p.swap_lbo_sbo ? make_desc(a_addr + ks * 2 * (BM * 16), 128, BM * 16)
                                            : make_desc(a_addr + ks * 2 * (BM * 16), BM * 16, 128);

@@ -16,6 +16,25 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Warp index as a value the compiler knows to be warp-uniform, and a one-lane election that keeps the
+// enclosing branch uniform.  tcgen05.mma / commit take their operands from uniform registers: issued under a
+// divergent `tid == 0` branch the compiler wraps every instruction in an ELECT + R2UR waterfall loop
+// (~100 cycles per MMA); under `if (warp == W) if (elect_one())` the operands stay in uniform registers.
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // 64-bit shared-memory matrix descriptor (SM100 UMMA): start address [0,14), LBO [16,30), SBO [32,46) all in
 // 16-byte units, descriptor version 1 at [46,48), layout type [61,64) = 0 (no swizzle).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
