@@ -29,8 +29,27 @@ SETS = {"msc": (3334, 300), "msc_n": (3334, 300), "conv1d_msc": (3334, 300),
         "ssd": (20000, 50), "enhanced": (20000, 50), "two_stage": (20000, 50)}
 S = 320
 
-# algorithmic work per A-scan of each kernel (DESIGN.md "Kernels"): (FLOPs, HBM bytes)
-KERNEL_WORK = {}
+# Algorithmic work per A-scan of the fused kernels: (FLOPs = 2*MAC, HBM bytes, bound).
+# "bound" is the roofline the kernel is judged against: its algorithmic intensity is above the ridge
+# (~210 FLOP/B with the measured peaks) for the tensor-bound ones.
+def kernel_work(kind, n_per):
+    if kind in ("msc", "msc_n"):
+        attn = 2 * 64 * 192 + 2 * 2 * n_per * 64 + 2 * 64 * 64
+        return {
+            "msc_encoder_tc": (2 * (8 * 3 + 16 * 24) * S + 2 * S * 128 + 2 * 128 * 64, 2 * S + 4 * 64, "tensor"),
+            "msc_attn_block": (attn, 2 * 4 * 64, "tensor"),
+            "msc_ffn_head": (2 * 2 * 64 * 32 + 2 * 64 * 3, 4 * 64 + 12, "hbm"),
+            "msc_front": (2 * (8 * 3 + 16 * 24) * S, 2 * 4 * S, "hbm"),
+        }
+    conv = {"two_stage": 2 * 32 * 32 * (3 + 5 + 7 + 11) * S, "ssd": 2 * (64 * 128 * 5 + 128 * 256 * 3) * S,
+            "conv1d_msc": 2 * (64 * 128 * 3 + 128 * 128) * S,
+            "enhanced": 2 * (4 * 64 * 32 * 3 + 128 * 128 + 6 * 128 * 128 * 3) * S}
+    return {"conv_tc": (conv[kind], 0, "tensor")}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/), per A-scan; None until a capture of the current kernel exists
+NCU_TRAFFIC_PER_ASCAN = {"msc_encoder_tc": None}
 
 
 def peaks():
@@ -242,7 +261,7 @@ def main():
         total_ms = sum(v[1] for v in prof.values()) or 1.0
         top = max(prof.items(), key=lambda kv: kv[1][1])
         name, (n_launch, k_ms) = top
-        work = KERNEL_WORK.get(name)
+        work = kernel_work(kind, n_per).get(name)
         roof = {"kernel": name, "share_of_step": k_ms / total_ms, "launches": n_launch,
                 "avg_launch_ms": k_ms / n_launch, "peak_source": pk["source"]}
         if work:
@@ -251,13 +270,17 @@ def main():
             t = (k_ms / n_launch) * 1e-3
             if bound == "tensor":
                 ach = flops * per_launch_ascans / t / 1e12
-                roof.update(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"])
+                roof.update(bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
+                            hbm_gbs=nbytes * per_launch_ascans / t / 1e9, flop_per_ascan=flops, bytes_per_ascan=nbytes)
             else:
                 ach = nbytes * per_launch_ascans / t / 1e9
-                roof.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"])
+                roof.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                            flop_per_ascan=flops, bytes_per_ascan=nbytes)
+            tr = NCU_TRAFFIC_PER_ASCAN.get(name)
+            roof["traffic"] = tr * per_launch_ascans if tr else None
         else:
             roof.update(bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None)
-        roof["traffic"] = None
+        roof.setdefault("traffic", None)
         line = {
             "metric": "A-scans/sec", "value": value, "unit": "A-scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

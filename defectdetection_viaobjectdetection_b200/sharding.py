@@ -1,0 +1,58 @@
+"""Sharding of a scan volume across the GPUs of one box.
+
+Sets (windows) are independent: attention, the set-axis convolution, the recurrences and the softmax over N
+never cross a set, and BatchNorm uses running statistics, so a volume shards by contiguous blocks of sets
+(= contiguous scan positions) with NO collective on the data path.  One process per GPU, one library
+context per process.  The only exchange is optional: gathering the per-shard detection records, a few
+bytes per kept A-scan, with ``torch.distributed`` (NCCL over NVLink on GPUs, gloo on CPU for tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import DETECTION
+
+
+def shard_range(n_sets, world_size, rank):
+    """Contiguous, near-equal blocks in scan order: the first ``n_sets % world_size`` ranks get one more set."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(n_sets), int(world_size))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def msc_shard_range(n_scans, seq_length, world_size, rank):
+    """Shard a run of ``n_scans`` A-scans that will be cut with the signals/ windowing rule
+    (json_dataset.py:84-103): whole windows per rank, the end-anchored (overlapping) last window stays
+    with the rank that owns the last scans.  Returns (first_window, last_window_exclusive, n_windows)."""
+    n_windows = 0 if n_scans < seq_length else -(-n_scans // seq_length)
+    lo, hi = shard_range(n_windows, world_size, rank)
+    return lo, hi, n_windows
+
+
+def all_gather_records(records, first_set=0, group=None, device=None):
+    """Every rank contributes its structured detection records (dtype DETECTION, ``set_index`` local to the
+    shard); returns the records of the whole volume in scan order with global ``set_index``.
+    Variable-length: counts are exchanged first, payloads are padded to the longest shard."""
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device(device) if device is not None else (
+        torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    rec = np.ascontiguousarray(records).copy()
+    rec["set_index"] += int(first_set)
+    n = torch.tensor([len(rec)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1) * DETECTION.itemsize
+    payload = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    if len(rec):
+        raw = torch.from_numpy(rec.view(np.uint8).reshape(-1))
+        payload[: raw.numel()] = raw.to(dev)
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    parts = [g[: c * DETECTION.itemsize].cpu().numpy().view(DETECTION) for g, c in zip(gathered, counts)]
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=DETECTION)

@@ -1,0 +1,72 @@
+"""N > 1 path on CPU: world_size-2 gloo run of the shard arithmetic and the detection all-gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from defectdetection_viaobjectdetection_b200 import sharding
+from defectdetection_viaobjectdetection_b200._lib import DETECTION
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_records(first, last, seed):
+    """Deterministic records for sets [first, last): what a shard's predict_records would return."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for b in range(first, last):
+        for i in sorted(rng.choice(50, size=rng.integers(0, 6), replace=False)):
+            rows.append((b - first, i, 1, int(i * 3), int(i * 5), 0.1 * i, 0.2 * i, 0.5, 0.0, 0.0, 0.5 + b))
+    return np.array(rows, dtype=DETECTION) if rows else np.zeros(0, dtype=DETECTION)
+
+
+def _worker(rank, world, port, n_sets, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_range(n_sets, world, rank)
+    rec = _fake_records(lo, hi, seed=lo)
+    full = sharding.all_gather_records(rec, first_set=lo)
+    if rank == 0:
+        np.save(out, full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 9, 3334, 160000):
+        for w in (1, 2, 4, 8):
+            spans = [sharding.shard_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    lo, hi, nw = sharding.msc_shard_range(1000, 300, 2, 1)
+    assert (lo, hi, nw) == (2, 4, 4)
+
+
+def test_all_gather_records_world2_gloo(tmp_path):
+    n_sets, world = 37, 2
+    out = str(tmp_path / "gathered.npy")
+    mp.spawn(_worker, args=(world, _free_port(), n_sets, out), nprocs=world, join=True)
+    got = np.load(out)
+    parts = []
+    for r in range(world):
+        lo, hi = sharding.shard_range(n_sets, world, r)
+        p = _fake_records(lo, hi, seed=lo)
+        p["set_index"] += lo
+        parts.append(p)
+    ref = np.concatenate(parts)
+    assert len(got) == len(ref) > 0
+    for f in DETECTION.names:
+        np.testing.assert_array_equal(got[f], ref[f], err_msg=f)
+    # scan order: (set, position) non-decreasing
+    key = got["set_index"].astype(np.int64) * 1000 + got["position"]
+    assert np.all(np.diff(key) > 0)
