@@ -20,7 +20,7 @@ SYMBOLS = (
     "paut_ctx_set_workspace_limit", "paut_model_create", "paut_model_destroy", "paut_model_set_tensor",
     "paut_model_finalize", "paut_model_num_keys", "paut_model_key", "paut_forward", "paut_postprocess",
     "paut_window_gather", "paut_window_table_host", "paut_ctx_launch_count", "paut_ctx_profile_begin",
-    "paut_ctx_profile_end", "paut_op_linear",
+    "paut_ctx_profile_end", "paut_op_linear", "paut_debug_mma",
 )
 
 
@@ -85,6 +85,7 @@ def load():
         "paut_ctx_profile_begin": (i32, [vp]),
         "paut_ctx_profile_end": (i32, [vp, C.c_char_p, i64]),
         "paut_op_linear": (i32, [vp, vp, i64, i32, vp, vp, i32, vp, i32, i32]),
+        "paut_debug_mma": (i32, [vp, i32, i32, i32, i32, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

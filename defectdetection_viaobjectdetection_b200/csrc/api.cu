@@ -333,6 +333,16 @@ int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float*
   });
 }
 
+// micro-benchmark / descriptor experiments (tools/mma_probe.py); not part of the product path
+int paut_debug_mma(paut_ctx* ctx, int mode, int N, int reps, int lbo, int alt, float* out_dev) {
+  if (!ctx) return PAUT_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    PAUT_CUDA(cudaSetDevice(ctx->c.device));
+    paut::op_debug_mma(ctx->c, mode, N, reps, lbo, alt, out_dev);
+    PAUT_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  });
+}
+
 // Window tables: rule 0 = json_dataset.py:84-103 (end-anchored last window, short runs skipped),
 // rule 1 = dataset_preparation.py:222-282 (zero-pad short runs, overlapping windows + tail).
 int paut_window_table_host(int rule, int64_t n, int64_t L, int32_t* pairs, int cap) {

@@ -65,6 +65,7 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SOFTPL
 void op_transpose_sn(Ctx& c, const void* x, int x_dtype, float* out, int64_t B, int S, int N);
 // any dtype -> fp32 copy
 void op_to_f32(Ctx& c, const void* x, int x_dtype, float* out, int64_t n);
+void op_to_bf16(Ctx& c, const float* x, void* out, int64_t n);
 
 // Conv1d with C_in = 1 (+ folded BN, optional ReLU): x [A,S] -> out [A,S,Cout].  w is [k][Cout].
 void op_stem_conv(Ctx& c, const float* x, int64_t A, int S, const float* w, const float* shift, int k,
@@ -192,6 +193,7 @@ void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bq
 void op_msc_ffn_head(Ctx& c, const float* x, const float* pre, const float* pre_g, const float* pre_b, const void* W1,
                      const float* b1, const void* W2, const float* b2, const float* ln_g, const float* ln_b,
                      const void* Wc, const float* bc, float* prob, float* start, float* end, int64_t M);
+void op_debug_mma(Ctx& c, int mode, int N, int reps, int lbo, int alt, float* out_dev);
 // MSC head (NN_models.py:123-127): o [M,3] -> sigmoid / tanh*0.5+0.5 into three arrays
 void op_msc_head(Ctx& c, const float* o, int64_t M, float* prob, float* start, float* end);
 // logits[:, 1:] += anomaly (model.py:332, enhanced_model.py:550)

@@ -647,6 +647,12 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
   if (enc_tc.ready) {
     // bf16 mode: conv1 -> conv2 -> channel mean -> MLP -> + position table in one tcgen05 kernel
     h = c.allocf((size_t)A * D);
+    if (x_dtype != PAUT_BF16) {              // the fused encoder streams bf16 rows with cp.async
+      void* xb = c.alloc((size_t)A * S * sizeof(__nv_bfloat16));
+      op_to_bf16(c, static_cast<const float*>(xin), xb, A * S);
+      xin = xb;
+      x_dtype = PAUT_BF16;
+    }
     op_msc_encoder_tc(c, xin, x_dtype, A, S, N, raw["conv1d.0.weight"], raw["conv1d.0.bias"], enc_tc.Bc, enc_tc.W1p,
                       lin["shared_layer.0"].b, enc_tc.W2p, l2.b, raw["position_encoding.encoding"], h);
   } else {

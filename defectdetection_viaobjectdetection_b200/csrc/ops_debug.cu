@@ -1,0 +1,74 @@
+// Debug / micro-benchmark entry points (not on any product path): tcgen05.mma cost per shape and the
+// overlapping-chunk descriptor experiment that the conv kernels' tap addressing relies on.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace paut {
+using namespace tc;
+namespace {
+
+// mode 0: issue `reps` MMAs of shape 128 x N x 16 (operands: whatever is in shared memory), report cycles
+// mode 1: overlapped A view. A rows are 16 B apart, chunk 1 of row r = row r+1 (LBO = lbo bytes); B = identity
+//         (16 x 16), so D[r][n] must equal n < 8 ? buf[r][n] : buf[r + lbo/16][n - 8].
+__global__ void __launch_bounds__(128) k_debug_mma(int mode, int N, int reps, int lbo, int a_from_far, float* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
+  unsigned char* A = smem;                    // up to 64 KB
+  unsigned char* B = smem + 65536;            // up to 64 KB
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  // fill: A row r (16 B = 8 bf16) = r*8 + e scaled small; B = identity in the canonical [2 chunks][N rows][16B] layout
+  for (int i = tid; i < 65536 / 2; i += 128) {
+    const int r = i / 8, e = i % 8;
+    reinterpret_cast<__nv_bfloat16*>(A)[i] = __float2bfloat16_rn((float)((r * 8 + e) % 251));
+  }
+  for (int i = tid; i < 65536 / 2; i += 128) reinterpret_cast<__nv_bfloat16*>(B)[i] = __float2bfloat16_rn(0.f);
+  __syncthreads();
+  if (mode == 1) {
+    // B[n][k] = (n == k): chunk c (k = 8c..8c+7), row n at B + c*(N*16) + n*16
+    for (int n = tid; n < 16; n += 128) {
+      const int c = n / 8, e = n % 8;
+      reinterpret_cast<__nv_bfloat16*>(B + c * (N * 16) + n * 16)[e] = __float2bfloat16_rn(1.f);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  long long t0 = 0, t1 = 0;
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, N);
+      const uint64_t ad = make_desc(smem_u32(A), mode == 1 ? lbo : 2048, 128);
+      const uint64_t bd = make_desc(smem_u32(B), N * 16, 128);
+      t0 = clock64();
+      for (int i = 0; i < reps; ++i) mma_bf16_ss(tmem + (a_from_far ? (i & 1) * 256 : 0), ad, bd, idesc, mode == 1 ? 0u : 1u);
+      mma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) { t1 = clock64(); }
+  tc_fence_after();
+  if (mode == 0) {
+    if (tid == 0) out[0] = (float)(t1 - t0) / (float)reps;
+  } else {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+    for (int j = 0; j < 16; ++j) out[(warp * 32 + lane) * 16 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+void op_debug_mma(Ctx& c, int mode, int N, int reps, int lbo, int alt, float* out_dev) {
+  PAUT_CUDA(cudaFuncSetAttribute(k_debug_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+  k_debug_mma<<<1, 128, 131072, c.stream>>>(mode, N, reps, lbo, alt, out_dev);
+  c.launched("debug_mma");
+}
+}  // namespace paut

@@ -47,6 +47,20 @@ void op_to_f32(Ctx& c, const void* x, int x_dtype, float* out, int64_t n) {
   c.launched("to_f32");
 }
 
+__global__ void k_to_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+}
+void op_to_bf16(Ctx& c, const float* x, void* out, int64_t n) {
+  if (c.dry) return;
+  PAUT_CHECK(n % 4 == 0, PAUT_ERR_UNSUPPORTED, "to_bf16: element count must be a multiple of 4");
+  k_to_bf16<<<grid_for(n / 4, 256), 256, 0, c.stream>>>(x, static_cast<__nv_bfloat16*>(out), n / 4);
+  c.launched("to_bf16");
+}
+
 // [B,S,N] -> [B,N,S] through a 32x32 shared tile (coalesced on both sides)
 __global__ void k_transpose_sn(const void* __restrict__ x, int dtype, float* __restrict__ out, int S, int N) {
   __shared__ float tile[32][33];

@@ -31,10 +31,11 @@ namespace {
 
 constexpr int H0 = 128, H1 = 64;
 constexpr int ENC_COMPUTE = 640;        // 20 compute warps: 2 conv1 items per thread, 1 epilogue unit (tile, quarter) per warp
-constexpr int ENC_THREADS = ENC_COMPUTE + 32;   // + 1 issuer warp (tcgen05.mma for the conv groups)
+constexpr int ENC_THREADS = ENC_COMPUTE + 64;   // + MMA issuer warp (20) + x loader warp (21), on different schedulers
 constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
 constexpr int D1_COL = 320, D2_COL = 448;
 constexpr int XS_PAD = 16;
+constexpr int XS_SLOTS = 4;              // x staging ring: cp.async prefetch runs ~3 groups ahead of conv1
 
 struct MscEncArgs {
   const void* x;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_w[2], bar_l2;
+  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_w[2], bar_l2;
   __shared__ uint32_t tmem_slot;
 
   const int S = p.S;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   unsigned char* A2 = smem + 2 * im_bytes;         // [S/8 chunks][128 rows][16 B]
   unsigned char* WR = A2 + (size_t)(S / 8) * A2_LBO;   // [2][8 chunks][128 rows][16 B]
   unsigned char* BC = WR + 2 * 16384;              // [4 chunks][32 rows][16 B]
-  __nv_bfloat16* XS = reinterpret_cast<__nv_bfloat16*>(BC + 2048);   // [2][2][S + 16]
+  __nv_bfloat16* XS = reinterpret_cast<__nv_bfloat16*>(BC + 2048);   // [XS_SLOTS][2][S + 16]
   const int xs_stride = S + XS_PAD;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   if (tid == 0) {
     mbar_init(&bar_conv[0], 1); mbar_init(&bar_conv[1], 1);
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
+    for (int i = 0; i < XS_SLOTS; ++i) mbar_init(&bar_x[i], 32);
     mbar_init(&bar_w[0], 1); mbar_init(&bar_w[1], 1);
     mbar_init(&bar_l2, 1);
     fence_mbar_init();
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
         *reinterpret_cast<uint4*>(im + 2 * im_chunk + (tid * S + S - 1) * 16) = make_uint4(0, 0, 0, 0);   // act1[S]
       }
     }
-    for (int i = tid; i < 2 * 2 * xs_stride; i += ENC_THREADS) XS[i] = __float2bfloat16_rn(0.f);
+    for (int i = tid; i < XS_SLOTS * 2 * xs_stride; i += ENC_THREADS) XS[i] = __float2bfloat16_rn(0.f);
   }
   // per-thread conv1 weights: this thread always computes channels 4*hf .. 4*hf+3
   const int hf = tid & 1;
@@ -138,29 +140,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc_conv = make_idesc_bf16(128, 32);
 
-  // x prefetch registers: thread t < S/4 owns 8 samples of one of the two A-scans of the group
+  // x staging (loader warp): lane l owns the 16-byte parts l, l+32, l+64 of the 2*S/8 parts of a group.
+  // cp.async writes them straight into the ring slot; the slot's mbarrier (32 arrivals) completes when the
+  // copies of every lane have landed, so nobody ever waits on HBM latency.  All addressing is precomputed:
+  // per group the source advances by 2*S elements and the slot offset rotates.
   const int xparts = S / 8;
-  const bool xloader = tid < 2 * xparts;
-  const int x_al = tid / xparts, x_part = tid % xparts;
-  uint4 xr = make_uint4(0, 0, 0, 0);
-  auto prefetch_x = [&](int g) {
-    xr = make_uint4(0, 0, 0, 0);
-    if (!xloader) return;
-    const int64_t a = a0 + 2 * g + x_al;
-    if (a >= p.A) return;
-    if (p.x_dtype == PAUT_BF16) {
-      xr = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.x) + a * S + x_part * 8));
-    } else {
-      const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + a * S + x_part * 8);
-      const float4 u = __ldg(src), v = __ldg(src + 1);
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(u.x, u.y), h1 = __floats2bfloat162_rn(u.z, u.w);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y), h3 = __floats2bfloat162_rn(v.z, v.w);
-      xr.x = *reinterpret_cast<uint32_t*>(&h0); xr.y = *reinterpret_cast<uint32_t*>(&h1);
-      xr.z = *reinterpret_cast<uint32_t*>(&h2); xr.w = *reinterpret_cast<uint32_t*>(&h3);
-    }
-  };
 
-  // epilogue of one conv group: TMEM -> f = y16 + y17 + sum|y_c| -> bf16 -> A2[row = A-scan][k = position]
+  // epilogue of one conv group.  Everything about a thread's output element except the group index is a
+  // thread constant: row r = T*128 + q*32 + lane of the group -> (A-scan al, position pos) -> operand byte offset.
+  const uint32_t a2_base = smem_u32(A2);
   auto conv_epilogue = [&](int g) {
     const int buf = g & 1;
     mbar_wait(&bar_conv[buf], (g >> 1) & 1);
@@ -170,15 +158,16 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + T * 32;
       float y[16], s0, s1;
       tmem_ld18(taddr, y, s0, s1);
-      float f = s0 + s1;
+      // two independent accumulation chains (|.| is a free source modifier)
+      float f0 = s0, f1 = s1;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) f += fabsf(y[c]);
-      const int r = T * 128 + q * 32 + lane;        // row inside the group
+      for (int c = 0; c < 16; c += 2) { f0 += fabsf(y[c]); f1 += fabsf(y[c + 1]); }
+      const int r = T * 128 + q * 32 + lane;
       const int al = r >= S ? 1 : 0;
       const int pos = r - al * S;
-      const int arow = 2 * g + al;                  // A-scan row inside the CTA tile
-      *reinterpret_cast<__nv_bfloat16*>(A2 + (size_t)(pos >> 3) * A2_LBO + arow * 16 + (pos & 7) * 2) =
-          __float2bfloat16_rn(f);
+      const uint32_t off = (uint32_t)(pos >> 3) * A2_LBO + (uint32_t)al * 16 + (uint32_t)(pos & 7) * 2;
+      const __nv_bfloat16 fb = __float2bfloat16_rn(f0 + f1);
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
     }
   };
 
@@ -186,66 +175,121 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   unsigned long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
   if (warp == ENC_COMPUTE / 32) {
-    // ================= issuer warp: conv2 MMAs of every group, decoupled from the compute warps =================
+    // ================= MMA issuer warp: conv2 MMAs of every group, decoupled from the compute warps ====
+    // (it shares its scheduler with five busy compute warps, so its instruction path is kept minimal:
+    //  descriptors are precomputed, the tile loop is unrolled)
+    const uint64_t adb[2] = {make_desc(smem_u32(IM), im_chunk, 128), make_desc(smem_u32(IM) + im_bytes, im_chunk, 128)};
+    const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
+    const uint64_t bd1 = bd0 + (uint64_t)((2 * 512) >> 4);
+    const uint64_t a_ks = (uint64_t)((2 * im_chunk) >> 4);
+    const bool leader = elect_one();
     for (int g = 0; g < ngroups; ++g) {
       const int buf = g & 1;
+      const long long i0 = probe ? clock64() : 0;
       mbar_wait(&bar_full[buf], (g >> 1) & 1);          // im2col operand of group g is complete
-      if (elect_one()) {
+      const long long i1 = probe ? clock64() : 0;
+      if (leader) {
         tc_fence_after();
-        // descriptors differ only in their 14-bit start-address field: add (byte offset >> 4)
-        const uint64_t ad0 = make_desc(smem_u32(IM) + buf * im_bytes, im_chunk, 128);
-        const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
-        const uint64_t a_ks = (uint64_t)((2 * im_chunk) >> 4), b_ks = (uint64_t)((2 * 512) >> 4);
-        for (int T = 0; T < tiles; ++T) {
-          const uint32_t d = tmem + buf * (tiles * 32) + T * 32;
-          const uint64_t ad = ad0 + (uint64_t)(T * (2048 >> 4));
-          mma_bf16_ss(d, ad, bd0, idesc_conv, 0u);
-          mma_bf16_ss(d, ad + a_ks, bd0 + b_ks, idesc_conv, 1u);
+        const uint64_t ad0 = adb[buf];
+        const uint32_t d0 = tmem + buf * (tiles * 32);
+#pragma unroll
+        for (int T = 0; T < 5; ++T) {
+          if (T < tiles) {
+            const uint64_t ad = ad0 + (uint64_t)(T * (2048 >> 4));
+            mma_bf16_ss(d0 + T * 32, ad, bd0, idesc_conv, 0u);
+            mma_bf16_ss(d0 + T * 32, ad + a_ks, bd1, idesc_conv, 1u);
+          }
         }
         mma_commit(&bar_conv[buf]);
       }
       __syncwarp();
+      if (probe) {
+        const long long i2 = clock64();
+        tsum[0] += i1 - i0;    // waiting for the operand
+        tsum[2] += i2 - i1;    // MMA issue + commit
+      }
+    }
+    if (probe) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) p.dbg[warp * 8 + i] = tsum[i];
+    }
+  } else if (warp == ENC_COMPUTE / 32 + 1) {
+    // ================= x loader warp =================
+    const __nv_bfloat16* src[3];
+    uint32_t dst[3];
+    int glim[3];                                           // first group whose A-scan is out of range
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = lane + 32 * j;
+      const int al = i < 2 * xparts ? i / xparts : 0, part = i < 2 * xparts ? i - al * xparts : 0;
+      src[j] = static_cast<const __nv_bfloat16*>(p.x) + (a0 + al) * S + part * 8;
+      dst[j] = smem_u32(XS) + (uint32_t)(al * xs_stride + 8 + part * 8) * 2;
+      const int64_t left = p.A - (a0 + al);                // A-scans a0+al, a0+al+2, ... : valid while 2g < left
+      glim[j] = i < 2 * xparts ? (int)((left > 0 ? left + 1 : 0) / 2) : -1;   // -1: lane has no part j
+    }
+    const uint32_t slot_bytes = (uint32_t)(2 * xs_stride * 2);
+    auto issue_x = [&](int g) {
+      const uint32_t so = (uint32_t)(g & (XS_SLOTS - 1)) * slot_bytes;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (glim[j] < 0) continue;
+        if (g < glim[j]) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[j] + so), "l"(src[j] + (size_t)g * 2 * S) : "memory");
+        } else {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst[j] + so), "r"(0) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_x[g & (XS_SLOTS - 1)])) : "memory");
+    };
+    for (int g = 0; g < XS_SLOTS; ++g) issue_x(g);
+    for (int g = 0; g + XS_SLOTS < ngroups; ++g) {
+      mbar_wait(&bar_full[g & 1], (g >> 1) & 1);          // conv1 of group g has consumed its x ring slot
+      issue_x(g + XS_SLOTS);
     }
   } else {
     // ================= compute warps =================
-    prefetch_x(0);
-    if (xloader) *reinterpret_cast<uint4*>(XS + x_al * xs_stride + 8 + x_part * 8) = xr;
-    prefetch_x(1);
-    named_sync(1, ENC_COMPUTE);
+    const int cpos = tid >> 1;                                    // position inside the A-scan
+    const bool c_active = tid < 2 * S;                            // (2*S <= ENC_COMPUTE for every supported S)
+    const bool c_up = cpos + 1 < S, c_dn = cpos > 0;
+    const uint32_t xs_base = smem_u32(XS), im_base = smem_u32(IM);
+    const uint32_t c_xoff = (uint32_t)(8 + cpos) * 2;
+    const uint32_t c_doff = (uint32_t)cpos * 16 + (uint32_t)hf * 8;
     for (int g = 0; g < ngroups; ++g) {
       const int buf = g & 1;
-      const __nv_bfloat16* xs = XS + buf * 2 * xs_stride;
       const long long c0 = probe ? clock64() : 0;
-      // x of group g+1 goes to the other staging buffer (its last reader, conv1 of group g-1, finished before
-      // the previous compute-warp barrier); x of group g+2 starts its trip from HBM
-      if (g + 1 < ngroups) {
-        if (xloader) *reinterpret_cast<uint4*>(XS + (buf ^ 1) * 2 * xs_stride + x_al * xs_stride + 8 + x_part * 8) = xr;
-        if (g + 2 < ngroups) prefetch_x(g + 2);
-      }
+      mbar_wait(&bar_x[g & (XS_SLOTS - 1)], (g / XS_SLOTS) & 1);   // x of this group has landed in its ring slot
       // ---- conv1 + ReLU -> im2col operand (3 shifted copies of the 8-channel vector of each position).
       // The buffer is free: the MMAs of group g-2 completed before the epilogue of group g-2 ran.
-      unsigned char* im = IM + buf * im_bytes;
-      for (int item = tid; item < 2 * rows; item += ENC_COMPUTE) {
-        const int pp = item >> 1;
-        const int al = pp >= S ? 1 : 0;
-        const int pos = pp - al * S;
-        const __nv_bfloat16* xp = xs + al * xs_stride + 8 + pos;
-        const float x0 = __bfloat162float(xp[-1]), x1 = __bfloat162float(xp[0]), x2 = __bfloat162float(xp[1]);
-        float v[4];
+      // Thread = (position cpos, channel half hf) of BOTH A-scans of the group: all offsets are constants.
+      if (c_active) {
+        const uint32_t xs_a = xs_base + (uint32_t)(g & (XS_SLOTS - 1)) * (uint32_t)(2 * xs_stride * 2) + c_xoff;
+        const uint32_t im_a = im_base + (uint32_t)buf * im_bytes + c_doff;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-        const uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
-        // A[row, tap t] = act1[row + t - 1]  =>  act1[pos] lands in row pos + 1 - t of tap t
-        unsigned char* dst = im + (size_t)pp * 16 + hf * 8;
-        if (pos + 1 < S) *reinterpret_cast<uint2*>(dst + 16) = pk;                       // tap 0, row pos + 1
-        *reinterpret_cast<uint2*>(dst + im_chunk) = pk;                                  // tap 1, row pos
-        if (pos > 0) *reinterpret_cast<uint2*>(dst + 2 * im_chunk - 16) = pk;            // tap 2, row pos - 1
+        for (int al = 0; al < 2; ++al) {
+          const uint32_t xa = xs_a + (uint32_t)al * (uint32_t)(xs_stride * 2);
+          uint16_t h0, h1, h2;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h0) : "r"(xa - 2));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h1) : "r"(xa));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h2) : "r"(xa + 2));
+          const float x0 = __uint_as_float((uint32_t)h0 << 16), x1 = __uint_as_float((uint32_t)h1 << 16),
+                      x2 = __uint_as_float((uint32_t)h2 << 16);
+          float v[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+          const uint32_t k0 = *reinterpret_cast<uint32_t*>(&p0), k1 = *reinterpret_cast<uint32_t*>(&p1);
+          // A[row, tap t] = act1[row + t - 1]  =>  act1[pos] lands in row pos + 1 - t of tap t
+          const uint32_t d = im_a + (uint32_t)al * (uint32_t)(S * 16);
+          if (c_up) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + 16), "r"(k0), "r"(k1) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + im_chunk), "r"(k0), "r"(k1) : "memory");
+          if (c_dn) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + 2 * im_chunk - 16), "r"(k0), "r"(k1) : "memory");
+        }
       }
       const long long c1 = probe ? clock64() : 0;
       fence_async_smem();
       tc_fence_before();
+      const long long c1b = probe ? clock64() : 0;
       named_sync(1, ENC_COMPUTE);                         // all compute warps: operand written, TMEM buffer drained
       if (tid == 0) mbar_arrive(&bar_full[buf]);          // hand the group to the issuer warp
       const long long c2 = probe ? clock64() : 0;
@@ -253,7 +297,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       if (probe) {
         const long long c4 = clock64();
         tsum[0] += c1 - c0;    // x staging + conv1
-        tsum[2] += c2 - c1;    // fence + compute-warp barrier (issue time)
+        tsum[1] += c1b - c1;   // proxy fence
+        tsum[2] += c2 - c1b;   // compute-warp barrier
         tsum[4] += c4 - c2;    // barrier release + epilogue of the previous group (incl. mbarrier wait)
       }
     }
@@ -407,11 +452,12 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
                        const float* pos, float* h) {
   if (c.dry) return;
   PAUT_CHECK(msc_encoder_tc_supported(S, H0, H1), PAUT_ERR_UNSUPPORTED, "msc encoder: unsupported signal length");
+  PAUT_CHECK(x_dtype == PAUT_BF16, PAUT_ERR_INVALID, "msc encoder: input must be bf16 (cast fp32 first)");
   MscEncArgs p;
   p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset; p.w1 = w1; p.b1 = b1;
   p.Bc = static_cast<const __nv_bfloat16*>(Bc); p.W1p = static_cast<const __nv_bfloat16*>(W1p); p.bl1 = bl1;
   p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
-  const size_t smem = (size_t)2 * 4 * (2 * S) * 16 + (size_t)(S / 8) * A2_LBO + 2 * 16384 + 2048 + (size_t)2 * 2 * (S + XS_PAD) * 2;
+  const size_t smem = (size_t)2 * 4 * (2 * S) * 16 + (size_t)(S / 8) * A2_LBO + 2 * 16384 + 2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
   PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (A + 127) / 128;
@@ -426,7 +472,7 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
     PAUT_CUDA(cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
     fprintf(stderr, "[enc probe] per-group cycles (CTA 0): warp  conv1  fence  barrier  mma_issue  epilogue\n");
-    for (int w = 0; w < ENC_THREADS / 32; w += 3)
+    for (int w = 0; w <= ENC_COMPUTE / 32; w += (w < 18 ? 6 : 1))
       fprintf(stderr, "[enc probe] %4d %6llu %6llu %8llu %9llu %9llu\n", w, hbuf[w * 8] / 64, hbuf[w * 8 + 1] / 64,
               hbuf[w * 8 + 2] / 64, hbuf[w * 8 + 3] / 64, hbuf[w * 8 + 4] / 64);
   }

@@ -174,6 +174,9 @@ int paut_window_table_host(int rule, int64_t n, int64_t L, int32_t* pairs_host, 
 int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float* W, const float* bias, int N,
                    float* C, int act, int impl);
 
+/* Micro-benchmark of tcgen05.mma shapes and descriptor experiments (tools/mma_probe.py); debugging aid. */
+int paut_debug_mma(paut_ctx* ctx, int mode, int N, int reps, int lbo, int alt, float* out_dev);
+
 /* Instrumentation: number of kernels this ctx launched since creation (bench.py's gpu_launches). */
 int64_t paut_ctx_launch_count(const paut_ctx* ctx);
 /* Per-kernel device timing: between begin and end every launch on the ctx is followed by a CUDA event
