@@ -29,12 +29,14 @@ using namespace tc;
 
 namespace {
 
-constexpr int CT_STAGES = 3;
-constexpr int CT_THREADS = 256;
+constexpr int CT_STAGES = 4;
+constexpr int CT_THREADS = 256;          // warps 0-3 epilogue, 4 MMA issuer, 5-6 cp.async loaders, 7 spare
+constexpr int CT_LOADERS = 64;
+constexpr int CT_LAG = 2;                // loader arrives on stage j-LAG after issuing stage j
 
 struct ConvTcArgs {
   const __nv_bfloat16* in;      // flat rows [R, Cin]
-  int64_t R;                    // total flat rows (multiple of 8 not required)
+  int64_t R;                    // total flat rows
   int Cin, Cout;
   const __nv_bfloat16* Wp;      // [Cout/NT][Cin/CB blocks][taps][CB/8 chunks][NT rows][8]
   const float* shift;           // [Cout]
@@ -49,7 +51,7 @@ struct ConvTcArgs {
   int L, Lp, H0;                // geometry: valid rows per A-scan, period, leading halo
   int64_t A;
   int wrows;                    // window rows = 128 + (taps-1)*dil
-  int a_stage_bytes, b_stage_bytes;
+  int a_stage_bytes, w_bytes;   // one A stage; all weights of one N tile
   int64_t num_tiles;            // row tiles
 };
 
@@ -57,9 +59,10 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Persistent CTA = one N tile (weights resident in shared memory) x a strided set of 128-row tiles.
 __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t stage_free[CT_STAGES], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full[CT_STAGES], empty[CT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float pool_s[4][2][16];
 
@@ -68,59 +71,85 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   const int ntn = p.Cout / NT;
   const int ncb = p.Cin / p.CB;
   const int chunks = p.CB / 8;
-  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  const int64_t work_total = p.num_tiles * ntn;
+  const int nt = blockIdx.x % ntn;                         // this CTA's N tile
+  const int64_t tile0 = blockIdx.x / ntn, tstep = gridDim.x / ntn;
+  unsigned char* Wres = smem;                              // [ncb][taps][chunks][NT][16 B]
+  unsigned char* Aring = smem + p.w_bytes;                 // [CT_STAGES][chunks][wrows][16 B]
 
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
-    for (int s = 0; s < CT_STAGES; ++s) mbar_init(&stage_free[s], 1);
+    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&full[s], CT_LOADERS); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
     fence_mbar_init();
   }
+  {  // resident weights of this N tile: one contiguous block in the packed layout
+    const uint4* src = reinterpret_cast<const uint4*>(p.Wp) + (size_t)nt * (p.w_bytes / 16);
+    uint4* dst = reinterpret_cast<uint4*>(Wres);
+    for (int i = tid; i < p.w_bytes / 16; i += CT_THREADS) dst[i] = __ldg(src + i);
+  }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t idesc = make_idesc_bf16(128, NT);
 
-  if (warp < 4) {
-    // ================= loader / MMA group =================
-    int stage = 0;
-    uint32_t stage_use = 0;                 // number of times the ring wrapped (phase tracking)
-    int it = 0;
-    for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x, ++it) {
-      const int64_t tile = w / ntn;
-      const int nt = (int)(w - tile * ntn);
-      const int64_t r0 = tile * 128;
-      const int acc = it & 1;
+  if (warp >= 5 && warp <= 6) {
+    // ================= loaders: cp.async of the A windows, CT_LAG stages of look-ahead =================
+    const int l = tid - 5 * 32;                             // 0..63
+    const int ch = l & 7;                                   // fixed chunk (8 lanes cover one 128-byte row)
+    const int rsub = l >> 3;                                // rows rsub, rsub+8, ...
+    const uint32_t a_ring = smem_u32(Aring);
+    int stage = 0, issued = 0;
+    uint32_t use = 0;
+    auto arrive_stage = [&](int j) {                        // stage index of the j-th issued block
+      mbar_arrive(&full[j % CT_STAGES]);
+    };
+    for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep) {
+      const int64_t wr0 = tile * 128 - (int64_t)p.pad * p.dil;
       for (int cb = 0; cb < ncb; ++cb) {
-        // wait until the MMAs that last read this stage have completed
-        if (stage_use > 0) mbar_wait(&stage_free[stage], (stage_use - 1) & 1);
-        unsigned char* As = smem + (size_t)stage * stage_bytes;
-        unsigned char* Bs = As + p.a_stage_bytes;
-        // ---- A window: rows [r0 - pad*dil, +wrows) x CB channels of this block -> [chunk][row][16 B]
-        const int64_t wr0 = r0 - (int64_t)p.pad * p.dil;
-        for (int i = tid; i < chunks * p.wrows; i += 128) {
-          const int ch = i / p.wrows, r = i - ch * p.wrows;
-          const int64_t row = wr0 + r;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (row >= 0 && row < p.R)
-            v = __ldg(reinterpret_cast<const uint4*>(p.in + row * p.Cin + cb * p.CB + ch * 8));
-          *reinterpret_cast<uint4*>(As + (size_t)ch * p.wrows * 16 + r * 16) = v;
+        if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);        // MMAs that read this slot are done
+        if (ch < chunks) {
+          const uint32_t dst0 = a_ring + (uint32_t)stage * p.a_stage_bytes + (uint32_t)(ch * p.wrows) * 16;
+          const __nv_bfloat16* src0 = p.in + (size_t)cb * p.CB + ch * 8;
+          for (int r = rsub; r < p.wrows; r += 8) {
+            const int64_t row = wr0 + r;
+            const bool ok = row >= 0 && row < p.R;
+            const __nv_bfloat16* src = src0 + (ok ? row : 0) * p.Cin;
+            // src-size 0 zero-fills the 16 bytes (rows outside the volume)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)r * 16), "l"(src),
+                         "r"(ok ? 16 : 0)
+                         : "memory");
+          }
         }
-        // ---- B block: all taps of (nt, cb): contiguous taps*chunks*NT*16 bytes
-        {
-          const int n16 = p.taps * chunks * NT;
-          const uint4* src = reinterpret_cast<const uint4*>(p.Wp) + ((size_t)nt * ncb + cb) * n16;
-          uint4* dst = reinterpret_cast<uint4*>(Bs);
-          for (int i = tid; i < n16; i += 128) dst[i] = __ldg(src + i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        ++issued;
+        if (issued > CT_LAG) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(CT_LAG) : "memory");
+          fence_async_smem();
+          arrive_stage(issued - 1 - CT_LAG);
         }
-        fence_async_smem();
-        named_sync(1, 128);
-        if (warp == 0 && elect_one()) {
-          if (cb == 0 && it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
+        if (++stage == CT_STAGES) { stage = 0; ++use; }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_async_smem();
+    for (int j = (issued > CT_LAG ? issued - CT_LAG : 0); j < issued; ++j) arrive_stage(j);
+  } else if (warp == 4) {
+    // ================= MMA issuer (one elected lane) =================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(128, NT);
+    const uint32_t a_ring = smem_u32(Aring), w_addr = smem_u32(Wres);
+    int stage = 0, it = 0;
+    uint32_t use = 0;
+    for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it) {
+      const int acc = it & 1;
+      if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);         // epilogue drained this accumulator
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(&full[stage], use & 1);
+        if (leader) {
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem) + stage * stage_bytes, b_addr = a_addr + p.a_stage_bytes;
+          const uint32_t a_addr = a_ring + (uint32_t)stage * p.a_stage_bytes;
+          const uint32_t b_addr = w_addr + (uint32_t)(cb * p.taps * chunks * NT) * 16;
           const uint32_t d = tmem + acc * 128;
           for (int t = 0; t < p.taps; ++t)
             for (int ks = 0; ks < chunks / 2; ++ks) {
@@ -128,19 +157,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
               const uint64_t bd = make_desc(b_addr + (uint32_t)((t * chunks + ks * 2) * NT) * 16, NT * 16, 128);
               mma_bf16_ss(d, ad, bd, idesc, (cb | t | ks) ? 1u : 0u);
             }
-          mma_commit(&stage_free[stage]);
+          mma_commit(&empty[stage]);
           if (cb == ncb - 1) mma_commit(&acc_full[acc]);
         }
-        if (++stage == CT_STAGES) { stage = 0; ++stage_use; }
+        __syncwarp();
+        if (++stage == CT_STAGES) { stage = 0; ++use; }
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ================= epilogue group =================
-    const int q = warp - 4;                 // TMEM lane quarter (warp % 4)
+    const int q = warp;                     // TMEM lane quarter
     int it = 0;
-    for (int64_t w = blockIdx.x; w < work_total; w += gridDim.x, ++it) {
-      const int64_t tile = w / ntn;
-      const int nt = (int)(w - tile * ntn);
+    for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -159,8 +187,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, v);
         const int n = nt * NT + c0;
         if (valid) {
+          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + n);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __ldg(p.shift + n + j);
+          for (int j = 0; j < 4; ++j) {
+            const float4 sh = __ldg(sh4 + j);
+            v[4 * j] += sh.x; v[4 * j + 1] += sh.y; v[4 * j + 2] += sh.z; v[4 * j + 3] += sh.w;
+          }
           if (p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + row * p.ldr + n);
             const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
@@ -198,8 +230,6 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
             float u[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) u[j] = (valid && seg == sgm) ? v[j] : 0.f;
-            // transpose-reduce: after the 4 halving steps lane l holds the sum of column (l & 15) over a
-            // 16-lane half; one more shuffle folds the two halves.
 #pragma unroll
             for (int step = 0; step < 4; ++step) {
               const int half = 8 >> step;                    // values kept per lane after this step
@@ -213,19 +243,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
                 }
               }
             }
-            float tot = u[0] + __shfl_xor_sync(0xffffffffu, u[0], 16);
-            // lane l (< 16) now holds a column; which one: bits of l select the kept halves
-            if (lane < 16) {
-              const int col = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
-              pool_s[q][sgm][col] = tot;
-            }
+            const float tot = u[0] + __shfl_xor_sync(0xffffffffu, u[0], 16);
+            if (lane < 16) pool_s[q][sgm][lane] = tot;        // lane l < 16 holds column l
           }
           named_sync(2, 128);
-          if (tid - 128 < 32) {
-            const int t = tid - 128;
-            const int sgm = t >> 4, col = t & 15;
-            const float s = pool_s[0][sgm][col] + pool_s[1][sgm][col] + pool_s[2][sgm][col] + pool_s[3][sgm][col];
-            p.pool[((size_t)tile * 2 + sgm) * p.Cout + n + col] = s;
+          if (tid < 32) {
+            const int sgm = tid >> 4, col = tid & 15;
+            const float sum = pool_s[0][sgm][col] + pool_s[1][sgm][col] + pool_s[2][sgm][col] + pool_s[3][sgm][col];
+            p.pool[((size_t)tile * 2 + sgm) * p.Cout + n + col] = sum;
           }
           named_sync(2, 128);
         }
@@ -347,17 +372,19 @@ int conv_tc_nt(int Cout) {
   return 0;
 }
 
-// input-channel block: the largest of 64/32/16 dividing Cin whose 3-stage ring fits ~200 KB of shared memory
+// input-channel block: the largest of 64/32/16 dividing Cin such that the resident weights of one N tile plus
+// the CT_STAGES-deep window ring fit the shared memory of one CTA
 int conv_tc_cb(int Cin, int taps, int Cout) {
   const int NT = conv_tc_nt(Cout);
+  const size_t w = (size_t)taps * Cin * NT * 2;
   for (int cb : {64, 32, 16}) {
     if (Cin % cb != 0) continue;
     const size_t a = (size_t)(cb / 8) * (128 + (taps - 1) * 8) * 16 + 128;     // worst-case dilation 8
-    const size_t b = (size_t)taps * (cb / 8) * NT * 16;
-    if (CT_STAGES * (a + b) <= 200 * 1024) return cb;
+    if (w + CT_STAGES * a <= 220 * 1024) return cb;
   }
   return 0;
 }
+
 // weights [taps][Cin][Cout] fp32 (BN scale folded, as packed for the fp32 path) -> bf16 blocks
 // [Cout/NT][Cin/CB][taps][CB/8][NT][8]
 void conv_tc_pack(const float* w, int taps, int Cin, int Cout, std::vector<uint16_t>& out) {
@@ -390,16 +417,17 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   p.R = (int64_t)flat_rows(a.A, a.L, a.halo);
   p.wrows = 128 + (a.taps - 1) * a.dil;
   p.a_stage_bytes = ((p.CB / 8) * p.wrows * 16 + 127) & ~127;
-  p.b_stage_bytes = a.taps * (p.CB / 8) * p.NT * 16;
+  p.w_bytes = a.taps * a.Cin * p.NT * 2;                   // all weights of one N tile
   p.num_tiles = (p.R + 127) / 128;
-  const size_t smem = (size_t)CT_STAGES * (p.a_stage_bytes + p.b_stage_bytes);
-  PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "conv_tc: stage does not fit shared memory");
+  const size_t smem = (size_t)p.w_bytes + (size_t)CT_STAGES * p.a_stage_bytes;
+  PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "conv_tc: weights + ring do not fit shared memory");
   if (smem > c.conv_tc_smem_configured) {
     PAUT_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     c.conv_tc_smem_configured = smem;
   }
-  const int64_t work = p.num_tiles * (a.Cout / p.NT);
-  const int grid = (int)std::min<int64_t>(work, c.num_sms);
+  const int ntn = a.Cout / p.NT;
+  int grid = (c.num_sms / ntn) * ntn;                       // every N tile gets the same number of CTAs
+  if ((int64_t)grid > p.num_tiles * ntn) grid = (int)(p.num_tiles * ntn);
   k_conv_tc<<<grid, CT_THREADS, smem, c.stream>>>(p);
   c.launched("conv_tc");
   if (a.pool_partial && a.pool_out) {
