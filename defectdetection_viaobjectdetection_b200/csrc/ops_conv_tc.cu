@@ -18,6 +18,8 @@
 // column sums for the pooled mean.  Two TMEM accumulators let tile i+1's MMAs overlap tile i's epilogue.
 // CTAs are persistent over (row tile, N tile) pairs.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -29,10 +31,11 @@ using namespace tc;
 
 namespace {
 
-constexpr int CT_STAGES = 4;
-constexpr int CT_THREADS = 256;          // warps 0-3 epilogue, 4 MMA issuer, 5-6 cp.async loaders, 7 spare
-constexpr int CT_LOADERS = 64;
-constexpr int CT_LAG = 2;                // loader arrives on stage j-LAG after issuing stage j
+constexpr int CT_STAGES = 5;
+constexpr int CT_THREADS = 672;          // warps 0-15 epilogue (4 per TMEM quarter), 16 MMA issuer, 17-20 cp.async loaders
+constexpr int CT_EPI = 512;
+constexpr int CT_LOADERS = 128;
+constexpr int CT_LAG = 4;                // loader arrives on stage j-LAG after issuing stage j
 
 struct ConvTcArgs {
   const __nv_bfloat16* in;      // flat rows [R, Cin]
@@ -53,6 +56,7 @@ struct ConvTcArgs {
   int wrows;                    // window rows = 128 + (taps-1)*dil
   int a_stage_bytes, w_bytes;   // one A stage; all weights of one N tile
   int64_t num_tiles;            // row tiles
+  unsigned long long* dbg;      // optional cycle probe (PAUT_CONV_DEBUG=1): CTA 0 role timings
 };
 
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
@@ -60,11 +64,13 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 }
 
 // Persistent CTA = one N tile (weights resident in shared memory) x a strided set of 128-row tiles.
-__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 672 threads -> <= 97 registers
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[CT_STAGES], empty[CT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float pool_s[4][2][16];
+  __shared__ float pool_s[4][2][128];
+  __shared__ float tsm[16][32 * 17];
+  __shared__ __align__(16) float shift_s[128];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
   const int NT = p.NT;
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
     for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&full[s], CT_LOADERS); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], CT_EPI); }
     fence_mbar_init();
   }
   {  // resident weights of this N tile: one contiguous block in the packed layout
@@ -87,17 +93,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
     uint4* dst = reinterpret_cast<uint4*>(Wres);
     for (int i = tid; i < p.w_bytes / 16; i += CT_THREADS) dst[i] = __ldg(src + i);
   }
+  for (int i = tid; i < NT; i += CT_THREADS) shift_s[i] = __ldg(p.shift + nt * NT + i);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16 || warp == 17);
+  unsigned long long pt[4] = {0, 0, 0, 0};
 
-  if (warp >= 5 && warp <= 6) {
+  if (warp >= 17) {
     // ================= loaders: cp.async of the A windows, CT_LAG stages of look-ahead =================
-    const int l = tid - 5 * 32;                             // 0..63
+    const int l = tid - 17 * 32;                            // 0..127
     const int ch = l & 7;                                   // fixed chunk (8 lanes cover one 128-byte row)
-    const int rsub = l >> 3;                                // rows rsub, rsub+8, ...
+    const int rsub = l >> 3;                                // rows rsub, rsub+16, ...
     const uint32_t a_ring = smem_u32(Aring);
     int stage = 0, issued = 0;
     uint32_t use = 0;
@@ -107,18 +116,31 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
     for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep) {
       const int64_t wr0 = tile * 128 - (int64_t)p.pad * p.dil;
       for (int cb = 0; cb < ncb; ++cb) {
+        const long long q0 = probe ? clock64() : 0;
         if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);        // MMAs that read this slot are done
+        const long long q1 = probe ? clock64() : 0;
         if (ch < chunks) {
-          const uint32_t dst0 = a_ring + (uint32_t)stage * p.a_stage_bytes + (uint32_t)(ch * p.wrows) * 16;
-          const __nv_bfloat16* src0 = p.in + (size_t)cb * p.CB + ch * 8;
-          for (int r = rsub; r < p.wrows; r += 8) {
-            const int64_t row = wr0 + r;
-            const bool ok = row >= 0 && row < p.R;
-            const __nv_bfloat16* src = src0 + (ok ? row : 0) * p.Cin;
-            // src-size 0 zero-fills the 16 bytes (rows outside the volume)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)r * 16), "l"(src),
-                         "r"(ok ? 16 : 0)
-                         : "memory");
+          uint32_t dst = a_ring + (uint32_t)stage * p.a_stage_bytes + (uint32_t)(ch * p.wrows + rsub) * 16;
+          if (wr0 >= 0 && wr0 + p.wrows <= p.R) {
+            // interior tile (all but the first/last of the volume): no per-row bounds checks, incremental addressing
+            const __nv_bfloat16* src = p.in + (size_t)(wr0 + rsub) * p.Cin + (size_t)cb * p.CB + ch * 8;
+            const size_t sstep = (size_t)16 * p.Cin;
+            for (int r = rsub; r < p.wrows; r += 16) {
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+              dst += 256;
+              src += sstep;
+            }
+          } else {
+            const __nv_bfloat16* src0 = p.in + (size_t)cb * p.CB + ch * 8;
+            for (int r = rsub; r < p.wrows; r += 16) {
+              const int64_t row = wr0 + r;
+              const bool ok = row >= 0 && row < p.R;
+              // src-size 0 zero-fills the 16 bytes (rows outside the volume)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src0 + (ok ? row : 0) * p.Cin),
+                           "r"(ok ? 16 : 0)
+                           : "memory");
+              dst += 256;
+            }
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -128,13 +150,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
           fence_async_smem();
           arrive_stage(issued - 1 - CT_LAG);
         }
+        if (probe) { const long long q2 = clock64(); pt[0] += q1 - q0; pt[1] += q2 - q1; pt[2] += 1; }
         if (++stage == CT_STAGES) { stage = 0; ++use; }
       }
     }
+    if (probe) { p.dbg[0] = pt[0]; p.dbg[1] = pt[1]; p.dbg[2] = pt[2]; }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fence_async_smem();
     for (int j = (issued > CT_LAG ? issued - CT_LAG : 0); j < issued; ++j) arrive_stage(j);
-  } else if (warp == 4) {
+  } else if (warp == 16) {
     // ================= MMA issuer (one elected lane) =================
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(128, NT);
@@ -143,54 +167,77 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
     uint32_t use = 0;
     for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
+      const long long m0 = probe ? clock64() : 0;
       if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);         // epilogue drained this accumulator
+      if (probe) pt[0] += clock64() - m0;
       for (int cb = 0; cb < ncb; ++cb) {
+        const long long m1 = probe ? clock64() : 0;
         mbar_wait(&full[stage], use & 1);
+        const long long m2 = probe ? clock64() : 0;
         if (leader) {
           tc_fence_after();
           const uint32_t a_addr = a_ring + (uint32_t)stage * p.a_stage_bytes;
           const uint32_t b_addr = w_addr + (uint32_t)(cb * p.taps * chunks * NT) * 16;
           const uint32_t d = tmem + acc * 128;
-          for (int t = 0; t < p.taps; ++t)
+          // descriptors advance by constant amounts in their 14-bit address field (16-byte units)
+          uint64_t ad_t = make_desc(a_addr, p.wrows * 16, 128);
+          uint64_t bd = make_desc(b_addr, NT * 16, 128);
+          const uint64_t a_ks = (uint64_t)(2 * p.wrows), a_t = (uint64_t)p.dil, b_step = (uint64_t)(2 * NT);
+          uint32_t accum = cb ? 1u : 0u;
+          for (int t = 0; t < p.taps; ++t) {
+            uint64_t ad = ad_t;
             for (int ks = 0; ks < chunks / 2; ++ks) {
-              const uint64_t ad = make_desc(a_addr + (uint32_t)(ks * 2 * p.wrows + t * p.dil) * 16, p.wrows * 16, 128);
-              const uint64_t bd = make_desc(b_addr + (uint32_t)((t * chunks + ks * 2) * NT) * 16, NT * 16, 128);
-              mma_bf16_ss(d, ad, bd, idesc, (cb | t | ks) ? 1u : 0u);
+              mma_bf16_ss(d, ad, bd, idesc, accum);
+              accum = 1u;
+              ad += a_ks;
+              bd += b_step;
             }
+            ad_t += a_t;
+          }
           mma_commit(&empty[stage]);
           if (cb == ncb - 1) mma_commit(&acc_full[acc]);
         }
         __syncwarp();
+        if (probe) { pt[1] += m2 - m1; pt[2] += clock64() - m2; pt[3] += 1; }
         if (++stage == CT_STAGES) { stage = 0; ++use; }
       }
     }
-  } else if (warp < 4) {
-    // ================= epilogue group =================
-    const int q = warp;                     // TMEM lane quarter
+    if (probe) { p.dbg[8] = pt[0]; p.dbg[9] = pt[1]; p.dbg[10] = pt[2]; p.dbg[11] = pt[3]; }
+  } else if (warp < 16) {
+    // ================= epilogue group: warp w owns TMEM lane quarter w%4 and column quarter w/4 ==============
+    const int q = warp & 3;
+    const int cq = warp >> 2;
     int it = 0;
     for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
+      const long long e0 = probe ? clock64() : 0;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      const long long e1 = probe ? clock64() : 0;
       tc_fence_after();
       const int64_t row = tile * 128 + q * 32 + lane;
       // geometry of this row: which A-scan, valid or halo
-      const int64_t rel = row - p.H0;
-      const int64_t a_of_row = rel >= 0 ? rel / p.Lp : -1;
-      const int l_of_row = rel >= 0 ? (int)(rel - a_of_row * p.Lp) : p.L;
+      // (32-bit arithmetic: 64-bit integer division is emulated and costs hundreds of cycles per tile)
+      const int rel = (int)row - p.H0;
+      const int a_of_row = rel >= 0 ? (int)((unsigned)rel / (unsigned)p.Lp) : -1;
+      const int l_of_row = rel >= 0 ? rel - a_of_row * p.Lp : p.L;
       const bool valid = rel >= 0 && a_of_row < p.A && l_of_row < p.L && row < p.R;
       // first A-scan touched by the tile (segment 0); rows of the next one are segment 1
-      const int64_t rel0 = tile * 128 - p.H0;
-      const int64_t a_first = rel0 >= 0 ? rel0 / p.Lp : 0;
-      const int seg = (int)(a_of_row - a_first);
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, v);
+      const int rel0 = (int)(tile * 128) - p.H0;
+      const int a_first = rel0 >= 0 ? (int)((unsigned)rel0 / (unsigned)p.Lp) : 0;
+      const int seg = a_of_row - a_first;
+      // does the tile reach into a second A-scan?  (last row of the tile, tile-uniform)
+      const int rel_last = (int)(tile * 128) + 127 - p.H0;
+      const bool has_seg1 = rel_last >= 0 && (int)((unsigned)rel_last / (unsigned)p.Lp) > a_first;
+      // first tile-local row of the second A-scan (128 if the tile holds a single A-scan)
+      const int seg1_row = p.H0 + (a_first + 1) * p.Lp - (int)(tile * 128);
+      const int split_row = (has_seg1 && seg1_row < 128) ? (int)(seg1_row > 0 ? seg1_row : 0) : 128;
+      auto process = [&](int c0, float (&v)[16]) {
         const int n = nt * NT + c0;
         if (valid) {
-          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + n);
+          const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 sh = __ldg(sh4 + j);
+            const float4 sh = sh4[j];
             v[4 * j] += sh.x; v[4 * j + 1] += sh.y; v[4 * j + 2] += sh.z; v[4 * j + 3] += sh.w;
           }
           if (p.res) {
@@ -224,40 +271,60 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         if (p.pool) {
-          // column sums of the tile per segment, reduced in a fixed order: lanes (butterfly) -> 4 warps
+          // column sums of this warp's 32 rows, split by segment: transpose through a padded per-warp tile
+          // (independent LDS/FADD, no shuffle chains); the four warps' partials are combined once per tile
+          float* tw = &tsm[warp][0];
 #pragma unroll
-          for (int sgm = 0; sgm < 2; ++sgm) {
-            float u[16];
+          for (int j = 0; j < 16; ++j) tw[lane * 17 + j] = v[j];          // invalid rows are already zero
+          __syncwarp();
+          const int col = lane & 15, rbase = (lane >> 4) * 16;
+          float st = 0.f, s1 = 0.f;                    // all rows; rows of the second A-scan (tile-uniform branch)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) u[j] = (valid && seg == sgm) ? v[j] : 0.f;
+          for (int r = 0; r < 16; ++r) st += tw[(rbase + r) * 17 + col];
+          if (has_seg1) {
 #pragma unroll
-            for (int step = 0; step < 4; ++step) {
-              const int half = 8 >> step;                    // values kept per lane after this step
-              const bool upper = (lane >> (3 - step)) & 1;   // lane bit 3,2,1,0
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (j < half) {
-                  const float send = upper ? u[j] : u[j + half];
-                  const float keep = upper ? u[j + half] : u[j];
-                  u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8 >> step);
-                }
-              }
-            }
-            const float tot = u[0] + __shfl_xor_sync(0xffffffffu, u[0], 16);
-            if (lane < 16) pool_s[q][sgm][lane] = tot;        // lane l < 16 holds column l
+            for (int r = 0; r < 16; ++r) s1 += (q * 32 + rbase + r >= split_row) ? tw[(rbase + r) * 17 + col] : 0.f;
           }
-          named_sync(2, 128);
-          if (tid < 32) {
-            const int sgm = tid >> 4, col = tid & 15;
-            const float sum = pool_s[0][sgm][col] + pool_s[1][sgm][col] + pool_s[2][sgm][col] + pool_s[3][sgm][col];
-            p.pool[((size_t)tile * 2 + sgm) * p.Cout + n + col] = sum;
-          }
-          named_sync(2, 128);
+          st += __shfl_xor_sync(0xffffffffu, st, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          if (lane < 16) { pool_s[q][0][c0 + lane] = st - s1; pool_s[q][1][c0 + lane] = s1; }
+          __syncwarp();
+        }
+      };
+      if (NT == 128) {
+        uint32_t t32[32];
+        const long long l0 = probe ? clock64() : 0;
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + cq * 32, t32);   // one TMEM round trip per warp
+        if (probe) pt[3] += clock64() - l0;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t32[sub * 16 + j]);
+          process(cq * 32 + sub * 16, v);
+        }
+      } else {
+        for (int c0 = cq * 16; c0 < NT; c0 += 64) {
+          float v[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, v);
+          process(c0, v);
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);
+      mbar_arrive(&acc_empty[acc]);                        // accumulator drained: the next tile's MMAs may start
+      if (p.pool) {
+        named_sync(2, CT_EPI);
+        for (int i = tid; i < 2 * NT; i += CT_EPI) {
+          const int sgm = i / NT, col = i - sgm * NT;
+          const float sum = (sgm == 1 && !has_seg1) ? 0.f
+                            : pool_s[0][sgm][col] + pool_s[1][sgm][col] + pool_s[2][sgm][col] + pool_s[3][sgm][col];
+          p.pool[((size_t)tile * 2 + sgm) * p.Cout + nt * NT + col] = sum;
+        }
+        named_sync(2, CT_EPI);
+      }
+      if (probe) { pt[0] += e1 - e0; pt[1] += clock64() - e1; pt[2] += 1; }
     }
+    if (probe && warp == 0) { p.dbg[16] = pt[0]; p.dbg[17] = pt[1]; p.dbg[18] = pt[2]; p.dbg[19] = pt[3]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -408,6 +475,7 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   p.in = static_cast<const __nv_bfloat16*>(a.in); p.Cin = a.Cin; p.Cout = a.Cout;
   p.Wp = static_cast<const __nv_bfloat16*>(a.Wp); p.shift = a.shift; p.taps = a.taps; p.dil = a.dil; p.pad = a.pad;
   p.NT = conv_tc_nt(a.Cout); p.CB = conv_tc_cb(a.Cin, a.taps, a.Cout);
+  PAUT_CHECK((int64_t)flat_rows(a.A, a.L, a.halo) < (int64_t(1) << 31) - 256, PAUT_ERR_UNSUPPORTED, "conv_tc: too many rows in one launch");
   PAUT_CHECK(p.NT > 0 && p.CB > 0, PAUT_ERR_UNSUPPORTED, "conv_tc: channel counts must be multiples of 16");
   PAUT_CHECK(a.pad * a.dil <= a.halo && (a.taps - 1) * a.dil == 2 * a.pad * a.dil, PAUT_ERR_UNSUPPORTED,
              "conv_tc: needs 'same' padding no wider than the halo");
@@ -428,7 +496,20 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   const int ntn = a.Cout / p.NT;
   int grid = (c.num_sms / ntn) * ntn;                       // every N tile gets the same number of CTAs
   if ((int64_t)grid > p.num_tiles * ntn) grid = (int)(p.num_tiles * ntn);
+  static const bool debug = std::getenv("PAUT_CONV_DEBUG") != nullptr;
+  p.dbg = nullptr;
+  if (debug) { PAUT_CUDA(cudaMalloc(&p.dbg, 24 * sizeof(unsigned long long))); PAUT_CUDA(cudaMemset(p.dbg, 0, 24 * 8)); }
   k_conv_tc<<<grid, CT_THREADS, smem, c.stream>>>(p);
+  if (debug) {
+    unsigned long long h[24];
+    PAUT_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    fprintf(stderr, "[conv probe] Cin %d Cout %d taps %d | loader: wait_empty %llu issue %llu per stage (%llu stages) | "
+                    "mma: wait_acc_empty(total) %llu, per stage wait_full %llu issue %llu (%llu stages) | "
+                    "epilogue: per tile wait_full %llu process %llu (%llu tiles)\n",
+            a.Cin, a.Cout, a.taps, h[0] / (h[2] + !h[2]), h[1] / (h[2] + !h[2]), h[2], h[8], h[9] / (h[11] + !h[11]),
+            h[10] / (h[11] + !h[11]), h[11], h[16] / (h[18] + !h[18]), h[17] / (h[18] + !h[18]), h[19] / (h[18] + !h[18]), h[18]);
+  }
   c.launched("conv_tc");
   if (a.pool_partial && a.pool_out) {
     const int64_t n = a.A * a.Cout;
