@@ -313,7 +313,7 @@ int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float*
     a.bias = static_cast<const float*>(up(b.data(), b.size() * 4));
     try {
       if (impl == 1) {
-        const int nt = paut::tc_pick_ntile(N);
+        const int nt = paut::tc_pick_ntile(N, K);
         PAUT_CHECK(nt > 0, PAUT_ERR_UNSUPPORTED, "op_linear: tcgen05 path needs N to be a multiple of 16");
         std::vector<uint16_t> packed;
         int Kp = 0;

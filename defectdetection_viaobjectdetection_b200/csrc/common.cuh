@@ -109,7 +109,7 @@ struct LinArgs {
 };
 void op_linear(Ctx& c, const LinArgs& a);
 // tcgen05 path (ops_tc.cu): bf16 operands, fp32 accumulation in TMEM
-int tc_pick_ntile(int N);
+int tc_pick_ntile(int N, int K);
 void tc_pack_weight(const float* W, int N, int K, int NT, std::vector<uint16_t>& out, int* Kp_out);
 bool linear_tc_supported(const LinArgs& a);
 void op_linear_tc(Ctx& c, const LinArgs& a);
@@ -165,6 +165,9 @@ struct ConvTcLaunch {
   const void* in = nullptr;      // bf16 flat rows [R, Cin]
   int64_t A = 0;
   int L = 0, halo = CONV_HALO, Cin = 0, Cout = 0;
+  int Lp = 0, H0 = 0;            // explicit row geometry row(a,l) = H0 + a*Lp + l (0: the (L, halo) flat layout)
+  int NT = 0, CB = 0;            // tile plan the weights were packed with (conv_tc_plan)
+  bool skip_lo = false;          // space-to-depth stride-2 view: tap 0 only multiplies the upper half of Cin
   const void* Wp = nullptr;      // conv_tc_pack() layout
   const float* shift = nullptr;
   int taps = 1, dil = 1, pad = 0;  // pad in taps (PyTorch padding = pad * dil)
@@ -173,13 +176,12 @@ struct ConvTcLaunch {
   int ldr = 0;
   void* out = nullptr;           // bf16 flat rows [R, ldc] at column offset coff (nullable)
   int ldc = 0, coff = 0;
-  float* pool_partial = nullptr; // scratch [ceil(R/128)][2][Cout]
+  float* pool_partial = nullptr; // scratch [ceil(R/128)][3][Cout]
   float* pool_out = nullptr;     // [A, ldp] mean over L at column offset poff
   int ldp = 0, poff = 0;
 };
-int conv_tc_cb(int Cin, int taps, int Cout);
-int conv_tc_nt(int Cout);
-void conv_tc_pack(const float* w, int taps, int Cin, int Cout, std::vector<uint16_t>& out);
+bool conv_tc_plan(int Cin, int taps, int Cout, int max_dil, int* NT, int* CB);
+void conv_tc_pack(const float* w, int taps, int Cin, int Cout, int NT, int CB, std::vector<uint16_t>& out);
 size_t flat_rows(int64_t A, int L, int halo);
 void op_conv_tc(Ctx& c, const ConvTcLaunch& a);
 void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const float* w, const float* shift, int k,

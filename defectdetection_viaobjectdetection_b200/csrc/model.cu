@@ -248,7 +248,7 @@ Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int r
 // bf16 mode: additionally pack the weight for the tcgen05 GEMM (chunked K-major bf16)
 void Model::pack_tc(Lin& l, const std::vector<float>& W) {
   if (cfg.precision != PAUT_PRECISION_BF16) return;
-  const int nt = tc_pick_ntile(l.N);
+  const int nt = tc_pick_ntile(l.N, l.K);
   if (nt == 0) return;
   std::vector<uint16_t> packed;
   int Kp = 0;
@@ -267,7 +267,7 @@ Lin Model::pack_lin(const std::string& name) {
 
 // Conv1d (+ optional eval BatchNorm folded in): y = conv(x) * scale + shift,
 // scale = gamma / sqrt(var + eps), shift = (bias - mean) * scale + beta.
-ConvW Model::pack_conv(const std::string& cn, const std::string& bn) {
+ConvW Model::pack_conv(const std::string& cn, const std::string& bn, int max_dil, bool stride2) {
   const HostTensor& w = H(cn + ".weight");
   const HostTensor& b = H(cn + ".bias");
   const int Cout = (int)w.shape[0], Cin = (int)w.shape[1], taps = (int)w.shape[2];
@@ -295,14 +295,31 @@ ConvW Model::pack_conv(const std::string& cn, const std::string& bn) {
   cw.taps = taps;
   cw.w = upload(p);
   cw.shift = upload(shift);
-  if (cfg.precision == PAUT_PRECISION_BF16 && Cin % 16 == 0 && Cout % 16 == 0) {
-    std::vector<uint16_t> packed;
-    conv_tc_pack(p.data(), taps, Cin, Cout, packed);
+  auto up16 = [&](const std::vector<uint16_t>& v) {
     void* d = nullptr;
-    PAUT_CUDA(cudaMalloc(&d, packed.size() * sizeof(uint16_t)));
+    PAUT_CUDA(cudaMalloc(&d, v.size() * sizeof(uint16_t)));
     dev_allocs.push_back(d);
-    PAUT_CUDA(cudaMemcpy(d, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    cw.Wp = d;
+    PAUT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return d;
+  };
+  if (cfg.precision == PAUT_PRECISION_BF16 && conv_tc_plan(Cin, taps, Cout, max_dil, &cw.NT, &cw.CB)) {
+    std::vector<uint16_t> packed;
+    conv_tc_pack(p.data(), taps, Cin, Cout, cw.NT, cw.CB, packed);
+    cw.Wp = up16(packed);
+  }
+  if (cfg.precision == PAUT_PRECISION_BF16 && stride2 && taps == 3 &&
+      conv_tc_plan(2 * Cin, 2, Cout, 1, &cw.NT_s2, &cw.CB_s2)) {
+    // stride 2 as a 2-tap stride-1 conv over row pairs: tap 0 = [0 | W0], tap 1 = [W1 | W2]   (ops_conv_tc.cu)
+    std::vector<float> p2((size_t)2 * 2 * Cin * Cout, 0.f);
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int co = 0; co < Cout; ++co) {
+        p2[((size_t)0 * 2 * Cin + Cin + ci) * Cout + co] = p[((size_t)0 * Cin + ci) * Cout + co];
+        p2[((size_t)1 * 2 * Cin + ci) * Cout + co] = p[((size_t)1 * Cin + ci) * Cout + co];
+        p2[((size_t)1 * 2 * Cin + Cin + ci) * Cout + co] = p[((size_t)2 * Cin + ci) * Cout + co];
+      }
+    std::vector<uint16_t> packed;
+    conv_tc_pack(p2.data(), 2, 2 * Cin, Cout, cw.NT_s2, cw.CB_s2, packed);
+    cw.Wp_s2 = up16(packed);
   }
   return cw;
 }
@@ -388,7 +405,9 @@ void Model::finalize() {
 
   auto L = [&](const std::string& n) { lin[n] = pack_lin(n); };
   auto N_ = [&](const std::string& n) { ln[n] = pack_ln(n); };
-  auto C_ = [&](const std::string& n, const std::string& bn) { conv[n] = pack_conv(n, bn); };
+  auto C_ = [&](const std::string& n, const std::string& bn, int max_dil = 1, bool stride2 = false) {
+    conv[n] = pack_conv(n, bn, max_dil, stride2);
+  };
   auto R = [&](const std::string& n) { raw[n] = upload(H(n).data); };
   const int d = cfg.d_model;
 
@@ -487,13 +506,13 @@ void Model::finalize() {
     case PAUT_MODEL_ENHANCED: {
       const std::string e = "signal_encoder.";
       C_(e + "conv_init.0", e + "conv_init.1");
-      for (int i = 1; i <= 4; ++i) C_(e + "multi_scale.branch" + istr(i), "");
+      for (int i = 1; i <= 4; ++i) C_(e + "multi_scale.branch" + istr(i), "", 1 << (i - 1));
       C_(e + "multi_scale.combine.0", e + "multi_scale.combine.1");
       for (int r = 0; r < 3; ++r) {
         const std::string q = e + "res_blocks." + istr(r) + ".conv_block.";
-        C_(q + "0", q + "1"); C_(q + "3", q + "4");
+        C_(q + "0", q + "1", 1 << r); C_(q + "3", q + "4", 1 << r);
       }
-      C_(e + "pyramid_1", e + "pyramid_bn1"); C_(e + "pyramid_2", e + "pyramid_bn2");
+      C_(e + "pyramid_1", e + "pyramid_bn1", 1, true); C_(e + "pyramid_2", e + "pyramid_bn2", 1, true);
       L(e + "fc.0"); N_(e + "fc.1");
       R("sequence_transformer.pos_encoder.pe");
       for (int i = 0; i < cfg.num_layers; ++i)
@@ -620,12 +639,30 @@ struct G {
     ConvTcLaunch a;
     a.in = in; a.A = A; a.L = L; a.Cin = w.Cin; a.Cout = w.Cout; a.Wp = w.Wp; a.shift = w.shift; a.taps = w.taps;
     a.dil = dil; a.pad = w.taps / 2; a.relu = relu; a.res = res; a.ldr = ldr; a.out = out; a.ldc = ldc; a.coff = coff;
+    a.NT = w.NT; a.CB = w.CB;
     if (pool_out) {
       const size_t tiles = (flat_rows(A, L, CONV_HALO) + 127) / 128;
-      a.pool_partial = c.allocf(tiles * 2 * (size_t)w.Cout);
+      a.pool_partial = c.allocf(tiles * 3 * (size_t)w.Cout);
       a.pool_out = pool_out; a.ldp = ldp; a.poff = poff;
     }
     PAUT_CHECK(w.Wp != nullptr, PAUT_ERR_STATE, "conv_tc: weights were not packed for the tensor-core path");
+    op_conv_tc(c, a);
+  }
+  // Conv1d k3 stride 2 pad 1 (+BN shift, ReLU) on flat rows row(a,l) = H0 + a*Lp + l with L, Lp, H0 even: reads the
+  // input as [R/2, 2*Cin] row pairs and produces flat rows with (L/2, Lp/2, H0/2).  out may be null (pool only).
+  void convtc_s2(const __nv_bfloat16* in, int64_t A, int L, int Lp, int H0, const ConvW& w, __nv_bfloat16* out,
+                 float* pool_out, int ldp, int poff) {
+    PAUT_CHECK(w.Wp_s2 != nullptr && L % 2 == 0 && Lp % 2 == 0 && H0 % 2 == 0, PAUT_ERR_STATE,
+               "conv_tc stride 2: weights not packed or odd row geometry");
+    ConvTcLaunch a;
+    a.in = in; a.A = A; a.L = L / 2; a.Lp = Lp / 2; a.H0 = H0 / 2; a.Cin = 2 * w.Cin; a.Cout = w.Cout; a.Wp = w.Wp_s2;
+    a.NT = w.NT_s2; a.CB = w.CB_s2; a.skip_lo = true;
+    a.shift = w.shift; a.taps = 2; a.dil = 1; a.pad = 1; a.relu = true; a.out = out; a.ldc = w.Cout; a.coff = 0;
+    if (pool_out) {
+      const size_t tiles = ((size_t)a.H0 + (size_t)A * a.Lp + 127) / 128;
+      a.pool_partial = c.allocf(tiles * 3 * (size_t)w.Cout);
+      a.pool_out = pool_out; a.ldp = ldp; a.poff = poff;
+    }
     op_conv_tc(c, a);
   }
 };
@@ -888,12 +925,24 @@ void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_out
       g.convtc(bufA, A, S, conv[qn + "3"], dil, true, h, 128, spare, 128, 0, r == 2 ? feat : nullptr, 640, 0);
       std::swap(h, spare);
     }
-    // the two stride-2 pyramid convs still run on the fp32 CUDA-core kernel
-    float* hd = c.allocf((size_t)A * S * 128);
-    op_unflatten(c, h, A, S, CONV_HALO, 128, hd);
-    float* x1 = c.allocf((size_t)A * ((S + 1) / 2) * 256);
-    g.conv(hd, A, S, conv[e + "pyramid_1"], 1, 2, 1, true, nullptr, x1, 256, 0, feat, 640, 128, &L1);
-    g.conv(x1, A, L1, conv[e + "pyramid_2"], 1, 2, 1, true, nullptr, nullptr, 0, 0, feat, 640, 384, &L2);
+    const int Lp0 = S + CONV_HALO;
+    const ConvW& p1 = conv[e + "pyramid_1"];
+    const ConvW& p2 = conv[e + "pyramid_2"];
+    if (p1.Wp_s2 && p2.Wp_s2 && S % 4 == 0 && Lp0 % 4 == 0 && Lp0 / 4 >= 64) {
+      // stride-2 pyramid on the tensor cores through the space-to-depth view of the flat rows
+      L1 = S / 2; L2 = S / 4;
+      __nv_bfloat16* x1 = static_cast<__nv_bfloat16*>(
+          c.alloc(((size_t)CONV_HALO / 2 + (size_t)A * (Lp0 / 2)) * 256 * sizeof(__nv_bfloat16)));
+      g.convtc_s2(h, A, S, Lp0, CONV_HALO, p1, x1, feat, 640, 128);
+      g.convtc_s2(x1, A, L1, Lp0 / 2, CONV_HALO / 2, p2, nullptr, feat, 640, 384);
+    } else {
+      // short signals: the two stride-2 pyramid convs run on the fp32 CUDA-core kernel
+      float* hd = c.allocf((size_t)A * S * 128);
+      op_unflatten(c, h, A, S, CONV_HALO, 128, hd);
+      float* x1 = c.allocf((size_t)A * ((S + 1) / 2) * 256);
+      g.conv(hd, A, S, p1, 1, 2, 1, true, nullptr, x1, 256, 0, feat, 640, 128, &L1);
+      g.conv(x1, A, L1, p2, 1, 2, 1, true, nullptr, nullptr, 0, 0, feat, 640, 384, &L2);
+    }
   } else {
     float* s0 = c.allocf((size_t)A * S * 64);
     op_stem_conv(c, x, A, S, ci.w, ci.shift, ci.taps, ci.Cout, true, s0);

@@ -27,6 +27,9 @@ struct ConvW {
   const float* w = nullptr;      // [taps][Cin][Cout] (BN scale folded); Cin == 1 -> [taps][Cout]
   const float* shift = nullptr;  // folded bias
   const void* Wp = nullptr;      // bf16 blocks for the tcgen05 conv (bf16 mode, Cin and Cout multiples of 16)
+  int NT = 0, CB = 0;            // tile plan of Wp
+  const void* Wp_s2 = nullptr;   // stride-2 k3 conv as a 2-tap conv over the space-to-depth view (2*Cin channels)
+  int NT_s2 = 0, CB_s2 = 0;
   int Cin = 0, Cout = 0, taps = 0;
 };
 struct LNW {
@@ -94,7 +97,7 @@ struct Model {
   Lin pack_lin(const std::string& name);
   void pack_tc(Lin& l, const std::vector<float>& W);
   Lin pack_lin_rows(const std::string& wkey, const std::string& bkey, int row0, int rows);
-  ConvW pack_conv(const std::string& conv_name, const std::string& bn_name);
+  ConvW pack_conv(const std::string& conv_name, const std::string& bn_name, int max_dil = 1, bool stride2 = false);
   LNW pack_ln(const std::string& name);
   MHAW pack_mha(const std::string& name, int heads);
   TELW pack_tel(const std::string& name, int heads);

@@ -17,6 +17,12 @@
 // ReLU -> bf16 rows in HBM (halo rows are written as zeros to keep the layout invariant) and/or per-tile
 // column sums for the pooled mean.  Two TMEM accumulators let tile i+1's MMAs overlap tile i's epilogue.
 // CTAs are persistent over (row tile, N tile) pairs.
+//
+// Stride-2 convolutions (the enhanced encoder's pyramid) use the same kernel through a space-to-depth view:
+// flat rows [R, C] with an even period are read as [R/2, 2C] (row pair (2m, 2m+1) = one row of 2C channels), and
+//   y[l] = W0 x[2l-1] + W1 x[2l] + W2 x[2l+1]  =  [0 | W0] x2[l-1] + [W1 | W2] x2[l]
+// is a stride-1 convolution with two taps (offsets -1, 0) over 2C channels.  The all-zero half of tap 0 is
+// never multiplied (`skip_lo`), so the MMA work equals the real 3-tap convolution.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -50,7 +56,9 @@ struct ConvTcArgs {
   int ldr;
   __nv_bfloat16* out;           // flat rows [R, ldc] at column offset coff (nullable)
   int ldc, coff;
-  float* pool;                  // per-tile column sums [tiles][2 segments][Cout] (nullable)
+  float* pool;                  // per-tile column sums [tiles][nseg segments][Cout] (nullable)
+  int nseg;                     // A-scans a 128-row tile can touch: 2 (period >= 127 rows) or 3
+  int skip_lo;                  // space-to-depth stride-2 view: tap 0 multiplies only the upper half of Cin
   int L, Lp, H0;                // geometry: valid rows per A-scan, period, leading halo
   int64_t A;
   int wrows;                    // window rows = 128 + (taps-1)*dil
@@ -68,7 +76,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[CT_STAGES], empty[CT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float pool_s[4][2][128];
+  __shared__ float pool_s[4 * 2 * 128];                    // [TMEM quarter][segment][NT]; 4*nseg*NT <= 1024
   __shared__ float tsm[16][32 * 17];
   __shared__ __align__(16) float shift_s[128];
 
@@ -185,6 +193,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
           const uint64_t a_ks = (uint64_t)(2 * p.wrows), a_t = (uint64_t)p.dil, b_step = (uint64_t)(2 * NT);
           uint32_t accum = cb ? 1u : 0u;
           for (int t = 0; t < p.taps; ++t) {
+            if (p.skip_lo && t == 0 && 2 * cb < ncb) {       // [0 | W0]: the lower channel half of tap 0 is zero
+              ad_t += a_t;
+              bd += b_step * (uint64_t)(chunks / 2);
+              continue;
+            }
             uint64_t ad = ad_t;
             for (int ks = 0; ks < chunks / 2; ++ks) {
               mma_bf16_ss(d, ad, bd, idesc, accum);
@@ -221,16 +234,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
       const int a_of_row = rel >= 0 ? (int)((unsigned)rel / (unsigned)p.Lp) : -1;
       const int l_of_row = rel >= 0 ? rel - a_of_row * p.Lp : p.L;
       const bool valid = rel >= 0 && a_of_row < p.A && l_of_row < p.L && row < p.R;
-      // first A-scan touched by the tile (segment 0); rows of the next one are segment 1
+      // first A-scan touched by the tile (segment 0); rows of the following ones are segments 1 (and 2)
       const int rel0 = (int)(tile * 128) - p.H0;
       const int a_first = rel0 >= 0 ? (int)((unsigned)rel0 / (unsigned)p.Lp) : 0;
-      const int seg = a_of_row - a_first;
-      // does the tile reach into a second A-scan?  (last row of the tile, tile-uniform)
-      const int rel_last = (int)(tile * 128) + 127 - p.H0;
-      const bool has_seg1 = rel_last >= 0 && (int)((unsigned)rel_last / (unsigned)p.Lp) > a_first;
-      // first tile-local row of the second A-scan (128 if the tile holds a single A-scan)
+      // first tile-local rows of the second / third A-scan (tile-uniform; 128 = not in this tile)
       const int seg1_row = p.H0 + (a_first + 1) * p.Lp - (int)(tile * 128);
-      const int split_row = (has_seg1 && seg1_row < 128) ? (int)(seg1_row > 0 ? seg1_row : 0) : 128;
+      const int split1 = seg1_row < 128 ? seg1_row : 128;
+      const int split2 = (p.nseg > 2 && seg1_row + p.Lp < 128) ? seg1_row + p.Lp : 128;
+      const bool has_seg1 = split1 < 128, has_seg2 = split2 < 128;
       auto process = [&](int c0, float (&v)[16]) {
         const int n = nt * NT + c0;
         if (valid) {
@@ -278,16 +289,26 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
           for (int j = 0; j < 16; ++j) tw[lane * 17 + j] = v[j];          // invalid rows are already zero
           __syncwarp();
           const int col = lane & 15, rbase = (lane >> 4) * 16;
-          float st = 0.f, s1 = 0.f;                    // all rows; rows of the second A-scan (tile-uniform branch)
+          float st = 0.f, s1 = 0.f, s2 = 0.f;          // all rows; rows from the second / third A-scan on
 #pragma unroll
           for (int r = 0; r < 16; ++r) st += tw[(rbase + r) * 17 + col];
           if (has_seg1) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) s1 += (q * 32 + rbase + r >= split_row) ? tw[(rbase + r) * 17 + col] : 0.f;
+            for (int r = 0; r < 16; ++r) s1 += (q * 32 + rbase + r >= split1) ? tw[(rbase + r) * 17 + col] : 0.f;
+          }
+          if (has_seg2) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) s2 += (q * 32 + rbase + r >= split2) ? tw[(rbase + r) * 17 + col] : 0.f;
           }
           st += __shfl_xor_sync(0xffffffffu, st, 16);
           s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          if (lane < 16) { pool_s[q][0][c0 + lane] = st - s1; pool_s[q][1][c0 + lane] = s1; }
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (lane < 16) {
+            float* ps = pool_s + (q * p.nseg) * NT + c0 + lane;
+            ps[0] = st - s1;
+            ps[NT] = s1 - s2;
+            if (p.nseg > 2) ps[2 * NT] = s2;
+          }
           __syncwarp();
         }
       };
@@ -314,11 +335,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
       mbar_arrive(&acc_empty[acc]);                        // accumulator drained: the next tile's MMAs may start
       if (p.pool) {
         named_sync(2, CT_EPI);
-        for (int i = tid; i < 2 * NT; i += CT_EPI) {
+        for (int i = tid; i < p.nseg * NT; i += CT_EPI) {
           const int sgm = i / NT, col = i - sgm * NT;
-          const float sum = (sgm == 1 && !has_seg1) ? 0.f
-                            : pool_s[0][sgm][col] + pool_s[1][sgm][col] + pool_s[2][sgm][col] + pool_s[3][sgm][col];
-          p.pool[((size_t)tile * 2 + sgm) * p.Cout + nt * NT + col] = sum;
+          const float* ps = pool_s + sgm * NT + col;
+          const int qs = p.nseg * NT;
+          p.pool[((size_t)tile * p.nseg + sgm) * p.Cout + nt * NT + col] = ps[0] + ps[qs] + ps[2 * qs] + ps[3 * qs];
         }
         named_sync(2, CT_EPI);
       }
@@ -333,7 +354,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
 
 // pooled mean from the per-tile partial sums, in a fixed order: out[a, poff + c] = sum / L
 __global__ void k_pool_finish(const float* __restrict__ partial, float* __restrict__ out, int ldp, int poff,
-                              int64_t A, int C, int L, int Lp, int H0) {
+                              int64_t A, int C, int L, int Lp, int H0, int nseg) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= A * C) return;
   const int64_t a = idx / C;
@@ -344,7 +365,7 @@ __global__ void k_pool_finish(const float* __restrict__ partial, float* __restri
     const int64_t rel0 = t * 128 - H0;
     const int64_t a_first = rel0 >= 0 ? rel0 / Lp : 0;
     const int seg = (int)(a - a_first);
-    if (seg >= 0 && seg < 2) s += partial[((size_t)t * 2 + seg) * C + c];
+    if (seg >= 0 && seg < nseg) s += partial[((size_t)t * nseg + seg) * C + c];
   }
   out[a * ldp + poff + c] = s / (float)L;
 }
@@ -432,30 +453,32 @@ uint16_t f2bf_(float f) {
 
 }  // namespace
 
-int conv_tc_nt(int Cout) {
-  if (Cout % 16 != 0) return 0;
-  for (int nt = 128; nt >= 16; nt -= 16)
-    if (Cout % nt == 0) return nt;
-  return 0;
-}
-
-// input-channel block: the largest of 64/32/16 dividing Cin such that the resident weights of one N tile plus
-// the CT_STAGES-deep window ring fit the shared memory of one CTA
-int conv_tc_cb(int Cin, int taps, int Cout) {
-  const int NT = conv_tc_nt(Cout);
-  const size_t w = (size_t)taps * Cin * NT * 2;
-  for (int cb : {64, 32, 16}) {
-    if (Cin % cb != 0) continue;
-    const size_t a = (size_t)(cb / 8) * (128 + (taps - 1) * 8) * 16 + 128;     // worst-case dilation 8
-    if (w + CT_STAGES * a <= 220 * 1024) return cb;
+// Tile plan of one convolution: N tile NT (<= 128, divides Cout) and input-channel block CB (64/32/16, divides
+// Cin) such that the resident weights of one N tile plus the CT_STAGES-deep window ring fit the dynamic shared
+// memory left beside the kernel's static arrays.  Prefers the widest N tile (the A windows are re-read once
+// per N tile), then the deepest channel block.
+constexpr size_t CT_DYN_SMEM = 232448 - 40 * 1024;
+bool conv_tc_plan(int Cin, int taps, int Cout, int max_dil, int* NT_out, int* CB_out) {
+  if (Cout % 16 != 0 || Cin % 16 != 0) return false;
+  for (int nt = 128; nt >= 16; nt -= 16) {
+    if (Cout % nt != 0) continue;
+    const size_t w = (size_t)taps * Cin * nt * 2;
+    for (int cb : {64, 32, 16}) {
+      if (Cin % cb != 0) continue;
+      const size_t a = (((size_t)(cb / 8) * (128 + (taps - 1) * max_dil) * 16) + 127) & ~(size_t)127;
+      if (w + CT_STAGES * a <= CT_DYN_SMEM) {
+        *NT_out = nt;
+        *CB_out = cb;
+        return true;
+      }
+    }
   }
-  return 0;
+  return false;
 }
 
 // weights [taps][Cin][Cout] fp32 (BN scale folded, as packed for the fp32 path) -> bf16 blocks
 // [Cout/NT][Cin/CB][taps][CB/8][NT][8]
-void conv_tc_pack(const float* w, int taps, int Cin, int Cout, std::vector<uint16_t>& out) {
-  const int NT = conv_tc_nt(Cout), CB = conv_tc_cb(Cin, taps, Cout);
+void conv_tc_pack(const float* w, int taps, int Cin, int Cout, int NT, int CB, std::vector<uint16_t>& out) {
   const int ncb = Cin / CB, chunks = CB / 8;
   out.assign((size_t)taps * Cin * Cout, 0);
   for (int co = 0; co < Cout; ++co)
@@ -474,15 +497,24 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   ConvTcArgs p;
   p.in = static_cast<const __nv_bfloat16*>(a.in); p.Cin = a.Cin; p.Cout = a.Cout;
   p.Wp = static_cast<const __nv_bfloat16*>(a.Wp); p.shift = a.shift; p.taps = a.taps; p.dil = a.dil; p.pad = a.pad;
-  p.NT = conv_tc_nt(a.Cout); p.CB = conv_tc_cb(a.Cin, a.taps, a.Cout);
-  PAUT_CHECK((int64_t)flat_rows(a.A, a.L, a.halo) < (int64_t(1) << 31) - 256, PAUT_ERR_UNSUPPORTED, "conv_tc: too many rows in one launch");
-  PAUT_CHECK(p.NT > 0 && p.CB > 0, PAUT_ERR_UNSUPPORTED, "conv_tc: channel counts must be multiples of 16");
-  PAUT_CHECK(a.pad * a.dil <= a.halo && (a.taps - 1) * a.dil == 2 * a.pad * a.dil, PAUT_ERR_UNSUPPORTED,
-             "conv_tc: needs 'same' padding no wider than the halo");
+  p.NT = a.NT; p.CB = a.CB;
+  // geometry: row(a, l) = H0 + a*Lp + l; defaults to the standard flat layout of (L, halo)
+  p.L = a.L; p.Lp = a.Lp ? a.Lp : a.L + a.halo; p.H0 = a.Lp ? a.H0 : a.halo; p.A = a.A;
+  p.R = (int64_t)p.H0 + a.A * (int64_t)p.Lp;
+  PAUT_CHECK(p.R < (int64_t(1) << 31) - 256, PAUT_ERR_UNSUPPORTED, "conv_tc: too many rows in one launch");
+  PAUT_CHECK(p.NT > 0 && p.CB > 0 && a.Cout % p.NT == 0 && a.Cin % p.CB == 0, PAUT_ERR_UNSUPPORTED,
+             "conv_tc: channel counts must be multiples of 16 (no tile plan)");
+  // zero rows on both sides of every A-scan must cover the taps' reach
+  const int reach_l = a.pad * a.dil, reach_r = (a.taps - 1 - a.pad) * a.dil, gap = p.Lp - p.L;
+  PAUT_CHECK(reach_l >= 0 && reach_r >= 0 && reach_l <= gap && reach_r <= gap && reach_l <= p.H0, PAUT_ERR_UNSUPPORTED,
+             "conv_tc: padding wider than the zero rows between A-scans");
+  p.nseg = p.Lp >= 127 ? 2 : 3;
+  PAUT_CHECK(!a.pool_partial || (p.Lp >= 64 && 4 * p.nseg * p.NT <= 1024), PAUT_ERR_UNSUPPORTED,
+             "conv_tc: pooled mean needs a row period >= 64 (and N tile <= 64 below 127)");
+  p.skip_lo = a.skip_lo ? 1 : 0;
+  PAUT_CHECK(!p.skip_lo || (a.Cin / p.CB) % 2 == 0, PAUT_ERR_INVALID, "conv_tc: skip_lo needs an even number of channel blocks");
   p.relu = a.relu ? 1 : 0; p.res = static_cast<const __nv_bfloat16*>(a.res); p.ldr = a.ldr;
   p.out = static_cast<__nv_bfloat16*>(a.out); p.ldc = a.ldc; p.coff = a.coff; p.pool = a.pool_partial;
-  p.L = a.L; p.Lp = a.L + a.halo; p.H0 = a.halo; p.A = a.A;
-  p.R = (int64_t)flat_rows(a.A, a.L, a.halo);
   p.wrows = 128 + (a.taps - 1) * a.dil;
   p.a_stage_bytes = ((p.CB / 8) * p.wrows * 16 + 127) & ~127;
   p.w_bytes = a.taps * a.Cin * p.NT * 2;                   // all weights of one N tile
@@ -514,7 +546,7 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   if (a.pool_partial && a.pool_out) {
     const int64_t n = a.A * a.Cout;
     k_pool_finish<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(a.pool_partial, a.pool_out, a.ldp, a.poff, a.A,
-                                                                    a.Cout, a.L, a.L + a.halo, a.halo);
+                                                                    a.Cout, p.L, p.Lp, p.H0, p.nseg);
     c.launched("pool_finish");
   }
 }

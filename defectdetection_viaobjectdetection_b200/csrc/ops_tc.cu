@@ -1,12 +1,16 @@
 // tcgen05 tensor-core GEMM:  C[M,N] = epilogue(A[M,K] * W[N,K]^T)   bf16 operands, fp32 accumulate in TMEM.
 //
-// One CTA = one 128-row M tile x one N tile (NT <= 256 columns).  K is consumed in blocks of 64:
-// all four warps stage the A block (fp32 or bf16 activations -> bf16, canonical no-swizzle layout) and the
-// pre-packed weight block into a 2-stage shared-memory ring, one elected thread issues the four K=16
-// tcgen05.mma of the block and commits them to the stage's mbarrier; the ring lets the loads of block k+1
-// overlap the MMAs of block k.  The accumulator ([128 x NT] fp32) lives in TMEM; the epilogue reads it back
-// with tcgen05.ld (warp w <-> TMEM lanes 32w..32w+31 = rows), applies bias / activation / residual /
-// row-table and writes fp32.
+// Persistent, warp-specialised (544 threads, one CTA per SM):
+//   * a CTA owns ONE N tile (NT <= 256 columns) whose packed weights ([K/8 chunks][NT rows][16 B], K-major, no
+//     swizzle) stay resident in shared memory, and walks a strided set of 128-row M tiles;
+//   * 8 loader warps stream the fp32 activations of a [128 x 64] block with fully coalesced 128-bit loads (two
+//     rows per warp instruction), convert to bf16 and store the canonical K-major operand into a 4-stage ring
+//     (chunk stride 2048+16 B so that the 8-byte stores of a half-warp cover all banks); the loads of the next
+//     block are issued before the current one is converted, so two blocks per SM are always in flight;
+//   * one elected thread of the issuer warp runs the K loop (tcgen05.mma 128 x NT x 16), committing every block
+//     to its ring slot's "empty" barrier and the last block of a tile to the accumulator's "full" barrier;
+//   * 8 epilogue warps read the accumulator (two TMEM buffers: the MMAs of tile i+1 overlap the epilogue of
+//     tile i) with tcgen05.ld, apply bias / activation / residual / row table and write fp32 rows.
 #include <cstdlib>
 #include <cstring>
 
@@ -20,8 +24,13 @@ using namespace tc;
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;             // K elements per pipeline stage (8 chunks of 8)
-constexpr int STAGES = 2;
+constexpr int BK = 64;                       // K elements per ring stage (8 chunks of 8)
+constexpr int GT_STAGES = 4;
+constexpr int GT_EPI_WARPS = 8, GT_LOAD_WARPS = 8;
+constexpr int GT_THREADS = 32 * (GT_EPI_WARPS + 1 + GT_LOAD_WARPS);
+constexpr int GT_ALBO = 2048 + 16;           // chunk stride of the A operand (+16 B: bank skew)
+constexpr int GT_ASTAGE = 8 * GT_ALBO;
+constexpr size_t GT_DYN_SMEM = 232448 - 1536;   // opt-in limit minus the static barriers / bias
 
 __device__ __forceinline__ float tc_act(float v, int act) {
   switch (act) {
@@ -49,147 +58,182 @@ struct GemmTcArgs {
   int ldr;
   const float* table;
   int table_mod;
-  int swap_lbo_sbo;                // debug: exchange the two descriptor strides (PAUT_TC_SWAP=1)
+  uint32_t tmem_cols;              // power of two >= 2 * NT
 };
 
-__global__ void __launch_bounds__(128) k_gemm_tc(GemmTcArgs p) {
+__global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t mma_done[STAGES];
+  __shared__ __align__(8) uint64_t full[GT_STAGES], empty[GT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[256];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int ntile = blockIdx.y;
   const int NT = p.NT;
-  const uint32_t a_stage_bytes = BM * BK * 2;                 // 16 KB
-  const uint32_t b_stage_bytes = (uint32_t)NT * BK * 2;
-  unsigned char* As = smem;                                   // [STAGES][8 chunks][128 rows][16 B]
-  unsigned char* Bs = smem + STAGES * a_stage_bytes;          // [STAGES][8 chunks][NT rows][16 B]
+  const int ntn = p.N / NT;
+  const int nt = blockIdx.x % ntn;                                  // this CTA's N tile
+  const int64_t tile0 = blockIdx.x / ntn, tstep = gridDim.x / ntn;
+  const int64_t num_tiles = (p.M + BM - 1) / BM;
+  const int chunks_total = p.Kp / 8;
+  const int nkb = (p.Kp + BK - 1) / BK;
+  const int w_bytes = chunks_total * NT * 16;
+  unsigned char* Wres = smem;                                       // [chunks_total][NT][16 B]
+  unsigned char* Aring = smem + ((w_bytes + 127) & ~127);           // [GT_STAGES][8 chunks][GT_ALBO]
+  const uint32_t acc_stride = p.tmem_cols / 2;
 
-  uint32_t ncols = 32;
-  while ((int)ncols < NT) ncols <<= 1;
-  if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+  if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&mma_done[s], 1);
+    for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&full[s], GT_LOAD_WARPS); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], GT_EPI_WARPS * 32); }
     fence_mbar_init();
   }
+  {  // resident weights of this N tile: one contiguous block of the packed layout
+    const uint4* src = reinterpret_cast<const uint4*>(p.Wp) + (size_t)nt * (w_bytes / 16);
+    uint4* dst = reinterpret_cast<uint4*>(Wres);
+    for (int i = tid; i < w_bytes / 16; i += GT_THREADS) dst[i] = __ldg(src + i);
+  }
+  for (int i = tid; i < NT; i += GT_THREADS) bias_s[i] = p.bias ? __ldg(p.bias + nt * NT + i) : 0.f;
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = tmem_slot;
-  const uint32_t idesc = make_idesc_bf16(BM, NT);
+  const uint32_t tmem = tmem_slot;
 
-  const int nkb = (p.Kp + BK - 1) / BK;
-  const int chunks_total = p.Kp / 8;
-  const unsigned char* wp_tile = reinterpret_cast<const unsigned char*>(p.Wp) + (size_t)ntile * chunks_total * NT * 16;
-
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    if (kb >= STAGES) mbar_wait(&mma_done[s], ((kb / STAGES) - 1) & 1);     // MMAs that read this stage are done
-    const int k0 = kb * BK;
-    const int nchunks = min(8, chunks_total - kb * 8);                       // chunks in this block (even)
-    // ---- A block: warp w stages chunks w and w+4; lane = row within a group of 32 rows
-    unsigned char* a_dst = As + s * a_stage_bytes;
+  if (warp > GT_EPI_WARPS) {
+    // ================= loaders =================
+    const int lw = warp - (GT_EPI_WARPS + 1);                       // 0..7: rows lw*16 .. lw*16+15 of the tile
+    const int j = lane & 15;                                        // K quad of the block: k = k0 + 4j .. 4j+3
+    const int r0 = lw * 16 + (lane >> 4);                           // rows r0, r0+2, ..., r0+14
+    const uint32_t dst0 = smem_u32(Aring) + (uint32_t)(j >> 1) * GT_ALBO + (uint32_t)(j & 1) * 8 + (uint32_t)r0 * 16;
+    auto load = [&](int64_t tile, int kb, float4 (&v)[8]) {
+      const int k = kb * BK + 4 * j;
+      const bool kok = k + 4 <= p.K;
+      const int64_t m0 = tile * BM + r0;
+      const float* src = p.A + m0 * p.lda + k;
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int ch = warp + cc * 4;
-      if (ch < nchunks) {
-        const int k = k0 + ch * 8;
+      for (int i = 0; i < 8; ++i) {
+        v[i] = (kok && m0 + 2 * i < p.M) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)(2 * i) * p.lda))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store = [&](int stage, const float4 (&v)[8]) {
+      const uint32_t d = dst0 + (uint32_t)stage * GT_ASTAGE;
 #pragma unroll
-        for (int rg = 0; rg < 4; ++rg) {
-          const int r = rg * 32 + lane;
-          const int64_t m = m0 + r;
-          float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-          if (m < p.M) {
-            const float* src = p.A + m * p.lda + k;
-            if (k + 4 <= p.K) x0 = __ldg(reinterpret_cast<const float4*>(src));
-            if (k + 8 <= p.K) x1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i].x, v[i].y), h1 = __floats2bfloat162_rn(v[i].z, v[i].w);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + (uint32_t)i * 32), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                     "r"(*reinterpret_cast<uint32_t*>(&h1))
+                     : "memory");
+      }
+    };
+    int64_t tile = tile0;
+    int kb = 0, stage = 0;
+    uint32_t use = 0;
+    float4 cur[8], nxt[8];
+    bool have = tile < num_tiles;
+    if (have) load(tile, kb, cur);
+    while (have) {
+      int64_t tile_n = tile;
+      int kb_n = kb + 1;
+      if (kb_n == nkb) { kb_n = 0; tile_n += tstep; }
+      const bool have_n = tile_n < num_tiles;
+      if (have_n) load(tile_n, kb_n, nxt);                          // next block in flight while this one is stored
+      if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);         // MMAs that read this slot are done
+      store(stage, cur);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == GT_STAGES) { stage = 0; ++use; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      tile = tile_n; kb = kb_n; have = have_n;
+    }
+  } else if (warp == GT_EPI_WARPS) {
+    // ================= MMA issuer (one elected lane) =================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(BM, NT);
+    const uint32_t a_ring = smem_u32(Aring), w_addr = smem_u32(Wres);
+    const uint64_t a_ks = (uint64_t)((2 * GT_ALBO) >> 4), b_ks = (uint64_t)((2 * NT * 16) >> 4);
+    int stage = 0, it = 0;
+    uint32_t use = 0;
+    for (int64_t tile = tile0; tile < num_tiles; tile += tstep, ++it) {
+      const int acc = it & 1;
+      if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], use & 1);
+        if (leader) {
+          tc_fence_after();
+          const int nch = min(8, chunks_total - kb * 8);             // chunks of this block (even)
+          uint64_t ad = make_desc(a_ring + (uint32_t)stage * GT_ASTAGE, GT_ALBO, 128);
+          uint64_t bd = make_desc(w_addr + (uint32_t)(kb * 8 * NT) * 16, NT * 16, 128);
+          const uint32_t d = tmem + acc * acc_stride;
+          for (int ks = 0; ks < nch / 2; ++ks) {
+            mma_bf16_ss(d, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+            ad += a_ks;
+            bd += b_ks;
           }
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(x0.x, x0.y), h1 = __floats2bfloat162_rn(x0.z, x0.w);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(x1.x, x1.y), h3 = __floats2bfloat162_rn(x1.z, x1.w);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          pk.z = *reinterpret_cast<uint32_t*>(&h2);
-          pk.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(a_dst + ch * (BM * 16) + r * 16) = pk;
+          mma_commit(&empty[stage]);
+          if (kb == nkb - 1) mma_commit(&acc_full[acc]);
         }
+        __syncwarp();
+        if (++stage == GT_STAGES) { stage = 0; ++use; }
       }
     }
-    // ---- B block: contiguous nchunks * NT * 16 bytes of the packed weights
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(wp_tile + (size_t)kb * 8 * NT * 16);
-      uint4* dst = reinterpret_cast<uint4*>(Bs + s * b_stage_bytes);
-      const int n16 = nchunks * NT;
-      for (int i = tid; i < n16; i += 128) dst[i] = __ldg(src + i);
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (warp == 0 && elect_one()) {
+  } else {
+    // ================= epilogue: warp w owns TMEM lanes 32*(w%4).. and the 16-column groups w/4, w/4+2, ... ====
+    const int q = warp & 3;
+    int it = 0;
+    for (int64_t tile = tile0; tile < num_tiles; tile += tstep, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(As) + s * a_stage_bytes;
-      const uint32_t b_addr = smem_u32(Bs) + s * b_stage_bytes;
-      for (int ks = 0; ks < nchunks / 2; ++ks) {
-        const uint64_t ad = p.swap_lbo_sbo ? make_desc(a_addr + ks * 2 * (BM * 16), 128, BM * 16)
-                                           : make_desc(a_addr + ks * 2 * (BM * 16), BM * 16, 128);
-        const uint64_t bd = p.swap_lbo_sbo ? make_desc(b_addr + ks * 2 * (NT * 16), 128, NT * 16)
-                                           : make_desc(b_addr + ks * 2 * (NT * 16), NT * 16, 128);
-        mma_bf16_ss(tmem_d, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-      }
-      mma_commit(&mma_done[s]);
-    }
-  }
-  // ---- wait for the last commit (it covers every MMA issued before it)
-  {
-    const int last = nkb - 1;
-    mbar_wait(&mma_done[last & 1], (last / STAGES) & 1);
-  }
-  tc_fence_after();
-
-  // ---- epilogue: warp w owns rows 32w..32w+31 (= TMEM lanes)
-  const int64_t m = m0 + warp * 32 + lane;
-  const uint32_t t_row = tmem_d + ((uint32_t)(warp * 32) << 16);
-  const int nbase = ntile * NT;
-  for (int c0 = 0; c0 < NT; c0 += 16) {
-    float v[16];
-    tmem_ld16(t_row + c0, v);
-    if (m < p.M) {
-      const int n = nbase + c0;
+      const int64_t m = tile * BM + q * 32 + lane;
+      const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
+      for (int c0 = (warp >> 2) * 16; c0 < NT; c0 += 32) {
+        float v[16];
+        tmem_ld16(t_row + c0, v);
+        if (m < p.M) {
+          const int n = nt * NT + c0;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = tc_act(v[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f), p.act) + p.act_eps;
-      if (p.res) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.res + m * p.ldr + n);
+          for (int jj = 0; jj < 16; ++jj) v[jj] = tc_act(v[jj] + bias_s[c0 + jj], p.act) + p.act_eps;
+          if (p.res) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.res + m * p.ldr + n);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 r = __ldg(r4 + j);
-          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            for (int jj = 0; jj < 4; ++jj) {
+              const float4 r = __ldg(r4 + jj);
+              v[4 * jj] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
+            }
+          }
+          if (p.table) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.table + (m % p.table_mod) * p.N + n);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float4 r = __ldg(r4 + jj);
+              v[4 * jj] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
+            }
+          }
+          float4* dst = reinterpret_cast<float4*>(p.C + m * p.ldc + p.coff + n);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) dst[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
         }
       }
-      if (p.table) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.table + (m % p.table_mod) * p.N + n);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 r = __ldg(r4 + j);
-          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-        }
-      }
-      float4* dst = reinterpret_cast<float4*>(p.C + m * p.ldc + p.coff + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);                          // accumulator drained: the MMAs of tile it+2 may start
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, ncols);
+  if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
 }
 
 }  // namespace
 
-// N tile: the largest multiple of 16 that divides N and is <= 256
-int tc_pick_ntile(int N) {
+// N tile: the largest multiple of 16 that divides N, is <= 256 and whose resident weights (Kp * NT bf16) fit the
+// shared memory beside the activation ring
+int tc_pick_ntile(int N, int K) {
   if (N % 16 != 0) return 0;
+  const size_t Kp = (size_t)(K + 15) / 16 * 16;
   for (int nt = 256; nt >= 16; nt -= 16)
-    if (N % nt == 0) return nt;
+    if (N % nt == 0 && ((Kp * nt * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE <= GT_DYN_SMEM) return nt;
   return 0;
 }
 
@@ -216,7 +260,7 @@ void tc_pack_weight(const float* W, int N, int K, int NT, std::vector<uint16_t>&
 }
 
 bool linear_tc_supported(const LinArgs& a) {
-  return a.Wp != nullptr && a.NT >= 16 && a.lda % 4 == 0 && a.ldc % 4 == 0 && a.coff % 4 == 0 &&
+  return a.Wp != nullptr && a.NT >= 16 && a.NT <= 256 && a.N % a.NT == 0 && a.lda % 4 == 0 && a.ldc % 4 == 0 && a.coff % 4 == 0 &&
          (a.res == nullptr || a.ldr % 4 == 0) && a.K % 4 == 0;
 }
 
@@ -227,15 +271,21 @@ void op_linear_tc(Ctx& c, const LinArgs& a) {
   g.A = a.A; g.lda = a.lda; g.Wp = static_cast<const __nv_bfloat16*>(a.Wp); g.bias = a.bias; g.M = a.M; g.K = a.K;
   g.Kp = (a.K + 15) / 16 * 16; g.N = a.N; g.NT = a.NT; g.C = a.C; g.ldc = a.ldc; g.coff = a.coff; g.act = a.act;
   g.act_eps = a.act_eps; g.res = a.res; g.ldr = a.ldr; g.table = a.table; g.table_mod = a.table_mod;
-  static const int swap = std::getenv("PAUT_TC_SWAP") ? atoi(std::getenv("PAUT_TC_SWAP")) : 0;
-  g.swap_lbo_sbo = swap;
-  const size_t smem = (size_t)STAGES * (BM * BK * 2 + (size_t)a.NT * BK * 2);
+  g.tmem_cols = 32;
+  while ((int)g.tmem_cols < 2 * a.NT) g.tmem_cols <<= 1;
+  const size_t smem = (((size_t)g.Kp * a.NT * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE;
+  PAUT_CHECK(smem <= GT_DYN_SMEM && (int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED,
+             "linear_tc: resident weights do not fit shared memory (N tile too wide for this K)");
   if (smem > c.gemm_tc_smem_configured) {
     PAUT_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     c.gemm_tc_smem_configured = smem;
   }
-  dim3 grid((unsigned)((a.M + BM - 1) / BM), a.N / a.NT);
-  k_gemm_tc<<<grid, 128, smem, c.stream>>>(g);
+  const int ntn = a.N / a.NT;
+  const int64_t tiles = (a.M + BM - 1) / BM;
+  int64_t grid = (int64_t)(c.num_sms / ntn) * ntn;          // every N tile gets the same number of CTAs
+  if (grid < ntn) grid = ntn;
+  if (grid > tiles * ntn) grid = tiles * ntn;
+  k_gemm_tc<<<(unsigned)grid, GT_THREADS, smem, c.stream>>>(g);
   c.launched("linear_tc");
 }
 
