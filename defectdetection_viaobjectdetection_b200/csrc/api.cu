@@ -98,6 +98,9 @@ int paut_ctx_create(int device, void* cuda_stream, paut_ctx** out) {
     p->c.stream = static_cast<cudaStream_t>(cuda_stream);
     p->c.num_sms = prop.multiProcessorCount;
     p->c.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    // resident chunk budget: a tenth of the device memory, at most 16 GiB (five contexts -- one per scanner
+    // lane plus the caller's -- stay under half of a B200's 180 GB); larger chunks mean fuller grids
+    p->c.ws_limit = std::min<size_t>(size_t(16) << 30, std::max<size_t>(prop.totalGlobalMem / 10, size_t(256) << 20));
     *out = p;
   });
 }

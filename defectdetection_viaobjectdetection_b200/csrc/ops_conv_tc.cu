@@ -538,7 +538,7 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
     cudaFree(p.dbg);
     fprintf(stderr, "[conv probe] Cin %d Cout %d taps %d | loader: wait_empty %llu issue %llu per stage (%llu stages) | "
                     "mma: wait_acc_empty(total) %llu, per stage wait_full %llu issue %llu (%llu stages) | "
-                    "epilogue: per tile wait_full %llu process %llu (%llu tiles)\n",
+                    "epilogue: per tile wait_full %llu process %llu of which tmem_ld %llu (%llu tiles)\n",
             a.Cin, a.Cout, a.taps, h[0] / (h[2] + !h[2]), h[1] / (h[2] + !h[2]), h[2], h[8], h[9] / (h[11] + !h[11]),
             h[10] / (h[11] + !h[11]), h[11], h[16] / (h[18] + !h[18]), h[17] / (h[18] + !h[18]), h[19] / (h[18] + !h[18]), h[18]);
   }

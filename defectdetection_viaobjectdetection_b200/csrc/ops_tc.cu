@@ -30,7 +30,7 @@ constexpr int GT_EPI_WARPS = 8, GT_LOAD_WARPS = 8;
 constexpr int GT_THREADS = 32 * (GT_EPI_WARPS + 1 + GT_LOAD_WARPS);
 constexpr int GT_ALBO = 2048 + 16;           // chunk stride of the A operand (+16 B: bank skew)
 constexpr int GT_ASTAGE = 8 * GT_ALBO;
-constexpr size_t GT_DYN_SMEM = 232448 - 1536;   // opt-in limit minus the static barriers / bias
+constexpr size_t GT_DYN_SMEM = 232448 - 2304;   // opt-in limit minus the static barriers / bias
 
 __device__ __forceinline__ float tc_act(float v, int act) {
   switch (act) {

@@ -122,7 +122,7 @@ int paut_abi_version(void);
 int paut_ctx_create(int device, void* cuda_stream, paut_ctx** out);
 void paut_ctx_destroy(paut_ctx* ctx);
 const char* paut_last_error(const paut_ctx* ctx); /* ctx may be NULL: last create failure */
-/* Upper bound (bytes) of the private activation workspace a forward may use; default 2 GiB.
+/* Upper bound (bytes) of the private activation workspace a forward may use; default min(16 GiB, device memory / 10).
  * Larger batches are processed in resident chunks of whole sets. */
 int paut_ctx_set_workspace_limit(paut_ctx* ctx, uint64_t bytes);
 
