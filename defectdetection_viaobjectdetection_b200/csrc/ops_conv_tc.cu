@@ -11,12 +11,13 @@
 // t*dil rows (rows are uniformly 16 B apart inside a chunk), so no im2col copy exists anywhere.
 // The matching weight blocks ([tap][8 chunks][NT rows][16 B]) ride in the same pipeline stage.
 //
-// Warp roles (256 threads): warps 0-3 stage operands (ld.global -> st.shared) into a 3-deep ring and their
-// thread 0 issues the tcgen05.mma of each stage (commit -> stage-free barrier; last stage of a tile also
-// commits -> accumulator-full barrier); warps 4-7 are the epilogue: TMEM -> registers -> shift, residual,
-// ReLU -> bf16 rows in HBM (halo rows are written as zeros to keep the layout invariant) and/or per-tile
-// column sums for the pooled mean.  Two TMEM accumulators let tile i+1's MMAs overlap tile i's epilogue.
-// CTAs are persistent over (row tile, N tile) pairs.
+// Warp roles (416 threads): warps 9-12 stream the windows with cp.async into a 5-deep ring (weights of the CTA's
+// N tile are resident in shared memory); one elected thread of warp 8 issues the tcgen05.mma of each stage
+// (commit -> stage-free barrier; last stage of a tile also commits -> accumulator-full barrier); warps 0-7 are
+// the epilogue: TMEM -> registers -> per-warp swizzled shared-memory transposition -> shift, residual, ReLU ->
+// bf16 rows in HBM (halo rows are written as zeros to keep the layout invariant) and/or per-tile column sums
+// for the pooled mean, with 8 lanes per row so that loads and stores are 64 B per row.  Two TMEM accumulators
+// let tile i+1's MMAs overlap tile i's epilogue.  CTAs are persistent over (row tile, N tile) pairs.
 //
 // Stride-2 convolutions (the enhanced encoder's pyramid) use the same kernel through a space-to-depth view:
 // flat rows [R, C] with an even period are read as [R/2, 2C] (row pair (2m, 2m+1) = one row of 2C channels), and
@@ -38,8 +39,9 @@ using namespace tc;
 namespace {
 
 constexpr int CT_STAGES = 5;
-constexpr int CT_THREADS = 672;          // warps 0-15 epilogue (4 per TMEM quarter), 16 MMA issuer, 17-20 cp.async loaders
-constexpr int CT_EPI = 512;
+constexpr int CT_EPI_WARPS = 8;          // warps 0-7 epilogue (2 per TMEM lane quarter), 8 MMA issuer, 9-12 cp.async loaders
+constexpr int CT_EPI = CT_EPI_WARPS * 32;
+constexpr int CT_THREADS = CT_EPI + 32 + 128;
 constexpr int CT_LOADERS = 128;
 constexpr int CT_LAG = 4;                // loader arrives on stage j-LAG after issuing stage j
 
@@ -72,12 +74,12 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 }
 
 // Persistent CTA = one N tile (weights resident in shared memory) x a strided set of 128-row tiles.
-__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 672 threads -> <= 97 registers
+__global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[CT_STAGES], empty[CT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float pool_s[4 * 2 * 128];                    // [TMEM quarter][segment][NT]; 4*nseg*NT <= 1024
-  __shared__ float tsm[16][32 * 17];
+  __shared__ __align__(16) float pool_s[4 * 2 * 128];                    // [TMEM quarter][segment][NT]; 4*nseg*NT <= 1024
+  __shared__ __align__(128) float tsm[CT_EPI_WARPS][32 * 32];   // per-warp 32x32 fp32 transposition tile (swizzled)
   __shared__ __align__(16) float shift_s[128];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
@@ -107,12 +109,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16 || warp == 17);
+  const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == CT_EPI_WARPS || warp == CT_EPI_WARPS + 1);
   unsigned long long pt[4] = {0, 0, 0, 0};
 
-  if (warp >= 17) {
+  if (warp > CT_EPI_WARPS) {
     // ================= loaders: cp.async of the A windows, CT_LAG stages of look-ahead =================
-    const int l = tid - 17 * 32;                            // 0..127
+    const int l = tid - (CT_EPI_WARPS + 1) * 32;            // 0..127
     const int ch = l & 7;                                   // fixed chunk (8 lanes cover one 128-byte row)
     const int rsub = l >> 3;                                // rows rsub, rsub+16, ...
     const uint32_t a_ring = smem_u32(Aring);
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fence_async_smem();
     for (int j = (issued > CT_LAG ? issued - CT_LAG : 0); j < issued; ++j) arrive_stage(j);
-  } else if (warp == 16) {
+  } else if (warp == CT_EPI_WARPS) {
     // ================= MMA issuer (one elected lane) =================
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(128, NT);
@@ -216,132 +218,145 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {   // 
       }
     }
     if (probe) { p.dbg[8] = pt[0]; p.dbg[9] = pt[1]; p.dbg[10] = pt[2]; p.dbg[11] = pt[3]; }
-  } else if (warp < 16) {
-    // ================= epilogue group: warp w owns TMEM lane quarter w%4 and column quarter w/4 ==============
-    const int q = warp & 3;
-    const int cq = warp >> 2;
+  } else {
+    // ================= epilogue: warp w owns TMEM lane quarter q = w%4 and the 32-column passes h, h+2, ... (h = w/4)
+    // Row-per-lane accumulators go through a per-warp swizzled shared-memory tile once; everything else
+    // (shift, residual, ReLU, halo masking, bf16 stores, pooled sums) happens in the transposed domain where
+    // 8 lanes cover 32 consecutive columns of one row: residual loads and output stores touch 4 rows x 64 B
+    // per instruction instead of 32 rows x 16 B, which is what the L1 wavefront rate can sustain.
+    const int q = warp & 3, h = warp >> 2;
+    const int rr = lane >> 3, cg = lane & 7;               // transposed domain: rows rr + 4i, columns 4cg..4cg+3
+    const uint32_t tw = smem_u32(&tsm[warp][0]);
+    const int npass = (NT - 32 * h + 63) / 64 > 0 ? (NT - 32 * h + 63) / 64 : 0;      // passes at c0 = 32h + 64k < NT
+    float4 sh4[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = 32 * h + 64 * k + 4 * cg;
+      sh4[k] = c < NT ? *reinterpret_cast<const float4*>(shift_s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     int it = 0;
     for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
+      // ---- geometry of the tile (one division, tile-uniform): first A-scan, first rows of the next two
+      const int t0 = (int)(tile * 128);
+      const int rel0 = t0 - p.H0;
+      const int a_first = rel0 >= 0 ? (int)((unsigned)rel0 / (unsigned)p.Lp) : 0;
+      const int seg1_row = p.H0 + (a_first + 1) * p.Lp - t0;
+      const int split1 = seg1_row < 128 ? seg1_row : 128;
+      const int split2 = (p.nseg > 2 && seg1_row + p.Lp < 128) ? seg1_row + p.Lp : 128;
+      const bool has_seg1 = split1 < 128, has_seg2 = split2 < 128;
+      // validity of this lane's own row -> bit mask of the warp's 32 rows
+      const int trow = q * 32 + lane;
+      const int a_of_row = a_first + (trow >= split1 ? 1 : 0) + (trow >= split2 ? 1 : 0);
+      const int l_of_row = rel0 + trow - a_of_row * p.Lp;
+      const bool valid = l_of_row >= 0 && l_of_row < p.L && a_of_row < p.A && (int64_t)t0 + trow < p.R;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      // ---- residual rows of both passes, requested before the accumulator is waited for
+      uint2 rres[2][8];
+      if (p.res) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = 32 * h + 64 * k + 4 * cg;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = rr + 4 * i;
+            rres[k][i] = make_uint2(0u, 0u);
+            if (k < npass && c < NT && ((vmask >> rl) & 1u))
+              rres[k][i] = __ldg(reinterpret_cast<const uint2*>(p.res + ((int64_t)t0 + q * 32 + rl) * p.ldr + nt * NT + c));
+          }
+        }
+      }
       const long long e0 = probe ? clock64() : 0;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       const long long e1 = probe ? clock64() : 0;
       tc_fence_after();
-      const int64_t row = tile * 128 + q * 32 + lane;
-      // geometry of this row: which A-scan, valid or halo
-      // (32-bit arithmetic: 64-bit integer division is emulated and costs hundreds of cycles per tile)
-      const int rel = (int)row - p.H0;
-      const int a_of_row = rel >= 0 ? (int)((unsigned)rel / (unsigned)p.Lp) : -1;
-      const int l_of_row = rel >= 0 ? rel - a_of_row * p.Lp : p.L;
-      const bool valid = rel >= 0 && a_of_row < p.A && l_of_row < p.L && row < p.R;
-      // first A-scan touched by the tile (segment 0); rows of the following ones are segments 1 (and 2)
-      const int rel0 = (int)(tile * 128) - p.H0;
-      const int a_first = rel0 >= 0 ? (int)((unsigned)rel0 / (unsigned)p.Lp) : 0;
-      // first tile-local rows of the second / third A-scan (tile-uniform; 128 = not in this tile)
-      const int seg1_row = p.H0 + (a_first + 1) * p.Lp - (int)(tile * 128);
-      const int split1 = seg1_row < 128 ? seg1_row : 128;
-      const int split2 = (p.nseg > 2 && seg1_row + p.Lp < 128) ? seg1_row + p.Lp : 128;
-      const bool has_seg1 = split1 < 128, has_seg2 = split2 < 128;
-      auto process = [&](int c0, float (&v)[16]) {
-        const int n = nt * NT + c0;
-        if (valid) {
-          const float4* sh4 = reinterpret_cast<const float4*>(shift_s + c0);
+      if (npass == 0) {                                      // narrow N tile: this warp only keeps the barrier phases in step
+        tc_fence_before();
+        mbar_arrive(&acc_empty[acc]);
+      }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 sh = sh4[j];
-            v[4 * j] += sh.x; v[4 * j + 1] += sh.y; v[4 * j + 2] += sh.z; v[4 * j + 3] += sh.w;
+      for (int k = 0; k < 2; ++k) {
+        if (k < npass) {
+          const int c0 = 32 * h + 64 * k;
+          uint32_t t32[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, t32);
+          if (k == npass - 1) {                              // accumulator drained: the MMAs of tile it+2 may start
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
           }
-          if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + row * p.ldr + n);
-            const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
-            const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+          // row `lane`, 16-byte chunk c -> physical chunk c ^ (lane & 7): conflict-free both ways
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-              v[2 * j] += __low2float(h2);
-              v[2 * j + 1] += __high2float(h2);
+          for (int c = 0; c < 8; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tw + (uint32_t)lane * 128 + (uint32_t)((c ^ (lane & 7)) * 16)),
+                         "r"(t32[4 * c]), "r"(t32[4 * c + 1]), "r"(t32[4 * c + 2]), "r"(t32[4 * c + 3])
+                         : "memory");
+          __syncwarp();
+          const int col = c0 + 4 * cg;                       // first of this lane's 4 columns inside the N tile
+          const bool col_ok = col < NT;
+          float4 ps0 = make_float4(0.f, 0.f, 0.f, 0.f), ps1 = ps0, ps2 = ps0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = rr + 4 * i;
+            float4 t;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                         : "r"(tw + (uint32_t)rl * 128 + (uint32_t)((cg ^ (rl & 7)) * 16)));
+            t.x += sh4[k].x; t.y += sh4[k].y; t.z += sh4[k].z; t.w += sh4[k].w;
+            if (p.res) {
+              const __nv_bfloat162 r0 = *reinterpret_cast<const __nv_bfloat162*>(&rres[k][i].x);
+              const __nv_bfloat162 r1 = *reinterpret_cast<const __nv_bfloat162*>(&rres[k][i].y);
+              t.x += __low2float(r0); t.y += __high2float(r0); t.z += __low2float(r1); t.w += __high2float(r1);
+            }
+            if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+            if (!((vmask >> rl) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);          // halo rows stay zero
+            const int tr = q * 32 + rl;
+            if (p.out && col_ok && (int64_t)t0 + tr < p.R) {
+              __nv_bfloat162 o0 = __floats2bfloat162_rn(t.x, t.y), o1 = __floats2bfloat162_rn(t.z, t.w);
+              *reinterpret_cast<uint2*>(p.out + ((int64_t)t0 + tr) * p.ldc + p.coff + nt * NT + col) =
+                  make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
+            }
+            if (p.pool) {
+              ps0.x += t.x; ps0.y += t.y; ps0.z += t.z; ps0.w += t.w;
+              if (has_seg1 && tr >= split1) { ps1.x += t.x; ps1.y += t.y; ps1.z += t.z; ps1.w += t.w; }
+              if (has_seg2 && tr >= split2) { ps2.x += t.x; ps2.y += t.y; ps2.z += t.z; ps2.w += t.w; }
             }
           }
-          if (p.relu) {
+          if (p.pool) {
+            // sums over the warp's 32 rows: lanes with equal cg (xor 8, 16), fixed order
+            auto red = [&](float4& v) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int m = 8; m <= 16; m <<= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, m); v.y += __shfl_xor_sync(0xffffffffu, v.y, m);
+                v.z += __shfl_xor_sync(0xffffffffu, v.z, m); v.w += __shfl_xor_sync(0xffffffffu, v.w, m);
+              }
+            };
+            red(ps0);
+            if (has_seg1) red(ps1);
+            if (has_seg2) red(ps2);
+            if (lane < 8 && col_ok) {
+              float* ps = pool_s + (q * p.nseg) * NT + col;
+              *reinterpret_cast<float4*>(ps) = make_float4(ps0.x - ps1.x, ps0.y - ps1.y, ps0.z - ps1.z, ps0.w - ps1.w);
+              *reinterpret_cast<float4*>(ps + NT) = make_float4(ps1.x - ps2.x, ps1.y - ps2.y, ps1.z - ps2.z, ps1.w - ps2.w);
+              if (p.nseg > 2) *reinterpret_cast<float4*>(ps + 2 * NT) = ps2;
+            }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-        if (p.out && row < p.R) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.ldc + p.coff + n);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-        if (p.pool) {
-          // column sums of this warp's 32 rows, split by segment: transpose through a padded per-warp tile
-          // (independent LDS/FADD, no shuffle chains); the four warps' partials are combined once per tile
-          float* tw = &tsm[warp][0];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) tw[lane * 17 + j] = v[j];          // invalid rows are already zero
-          __syncwarp();
-          const int col = lane & 15, rbase = (lane >> 4) * 16;
-          float st = 0.f, s1 = 0.f, s2 = 0.f;          // all rows; rows from the second / third A-scan on
-#pragma unroll
-          for (int r = 0; r < 16; ++r) st += tw[(rbase + r) * 17 + col];
-          if (has_seg1) {
-#pragma unroll
-            for (int r = 0; r < 16; ++r) s1 += (q * 32 + rbase + r >= split1) ? tw[(rbase + r) * 17 + col] : 0.f;
-          }
-          if (has_seg2) {
-#pragma unroll
-            for (int r = 0; r < 16; ++r) s2 += (q * 32 + rbase + r >= split2) ? tw[(rbase + r) * 17 + col] : 0.f;
-          }
-          st += __shfl_xor_sync(0xffffffffu, st, 16);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          if (lane < 16) {
-            float* ps = pool_s + (q * p.nseg) * NT + c0 + lane;
-            ps[0] = st - s1;
-            ps[NT] = s1 - s2;
-            if (p.nseg > 2) ps[2 * NT] = s2;
-          }
-          __syncwarp();
-        }
-      };
-      if (NT == 128) {
-        uint32_t t32[32];
-        const long long l0 = probe ? clock64() : 0;
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + cq * 32, t32);   // one TMEM round trip per warp
-        if (probe) pt[3] += clock64() - l0;
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t32[sub * 16 + j]);
-          process(cq * 32 + sub * 16, v);
-        }
-      } else {
-        for (int c0 = cq * 16; c0 < NT; c0 += 64) {
-          float v[16];
-          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, v);
-          process(c0, v);
+          __syncwarp();                                      // the tile is rewritten by the next pass
         }
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);                        // accumulator drained: the next tile's MMAs may start
       if (p.pool) {
-        named_sync(2, CT_EPI);
-        for (int i = tid; i < p.nseg * NT; i += CT_EPI) {
-          const int sgm = i / NT, col = i - sgm * NT;
-          const float* ps = pool_s + sgm * NT + col;
-          const int qs = p.nseg * NT;
-          p.pool[((size_t)tile * p.nseg + sgm) * p.Cout + nt * NT + col] = ps[0] + ps[qs] + ps[2 * qs] + ps[3 * qs];
+        // combine the four lane quarters of this column half (128 threads, named barrier 2 + h), fixed order
+        named_sync(2 + h, 128);
+        const int tl = q * 32 + lane;                        // 0..127 within the half
+        const int qs = p.nseg * NT;
+        for (int i = tl; i < p.nseg * 64; i += 128) {
+          const int sgm = i >> 6, cc = i & 63;               // cc: 0..31 -> pass 0, 32..63 -> pass 1
+          const int col = 32 * h + 64 * (cc >> 5) + (cc & 31);
+          if ((cc >> 5) < npass && col < NT) {
+            const float* ps = pool_s + sgm * NT + col;
+            p.pool[((size_t)tile * p.nseg + sgm) * p.Cout + nt * NT + col] = ps[0] + ps[qs] + ps[2 * qs] + ps[3 * qs];
+          }
         }
-        named_sync(2, CT_EPI);
+        named_sync(2 + h, 128);
       }
       if (probe) { pt[0] += e1 - e0; pt[1] += clock64() - e1; pt[2] += 1; }
     }
@@ -416,6 +431,59 @@ __global__ void k_stem_flat(const void* __restrict__ x, int x_dtype, int64_t A, 
       pk[j] = *reinterpret_cast<uint32_t*>(&h2);
     }
     *reinterpret_cast<uint4*>(out + row * ldc + coff + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// Same stem, specialised: the tap count is a template parameter, a thread keeps the K x 8 weights of its 8
+// channels in registers and walks rows with 32-bit index arithmetic; consecutive threads write the consecutive
+// 16-byte channel groups of one row (full 128-byte lines for 64 channels).
+template <int K>
+__global__ void __launch_bounds__(256) k_stem_flat_t(const void* __restrict__ x, int x_dtype, int A, int S,
+                                                     const float* __restrict__ w, const float* __restrict__ shift,
+                                                     int Cout, int relu, __nv_bfloat16* __restrict__ out, int ldc,
+                                                     int coff, int Lp, int H0, int R) {
+  const int c8n = Cout >> 3;
+  const int c8 = threadIdx.x % c8n, rsub = threadIdx.x / c8n, rpb = 256 / c8n;
+  float wr[K][8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j] = __ldg(shift + c8 * 8 + j);
+#pragma unroll
+  for (int t = 0; t < K; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(w + t * Cout + c8 * 8 + j);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  const float* xf = static_cast<const float*>(x);
+  for (int row = blockIdx.x * rpb + rsub; row < R; row += gridDim.x * rpb) {
+    const int rel = row - H0;
+    const int a = rel >= 0 ? (int)((unsigned)rel / (unsigned)Lp) : -1;
+    const int l = rel - a * Lp;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (a >= 0 && a < A && l < S) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = sh[j];
+      const size_t base = (size_t)a * S;
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const int li = l + t - K / 2;
+        float xv = 0.f;
+        if (li >= 0 && li < S) xv = x_dtype == PAUT_BF16 ? __bfloat162float(xb[base + li]) : __ldg(xf + base + li);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[t][j], acc[j]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)row * ldc + coff + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -565,11 +633,27 @@ void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const fl
   if (c.dry) return;
   PAUT_CHECK(Cout % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0, PAUT_ERR_UNSUPPORTED, "stem_flat: channels must be multiples of 8");
   const int64_t R = (int64_t)flat_rows(A, S, halo);
-  const int64_t total = R * (Cout / 8);
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  k_stem_flat<<<(unsigned)blocks, 256, 0, c.stream>>>(x, x_dtype, A, S, w, shift, k, Cout, relu ? 1 : 0,
-                                                      static_cast<__nv_bfloat16*>(out), ldc, coff, S + halo, halo, R);
+  const int c8n = Cout / 8;
+  if (256 % c8n == 0 && R < (int64_t(1) << 31) - 4096 && (k == 3 || k == 5 || k == 7 || k == 11)) {
+    const int rpb = 256 / c8n;
+    int64_t blocks = (R + rpb - 1) / rpb;
+    if (blocks > (int64_t)c.num_sms * 16) blocks = (int64_t)c.num_sms * 16;
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+#define PAUT_STEM(KK)                                                                                          \
+  k_stem_flat_t<KK><<<(unsigned)blocks, 256, 0, c.stream>>>(x, x_dtype, (int)A, S, w, shift, Cout, relu ? 1 : 0, o, \
+                                                            ldc, coff, S + halo, halo, (int)R)
+    if (k == 3) PAUT_STEM(3);
+    else if (k == 5) PAUT_STEM(5);
+    else if (k == 7) PAUT_STEM(7);
+    else PAUT_STEM(11);
+#undef PAUT_STEM
+  } else {
+    const int64_t total = R * (Cout / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_stem_flat<<<(unsigned)blocks, 256, 0, c.stream>>>(x, x_dtype, A, S, w, shift, k, Cout, relu ? 1 : 0,
+                                                        static_cast<__nv_bfloat16*>(out), ldc, coff, S + halo, halo, R);
+  }
   c.launched("stem_flat");
 }
 

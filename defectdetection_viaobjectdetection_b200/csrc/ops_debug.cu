@@ -8,6 +8,8 @@ using namespace tc;
 namespace {
 
 // mode 0: issue `reps` MMAs of shape 128 x N x 16 (operands: whatever is in shared memory), report cycles
+// mode 2: A operand in TENSOR MEMORY (tcgen05.st -> TS-form MMA), B = identity: D[r][n] must equal A[r][n]
+// mode 3: cycles per TS-form MMA 128 x N x 16
 // mode 1: overlapped A view. A rows are 16 B apart, chunk 1 of row r = row r+1 (LBO = lbo bytes); B = identity
 //         (16 x 16), so D[r][n] must equal n < 8 ? buf[r][n] : buf[r + lbo/16][n - 8].
 __global__ void __launch_bounds__(128) k_debug_mma(int mode, int N, int reps, int lbo, int a_from_far, float* out) {
@@ -33,12 +35,54 @@ __global__ void __launch_bounds__(128) k_debug_mma(int mode, int N, int reps, in
       reinterpret_cast<__nv_bfloat16*>(B + c * (N * 16) + n * 16)[e] = __float2bfloat16_rn(1.f);
     }
   }
+  if (mode == 2) {
+    for (int n = tid; n < 16; n += 128) {
+      const int c = n / 8, e = n % 8;
+      reinterpret_cast<__nv_bfloat16*>(B + c * (N * 16) + n * 16)[e] = __float2bfloat16_rn(1.f);
+    }
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   long long t0 = 0, t1 = 0;
+  if (mode == 2 || mode == 3) {
+    // A[r][k] = (r*16 + k) % 251, two bf16 per 32-bit column (even k in the low half), 8 columns at column 256
+    uint32_t a[8];
+    const int r = warp * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn((float)((r * 16 + 2 * j) % 251), (float)((r * 16 + 2 * j + 1) % 251));
+      a[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
+                     tmem + ((uint32_t)(warp * 32) << 16) + 256),
+                 "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint64_t bd = make_desc(smem_u32(B), N * 16, 128);
+        t0 = clock64();
+        for (int i = 0; i < reps; ++i)
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.ne.b32 p, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+              "}\n" ::"r"(tmem + (a_from_far ? (i & 1) * 128 : 0)),
+              "r"(tmem + 256), "l"(bd), "r"(idesc), "r"(mode == 2 ? 0u : 1u)
+              : "memory");
+        mma_commit(&bar);
+      }
+      __syncwarp();
+    }
+  } else
   if (warp == 0) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, N);
@@ -53,7 +97,7 @@ __global__ void __launch_bounds__(128) k_debug_mma(int mode, int N, int reps, in
   mbar_wait(&bar, 0);
   if (tid == 0) { t1 = clock64(); }
   tc_fence_after();
-  if (mode == 0) {
+  if (mode == 0 || mode == 3) {
     if (tid == 0) out[0] = (float)(t1 - t0) / (float)reps;
   } else {
     float v[16];
