@@ -44,7 +44,7 @@ struct Ctx {
   int smem_optin = 0;
   size_t att_smem_configured = 0;
   size_t gemm_tc_smem_configured = 0;
-  size_t conv_tc_smem_configured = 0;
+  size_t conv_tc_smem_configured[4] = {0, 0, 0, 0};
   bool profiling = false;                // per-kernel CUDA-event timing (paut_ctx_profile_*)
   std::vector<std::pair<std::string, cudaEvent_t>> prof_events;
   bool dry = false;                      // allocation-only pass used to size chunks: ops do nothing

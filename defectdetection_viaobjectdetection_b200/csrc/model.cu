@@ -1091,18 +1091,28 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
       default: throw Error(PAUT_ERR_INVALID, "unknown model kind");
     }
   };
-  // size the chunk with two dry runs (allocation only): footprint(nb) = fixed + per_set * nb
-  c.dry = true;
-  c.reset(); run(0, 1); const size_t s1 = c.ws_off;
-  c.reset(); run(0, 2); const size_t s2 = c.ws_off;
-  c.dry = false;
-  c.reset();
-  const size_t per_set = s2 > s1 ? s2 - s1 : 1;
+  // size the chunk with dry runs (allocation only): the exact footprint of a candidate chunk is measured, and the
+  // chunk shrinks proportionally until it fits the workspace limit (the footprint is monotonic in the set count)
+  auto footprint = [&](int64_t nb) {
+    c.dry = true;
+    c.reset();
+    run(0, nb);
+    const size_t s = c.ws_off;
+    c.dry = false;
+    c.reset();
+    return s;
+  };
   const size_t slack = size_t(1) << 20;
-  int64_t chunk = c.ws_limit > s1 + slack ? (int64_t)((c.ws_limit - s1 - slack) / per_set) + 1 : 1;
-  if (chunk < 1) chunk = 1;
-  if (chunk > B) chunk = B;
-  c.reserve(s1 + per_set * (size_t)(chunk - 1) + slack);
+  int64_t chunk = B;
+  size_t need = footprint(chunk);
+  while (need + slack > c.ws_limit && chunk > 1) {
+    int64_t next = (int64_t)((double)chunk * (double)c.ws_limit / (double)(need + slack) * 0.97);
+    if (next >= chunk) next = chunk - 1;
+    if (next < 1) next = 1;
+    chunk = next;
+    need = footprint(chunk);
+  }
+  c.reserve(need + slack);
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     c.reset();
     run(b0, std::min<int64_t>(chunk, B - b0));

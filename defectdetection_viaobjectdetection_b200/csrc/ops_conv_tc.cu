@@ -74,6 +74,7 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 }
 
 // Persistent CTA = one N tile (weights resident in shared memory) x a strided set of 128-row tiles.
+template <bool OUT, bool POOL, bool RES>
 __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[CT_STAGES], empty[CT_STAGES], acc_full[2], acc_empty[2];
@@ -223,19 +224,37 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
     // Row-per-lane accumulators go through a per-warp swizzled shared-memory tile once; everything else
     // (shift, residual, ReLU, halo masking, bf16 stores, pooled sums) happens in the transposed domain where
     // 8 lanes cover 32 consecutive columns of one row: residual loads and output stores touch 4 rows x 64 B
-    // per instruction instead of 32 rows x 16 B, which is what the L1 wavefront rate can sustain.
+    // per instruction.  OUT / POOL / RES are compile-time, tile-uniform conditions (tile fully inside the
+    // volume, warp rows free of halo rows, tile inside one A-scan) select straight-line fast paths, and all
+    // addresses advance incrementally.
     const int q = warp & 3, h = warp >> 2;
     const int rr = lane >> 3, cg = lane & 7;               // transposed domain: rows rr + 4i, columns 4cg..4cg+3
     const uint32_t tw = smem_u32(&tsm[warp][0]);
-    const int npass = (NT - 32 * h + 63) / 64 > 0 ? (NT - 32 * h + 63) / 64 : 0;      // passes at c0 = 32h + 64k < NT
+    const int npass = (NT - 32 * h + 63) / 64;              // passes at c0 = 32h + 64k < NT
+    const float lo = p.relu ? 0.f : -INFINITY;              // ReLU as a branch-free max
     float4 sh4[2];
+    bool col_ok[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int c = 32 * h + 64 * k + 4 * cg;
-      sh4[k] = c < NT ? *reinterpret_cast<const float4*>(shift_s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      col_ok[k] = k < npass && c < NT;
+      sh4[k] = col_ok[k] ? *reinterpret_cast<const float4*>(shift_s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    uint32_t st_addr[8], ld_addr[8];                        // swizzled tile addresses (loop invariant)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      st_addr[c] = tw + (uint32_t)lane * 128 + (uint32_t)((c ^ (lane & 7)) * 16);
+      const int rl = rr + 4 * c;
+      ld_addr[c] = tw + (uint32_t)rl * 128 + (uint32_t)((cg ^ (rl & 7)) * 16);
+    }
+    // element offsets of this lane's first row (tile 0 of this CTA) in the output / residual; advanced per tile
+    const int64_t row0 = tile0 * 128 + q * 32 + rr;
+    int64_t o_off = row0 * p.ldc + p.coff + nt * NT + 32 * h + 4 * cg;
+    int64_t r_off = row0 * p.ldr + nt * NT + 32 * h + 4 * cg;
+    const int64_t o_tile = tstep * 128 * (int64_t)p.ldc, r_tile = tstep * 128 * (int64_t)p.ldr;
+    const int o_row4 = 4 * p.ldc, r_row4 = 4 * p.ldr;       // 4 rows further (elements)
     int it = 0;
-    for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it) {
+    for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it, o_off += o_tile, r_off += r_tile) {
       const int acc = it & 1;
       // ---- geometry of the tile (one division, tile-uniform): first A-scan, first rows of the next two
       const int t0 = (int)(tile * 128);
@@ -251,18 +270,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
       const int l_of_row = rel0 + trow - a_of_row * p.Lp;
       const bool valid = l_of_row >= 0 && l_of_row < p.L && a_of_row < p.A && (int64_t)t0 + trow < p.R;
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const bool all_valid = vmask == 0xffffffffu;           // warp-uniform
+      const bool in_volume = (int64_t)t0 + 128 <= p.R;       // tile-uniform: no row bound checks needed
       // ---- residual rows of both passes, requested before the accumulator is waited for
       uint2 rres[2][8];
-      if (p.res) {
+      if (RES) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const int c = 32 * h + 64 * k + 4 * cg;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rl = rr + 4 * i;
             rres[k][i] = make_uint2(0u, 0u);
-            if (k < npass && c < NT && ((vmask >> rl) & 1u))
-              rres[k][i] = __ldg(reinterpret_cast<const uint2*>(p.res + ((int64_t)t0 + q * 32 + rl) * p.ldr + nt * NT + c));
+            if (p.res != nullptr && col_ok[k] && (all_valid || ((vmask >> (rr + 4 * i)) & 1u)))
+              rres[k][i] = __ldg(reinterpret_cast<const uint2*>(p.res + r_off + 64 * k + (int64_t)i * r_row4));
           }
         }
       }
@@ -277,51 +296,63 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (k < npass) {
-          const int c0 = 32 * h + 64 * k;
           uint32_t t32[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, t32);
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + 32 * h + 64 * k, t32);
           if (k == npass - 1) {                              // accumulator drained: the MMAs of tile it+2 may start
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
           }
-          // row `lane`, 16-byte chunk c -> physical chunk c ^ (lane & 7): conflict-free both ways
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tw + (uint32_t)lane * 128 + (uint32_t)((c ^ (lane & 7)) * 16)),
-                         "r"(t32[4 * c]), "r"(t32[4 * c + 1]), "r"(t32[4 * c + 2]), "r"(t32[4 * c + 3])
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr[c]), "r"(t32[4 * c]), "r"(t32[4 * c + 1]),
+                         "r"(t32[4 * c + 2]), "r"(t32[4 * c + 3])
                          : "memory");
           __syncwarp();
-          const int col = c0 + 4 * cg;                       // first of this lane's 4 columns inside the N tile
-          const bool col_ok = col < NT;
-          float4 ps0 = make_float4(0.f, 0.f, 0.f, 0.f), ps1 = ps0, ps2 = ps0;
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(t[i].x), "=f"(t[i].y), "=f"(t[i].z), "=f"(t[i].w)
+                         : "r"(ld_addr[i]));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rl = rr + 4 * i;
-            float4 t;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                         : "r"(tw + (uint32_t)rl * 128 + (uint32_t)((cg ^ (rl & 7)) * 16)));
-            t.x += sh4[k].x; t.y += sh4[k].y; t.z += sh4[k].z; t.w += sh4[k].w;
-            if (p.res) {
+            t[i].x += sh4[k].x; t[i].y += sh4[k].y; t[i].z += sh4[k].z; t[i].w += sh4[k].w;
+            if (RES) {
               const __nv_bfloat162 r0 = *reinterpret_cast<const __nv_bfloat162*>(&rres[k][i].x);
               const __nv_bfloat162 r1 = *reinterpret_cast<const __nv_bfloat162*>(&rres[k][i].y);
-              t.x += __low2float(r0); t.y += __high2float(r0); t.z += __low2float(r1); t.w += __high2float(r1);
+              t[i].x += __low2float(r0); t[i].y += __high2float(r0); t[i].z += __low2float(r1); t[i].w += __high2float(r1);
             }
-            if (p.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-            if (!((vmask >> rl) & 1u)) t = make_float4(0.f, 0.f, 0.f, 0.f);          // halo rows stay zero
-            const int tr = q * 32 + rl;
-            if (p.out && col_ok && (int64_t)t0 + tr < p.R) {
-              __nv_bfloat162 o0 = __floats2bfloat162_rn(t.x, t.y), o1 = __floats2bfloat162_rn(t.z, t.w);
-              *reinterpret_cast<uint2*>(p.out + ((int64_t)t0 + tr) * p.ldc + p.coff + nt * NT + col) =
-                  make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
-            }
-            if (p.pool) {
-              ps0.x += t.x; ps0.y += t.y; ps0.z += t.z; ps0.w += t.w;
-              if (has_seg1 && tr >= split1) { ps1.x += t.x; ps1.y += t.y; ps1.z += t.z; ps1.w += t.w; }
-              if (has_seg2 && tr >= split2) { ps2.x += t.x; ps2.y += t.y; ps2.z += t.z; ps2.w += t.w; }
+            t[i].x = fmaxf(t[i].x, lo); t[i].y = fmaxf(t[i].y, lo); t[i].z = fmaxf(t[i].z, lo); t[i].w = fmaxf(t[i].w, lo);
+          }
+          if (!all_valid) {                                  // halo rows stay zero
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (!((vmask >> (rr + 4 * i)) & 1u)) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (OUT && col_ok[k]) {
+            __nv_bfloat16* op = p.out + o_off + 64 * k;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 o0 = __floats2bfloat162_rn(t[i].x, t[i].y), o1 = __floats2bfloat162_rn(t[i].z, t[i].w);
+              if (in_volume || (int64_t)t0 + q * 32 + rr + 4 * i < p.R)
+                *reinterpret_cast<uint2*>(op + (int64_t)i * o_row4) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
             }
           }
-          if (p.pool) {
+          if (POOL) {
+            float4 ps0 = make_float4(0.f, 0.f, 0.f, 0.f), ps1 = ps0, ps2 = ps0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ps0.x += t[i].x; ps0.y += t[i].y; ps0.z += t[i].z; ps0.w += t[i].w; }
+            if (has_seg1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (q * 32 + rr + 4 * i >= split1) { ps1.x += t[i].x; ps1.y += t[i].y; ps1.z += t[i].z; ps1.w += t[i].w; }
+            }
+            if (has_seg2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (q * 32 + rr + 4 * i >= split2) { ps2.x += t[i].x; ps2.y += t[i].y; ps2.z += t[i].z; ps2.w += t[i].w; }
+            }
             // sums over the warp's 32 rows: lanes with equal cg (xor 8, 16), fixed order
             auto red = [&](float4& v) {
 #pragma unroll
@@ -333,8 +364,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
             red(ps0);
             if (has_seg1) red(ps1);
             if (has_seg2) red(ps2);
-            if (lane < 8 && col_ok) {
-              float* ps = pool_s + (q * p.nseg) * NT + col;
+            if (lane < 8 && col_ok[k]) {
+              float* ps = pool_s + (q * p.nseg) * NT + 32 * h + 64 * k + 4 * cg;
               *reinterpret_cast<float4*>(ps) = make_float4(ps0.x - ps1.x, ps0.y - ps1.y, ps0.z - ps1.z, ps0.w - ps1.w);
               *reinterpret_cast<float4*>(ps + NT) = make_float4(ps1.x - ps2.x, ps1.y - ps2.y, ps1.z - ps2.z, ps1.w - ps2.w);
               if (p.nseg > 2) *reinterpret_cast<float4*>(ps + 2 * NT) = ps2;
@@ -343,7 +374,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
           __syncwarp();                                      // the tile is rewritten by the next pass
         }
       }
-      if (p.pool) {
+      if (POOL) {
         // combine the four lane quarters of this column half (128 threads, named barrier 2 + h), fixed order
         named_sync(2 + h, 128);
         const int tl = q * 32 + lane;                        // 0..127 within the half
@@ -435,15 +466,17 @@ __global__ void k_stem_flat(const void* __restrict__ x, int x_dtype, int64_t A, 
 }
 
 // Same stem, specialised: the tap count is a template parameter, a thread keeps the K x 8 weights of its 8
-// channels in registers and walks rows with 32-bit index arithmetic; consecutive threads write the consecutive
-// 16-byte channel groups of one row (full 128-byte lines for 64 channels).
+// channels in registers and produces 4 consecutive rows per step from one sliding window of K+3 input samples
+// (independent FMA chains, 32-bit index arithmetic); consecutive threads write the consecutive 16-byte channel
+// groups of one row (full 128-byte lines for 64 channels).
+constexpr int STEM_RPT = 4;
 template <int K>
 __global__ void __launch_bounds__(256) k_stem_flat_t(const void* __restrict__ x, int x_dtype, int A, int S,
                                                      const float* __restrict__ w, const float* __restrict__ shift,
                                                      int Cout, int relu, __nv_bfloat16* __restrict__ out, int ldc,
                                                      int coff, int Lp, int H0, int R) {
   const int c8n = Cout >> 3;
-  const int c8 = threadIdx.x % c8n, rsub = threadIdx.x / c8n, rpb = 256 / c8n;
+  const int c8 = threadIdx.x % c8n, rsub = threadIdx.x / c8n, rpb = (256 / c8n) * STEM_RPT;
   float wr[K][8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sh[j] = __ldg(shift + c8 * 8 + j);
@@ -453,37 +486,68 @@ __global__ void __launch_bounds__(256) k_stem_flat_t(const void* __restrict__ x,
     for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(w + t * Cout + c8 * 8 + j);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const float* xf = static_cast<const float*>(x);
-  for (int row = blockIdx.x * rpb + rsub; row < R; row += gridDim.x * rpb) {
-    const int rel = row - H0;
+  const float lo = relu ? 0.f : -INFINITY;
+  for (int row0 = blockIdx.x * rpb + rsub * STEM_RPT; row0 < R; row0 += gridDim.x * rpb) {
+    const int rel = row0 - H0;
     const int a = rel >= 0 ? (int)((unsigned)rel / (unsigned)Lp) : -1;
-    const int l = rel - a * Lp;
-    float acc[8];
+    const int l = rel - a * Lp;                              // position of the first row inside its period
+    const bool scan_ok = a >= 0 && a < A;
+    // sliding window: samples l - K/2 .. l + RPT - 1 + K/2 of A-scan a (zero outside [0, S))
+    float xw[K + STEM_RPT - 1];
+    const size_t base = (size_t)(scan_ok ? a : 0) * S;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (a >= 0 && a < A && l < S) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = sh[j];
-      const size_t base = (size_t)a * S;
-#pragma unroll
-      for (int t = 0; t < K; ++t) {
-        const int li = l + t - K / 2;
-        float xv = 0.f;
-        if (li >= 0 && li < S) xv = x_dtype == PAUT_BF16 ? __bfloat162float(xb[base + li]) : __ldg(xf + base + li);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[t][j], acc[j]);
-      }
-      if (relu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-      }
+    for (int i = 0; i < K + STEM_RPT - 1; ++i) {
+      const int li = l - K / 2 + i;
+      xw[i] = 0.f;
+      if (scan_ok && li >= 0 && li < S) xw[i] = x_dtype == PAUT_BF16 ? __bfloat162float(xb[base + li]) : __ldg(xf + base + li);
     }
-    uint32_t pk[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    for (int j = 0; j < STEM_RPT; ++j) {
+      const int row = row0 + j;
+      if (row >= R) break;
+      // rows l+j >= S are halo rows (zero); a group that runs past the period (l+j >= Lp) starts the next A-scan
+      // and takes the general path below
+      float acc[8];
+      const int lj = l + j;
+      if (lj < Lp) {
+        const bool ok = scan_ok && lj < S;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = ok ? sh[c] : 0.f;
+        if (ok) {
+#pragma unroll
+          for (int t = 0; t < K; ++t)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fmaf(xw[j + t], wr[t][c], acc[c]);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], lo);
+        }
+      } else {
+        const int a2 = a + 1, l2 = lj - Lp;
+        const bool ok = a2 >= 0 && a2 < A && l2 < S;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = ok ? sh[c] : 0.f;
+        if (ok) {
+          const size_t b2 = (size_t)a2 * S;
+#pragma unroll
+          for (int t = 0; t < K; ++t) {
+            const int li = l2 + t - K / 2;
+            float xv = 0.f;
+            if (li >= 0 && li < S) xv = x_dtype == PAUT_BF16 ? __bfloat162float(xb[b2 + li]) : __ldg(xf + b2 + li);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fmaf(xv, wr[t][c], acc[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = fmaxf(acc[c], lo);
+        }
+      }
+      uint32_t pk[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * c], acc[2 * c + 1]);
+        pk[c] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(out + (size_t)row * ldc + coff + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    *reinterpret_cast<uint4*>(out + (size_t)row * ldc + coff + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -589,9 +653,16 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   p.num_tiles = (p.R + 127) / 128;
   const size_t smem = (size_t)p.w_bytes + (size_t)CT_STAGES * p.a_stage_bytes;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "conv_tc: weights + ring do not fit shared memory");
-  if (smem > c.conv_tc_smem_configured) {
-    PAUT_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    c.conv_tc_smem_configured = smem;
+  // four compiled epilogue variants: (out), (out + residual), (pool), (out + pool [+ residual, null-checked])
+  const bool v_out = p.out != nullptr, v_pool = p.pool != nullptr, v_res = p.res != nullptr;
+  PAUT_CHECK(v_out || v_pool, PAUT_ERR_INVALID, "conv_tc: neither an output nor a pooled output was requested");
+  PAUT_CHECK(!v_res || v_out, PAUT_ERR_UNSUPPORTED, "conv_tc: residual without an output tensor");
+  void (*kern)(ConvTcArgs) = v_pool ? (v_out ? k_conv_tc<true, true, true> : k_conv_tc<false, true, false>)
+                                    : (v_res ? k_conv_tc<true, false, true> : k_conv_tc<true, false, false>);
+  const int variant = v_pool ? (v_out ? 3 : 2) : (v_res ? 1 : 0);
+  if (smem > c.conv_tc_smem_configured[variant]) {
+    PAUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c.conv_tc_smem_configured[variant] = smem;
   }
   const int ntn = a.Cout / p.NT;
   int grid = (c.num_sms / ntn) * ntn;                       // every N tile gets the same number of CTAs
@@ -599,7 +670,7 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   static const bool debug = std::getenv("PAUT_CONV_DEBUG") != nullptr;
   p.dbg = nullptr;
   if (debug) { PAUT_CUDA(cudaMalloc(&p.dbg, 24 * sizeof(unsigned long long))); PAUT_CUDA(cudaMemset(p.dbg, 0, 24 * 8)); }
-  k_conv_tc<<<grid, CT_THREADS, smem, c.stream>>>(p);
+  kern<<<grid, CT_THREADS, smem, c.stream>>>(p);
   if (debug) {
     unsigned long long h[24];
     PAUT_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
@@ -635,7 +706,7 @@ void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const fl
   const int64_t R = (int64_t)flat_rows(A, S, halo);
   const int c8n = Cout / 8;
   if (256 % c8n == 0 && R < (int64_t(1) << 31) - 4096 && (k == 3 || k == 5 || k == 7 || k == 11)) {
-    const int rpb = 256 / c8n;
+    const int rpb = (256 / c8n) * STEM_RPT;
     int64_t blocks = (R + rpb - 1) / rpb;
     if (blocks > (int64_t)c.num_sms * 16) blocks = (int64_t)c.num_sms * 16;
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);

@@ -3,19 +3,22 @@
 //        -> Linear 128->64 + ReLU -> + position table            (NN_models.py:111-121, :11-14)
 // One CTA = 128 A-scans; nothing but x and the 64-wide result touches HBM.
 //
-//  conv1 (C_in = 1, 24 MACs/position) runs on the CUDA cores straight into an im2col operand in shared
-//  memory: row = position, K = 3 taps x 8 channels (+ a constant chunk [1,1,0..] that carries the bias as
-//  a bf16 hi+lo pair), so conv2 is a plain [128 x 32] x [32 x 32] tcgen05.mma per 128 positions.
+//  conv1 (C_in = 1, 24 MACs/position) runs on the CUDA cores and writes its 8-channel bf16 vector ONCE, as one
+//  16-byte row per position (rows -1 and S of every A-scan are zero).  conv2 needs no im2col copy: a K=16
+//  tcgen05.mma takes its two 8-channel K chunks from the SAME buffer through an overlapping descriptor
+//  (chunk stride LBO = 16 B, i.e. the next position): MMA 1 = taps 0,1 (rows p-1, p), MMA 2 = tap 2 (row p+1)
+//  plus a constant chunk [1,1,0..] that carries the bias as a bf16 hi+lo pair (its LBO points at a constant
+//  region).  An A-scan of S = 320 positions is covered by the M tiles at rows 0, 128 and 192.
 //  Its 32 output columns are the 16 channels (bias included) plus hi/lo halves of their sum, which turns
 //  ReLU + channel-mean into   sum_c relu(y_c) = (sum_c y_c + sum_c |y_c|) / 2   -- 18 FADDs per position in
 //  the epilogue instead of bias + max + add per channel.  The factor 1/32 is folded into the S->128 weights.
 //  The epilogue writes f (bf16) directly in the canonical K-major operand layout of the next GEMM, so the
 //  two Linear layers are tcgen05.mma on operands that never left shared memory; their accumulators live
-//  in TMEM next to the double-buffered conv accumulators (2 x 160 + 128 + 64 = 512 columns).
+//  in TMEM, reusing the columns of the double-buffered conv accumulators (2 x 192) once the conv stage is over.
 //
-//  Pipeline per group of 2 A-scans (= 5 M tiles): conv1(g) on all warps -> one thread issues the 10 MMAs of
-//  group g and commits them to an mbarrier -> all warps run the epilogue of group g-1 while those MMAs
-//  execute (im2col buffers and TMEM accumulators are double-buffered).
+//  Pipeline per group of 2 A-scans (= 6 M tiles): conv1(g) on all warps -> the issuer warp issues the 12 MMAs
+//  of group g and commits them to an mbarrier -> all warps run the epilogue of group g-1 while those MMAs
+//  execute (conv1 buffers and TMEM accumulators are double-buffered).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,7 +36,8 @@ constexpr int H0 = 128, H1 = 64;
 constexpr int ENC_COMPUTE = 640;        // 20 compute warps: 2 conv1 items per thread, 1 epilogue unit (tile, quarter) per warp
 constexpr int ENC_THREADS = ENC_COMPUTE + 64;   // + MMA issuer warp (20) + x loader warp (21), on different schedulers
 constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
-constexpr int D1_COL = 320, D2_COL = 448;
+constexpr int D1_COL = 0, D2_COL = 128;     // alias the conv accumulators (dead by then)
+constexpr int SCR_BYTES = 49152;            // linear-stage scratch: A3 (32 KB) + W2p (16 KB)
 constexpr int XS_PAD = 16;
 constexpr int XS_SLOTS = 4;              // x staging ring: cp.async prefetch runs ~3 groups ahead of conv1
 
@@ -87,16 +91,20 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   __shared__ uint32_t tmem_slot;
 
   const int S = p.S;
-  const int rows = 2 * S;                          // im2col rows of one group (2 A-scans)
-  const int tiles = rows / 128;
-  const uint32_t im_chunk = (uint32_t)rows * 16;
-  const uint32_t im_bytes = 4 * im_chunk;
-  unsigned char* IM = smem;                        // [2][4 chunks][rows][16 B]
-  unsigned char* A2 = smem + 2 * im_bytes;         // [S/8 chunks][128 rows][16 B]
+  const int nta = (S + 127) / 128;                 // M tiles per A-scan
+  const int tiles = 2 * nta;                       // per group (2 A-scans)
+  const uint32_t act_scan = (uint32_t)(S + 2) * 16;   // one A-scan of conv1 output: zero row, S rows, zero row
+  const uint32_t act_buf = 2 * act_scan;           // one group
+  unsigned char* ACT = smem;                       // [2 buffers][2 A-scans][S + 2 rows][16 B]
+  unsigned char* ONES = smem + ((2 * act_buf + 127) & ~127u);   // [128 rows][16 B] = [1, 1, 0, ..]: the bias chunk
+  unsigned char* IM = ONES + 2048;                 // linear-stage scratch (A3, W2p)
+  unsigned char* A2 = IM + SCR_BYTES;              // [S/8 chunks][128 rows][16 B]
   unsigned char* WR = A2 + (size_t)(S / 8) * A2_LBO;   // [2][8 chunks][128 rows][16 B]
   unsigned char* BC = WR + 2 * 16384;              // [4 chunks][32 rows][16 B]
   __nv_bfloat16* XS = reinterpret_cast<__nv_bfloat16*>(BC + 2048);   // [XS_SLOTS][2][S + 16]
   const int xs_stride = S + XS_PAD;
+  __shared__ uint32_t unit_tab[48];                // conv epilogue work units (al, tile, quarter, first position)
+  __shared__ int unit_cnt[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
   const int64_t a0 = (int64_t)blockIdx.x * 128;
@@ -113,17 +121,38 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   }
   for (int i = tid; i < 128; i += ENC_THREADS) reinterpret_cast<uint4*>(BC)[i] = reinterpret_cast<const uint4*>(p.Bc)[i];
   {
-    // constant chunk 3 (K = 24..31) = [1, 1, 0, 0, 0, 0, 0, 0]; zero rows of tap 0 / tap 2 at the A-scan edges
+    // bias chunk [1, 1, 0, 0, 0, 0, 0, 0] for every row; zero rows act1[-1] and act1[S] of every A-scan
     const uint4 ones = make_uint4(0x3F803F80u, 0u, 0u, 0u);
-    for (int b = 0; b < 2; ++b) {
-      unsigned char* im = IM + b * im_bytes;
-      for (int r = tid; r < rows; r += ENC_THREADS) *reinterpret_cast<uint4*>(im + 3 * im_chunk + r * 16) = ones;
-      if (tid < 2) {
-        *reinterpret_cast<uint4*>(im + 0 * im_chunk + (tid * S) * 16) = make_uint4(0, 0, 0, 0);           // act1[-1]
-        *reinterpret_cast<uint4*>(im + 2 * im_chunk + (tid * S + S - 1) * 16) = make_uint4(0, 0, 0, 0);   // act1[S]
-      }
+    for (int r = tid; r < 128; r += ENC_THREADS) reinterpret_cast<uint4*>(ONES)[r] = ones;
+    if (tid < 8) {
+      const int b = tid >> 2, al = (tid >> 1) & 1, edge = tid & 1;
+      *reinterpret_cast<uint4*>(ACT + b * act_buf + al * act_scan + (edge ? (S + 1) * 16 : 0)) = make_uint4(0, 0, 0, 0);
     }
     for (int i = tid; i < XS_SLOTS * 2 * xs_stride; i += ENC_THREADS) XS[i] = __float2bfloat16_rn(0.f);
+    // conv epilogue units: (A-scan al, tile k, lane quarter q) whose 32 positions are owned by that tile; the
+    // positions covered by both of the last two tiles alternate between them (and with al) so that every lane
+    // quarter gets the same number of units.  Bucketed by q: a warp can only read its own TMEM lane quarter.
+    if (tid == 0) {
+      const int r0_last = S >= 128 ? S - 128 : 0, dup_hi = 128 * (nta - 1);
+      int cnt[4] = {0, 0, 0, 0};
+      for (int al = 0; al < 2; ++al)
+        for (int k = 0; k < nta; ++k) {
+          const int r0 = k == nta - 1 ? r0_last : 128 * k;
+          for (int q = 0; q < 4; ++q) {
+            const int pos0 = r0 + 32 * q;
+            if (pos0 >= S) continue;
+            bool own = true;
+            if (nta >= 2 && pos0 >= r0_last && pos0 < dup_hi) {       // covered by tiles nta-2 and nta-1
+              const int owner = ((((pos0 - r0_last) >> 5) + al) & 1) ? nta - 1 : nta - 2;
+              own = owner == k;
+            } else if (k == nta - 1 && pos0 < dup_hi) {
+              own = false;
+            }
+            if (own) unit_tab[q * 12 + cnt[q]++] = (uint32_t)al | ((uint32_t)k << 1) | ((uint32_t)pos0 << 8);
+          }
+        }
+      for (int q = 0; q < 4; ++q) unit_cnt[q] = cnt[q];
+    }
   }
   // per-thread conv1 weights: this thread always computes channels 4*hf .. 4*hf+3
   const int hf = tid & 1;
@@ -139,6 +168,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc_conv = make_idesc_bf16(128, 32);
+  const uint32_t act_base = smem_u32(ACT), ones_base = smem_u32(ONES);
 
   // x staging (loader warp): lane l owns the 16-byte parts l, l+32, l+64 of the 2*S/8 parts of a group.
   // cp.async writes them straight into the ring slot; the slot's mbarrier (32 arrivals) completes when the
@@ -154,17 +184,17 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     mbar_wait(&bar_conv[buf], (g >> 1) & 1);
     tc_fence_after();
     const int q = warp & 3;
-    for (int T = warp >> 2; T < tiles; T += ENC_COMPUTE / 128) {
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + T * 32;
+    const int nu = unit_cnt[q];
+    for (int u = warp >> 2; u < nu; u += ENC_COMPUTE / 128) {
+      const uint32_t e = unit_tab[q * 12 + u];
+      const int al = e & 1, k = (e >> 1) & 7, pos = (int)(e >> 8) + lane;
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + (al * nta + k) * 32;
       float y[16], s0, s1;
       tmem_ld18(taddr, y, s0, s1);
       // two independent accumulation chains (|.| is a free source modifier)
       float f0 = s0, f1 = s1;
 #pragma unroll
       for (int c = 0; c < 16; c += 2) { f0 += fabsf(y[c]); f1 += fabsf(y[c + 1]); }
-      const int r = T * 128 + q * 32 + lane;
-      const int al = r >= S ? 1 : 0;
-      const int pos = r - al * S;
       const uint32_t off = (uint32_t)(pos >> 3) * A2_LBO + (uint32_t)al * 16 + (uint32_t)(pos & 7) * 2;
       const __nv_bfloat16 fb = __float2bfloat16_rn(f0 + f1);
       asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
@@ -178,26 +208,33 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     // ================= MMA issuer warp: conv2 MMAs of every group, decoupled from the compute warps ====
     // (it shares its scheduler with five busy compute warps, so its instruction path is kept minimal:
     //  descriptors are precomputed, the tile loop is unrolled)
-    const uint64_t adb[2] = {make_desc(smem_u32(IM), im_chunk, 128), make_desc(smem_u32(IM) + im_bytes, im_chunk, 128)};
+    // MMA 1 of a tile: chunks = rows p-1 and p (LBO 16 B); MMA 2: row p+1 and the bias chunk.  Descriptors of a
+    // tile differ from the buffer's base descriptor only by the start address (and, for MMA 2, the LBO that
+    // must keep pointing at ONES): both are 16-byte-unit fields, so they advance by plain additions.
     const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
     const uint64_t bd1 = bd0 + (uint64_t)((2 * 512) >> 4);
-    const uint64_t a_ks = (uint64_t)((2 * im_chunk) >> 4);
     const bool leader = elect_one();
+    const int r0_last = S >= 128 ? S - 128 : 0;
     for (int g = 0; g < ngroups; ++g) {
       const int buf = g & 1;
       const long long i0 = probe ? clock64() : 0;
-      mbar_wait(&bar_full[buf], (g >> 1) & 1);          // im2col operand of group g is complete
+      mbar_wait(&bar_full[buf], (g >> 1) & 1);          // conv1 output of group g is complete
       const long long i1 = probe ? clock64() : 0;
       if (leader) {
         tc_fence_after();
-        const uint64_t ad0 = adb[buf];
         const uint32_t d0 = tmem + buf * (tiles * 32);
 #pragma unroll
-        for (int T = 0; T < 5; ++T) {
-          if (T < tiles) {
-            const uint64_t ad = ad0 + (uint64_t)(T * (2048 >> 4));
-            mma_bf16_ss(d0 + T * 32, ad, bd0, idesc_conv, 0u);
-            mma_bf16_ss(d0 + T * 32, ad + a_ks, bd1, idesc_conv, 1u);
+        for (int al = 0; al < 2; ++al) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (k < nta) {
+              const int r0 = k == nta - 1 ? r0_last : 128 * k;
+              const uint32_t a1 = act_base + (uint32_t)buf * act_buf + (uint32_t)al * act_scan + (uint32_t)r0 * 16;
+              const uint32_t a2 = a1 + 32;
+              const uint32_t d = d0 + (al * nta + k) * 32;
+              mma_bf16_ss(d, make_desc(a1, 16, 128), bd0, idesc_conv, 0u);
+              mma_bf16_ss(d, make_desc(a2, ones_base - a2, 128), bd1, idesc_conv, 1u);
+            }
           }
         }
         mma_commit(&bar_conv[buf]);
@@ -250,10 +287,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     // ================= compute warps =================
     const int cpos = tid >> 1;                                    // position inside the A-scan
     const bool c_active = tid < 2 * S;                            // (2*S <= ENC_COMPUTE for every supported S)
-    const bool c_up = cpos + 1 < S, c_dn = cpos > 0;
-    const uint32_t xs_base = smem_u32(XS), im_base = smem_u32(IM);
+    const uint32_t xs_base = smem_u32(XS);
     const uint32_t c_xoff = (uint32_t)(8 + cpos) * 2;
-    const uint32_t c_doff = (uint32_t)cpos * 16 + (uint32_t)hf * 8;
+    const uint32_t c_doff = (uint32_t)(cpos + 1) * 16 + (uint32_t)hf * 8;       // row 0 of an A-scan buffer is act1[-1]
     for (int g = 0; g < ngroups; ++g) {
       const int buf = g & 1;
       const long long c0 = probe ? clock64() : 0;
@@ -263,7 +299,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       // Thread = (position cpos, channel half hf) of BOTH A-scans of the group: all offsets are constants.
       if (c_active) {
         const uint32_t xs_a = xs_base + (uint32_t)(g & (XS_SLOTS - 1)) * (uint32_t)(2 * xs_stride * 2) + c_xoff;
-        const uint32_t im_a = im_base + (uint32_t)buf * im_bytes + c_doff;
+        const uint32_t im_a = act_base + (uint32_t)buf * act_buf + c_doff;
 #pragma unroll
         for (int al = 0; al < 2; ++al) {
           const uint32_t xa = xs_a + (uint32_t)al * (uint32_t)(xs_stride * 2);
@@ -279,11 +315,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
             v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
           __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
           const uint32_t k0 = *reinterpret_cast<uint32_t*>(&p0), k1 = *reinterpret_cast<uint32_t*>(&p1);
-          // A[row, tap t] = act1[row + t - 1]  =>  act1[pos] lands in row pos + 1 - t of tap t
-          const uint32_t d = im_a + (uint32_t)al * (uint32_t)(S * 16);
-          if (c_up) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + 16), "r"(k0), "r"(k1) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + im_chunk), "r"(k0), "r"(k1) : "memory");
-          if (c_dn) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d + 2 * im_chunk - 16), "r"(k0), "r"(k1) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(im_a + (uint32_t)al * act_scan), "r"(k0), "r"(k1) : "memory");
         }
       }
       const long long c1 = probe ? clock64() : 0;
@@ -310,9 +342,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   }
   __syncthreads();
   // ---- Linear S -> 128 (+ReLU): A = A2 (resident), B streamed from L2 through a 2-stage ring
-  // W2p (16 KB) is parked in the second im2col buffer meanwhile (its MMAs are complete: epilogue waited)
+  // W2p (16 KB) is parked in the scratch region meanwhile
   for (int i = tid; i < 1024; i += ENC_THREADS)
-    reinterpret_cast<uint4*>(IM + im_bytes)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2p) + i);
+    reinterpret_cast<uint4*>(IM + 32768)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2p) + i);
   const int nkb = S / 64;
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb & 1;
@@ -338,7 +370,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   }
   mbar_wait(&bar_w[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
   tc_fence_after();
-  // ---- epilogue 1: relu(D1 + b) -> bf16 -> A3 (aliases the first im2col buffer), K-major for the next GEMM
+  // ---- epilogue 1: relu(D1 + b) -> bf16 -> A3 (scratch region), K-major for the next GEMM
   {
     unsigned char* A3 = IM;
     const int q = warp & 3;
@@ -364,7 +396,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   if (warp == 0) {
     if (elect_one()) {
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(IM), b_addr = smem_u32(IM) + im_bytes;
+      const uint32_t a_addr = smem_u32(IM), b_addr = smem_u32(IM) + 32768;
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)
         mma_bf16_ss(tmem + D2_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
@@ -457,7 +489,8 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
   p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset; p.w1 = w1; p.b1 = b1;
   p.Bc = static_cast<const __nv_bfloat16*>(Bc); p.W1p = static_cast<const __nv_bfloat16*>(W1p); p.bl1 = bl1;
   p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
-  const size_t smem = (size_t)2 * 4 * (2 * S) * 16 + (size_t)(S / 8) * A2_LBO + 2 * 16384 + 2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
+  const size_t smem = (((size_t)2 * 2 * (S + 2) * 16 + 127) & ~(size_t)127) + 2048 + SCR_BYTES + (size_t)(S / 8) * A2_LBO + 2 * 16384 +
+                      2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
   PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (A + 127) / 128;
