@@ -37,7 +37,6 @@ constexpr int ENC_COMPUTE = 640;        // 20 compute warps: 2 conv1 items per t
 constexpr int ENC_THREADS = ENC_COMPUTE + 64;   // + MMA issuer warp (20) + x loader warp (21), on different schedulers
 constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
 constexpr int D1_COL = 0, D2_COL = 128;     // alias the conv accumulators (dead by then)
-constexpr int SCR_BYTES = 49152;            // linear-stage scratch: A3 (32 KB) + W2p (16 KB)
 constexpr int XS_PAD = 16;
 constexpr int XS_SLOTS = 4;              // x staging ring: cp.async prefetch runs ~3 groups ahead of conv1
 
@@ -87,8 +86,10 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_w[2], bar_l2;
+  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_l1, bar_l2;
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t unit_tab[48];                // conv epilogue work units (al, tile, quarter, first position)
+  __shared__ int unit_cnt[4];
 
   const int S = p.S;
   const int nta = (S + 127) / 128;                 // M tiles per A-scan
@@ -97,17 +98,17 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   const uint32_t act_buf = 2 * act_scan;           // one group
   unsigned char* ACT = smem;                       // [2 buffers][2 A-scans][S + 2 rows][16 B]
   unsigned char* ONES = smem + ((2 * act_buf + 127) & ~127u);   // [128 rows][16 B] = [1, 1, 0, ..]: the bias chunk
-  unsigned char* IM = ONES + 2048;                 // linear-stage scratch (A3, W2p)
-  unsigned char* A2 = IM + SCR_BYTES;              // [S/8 chunks][128 rows][16 B]
-  unsigned char* WR = A2 + (size_t)(S / 8) * A2_LBO;   // [2][8 chunks][128 rows][16 B]
-  unsigned char* BC = WR + 2 * 16384;              // [4 chunks][32 rows][16 B]
+  unsigned char* W1S = ONES + 2048;                // shared_layer.0 / 32, resident: [S/8 chunks][128 rows][16 B]
+  unsigned char* W2S = W1S + (size_t)S * 256;      // shared_layer.2, resident: [16 chunks][64 rows][16 B]
+  unsigned char* A2 = W2S + 16384;                 // [S/8 chunks][128 rows][16 B] (+16 B skew per chunk);
+                                                   // its head is reused as A3 [16 chunks][128 rows][16 B]
+  unsigned char* BC = A2 + (size_t)(S / 8) * A2_LBO;   // [4 chunks][32 rows][16 B]
   __nv_bfloat16* XS = reinterpret_cast<__nv_bfloat16*>(BC + 2048);   // [XS_SLOTS][2][S + 16]
   const int xs_stride = S + XS_PAD;
-  __shared__ uint32_t unit_tab[48];                // conv epilogue work units (al, tile, quarter, first position)
-  __shared__ int unit_cnt[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
-  const int64_t a0 = (int64_t)blockIdx.x * 128;
+  const int64_t nblocks = (p.A + 127) / 128;       // blocks of 128 A-scans, walked with stride gridDim.x
+  constexpr int ngroups = 64;
 
   // ---- one-time setup
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -115,11 +116,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     mbar_init(&bar_conv[0], 1); mbar_init(&bar_conv[1], 1);
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
     for (int i = 0; i < XS_SLOTS; ++i) mbar_init(&bar_x[i], 32);
-    mbar_init(&bar_w[0], 1); mbar_init(&bar_w[1], 1);
+    mbar_init(&bar_l1, 1);
     mbar_init(&bar_l2, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < 128; i += ENC_THREADS) reinterpret_cast<uint4*>(BC)[i] = reinterpret_cast<const uint4*>(p.Bc)[i];
+  for (int i = tid; i < S * 16; i += ENC_THREADS) reinterpret_cast<uint4*>(W1S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W1p) + i);
+  for (int i = tid; i < 1024; i += ENC_THREADS) reinterpret_cast<uint4*>(W2S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2p) + i);
   {
     // bias chunk [1, 1, 0, 0, 0, 0, 0, 0] for every row; zero rows act1[-1] and act1[S] of every A-scan
     const uint4 ones = make_uint4(0x3F803F80u, 0u, 0u, 0u);
@@ -163,87 +166,60 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
 #pragma unroll
     for (int t = 0; t < 3; ++t) cw[c][t] = p.w1[(hf * 4 + c) * 3 + t];
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc_conv = make_idesc_bf16(128, 32);
   const uint32_t act_base = smem_u32(ACT), ones_base = smem_u32(ONES);
-
-  // x staging (loader warp): lane l owns the 16-byte parts l, l+32, l+64 of the 2*S/8 parts of a group.
-  // cp.async writes them straight into the ring slot; the slot's mbarrier (32 arrivals) completes when the
-  // copies of every lane have landed, so nobody ever waits on HBM latency.  All addressing is precomputed:
-  // per group the source advances by 2*S elements and the slot offset rotates.
   const int xparts = S / 8;
-
-  // epilogue of one conv group.  Everything about a thread's output element except the group index is a
-  // thread constant: row r = T*128 + q*32 + lane of the group -> (A-scan al, position pos) -> operand byte offset.
   const uint32_t a2_base = smem_u32(A2);
-  auto conv_epilogue = [&](int g) {
-    const int buf = g & 1;
-    mbar_wait(&bar_conv[buf], (g >> 1) & 1);
-    tc_fence_after();
-    const int q = warp & 3;
-    const int nu = unit_cnt[q];
-    for (int u = warp >> 2; u < nu; u += ENC_COMPUTE / 128) {
-      const uint32_t e = unit_tab[q * 12 + u];
-      const int al = e & 1, k = (e >> 1) & 7, pos = (int)(e >> 8) + lane;
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + (al * nta + k) * 32;
-      float y[16], s0, s1;
-      tmem_ld18(taddr, y, s0, s1);
-      // two independent accumulation chains (|.| is a free source modifier)
-      float f0 = s0, f1 = s1;
-#pragma unroll
-      for (int c = 0; c < 16; c += 2) { f0 += fabsf(y[c]); f1 += fabsf(y[c + 1]); }
-      const uint32_t off = (uint32_t)(pos >> 3) * A2_LBO + (uint32_t)al * 16 + (uint32_t)(pos & 7) * 2;
-      const __nv_bfloat16 fb = __float2bfloat16_rn(f0 + f1);
-      asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
-    }
-  };
 
-  const int ngroups = 64;
+  // Groups are numbered globally over the blocks this CTA walks: G = it * 64 + g.  Every ring / double buffer
+  // (conv1 buffers, TMEM accumulators, x slots) and every barrier parity is a function of G only, so the three
+  // roles run through block boundaries without any extra synchronisation.
   unsigned long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
   if (warp == ENC_COMPUTE / 32) {
     // ================= MMA issuer warp: conv2 MMAs of every group, decoupled from the compute warps ====
-    // (it shares its scheduler with five busy compute warps, so its instruction path is kept minimal:
-    //  descriptors are precomputed, the tile loop is unrolled)
-    // MMA 1 of a tile: chunks = rows p-1 and p (LBO 16 B); MMA 2: row p+1 and the bias chunk.  Descriptors of a
-    // tile differ from the buffer's base descriptor only by the start address (and, for MMA 2, the LBO that
-    // must keep pointing at ONES): both are 16-byte-unit fields, so they advance by plain additions.
+    // MMA 1 of a tile: chunks = rows p-1 and p (LBO 16 B); MMA 2: row p+1 and the bias chunk (LBO -> ONES).
     const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
     const uint64_t bd1 = bd0 + (uint64_t)((2 * 512) >> 4);
     const bool leader = elect_one();
     const int r0_last = S >= 128 ? S - 128 : 0;
-    for (int g = 0; g < ngroups; ++g) {
-      const int buf = g & 1;
-      const long long i0 = probe ? clock64() : 0;
-      mbar_wait(&bar_full[buf], (g >> 1) & 1);          // conv1 output of group g is complete
-      const long long i1 = probe ? clock64() : 0;
-      if (leader) {
-        tc_fence_after();
-        const uint32_t d0 = tmem + buf * (tiles * 32);
+    int G = 0;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      for (int g = 0; g < ngroups; ++g, ++G) {
+        const int buf = G & 1;
+        const long long i0 = probe ? clock64() : 0;
+        mbar_wait(&bar_full[buf], (G >> 1) & 1);          // conv1 output of group G is complete
+        const long long i1 = probe ? clock64() : 0;
+        if (leader) {
+          tc_fence_after();
+          const uint32_t d0 = tmem + buf * (tiles * 32);
 #pragma unroll
-        for (int al = 0; al < 2; ++al) {
+          for (int al = 0; al < 2; ++al) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            if (k < nta) {
-              const int r0 = k == nta - 1 ? r0_last : 128 * k;
-              const uint32_t a1 = act_base + (uint32_t)buf * act_buf + (uint32_t)al * act_scan + (uint32_t)r0 * 16;
-              const uint32_t a2 = a1 + 32;
-              const uint32_t d = d0 + (al * nta + k) * 32;
-              mma_bf16_ss(d, make_desc(a1, 16, 128), bd0, idesc_conv, 0u);
-              mma_bf16_ss(d, make_desc(a2, ones_base - a2, 128), bd1, idesc_conv, 1u);
+            for (int k = 0; k < 3; ++k) {
+              if (k < nta) {
+                const int r0 = k == nta - 1 ? r0_last : 128 * k;
+                const uint32_t a1 = act_base + (uint32_t)buf * act_buf + (uint32_t)al * act_scan + (uint32_t)r0 * 16;
+                const uint32_t a2 = a1 + 32;
+                const uint32_t d = d0 + (al * nta + k) * 32;
+                mma_bf16_ss(d, make_desc(a1, 16, 128), bd0, idesc_conv, 0u);
+                mma_bf16_ss(d, make_desc(a2, ones_base - a2, 128), bd1, idesc_conv, 1u);
+              }
             }
           }
+          mma_commit(&bar_conv[buf]);
         }
-        mma_commit(&bar_conv[buf]);
-      }
-      __syncwarp();
-      if (probe) {
-        const long long i2 = clock64();
-        tsum[0] += i1 - i0;    // waiting for the operand
-        tsum[2] += i2 - i1;    // MMA issue + commit
+        __syncwarp();
+        if (probe) {
+          const long long i2 = clock64();
+          tsum[0] += i1 - i0;    // waiting for the operand
+          tsum[2] += i2 - i1;    // MMA issue + commit
+        }
       }
     }
     if (probe) {
@@ -252,36 +228,48 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     }
   } else if (warp == ENC_COMPUTE / 32 + 1) {
     // ================= x loader warp =================
-    const __nv_bfloat16* src[3];
+    // lane l owns the 16-byte parts l, l+32, l+64 of the 2*S/8 parts of a group.  cp.async writes them straight
+    // into the ring slot; the slot's mbarrier (32 arrivals) completes when the copies of every lane have landed.
+    int al_[3], part_[3];
     uint32_t dst[3];
-    int glim[3];                                           // first group whose A-scan is out of range
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int i = lane + 32 * j;
-      const int al = i < 2 * xparts ? i / xparts : 0, part = i < 2 * xparts ? i - al * xparts : 0;
-      src[j] = static_cast<const __nv_bfloat16*>(p.x) + (a0 + al) * S + part * 8;
-      dst[j] = smem_u32(XS) + (uint32_t)(al * xs_stride + 8 + part * 8) * 2;
-      const int64_t left = p.A - (a0 + al);                // A-scans a0+al, a0+al+2, ... : valid while 2g < left
-      glim[j] = i < 2 * xparts ? (int)((left > 0 ? left + 1 : 0) / 2) : -1;   // -1: lane has no part j
+      al_[j] = i < 2 * xparts ? i / xparts : -1;
+      part_[j] = i < 2 * xparts ? i - al_[j] * xparts : 0;
+      dst[j] = smem_u32(XS) + (uint32_t)((al_[j] > 0 ? al_[j] : 0) * xs_stride + 8 + part_[j] * 8) * 2;
     }
     const uint32_t slot_bytes = (uint32_t)(2 * xs_stride * 2);
-    auto issue_x = [&](int g) {
-      const uint32_t so = (uint32_t)(g & (XS_SLOTS - 1)) * slot_bytes;
+    const __nv_bfloat16* xg = static_cast<const __nv_bfloat16*>(p.x);
+    auto issue_x = [&](int64_t blk, int g, int G) {
+      const uint32_t so = (uint32_t)(G & (XS_SLOTS - 1)) * slot_bytes;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        if (glim[j] < 0) continue;
-        if (g < glim[j]) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[j] + so), "l"(src[j] + (size_t)g * 2 * S) : "memory");
+        if (al_[j] < 0) continue;
+        const int64_t a = blk * 128 + 2 * g + al_[j];
+        if (a < p.A) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[j] + so), "l"(xg + a * S + part_[j] * 8) : "memory");
         } else {
           asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst[j] + so), "r"(0) : "memory");
         }
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_x[g & (XS_SLOTS - 1)])) : "memory");
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_x[G & (XS_SLOTS - 1)])) : "memory");
     };
-    for (int g = 0; g < XS_SLOTS; ++g) issue_x(g);
-    for (int g = 0; g + XS_SLOTS < ngroups; ++g) {
-      mbar_wait(&bar_full[g & 1], (g >> 1) & 1);          // conv1 of group g has consumed its x ring slot
-      issue_x(g + XS_SLOTS);
+    // the producer runs XS_SLOTS groups ahead of the consumer; (blk_p, g_p, G_p) is the next group to request
+    int64_t blk_p = blockIdx.x;
+    int g_p = 0, G_p = 0, G = 0;
+    auto advance = [&]() {
+      if (++g_p == ngroups) { g_p = 0; blk_p += gridDim.x; }
+      ++G_p;
+    };
+    for (int i = 0; i < XS_SLOTS && blk_p < nblocks; ++i) { issue_x(blk_p, g_p, G_p); advance(); }
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      for (int g = 0; g < ngroups; ++g, ++G) {
+        if (blk_p >= nblocks) break;
+        mbar_wait(&bar_full[G & 1], (G >> 1) & 1);        // conv1 of group G has consumed its x ring slot
+        issue_x(blk_p, g_p, G_p);
+        advance();
+      }
     }
   } else {
     // ================= compute warps =================
@@ -290,141 +278,157 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     const uint32_t xs_base = smem_u32(XS);
     const uint32_t c_xoff = (uint32_t)(8 + cpos) * 2;
     const uint32_t c_doff = (uint32_t)(cpos + 1) * 16 + (uint32_t)hf * 8;       // row 0 of an A-scan buffer is act1[-1]
-    for (int g = 0; g < ngroups; ++g) {
-      const int buf = g & 1;
-      const long long c0 = probe ? clock64() : 0;
-      mbar_wait(&bar_x[g & (XS_SLOTS - 1)], (g / XS_SLOTS) & 1);   // x of this group has landed in its ring slot
-      // ---- conv1 + ReLU -> im2col operand (3 shifted copies of the 8-channel vector of each position).
-      // The buffer is free: the MMAs of group g-2 completed before the epilogue of group g-2 ran.
-      // Thread = (position cpos, channel half hf) of BOTH A-scans of the group: all offsets are constants.
-      if (c_active) {
-        const uint32_t xs_a = xs_base + (uint32_t)(g & (XS_SLOTS - 1)) * (uint32_t)(2 * xs_stride * 2) + c_xoff;
-        const uint32_t im_a = act_base + (uint32_t)buf * act_buf + c_doff;
+    const int q = warp & 3;
+
+    // epilogue of one conv group: f[pos] = sum_c relu(y_c) / 32-scale folded into W1 -> bf16 K-major operand of L1
+    auto conv_epilogue = [&](int G, int g) {
+      const int buf = G & 1;
+      mbar_wait(&bar_conv[buf], (G >> 1) & 1);
+      tc_fence_after();
+      const int nu = unit_cnt[q];
+      for (int u = warp >> 2; u < nu; u += ENC_COMPUTE / 128) {
+        const uint32_t e = unit_tab[q * 12 + u];
+        const int al = e & 1, k = (e >> 1) & 7, pos = (int)(e >> 8) + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + (al * nta + k) * 32;
+        float y[16], s0, s1;
+        tmem_ld18(taddr, y, s0, s1);
+        // two independent accumulation chains (|.| is a free source modifier)
+        float f0 = s0, f1 = s1;
 #pragma unroll
-        for (int al = 0; al < 2; ++al) {
-          const uint32_t xa = xs_a + (uint32_t)al * (uint32_t)(xs_stride * 2);
-          uint16_t h0, h1, h2;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h0) : "r"(xa - 2));
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h1) : "r"(xa));
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h2) : "r"(xa + 2));
-          const float x0 = __uint_as_float((uint32_t)h0 << 16), x1 = __uint_as_float((uint32_t)h1 << 16),
-                      x2 = __uint_as_float((uint32_t)h2 << 16);
-          float v[4];
+        for (int c = 0; c < 16; c += 2) { f0 += fabsf(y[c]); f1 += fabsf(y[c + 1]); }
+        const uint32_t off = (uint32_t)(pos >> 3) * A2_LBO + (uint32_t)al * 16 + (uint32_t)(pos & 7) * 2;
+        const __nv_bfloat16 fb = __float2bfloat16_rn(f0 + f1);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
+      }
+    };
+
+    int G = 0, it = 0;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+      const int64_t a0 = blk * 128;
+      for (int g = 0; g < ngroups; ++g, ++G) {
+        const int buf = G & 1;
+        const long long c0 = probe ? clock64() : 0;
+        mbar_wait(&bar_x[G & (XS_SLOTS - 1)], (G / XS_SLOTS) & 1);   // x of this group has landed in its ring slot
+        // ---- conv1 + ReLU -> one 16-byte row per position.  The buffer is free: the MMAs of group G-2 completed
+        // before the epilogue of group G-2 ran.  Thread = (position cpos, channel half hf) of BOTH A-scans.
+        if (c_active) {
+          const uint32_t xs_a = xs_base + (uint32_t)(G & (XS_SLOTS - 1)) * (uint32_t)(2 * xs_stride * 2) + c_xoff;
+          const uint32_t im_a = act_base + (uint32_t)buf * act_buf + c_doff;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-          const uint32_t k0 = *reinterpret_cast<uint32_t*>(&p0), k1 = *reinterpret_cast<uint32_t*>(&p1);
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(im_a + (uint32_t)al * act_scan), "r"(k0), "r"(k1) : "memory");
+          for (int al = 0; al < 2; ++al) {
+            const uint32_t xa = xs_a + (uint32_t)al * (uint32_t)(xs_stride * 2);
+            uint16_t h0, h1, h2;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h0) : "r"(xa - 2));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h1) : "r"(xa));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h2) : "r"(xa + 2));
+            const float x0 = __uint_as_float((uint32_t)h0 << 16), x1 = __uint_as_float((uint32_t)h1 << 16),
+                        x2 = __uint_as_float((uint32_t)h2 << 16);
+            float v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+            const uint32_t k0 = *reinterpret_cast<uint32_t*>(&p0), k1 = *reinterpret_cast<uint32_t*>(&p1);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(im_a + (uint32_t)al * act_scan), "r"(k0), "r"(k1) : "memory");
+          }
+        }
+        const long long c1 = probe ? clock64() : 0;
+        fence_async_smem();
+        tc_fence_before();
+        const long long c1b = probe ? clock64() : 0;
+        named_sync(1, ENC_COMPUTE);                         // all compute warps: operand written, TMEM buffer drained
+        if (tid == 0) mbar_arrive(&bar_full[buf]);          // hand the group to the issuer warp
+        const long long c2 = probe ? clock64() : 0;
+        if (g > 0) conv_epilogue(G - 1, g - 1);
+        if (probe) {
+          const long long c4 = clock64();
+          tsum[0] += c1 - c0;    // x staging + conv1
+          tsum[1] += c1b - c1;   // proxy fence
+          tsum[2] += c2 - c1b;   // compute-warp barrier
+          tsum[4] += c4 - c2;    // barrier release + epilogue of the previous group (incl. mbarrier wait)
         }
       }
-      const long long c1 = probe ? clock64() : 0;
+      conv_epilogue(G - 1, ngroups - 1);
+      const long long l0 = probe ? clock64() : 0;
+      // ---- Linear S -> 128 (+ReLU): A = A2, B = W1S, both resident; accumulator D1 reuses the conv columns
       fence_async_smem();
       tc_fence_before();
-      const long long c1b = probe ? clock64() : 0;
-      named_sync(1, ENC_COMPUTE);                         // all compute warps: operand written, TMEM buffer drained
-      if (tid == 0) mbar_arrive(&bar_full[buf]);          // hand the group to the issuer warp
-      const long long c2 = probe ? clock64() : 0;
-      if (g > 0) conv_epilogue(g - 1);
-      if (probe) {
-        const long long c4 = clock64();
-        tsum[0] += c1 - c0;    // x staging + conv1
-        tsum[1] += c1b - c1;   // proxy fence
-        tsum[2] += c2 - c1b;   // compute-warp barrier
-        tsum[4] += c4 - c2;    // barrier release + epilogue of the previous group (incl. mbarrier wait)
+      named_sync(1, ENC_COMPUTE);
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(A2), b_addr = smem_u32(W1S);
+          for (int ks = 0; ks < S / 16; ++ks)
+            mma_bf16_ss(tmem + D1_COL, make_desc(a_addr + ks * 2 * A2_LBO, A2_LBO, 128),
+                        make_desc(b_addr + ks * 2 * 2048, 2048, 128), make_idesc_bf16(128, H0), ks ? 1u : 0u);
+          mma_commit(&bar_l1);
+        }
+        __syncwarp();
       }
+      mbar_wait(&bar_l1, it & 1);
+      tc_fence_after();
+      // ---- epilogue 1: relu(D1 + b) -> bf16 -> A3 (head of A2: its MMAs are complete), K-major for the next GEMM
+      {
+        unsigned char* A3 = A2;
+        const int r = q * 32 + lane;
+        for (int n = (warp >> 2) * 16; n < H0; n += (ENC_COMPUTE / 128) * 16) {
+          float v[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D1_COL + n, v);
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(v[2 * j] + __ldg(p.bl1 + n + 2 * j), 0.f),
+                                                      fmaxf(v[2 * j + 1] + __ldg(p.bl1 + n + 2 * j + 1), 0.f));
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          *reinterpret_cast<uint4*>(A3 + (size_t)(n >> 3) * 2048 + r * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(A3 + (size_t)((n >> 3) + 1) * 2048 + r * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      named_sync(1, ENC_COMPUTE);
+      // ---- Linear 128 -> 64
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(A2), b_addr = smem_u32(W2S);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16_ss(tmem + D2_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
+                        make_desc(b_addr + ks * 2 * 1024, 1024, 128), make_idesc_bf16(128, H1), ks ? 1u : 0u);
+          mma_commit(&bar_l2);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&bar_l2, it & 1);
+      tc_fence_after();
+      // ---- epilogue 2: relu(D2 + b) + position table -> h (fp32)
+      {
+        const int64_t a = a0 + q * 32 + lane;
+        for (int n = (warp >> 2) * 16; n < H1; n += (ENC_COMPUTE / 128) * 16) {
+          float v[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D2_COL + n, v);
+          if (a < p.A) {
+            const float* pr = p.pos + (a % p.Nset) * H1 + n;
+            float4* dst = reinterpret_cast<float4*>(p.h + a * H1 + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bl2 + n) + j);
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(pr) + j);
+              dst[j] = make_float4(fmaxf(v[4 * j] + b4.x, 0.f) + t4.x, fmaxf(v[4 * j + 1] + b4.y, 0.f) + t4.y,
+                                   fmaxf(v[4 * j + 2] + b4.z, 0.f) + t4.z, fmaxf(v[4 * j + 3] + b4.w, 0.f) + t4.w);
+            }
+          }
+        }
+      }
+      // the next block's conv epilogues rewrite A2 and its MMAs rewrite the TMEM columns of D1 / D2: both are
+      // ordered behind this point by the group hand-off (proxy fence + tcgen05 fence + named barrier + arrive)
+      if (probe) tsum[5] += clock64() - l0;
     }
     if (probe) {
 #pragma unroll
-      for (int i = 0; i < 5; ++i) p.dbg[warp * 8 + i] = tsum[i];
-    }
-    conv_epilogue(ngroups - 1);
-  }
-  __syncthreads();
-  // ---- Linear S -> 128 (+ReLU): A = A2 (resident), B streamed from L2 through a 2-stage ring
-  // W2p (16 KB) is parked in the scratch region meanwhile
-  for (int i = tid; i < 1024; i += ENC_THREADS)
-    reinterpret_cast<uint4*>(IM + 32768)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2p) + i);
-  const int nkb = S / 64;
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    if (kb >= 2) mbar_wait(&bar_w[s], ((kb >> 1) - 1) & 1);
-    const uint4* src = reinterpret_cast<const uint4*>(p.W1p) + (size_t)kb * 1024;
-    uint4* dst = reinterpret_cast<uint4*>(WR + s * 16384);
-    for (int i = tid; i < 1024; i += ENC_THREADS) dst[i] = __ldg(src + i);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(A2) + kb * 8 * A2_LBO, b_addr = smem_u32(WR) + s * 16384;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_bf16_ss(tmem + D1_COL, make_desc(a_addr + ks * 2 * A2_LBO, A2_LBO, 128),
-                      make_desc(b_addr + ks * 2 * 2048, 2048, 128), make_idesc_bf16(128, H0), (kb | ks) ? 1u : 0u);
-        mma_commit(&bar_w[s]);
-      }
-      __syncwarp();
-    }
-  }
-  mbar_wait(&bar_w[(nkb - 1) & 1], ((nkb - 1) >> 1) & 1);
-  tc_fence_after();
-  // ---- epilogue 1: relu(D1 + b) -> bf16 -> A3 (scratch region), K-major for the next GEMM
-  {
-    unsigned char* A3 = IM;
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    for (int n = (warp >> 2) * 16; n < H0 && warp < ENC_COMPUTE / 32; n += (ENC_COMPUTE / 128) * 16) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D1_COL + n, v);
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(v[2 * j] + __ldg(p.bl1 + n + 2 * j), 0.f),
-                                                  fmaxf(v[2 * j + 1] + __ldg(p.bl1 + n + 2 * j + 1), 0.f));
-        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-      }
-      *reinterpret_cast<uint4*>(A3 + (size_t)(n >> 3) * 2048 + r * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(A3 + (size_t)((n >> 3) + 1) * 2048 + r * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    }
-  }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  // ---- Linear 128 -> 64
-  if (warp == 0) {
-    if (elect_one()) {
-      tc_fence_after();
-      const uint32_t a_addr = smem_u32(IM), b_addr = smem_u32(IM) + 32768;
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks)
-        mma_bf16_ss(tmem + D2_COL, make_desc(a_addr + ks * 2 * 2048, 2048, 128),
-                    make_desc(b_addr + ks * 2 * 1024, 1024, 128), make_idesc_bf16(128, H1), ks ? 1u : 0u);
-      mma_commit(&bar_l2);
-    }
-    __syncwarp();
-  }
-  mbar_wait(&bar_l2, 0);
-  tc_fence_after();
-  // ---- epilogue 2: relu(D2 + b) + position table -> h (fp32)
-  {
-    const int q = warp & 3;
-    const int64_t a = a0 + q * 32 + lane;
-    for (int n = (warp >> 2) * 16; n < H1 && warp < ENC_COMPUTE / 32; n += (ENC_COMPUTE / 128) * 16) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + D2_COL + n, v);
-      if (a < p.A) {
-        const float* pr = p.pos + (a % p.Nset) * H1 + n;
-        float4* dst = reinterpret_cast<float4*>(p.h + a * H1 + n);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bl2 + n) + j);
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(pr) + j);
-          dst[j] = make_float4(fmaxf(v[4 * j] + b4.x, 0.f) + t4.x, fmaxf(v[4 * j + 1] + b4.y, 0.f) + t4.y,
-                               fmaxf(v[4 * j + 2] + b4.z, 0.f) + t4.z, fmaxf(v[4 * j + 3] + b4.w, 0.f) + t4.w);
-        }
-      }
+      for (int i = 0; i < 6; ++i) p.dbg[warp * 8 + i] = tsum[i];
     }
   }
   tc_fence_before();
@@ -489,12 +493,13 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
   p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset; p.w1 = w1; p.b1 = b1;
   p.Bc = static_cast<const __nv_bfloat16*>(Bc); p.W1p = static_cast<const __nv_bfloat16*>(W1p); p.bl1 = bl1;
   p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
-  const size_t smem = (((size_t)2 * 2 * (S + 2) * 16 + 127) & ~(size_t)127) + 2048 + SCR_BYTES + (size_t)(S / 8) * A2_LBO + 2 * 16384 +
-                      2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
+  const size_t smem = (((size_t)2 * 2 * (S + 2) * 16 + 127) & ~(size_t)127) + 2048 + (size_t)S * 256 + 16384 +
+                      (size_t)(S / 8) * A2_LBO + 2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
   PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t grid = (A + 127) / 128;
-  PAUT_CHECK(grid < (int64_t(1) << 31), PAUT_ERR_INVALID, "msc encoder: too many A-scans");
+  const int64_t nblocks = (A + 127) / 128;
+  PAUT_CHECK(nblocks < (int64_t(1) << 24), PAUT_ERR_INVALID, "msc encoder: too many A-scans in one launch");
+  const int64_t grid = nblocks < c.num_sms ? nblocks : c.num_sms;      // persistent: one CTA per SM
   static const bool debug = std::getenv("PAUT_ENC_DEBUG") != nullptr;
   p.dbg = nullptr;
   if (debug) PAUT_CUDA(cudaMalloc(&p.dbg, sizeof(unsigned long long) * 8 * (ENC_THREADS / 32)));
@@ -504,10 +509,11 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
     std::vector<unsigned long long> hbuf(8 * (ENC_THREADS / 32));
     PAUT_CUDA(cudaMemcpy(hbuf.data(), p.dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
-    fprintf(stderr, "[enc probe] per-group cycles (CTA 0): warp  conv1  fence  barrier  mma_issue  epilogue\n");
+    fprintf(stderr, "[enc probe] per-group cycles (CTA 0): warp  conv1  fence  barrier  mma_issue  epilogue | linear stage per block\n");
+    const unsigned long long nb0 = (unsigned long long)((nblocks + grid - 1) / grid), ng = 64 * nb0;   // CTA 0's share
     for (int w = 0; w <= ENC_COMPUTE / 32; w += (w < 18 ? 6 : 1))
-      fprintf(stderr, "[enc probe] %4d %6llu %6llu %8llu %9llu %9llu\n", w, hbuf[w * 8] / 64, hbuf[w * 8 + 1] / 64,
-              hbuf[w * 8 + 2] / 64, hbuf[w * 8 + 3] / 64, hbuf[w * 8 + 4] / 64);
+      fprintf(stderr, "[enc probe] %4d %6llu %6llu %8llu %9llu %9llu | %llu\n", w, hbuf[w * 8] / ng, hbuf[w * 8 + 1] / ng,
+              hbuf[w * 8 + 2] / ng, hbuf[w * 8 + 3] / ng, hbuf[w * 8 + 4] / ng, hbuf[w * 8 + 5] / nb0);
   }
 }
 
