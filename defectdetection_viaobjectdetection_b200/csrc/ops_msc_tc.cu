@@ -3,25 +3,28 @@
 //        -> Linear 128->64 + ReLU -> + position table            (NN_models.py:111-121, :11-14)
 // One CTA = 128 A-scans; nothing but x and the 64-wide result touches HBM.
 //
-//  conv1 (C_in = 1, 24 MACs/position) runs on the CUDA cores and writes its 8-channel bf16 vector ONCE, as one
-//  16-byte row per position (rows -1 and S of every A-scan are zero).  conv2 needs no im2col copy: a K=16
-//  tcgen05.mma takes its two 8-channel K chunks from the SAME buffer through an overlapping descriptor
-//  (chunk stride LBO = 16 B, i.e. the next position): MMA 1 = taps 0,1 (rows p-1, p), MMA 2 = tap 2 (row p+1)
-//  plus a constant chunk [1,1,0..] that carries the bias as a bf16 hi+lo pair (its LBO points at a constant
-//  region).  An A-scan of S = 320 positions is covered by the M tiles at rows 0, 128 and 192.
+//  conv1 (C_in = 1, 24 MACs/position) runs on the CUDA cores in packed fp16 (HFMA2), one thread per position;
+//  a thread gets the 8-channel vectors of its two neighbours by warp shuffle and writes its im2col row
+//  [tap0 | tap1 | tap2 | 1,1,0..] (32 fp16 = 16 words; the constant chunk carries the bias as an fp16 hi+lo
+//  pair) straight into TENSOR MEMORY with tcgen05.st.  conv2 is then two TS-form tcgen05.mma per 128
+//  positions (A operand in TMEM, B = packed weights in shared memory): 16 cycles each instead of the ~60 an
+//  SS-form MMA spends fetching a 4 KB A tile from shared memory, and no im2col bytes ever touch shared memory.
 //  Its 32 output columns are the 16 channels (bias included) plus hi/lo halves of their sum, which turns
 //  ReLU + channel-mean into   sum_c relu(y_c) = (sum_c y_c + sum_c |y_c|) / 2   -- 18 FADDs per position in
 //  the epilogue instead of bias + max + add per channel.  The factor 1/32 is folded into the S->128 weights.
 //  The epilogue writes f (bf16) directly in the canonical K-major operand layout of the next GEMM, so the
 //  two Linear layers are tcgen05.mma on operands that never left shared memory; their accumulators live
-//  in TMEM, reusing the columns of the double-buffered conv accumulators (2 x 192) once the conv stage is over.
+//  in TMEM, reusing the columns of the double-buffered conv stage once it is over.
 //
-//  Pipeline per group of 2 A-scans (= 6 M tiles): conv1(g) on all warps -> the issuer warp issues the 12 MMAs
+//  Pipeline per group of 2 A-scans (= S/64 M tiles): conv1(g) on all warps -> the issuer warp issues the MMAs
 //  of group g and commits them to an mbarrier -> all warps run the epilogue of group g-1 while those MMAs
-//  execute (conv1 buffers and TMEM accumulators are double-buffered).
+//  execute (TMEM operand rows and accumulators are double-buffered).  The CTA is persistent over blocks of 128
+//  A-scans; the weights of both Linear layers stay resident in shared memory.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -47,7 +50,7 @@ struct MscEncArgs {
   int S, Nset;
   const float* w1;                 // conv1d.0.weight [8][3]
   const float* b1;                 // conv1d.0.bias   [8]
-  const __nv_bfloat16* Bc;         // conv2 operand [4 chunks][32 rows][8]
+  const __nv_bfloat16* Bc;         // conv2 operand [4 chunks][32 rows][8], fp16 bit patterns
   const __nv_bfloat16* W1p;        // shared_layer.0 / 32, packed [S/8][128][8]
   const float* bl1;
   const __nv_bfloat16* W2p;        // shared_layer.2 packed [16][64][8]
@@ -88,17 +91,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_l1, bar_l2;
   __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t unit_tab[48];                // conv epilogue work units (al, tile, quarter, first position)
-  __shared__ int unit_cnt[4];
 
   const int S = p.S;
-  const int nta = (S + 127) / 128;                 // M tiles per A-scan
-  const int tiles = 2 * nta;                       // per group (2 A-scans)
-  const uint32_t act_scan = (uint32_t)(S + 2) * 16;   // one A-scan of conv1 output: zero row, S rows, zero row
-  const uint32_t act_buf = 2 * act_scan;           // one group
-  unsigned char* ACT = smem;                       // [2 buffers][2 A-scans][S + 2 rows][16 B]
-  unsigned char* ONES = smem + ((2 * act_buf + 127) & ~127u);   // [128 rows][16 B] = [1, 1, 0, ..]: the bias chunk
-  unsigned char* W1S = ONES + 2048;                // shared_layer.0 / 32, resident: [S/8 chunks][128 rows][16 B]
+  const int tiles = S / 64;                        // M tiles per group of 2 A-scans (S % 64 == 0)
+  const int tbuf = tiles * 48;                     // TMEM columns of one group: 16 (A operand) + 32 (accumulator) per tile
+  unsigned char* W1S = smem;                       // shared_layer.0 / 32, resident: [S/8 chunks][128 rows][16 B]
   unsigned char* W2S = W1S + (size_t)S * 256;      // shared_layer.2, resident: [16 chunks][64 rows][16 B]
   unsigned char* A2 = W2S + 16384;                 // [S/8 chunks][128 rows][16 B] (+16 B skew per chunk);
                                                    // its head is reused as A3 [16 chunks][128 rows][16 B]
@@ -123,56 +120,21 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   for (int i = tid; i < 128; i += ENC_THREADS) reinterpret_cast<uint4*>(BC)[i] = reinterpret_cast<const uint4*>(p.Bc)[i];
   for (int i = tid; i < S * 16; i += ENC_THREADS) reinterpret_cast<uint4*>(W1S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W1p) + i);
   for (int i = tid; i < 1024; i += ENC_THREADS) reinterpret_cast<uint4*>(W2S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2p) + i);
-  {
-    // bias chunk [1, 1, 0, 0, 0, 0, 0, 0] for every row; zero rows act1[-1] and act1[S] of every A-scan
-    const uint4 ones = make_uint4(0x3F803F80u, 0u, 0u, 0u);
-    for (int r = tid; r < 128; r += ENC_THREADS) reinterpret_cast<uint4*>(ONES)[r] = ones;
-    if (tid < 8) {
-      const int b = tid >> 2, al = (tid >> 1) & 1, edge = tid & 1;
-      *reinterpret_cast<uint4*>(ACT + b * act_buf + al * act_scan + (edge ? (S + 1) * 16 : 0)) = make_uint4(0, 0, 0, 0);
-    }
-    for (int i = tid; i < XS_SLOTS * 2 * xs_stride; i += ENC_THREADS) XS[i] = __float2bfloat16_rn(0.f);
-    // conv epilogue units: (A-scan al, tile k, lane quarter q) whose 32 positions are owned by that tile; the
-    // positions covered by both of the last two tiles alternate between them (and with al) so that every lane
-    // quarter gets the same number of units.  Bucketed by q: a warp can only read its own TMEM lane quarter.
-    if (tid == 0) {
-      const int r0_last = S >= 128 ? S - 128 : 0, dup_hi = 128 * (nta - 1);
-      int cnt[4] = {0, 0, 0, 0};
-      for (int al = 0; al < 2; ++al)
-        for (int k = 0; k < nta; ++k) {
-          const int r0 = k == nta - 1 ? r0_last : 128 * k;
-          for (int q = 0; q < 4; ++q) {
-            const int pos0 = r0 + 32 * q;
-            if (pos0 >= S) continue;
-            bool own = true;
-            if (nta >= 2 && pos0 >= r0_last && pos0 < dup_hi) {       // covered by tiles nta-2 and nta-1
-              const int owner = ((((pos0 - r0_last) >> 5) + al) & 1) ? nta - 1 : nta - 2;
-              own = owner == k;
-            } else if (k == nta - 1 && pos0 < dup_hi) {
-              own = false;
-            }
-            if (own) unit_tab[q * 12 + cnt[q]++] = (uint32_t)al | ((uint32_t)k << 1) | ((uint32_t)pos0 << 8);
-          }
-        }
-      for (int q = 0; q < 4; ++q) unit_cnt[q] = cnt[q];
-    }
-  }
-  // per-thread conv1 weights: this thread always computes channels 4*hf .. 4*hf+3
-  const int hf = tid & 1;
-  float cw[4][3], cb[4];
+  for (int i = tid; i < XS_SLOTS * 2 * xs_stride; i += ENC_THREADS) XS[i] = __float2bfloat16_rn(0.f);
+  // per-thread conv1 weights as fp16 pairs: channels (2j, 2j+1), taps 0..2
+  __half2 cw[4][3], cb[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    cb[c] = p.b1[hf * 4 + c];
+  for (int j = 0; j < 4; ++j) {
+    cb[j] = __floats2half2_rn(p.b1[2 * j], p.b1[2 * j + 1]);
 #pragma unroll
-    for (int t = 0; t < 3; ++t) cw[c][t] = p.w1[(hf * 4 + c) * 3 + t];
+    for (int t = 0; t < 3; ++t) cw[j][t] = __floats2half2_rn(p.w1[(2 * j) * 3 + t], p.w1[(2 * j + 1) * 3 + t]);
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t idesc_conv = make_idesc_bf16(128, 32);
-  const uint32_t act_base = smem_u32(ACT), ones_base = smem_u32(ONES);
+  const uint32_t idesc_conv = make_idesc_f16(128, 32);
   const int xparts = S / 8;
   const uint32_t a2_base = smem_u32(A2);
 
@@ -183,33 +145,26 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
   if (warp == ENC_COMPUTE / 32) {
     // ================= MMA issuer warp: conv2 MMAs of every group, decoupled from the compute warps ====
-    // MMA 1 of a tile: chunks = rows p-1 and p (LBO 16 B); MMA 2: row p+1 and the bias chunk (LBO -> ONES).
+    // two TS-form MMAs per tile: K chunks (tap 0, tap 1) = TMEM columns 0..7 of the tile's operand rows, then
+    // (tap 2, bias chunk) = columns 8..15
     const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
     const uint64_t bd1 = bd0 + (uint64_t)((2 * 512) >> 4);
     const bool leader = elect_one();
-    const int r0_last = S >= 128 ? S - 128 : 0;
     int G = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
       for (int g = 0; g < ngroups; ++g, ++G) {
         const int buf = G & 1;
         const long long i0 = probe ? clock64() : 0;
-        mbar_wait(&bar_full[buf], (G >> 1) & 1);          // conv1 output of group G is complete
+        mbar_wait(&bar_full[buf], (G >> 1) & 1);          // operand rows of group G are in tensor memory
         const long long i1 = probe ? clock64() : 0;
         if (leader) {
           tc_fence_after();
-          const uint32_t d0 = tmem + buf * (tiles * 32);
+          const uint32_t a0t = tmem + buf * tbuf, d0 = a0t + tiles * 16;
 #pragma unroll
-          for (int al = 0; al < 2; ++al) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              if (k < nta) {
-                const int r0 = k == nta - 1 ? r0_last : 128 * k;
-                const uint32_t a1 = act_base + (uint32_t)buf * act_buf + (uint32_t)al * act_scan + (uint32_t)r0 * 16;
-                const uint32_t a2 = a1 + 32;
-                const uint32_t d = d0 + (al * nta + k) * 32;
-                mma_bf16_ss(d, make_desc(a1, 16, 128), bd0, idesc_conv, 0u);
-                mma_bf16_ss(d, make_desc(a2, ones_base - a2, 128), bd1, idesc_conv, 1u);
-              }
+          for (int T = 0; T < 5; ++T) {
+            if (T < tiles) {
+              mma_f16_ts(d0 + T * 32, a0t + T * 16, bd0, idesc_conv, 0u);
+              mma_f16_ts(d0 + T * 32, a0t + T * 16 + 8, bd1, idesc_conv, 1u);
             }
           }
           mma_commit(&bar_conv[buf]);
@@ -273,32 +228,47 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     }
   } else {
     // ================= compute warps =================
-    const int cpos = tid >> 1;                                    // position inside the A-scan
+    // thread = one position of the group: P = tid -> A-scan al = P / S, position pos = P % S; warp w holds the
+    // rows of M tile w / 4, lane quarter w % 4 -- exactly the TMEM lanes a warp may access
     const bool c_active = tid < 2 * S;                            // (2*S <= ENC_COMPUTE for every supported S)
+    const int c_al = tid >= S ? 1 : 0, c_pos = tid - c_al * S;
     const uint32_t xs_base = smem_u32(XS);
-    const uint32_t c_xoff = (uint32_t)(8 + cpos) * 2;
-    const uint32_t c_doff = (uint32_t)(cpos + 1) * 16 + (uint32_t)hf * 8;       // row 0 of an A-scan buffer is act1[-1]
-    const int q = warp & 3;
+    const uint32_t c_xoff = (uint32_t)(c_al * xs_stride + 8 + c_pos) * 2;
+    const int q = warp & 3, T = warp >> 2;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    // this lane's output element of the conv epilogue (row q*32 + lane of tile T)
+    const uint32_t e_off = (uint32_t)(c_pos >> 3) * A2_LBO + (uint32_t)c_al * 16 + (uint32_t)(c_pos & 7) * 2;
 
-    // epilogue of one conv group: f[pos] = sum_c relu(y_c) / 32-scale folded into W1 -> bf16 K-major operand of L1
+    // conv1 + ReLU at the sample x1 with neighbours x0, x2: 8 channels as 4 fp16 pairs
+    auto conv1 = [&](float x0, float x1, float x2, uint32_t (&o)[4]) {
+      const __half2 h0 = __float2half2_rn(x0), h1 = __float2half2_rn(x1), h2 = __float2half2_rn(x2);
+      const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 v = __hmax2(__hfma2(cw[j][2], h2, __hfma2(cw[j][1], h1, __hfma2(cw[j][0], h0, cb[j]))), zero);
+        o[j] = *reinterpret_cast<const uint32_t*>(&v);
+      }
+    };
+    auto ldx = [&](uint32_t addr) {
+      uint16_t h;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+      return __uint_as_float((uint32_t)h << 16);
+    };
+
+    // epilogue of one conv group: f[pos] = sum_c relu(y_c) (the 1/32 lives in W1) -> bf16 K-major operand of L1
     auto conv_epilogue = [&](int G, int g) {
       const int buf = G & 1;
       mbar_wait(&bar_conv[buf], (G >> 1) & 1);
       tc_fence_after();
-      const int nu = unit_cnt[q];
-      for (int u = warp >> 2; u < nu; u += ENC_COMPUTE / 128) {
-        const uint32_t e = unit_tab[q * 12 + u];
-        const int al = e & 1, k = (e >> 1) & 7, pos = (int)(e >> 8) + lane;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (tiles * 32) + (al * nta + k) * 32;
+      if (c_active) {
         float y[16], s0, s1;
-        tmem_ld18(taddr, y, s0, s1);
+        tmem_ld18(tmem + t_lane + buf * tbuf + tiles * 16 + T * 32, y, s0, s1);
         // two independent accumulation chains (|.| is a free source modifier)
         float f0 = s0, f1 = s1;
 #pragma unroll
         for (int c = 0; c < 16; c += 2) { f0 += fabsf(y[c]); f1 += fabsf(y[c + 1]); }
-        const uint32_t off = (uint32_t)(pos >> 3) * A2_LBO + (uint32_t)al * 16 + (uint32_t)(pos & 7) * 2;
         const __nv_bfloat16 fb = __float2bfloat16_rn(f0 + f1);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + e_off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
       }
     };
 
@@ -309,34 +279,39 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
         const int buf = G & 1;
         const long long c0 = probe ? clock64() : 0;
         mbar_wait(&bar_x[G & (XS_SLOTS - 1)], (G / XS_SLOTS) & 1);   // x of this group has landed in its ring slot
-        // ---- conv1 + ReLU -> one 16-byte row per position.  The buffer is free: the MMAs of group G-2 completed
-        // before the epilogue of group G-2 ran.  Thread = (position cpos, channel half hf) of BOTH A-scans.
+        // ---- conv1 + ReLU -> im2col row in tensor memory.  The operand columns are free: the MMAs of group G-2
+        // completed before the epilogue of group G-2 ran.
         if (c_active) {
-          const uint32_t xs_a = xs_base + (uint32_t)(G & (XS_SLOTS - 1)) * (uint32_t)(2 * xs_stride * 2) + c_xoff;
-          const uint32_t im_a = act_base + (uint32_t)buf * act_buf + c_doff;
+          const uint32_t xa = xs_base + (uint32_t)(G & (XS_SLOTS - 1)) * (uint32_t)(2 * xs_stride * 2) + c_xoff;
+          const float xm = ldx(xa - 2), x0 = ldx(xa), xp = ldx(xa + 2);
+          uint32_t mid[4], lft[4], rgt[4];
+          conv1(xm, x0, xp, mid);
 #pragma unroll
-          for (int al = 0; al < 2; ++al) {
-            const uint32_t xa = xs_a + (uint32_t)al * (uint32_t)(xs_stride * 2);
-            uint16_t h0, h1, h2;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h0) : "r"(xa - 2));
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h1) : "r"(xa));
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h2) : "r"(xa + 2));
-            const float x0 = __uint_as_float((uint32_t)h0 << 16), x1 = __uint_as_float((uint32_t)h1 << 16),
-                        x2 = __uint_as_float((uint32_t)h2 << 16);
-            float v[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              v[c] = fmaxf(fmaf(cw[c][2], x2, fmaf(cw[c][1], x1, fmaf(cw[c][0], x0, cb[c]))), 0.f);
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-            const uint32_t k0 = *reinterpret_cast<uint32_t*>(&p0), k1 = *reinterpret_cast<uint32_t*>(&p1);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(im_a + (uint32_t)al * act_scan), "r"(k0), "r"(k1) : "memory");
+          for (int j = 0; j < 4; ++j) {
+            lft[j] = __shfl_up_sync(0xffffffffu, mid[j], 1);
+            rgt[j] = __shfl_down_sync(0xffffffffu, mid[j], 1);
           }
+          // warp edges: the neighbour lives in another warp (or beyond the A-scan: conv2 pads with zeros)
+          if (lane == 0) {
+            if (c_pos > 0) conv1(ldx(xa - 4), xm, x0, lft);
+            else { lft[0] = lft[1] = lft[2] = lft[3] = 0u; }
+          }
+          if (lane == 31) {
+            if (c_pos + 1 < S) conv1(x0, xp, ldx(xa + 4), rgt);
+            else { rgt[0] = rgt[1] = rgt[2] = rgt[3] = 0u; }
+          }
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+              ::"r"(tmem + t_lane + buf * tbuf + T * 16), "r"(lft[0]), "r"(lft[1]), "r"(lft[2]), "r"(lft[3]), "r"(mid[0]),
+              "r"(mid[1]), "r"(mid[2]), "r"(mid[3]), "r"(rgt[0]), "r"(rgt[1]), "r"(rgt[2]), "r"(rgt[3]), "r"(0x3C003C00u), "r"(0u),
+              "r"(0u), "r"(0u)
+              : "memory");
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         const long long c1 = probe ? clock64() : 0;
-        fence_async_smem();
         tc_fence_before();
         const long long c1b = probe ? clock64() : 0;
-        named_sync(1, ENC_COMPUTE);                         // all compute warps: operand written, TMEM buffer drained
+        named_sync(1, ENC_COMPUTE);                         // all compute warps: operand rows stored, accumulators drained
         if (tid == 0) mbar_arrive(&bar_full[buf]);          // hand the group to the issuer warp
         const long long c2 = probe ? clock64() : 0;
         if (g > 0) conv_epilogue(G - 1, g - 1);
@@ -453,34 +428,38 @@ float bf2f(uint16_t h) {
 
 bool msc_encoder_tc_supported(int S, int h0, int h1) { return h0 == H0 && h1 == H1 && S % 64 == 0 && S >= 64 && S <= 320; }
 
-// conv2 operand [4 chunks][32 rows][8]: rows 0..15 = channels (taps 0..2 in chunks 0..2, bias hi/lo in chunk 3),
-// row 16 / 17 = hi / lo halves of the column sums (so that y16 + y17 = sum_c y_c), rows 18..31 = 0.
+// conv2 operand [4 chunks][32 rows][8] as fp16: rows 0..15 = channels (taps 0..2 in chunks 0..2, bias hi/lo in
+// chunk 3), row 16 / 17 = hi / lo halves of the column sums (so that y16 + y17 = sum_c y_c), rows 18..31 = 0.
+// The weights are first rounded to bf16 (the precision contract of the bf16 mode); every such value with an
+// exponent >= -14 is exactly representable in fp16, whose 11-bit significand also makes the hi/lo pairs tighter.
 void msc_pack_conv2(const float* w2 /*[16][8][3]*/, const float* b2 /*[16]*/, std::vector<uint16_t>& out) {
   out.assign(4 * 32 * 8, 0);
+  auto f2h = [](float f) -> uint16_t { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; };
+  auto h2f = [](uint16_t u) -> float { __half h; memcpy(&h, &u, 2); return __half2float(h); };
   auto at = [&](int chunk, int row, int e) -> uint16_t& { return out[((size_t)chunk * 32 + row) * 8 + e]; };
   float wsum[3][8] = {}, bsum = 0.f;
   for (int n = 0; n < 16; ++n) {
     for (int t = 0; t < 3; ++t)
       for (int ci = 0; ci < 8; ++ci) {
-        const uint16_t h = f2bf(w2[(n * 8 + ci) * 3 + t]);
+        const uint16_t h = f2h(bf2f(f2bf(w2[(n * 8 + ci) * 3 + t])));
         at(t, n, ci) = h;
-        wsum[t][ci] += bf2f(h);
+        wsum[t][ci] += h2f(h);
       }
-    const uint16_t hi = f2bf(b2[n]);
-    const uint16_t lo = f2bf(b2[n] - bf2f(hi));
+    const uint16_t hi = f2h(b2[n]);
+    const uint16_t lo = f2h(b2[n] - h2f(hi));
     at(3, n, 0) = hi;
     at(3, n, 1) = lo;
-    bsum += bf2f(hi) + bf2f(lo);
+    bsum += h2f(hi) + h2f(lo);
   }
   for (int t = 0; t < 3; ++t)
     for (int ci = 0; ci < 8; ++ci) {
-      const uint16_t hi = f2bf(wsum[t][ci]);
+      const uint16_t hi = f2h(wsum[t][ci]);
       at(t, 16, ci) = hi;
-      at(t, 17, ci) = f2bf(wsum[t][ci] - bf2f(hi));
+      at(t, 17, ci) = f2h(wsum[t][ci] - h2f(hi));
     }
-  const uint16_t bhi = f2bf(bsum);
+  const uint16_t bhi = f2h(bsum);
   at(3, 16, 0) = bhi;
-  at(3, 16, 1) = f2bf(bsum - bf2f(bhi));
+  at(3, 16, 1) = f2h(bsum - h2f(bhi));
 }
 
 void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1, const float* b1,
@@ -493,8 +472,7 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
   p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset; p.w1 = w1; p.b1 = b1;
   p.Bc = static_cast<const __nv_bfloat16*>(Bc); p.W1p = static_cast<const __nv_bfloat16*>(W1p); p.bl1 = bl1;
   p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
-  const size_t smem = (((size_t)2 * 2 * (S + 2) * 16 + 127) & ~(size_t)127) + 2048 + (size_t)S * 256 + 16384 +
-                      (size_t)(S / 8) * A2_LBO + 2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
+  const size_t smem = (size_t)S * 256 + 16384 + (size_t)(S / 8) * A2_LBO + 2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
   PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t nblocks = (A + 127) / 128;
