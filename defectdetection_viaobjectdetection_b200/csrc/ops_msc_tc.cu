@@ -60,10 +60,10 @@ struct MscEncArgs {
   unsigned long long* dbg;         // optional cycle probe (PAUT_ENC_DEBUG=1): [warps][8] sums for CTA 0
 };
 
-// 18 accumulator columns of one row (16 channels + hi/lo of their sum) with a single wait; the wait names the
-// destination registers so that no use can be scheduled ahead of it
-__device__ __forceinline__ void tmem_ld18(uint32_t taddr, float (&y)[16], float& s0, float& s1) {
-  uint32_t r[18];
+// 18 accumulator columns of one row (16 channels + hi/lo of their sum): the two loads are issued first and
+// waited for later (tmem_wait18 names the destination registers so that no use can be scheduled ahead of it),
+// which lets the TMEM round trip overlap other work
+__device__ __forceinline__ void tmem_issue18(uint32_t taddr, uint32_t (&r)[18]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -71,16 +71,14 @@ __device__ __forceinline__ void tmem_ld18(uint32_t taddr, float (&y)[16], float&
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r[16]), "=r"(r[17]) : "r"(taddr + 16) : "memory");
+}
+__device__ __forceinline__ void tmem_wait18(uint32_t (&r)[18]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
                  "+r"(r[16]), "+r"(r[17])
                :
                : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(r[i]);
-  s0 = __uint_as_float(r[16]);
-  s1 = __uint_as_float(r[17]);
 }
 
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
@@ -256,17 +254,19 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     };
 
     // epilogue of one conv group: f[pos] = sum_c relu(y_c) (the 1/32 lives in W1) -> bf16 K-major operand of L1
-    auto conv_epilogue = [&](int G, int g) {
+    auto epi_issue = [&](int G, uint32_t (&r)[18]) {        // wait for the MMAs of group G, request this lane's row
       const int buf = G & 1;
       mbar_wait(&bar_conv[buf], (G >> 1) & 1);
       tc_fence_after();
+      if (c_active) tmem_issue18(tmem + t_lane + buf * tbuf + tiles * 16 + T * 32, r);
+    };
+    auto epi_finish = [&](int g, uint32_t (&r)[18]) {
       if (c_active) {
-        float y[16], s0, s1;
-        tmem_ld18(tmem + t_lane + buf * tbuf + tiles * 16 + T * 32, y, s0, s1);
+        tmem_wait18(r);
         // two independent accumulation chains (|.| is a free source modifier)
-        float f0 = s0, f1 = s1;
+        float f0 = __uint_as_float(r[16]), f1 = __uint_as_float(r[17]);
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) { f0 += fabsf(y[c]); f1 += fabsf(y[c + 1]); }
+        for (int c = 0; c < 16; c += 2) { f0 += fabsf(__uint_as_float(r[c])); f1 += fabsf(__uint_as_float(r[c + 1])); }
         const __nv_bfloat16 fb = __float2bfloat16_rn(f0 + f1);
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + e_off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
       }
@@ -291,14 +291,20 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
             lft[j] = __shfl_up_sync(0xffffffffu, mid[j], 1);
             rgt[j] = __shfl_down_sync(0xffffffffu, mid[j], 1);
           }
-          // warp edges: the neighbour lives in another warp (or beyond the A-scan: conv2 pads with zeros)
-          if (lane == 0) {
-            if (c_pos > 0) conv1(ldx(xa - 4), xm, x0, lft);
-            else { lft[0] = lft[1] = lft[2] = lft[3] = 0u; }
-          }
-          if (lane == 31) {
-            if (c_pos + 1 < S) conv1(x0, xp, ldx(xa + 4), rgt);
-            else { rgt[0] = rgt[1] = rgt[2] = rgt[3] = 0u; }
+          // warp edges: the left neighbour of lane 0 and the right neighbour of lane 31 live in other warps.  Both
+          // are computed by ONE extra conv1 instruction stream (lane 0: position p-1, lane 31: position p+1; the
+          // other lanes idle through it) instead of two divergent ones; beyond the A-scan conv2 pads with zeros.
+          {
+            const bool hi = lane == 31;
+            const float xe = ldx(hi ? xa + 4 : xa - 4);
+            uint32_t ext[4];
+            conv1(hi ? x0 : xe, hi ? xp : xm, hi ? xe : x0, ext);
+            const bool zl = c_pos == 0, zr = c_pos + 1 >= S;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (lane == 0) lft[j] = zl ? 0u : ext[j];
+              if (hi) rgt[j] = zr ? 0u : ext[j];
+            }
           }
           asm volatile(
               "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -306,15 +312,18 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
               "r"(mid[1]), "r"(mid[2]), "r"(mid[3]), "r"(rgt[0]), "r"(rgt[1]), "r"(rgt[2]), "r"(rgt[3]), "r"(0x3C003C00u), "r"(0u),
               "r"(0u), "r"(0u)
               : "memory");
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
+        // the accumulator rows of the previous group are requested while the operand store drains
+        uint32_t er[18];
+        if (g > 0) epi_issue(G - 1, er);
+        if (c_active) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         const long long c1 = probe ? clock64() : 0;
         tc_fence_before();
         const long long c1b = probe ? clock64() : 0;
         named_sync(1, ENC_COMPUTE);                         // all compute warps: operand rows stored, accumulators drained
         if (tid == 0) mbar_arrive(&bar_full[buf]);          // hand the group to the issuer warp
         const long long c2 = probe ? clock64() : 0;
-        if (g > 0) conv_epilogue(G - 1, g - 1);
+        if (g > 0) epi_finish(g - 1, er);
         if (probe) {
           const long long c4 = clock64();
           tsum[0] += c1 - c0;    // x staging + conv1
@@ -323,7 +332,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
           tsum[4] += c4 - c2;    // barrier release + epilogue of the previous group (incl. mbarrier wait)
         }
       }
-      conv_epilogue(G - 1, ngroups - 1);
+      {
+        uint32_t er[18];
+        epi_issue(G - 1, er);
+        epi_finish(ngroups - 1, er);
+      }
       const long long l0 = probe ? clock64() : 0;
       // ---- Linear S -> 128 (+ReLU): A = A2, B = W1S, both resident; accumulator D1 reuses the conv columns
       fence_async_smem();
