@@ -43,7 +43,9 @@ def kernel_work(kind, n_per):
         }
     conv = {"two_stage": 2 * 32 * 32 * (3 + 5 + 7 + 11) * S, "ssd": 2 * (64 * 128 * 5 + 128 * 256 * 3) * S,
             "conv1d_msc": 2 * (64 * 128 * 3 + 128 * 128) * S,
-            "enhanced": 2 * (4 * 64 * 32 * 3 + 128 * 128 + 6 * 128 * 128 * 3) * S}
+            # branches + combine + six residual convs at full length; the stride-2 pyramid at S/2 and S/4 outputs
+            "enhanced": 2 * (4 * 64 * 32 * 3 + 128 * 128 + 6 * 128 * 128 * 3) * S +
+                        2 * (128 * 256 * 3 * (S // 2) + 256 * 256 * 3 * (S // 4))}
     return {"conv_tc": (conv[kind], 0, "tensor")}
 
 

@@ -87,7 +87,7 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_l1, bar_l2;
+  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_xe[XS_SLOTS], bar_l1, bar_l2;
   __shared__ uint32_t tmem_slot;
 
   const int S = p.S;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   if (tid == 0) {
     mbar_init(&bar_conv[0], 1); mbar_init(&bar_conv[1], 1);
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
-    for (int i = 0; i < XS_SLOTS; ++i) mbar_init(&bar_x[i], 32);
+    for (int i = 0; i < XS_SLOTS; ++i) { mbar_init(&bar_x[i], 32); mbar_init(&bar_xe[i], 1); }
     mbar_init(&bar_l1, 1);
     mbar_init(&bar_l2, 1);
     fence_mbar_init();
@@ -208,20 +208,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_x[G & (XS_SLOTS - 1)])) : "memory");
     };
-    // the producer runs XS_SLOTS groups ahead of the consumer; (blk_p, g_p, G_p) is the next group to request
-    int64_t blk_p = blockIdx.x;
-    int g_p = 0, G_p = 0, G = 0;
-    auto advance = [&]() {
-      if (++g_p == ngroups) { g_p = 0; blk_p += gridDim.x; }
-      ++G_p;
-    };
-    for (int i = 0; i < XS_SLOTS && blk_p < nblocks; ++i) { issue_x(blk_p, g_p, G_p); advance(); }
+    // classic full / empty ring over the XS_SLOTS x slots: slot s is refilled for group G (G % XS_SLOTS == s) once
+    // the compute warps have released it after conv1 of group G - XS_SLOTS (bar_xe[s], one completion per use).
+    // Each barrier is waited on by exactly one side that can lag by at most one phase, so a parity wait can never
+    // alias -- waiting on the consumers' hand-off barrier instead could, when this warp fell two phases behind.
+    int G = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
       for (int g = 0; g < ngroups; ++g, ++G) {
-        if (blk_p >= nblocks) break;
-        mbar_wait(&bar_full[G & 1], (G >> 1) & 1);        // conv1 of group G has consumed its x ring slot
-        issue_x(blk_p, g_p, G_p);
-        advance();
+        if (G >= XS_SLOTS) mbar_wait(&bar_xe[G & (XS_SLOTS - 1)], ((G / XS_SLOTS) - 1) & 1);
+        issue_x(blk, g, G);
       }
     }
   } else {
@@ -321,7 +316,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
         tc_fence_before();
         const long long c1b = probe ? clock64() : 0;
         named_sync(1, ENC_COMPUTE);                         // all compute warps: operand rows stored, accumulators drained
-        if (tid == 0) mbar_arrive(&bar_full[buf]);          // hand the group to the issuer warp
+        if (tid == 0) {
+          mbar_arrive(&bar_full[buf]);                      // hand the group to the issuer warp
+          mbar_arrive(&bar_xe[G & (XS_SLOTS - 1)]);         // and its x slot back to the loader warp
+        }
         const long long c2 = probe ? clock64() : 0;
         if (g > 0) epi_finish(g - 1, er);
         if (probe) {
