@@ -37,7 +37,7 @@ namespace {
 
 constexpr int H0 = 128, H1 = 64;
 constexpr int ENC_COMPUTE = 640;        // 20 compute warps: 2 conv1 items per thread, 1 epilogue unit (tile, quarter) per warp
-constexpr int ENC_THREADS = ENC_COMPUTE + 64;   // + MMA issuer warp (20) + x loader warp (21), on different schedulers
+constexpr int ENC_THREADS = ENC_COMPUTE + 96;   // + MMA issuer warp (20) + x loader warp (21) + edge warp (22)
 constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
 constexpr int D1_COL = 0, D2_COL = 128;     // alias the conv accumulators (dead by then)
 constexpr int XS_PAD = 16;
@@ -85,9 +85,29 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// mbarrier wait / arrive on a precomputed shared-memory address (keeps the hot loop free of address arithmetic)
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
+template <bool PROBE>
 __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_xe[XS_SLOTS], bar_l1, bar_l2;
+  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_xe[XS_SLOTS], bar_e[XS_SLOTS], bar_l1, bar_l2;
+  __shared__ __align__(16) uint4 EB[XS_SLOTS][ENC_COMPUTE / 32 * 2];   // conv1 vectors just outside every warp's 32 positions
   __shared__ uint32_t tmem_slot;
 
   const int S = p.S;
@@ -110,7 +130,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   if (tid == 0) {
     mbar_init(&bar_conv[0], 1); mbar_init(&bar_conv[1], 1);
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
-    for (int i = 0; i < XS_SLOTS; ++i) { mbar_init(&bar_x[i], 32); mbar_init(&bar_xe[i], 1); }
+    for (int i = 0; i < XS_SLOTS; ++i) { mbar_init(&bar_x[i], 32); mbar_init(&bar_xe[i], 1); mbar_init(&bar_e[i], 1); }
     mbar_init(&bar_l1, 1);
     mbar_init(&bar_l2, 1);
     fence_mbar_init();
@@ -136,11 +156,31 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   const int xparts = S / 8;
   const uint32_t a2_base = smem_u32(A2);
 
+  // conv1 + ReLU at the sample x1 with neighbours x0, x2: 8 channels as 4 fp16 pairs
+  auto conv1 = [&](float x0, float x1, float x2, uint32_t (&o)[4]) {
+    const __half2 h0 = __float2half2_rn(x0), h1 = __float2half2_rn(x1), h2 = __float2half2_rn(x2);
+    const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 v = __hmax2(__hfma2(cw[j][2], h2, __hfma2(cw[j][1], h1, __hfma2(cw[j][0], h0, cb[j]))), zero);
+      o[j] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+  };
+  auto ldx = [&](uint32_t addr) {
+    uint16_t h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+    return __uint_as_float((uint32_t)h << 16);
+  };
+  const uint32_t xs_base = smem_u32(XS), eb_base = smem_u32(&EB[0][0]);
+  const uint32_t slot_bytes = (uint32_t)(2 * xs_stride * 2);
+  const uint32_t a_bar_x = smem_u32(&bar_x[0]), a_bar_xe = smem_u32(&bar_xe[0]), a_bar_e = smem_u32(&bar_e[0]),
+                 a_bar_conv = smem_u32(&bar_conv[0]), a_bar_full = smem_u32(&bar_full[0]);
+
   // Groups are numbered globally over the blocks this CTA walks: G = it * 64 + g.  Every ring / double buffer
   // (conv1 buffers, TMEM accumulators, x slots) and every barrier parity is a function of G only, so the three
   // roles run through block boundaries without any extra synchronisation.
   unsigned long long tsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+  const bool probe = PROBE && p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
   if (warp == ENC_COMPUTE / 32) {
     // ================= MMA issuer warp: conv2 MMAs of every group, decoupled from the compute warps ====
     // two TS-form MMAs per tile: K chunks (tap 0, tap 1) = TMEM columns 0..7 of the tile's operand rows, then
@@ -148,12 +188,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
     const uint64_t bd1 = bd0 + (uint64_t)((2 * 512) >> 4);
     const bool leader = elect_one();
-    int G = 0;
+    uint32_t G = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
       for (int g = 0; g < ngroups; ++g, ++G) {
-        const int buf = G & 1;
+        const uint32_t buf = G & 1;
         const long long i0 = probe ? clock64() : 0;
-        mbar_wait(&bar_full[buf], (G >> 1) & 1);          // operand rows of group G are in tensor memory
+        mbar_wait_a(a_bar_full + buf * 8, (G >> 1) & 1);  // operand rows of group G are in tensor memory
         const long long i1 = probe ? clock64() : 0;
         if (leader) {
           tc_fence_after();
@@ -192,9 +232,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       part_[j] = i < 2 * xparts ? i - al_[j] * xparts : 0;
       dst[j] = smem_u32(XS) + (uint32_t)((al_[j] > 0 ? al_[j] : 0) * xs_stride + 8 + part_[j] * 8) * 2;
     }
-    const uint32_t slot_bytes = (uint32_t)(2 * xs_stride * 2);
     const __nv_bfloat16* xg = static_cast<const __nv_bfloat16*>(p.x);
-    auto issue_x = [&](int64_t blk, int g, int G) {
+    auto issue_x = [&](int64_t blk, int g, uint32_t G) {
       const uint32_t so = (uint32_t)(G & (XS_SLOTS - 1)) * slot_bytes;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -212,11 +251,48 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     // the compute warps have released it after conv1 of group G - XS_SLOTS (bar_xe[s], one completion per use).
     // Each barrier is waited on by exactly one side that can lag by at most one phase, so a parity wait can never
     // alias -- waiting on the consumers' hand-off barrier instead could, when this warp fell two phases behind.
-    int G = 0;
+    uint32_t G = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
       for (int g = 0; g < ngroups; ++g, ++G) {
-        if (G >= XS_SLOTS) mbar_wait(&bar_xe[G & (XS_SLOTS - 1)], ((G / XS_SLOTS) - 1) & 1);
+        if (G >= XS_SLOTS) mbar_wait_a(a_bar_xe + (G & (XS_SLOTS - 1)) * 8, ((G / XS_SLOTS) - 1) & 1);
         issue_x(blk, g, G);
+      }
+    }
+  } else if (warp == ENC_COMPUTE / 32 + 2) {
+    // ================= edge warp =================
+    // A compute warp owns 32 consecutive positions and needs the conv1 vectors of the two positions just outside
+    // (conv2 taps -1 / +1 of its first / last row).  Computing them inside the compute warps costs a full
+    // instruction stream for two lanes; this otherwise idle warp produces all 2 x 20 of them per group as soon
+    // as the group's x has landed, and publishes them through bar_e (which therefore also implies "x landed").
+    int epos[2], exoff[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int e = lane + 32 * j;                          // entry = 2 * warp + side
+      const int w = e >> 1, side = e & 1;
+      const int P0 = 32 * w, al = P0 >= S ? 1 : 0, first = P0 - al * S;
+      epos[j] = e < 2 * (ENC_COMPUTE / 32) && P0 < 2 * S ? (side ? first + 32 : first - 1) : -2;   // -2: no entry
+      exoff[j] = (al * xs_stride + 8 + (epos[j] > -2 ? epos[j] : 0)) * 2;
+    }
+    uint32_t G = 0;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      for (int g = 0; g < ngroups; ++g, ++G) {
+        const uint32_t slot = G & (XS_SLOTS - 1);
+        mbar_wait_a(a_bar_x + slot * 8, (G / XS_SLOTS) & 1);         // x of the group has landed
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (epos[j] > -2) {
+            uint32_t o[4] = {0u, 0u, 0u, 0u};
+            if (epos[j] >= 0 && epos[j] < S) {                       // beyond the A-scan conv2 pads with zeros
+              const uint32_t xa = xs_base + slot * slot_bytes + (uint32_t)exoff[j];
+              conv1(ldx(xa - 2), ldx(xa), ldx(xa + 2), o);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(eb_base + (slot * (ENC_COMPUTE / 32 * 2) + lane + 32 * j) * 16),
+                         "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                         : "memory");
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(a_bar_e + slot * 8);
       }
     }
   } else {
@@ -225,33 +301,18 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     // rows of M tile w / 4, lane quarter w % 4 -- exactly the TMEM lanes a warp may access
     const bool c_active = tid < 2 * S;                            // (2*S <= ENC_COMPUTE for every supported S)
     const int c_al = tid >= S ? 1 : 0, c_pos = tid - c_al * S;
-    const uint32_t xs_base = smem_u32(XS);
     const uint32_t c_xoff = (uint32_t)(c_al * xs_stride + 8 + c_pos) * 2;
+    const uint32_t c_eoff = (uint32_t)(2 * warp + (lane == 31 ? 1 : 0)) * 16;
+    const bool c_edge = lane == 0 || lane == 31;
     const int q = warp & 3, T = warp >> 2;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     // this lane's output element of the conv epilogue (row q*32 + lane of tile T)
     const uint32_t e_off = (uint32_t)(c_pos >> 3) * A2_LBO + (uint32_t)c_al * 16 + (uint32_t)(c_pos & 7) * 2;
 
-    // conv1 + ReLU at the sample x1 with neighbours x0, x2: 8 channels as 4 fp16 pairs
-    auto conv1 = [&](float x0, float x1, float x2, uint32_t (&o)[4]) {
-      const __half2 h0 = __float2half2_rn(x0), h1 = __float2half2_rn(x1), h2 = __float2half2_rn(x2);
-      const __half2 zero = __float2half2_rn(0.f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __half2 v = __hmax2(__hfma2(cw[j][2], h2, __hfma2(cw[j][1], h1, __hfma2(cw[j][0], h0, cb[j]))), zero);
-        o[j] = *reinterpret_cast<const uint32_t*>(&v);
-      }
-    };
-    auto ldx = [&](uint32_t addr) {
-      uint16_t h;
-      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
-      return __uint_as_float((uint32_t)h << 16);
-    };
-
     // epilogue of one conv group: f[pos] = sum_c relu(y_c) (the 1/32 lives in W1) -> bf16 K-major operand of L1
-    auto epi_issue = [&](int G, uint32_t (&r)[18]) {        // wait for the MMAs of group G, request this lane's row
-      const int buf = G & 1;
-      mbar_wait(&bar_conv[buf], (G >> 1) & 1);
+    auto epi_issue = [&](uint32_t G, uint32_t (&r)[18]) {   // wait for the MMAs of group G, request this lane's row
+      const uint32_t buf = G & 1;
+      mbar_wait_a(a_bar_conv + buf * 8, (G >> 1) & 1);
       tc_fence_after();
       if (c_active) tmem_issue18(tmem + t_lane + buf * tbuf + tiles * 16 + T * 32, r);
     };
@@ -267,17 +328,18 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       }
     };
 
-    int G = 0, it = 0;
+    uint32_t G = 0;
+    int it = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
       const int64_t a0 = blk * 128;
       for (int g = 0; g < ngroups; ++g, ++G) {
-        const int buf = G & 1;
+        const uint32_t buf = G & 1, slot = G & (XS_SLOTS - 1);
         const long long c0 = probe ? clock64() : 0;
-        mbar_wait(&bar_x[G & (XS_SLOTS - 1)], (G / XS_SLOTS) & 1);   // x of this group has landed in its ring slot
+        mbar_wait_a(a_bar_e + slot * 8, (G / XS_SLOTS) & 1);          // x has landed and the edge vectors are published
         // ---- conv1 + ReLU -> im2col row in tensor memory.  The operand columns are free: the MMAs of group G-2
         // completed before the epilogue of group G-2 ran.
         if (c_active) {
-          const uint32_t xa = xs_base + (uint32_t)(G & (XS_SLOTS - 1)) * (uint32_t)(2 * xs_stride * 2) + c_xoff;
+          const uint32_t xa = xs_base + slot * slot_bytes + c_xoff;
           const float xm = ldx(xa - 2), x0 = ldx(xa), xp = ldx(xa + 2);
           uint32_t mid[4], lft[4], rgt[4];
           conv1(xm, x0, xp, mid);
@@ -286,20 +348,14 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
             lft[j] = __shfl_up_sync(0xffffffffu, mid[j], 1);
             rgt[j] = __shfl_down_sync(0xffffffffu, mid[j], 1);
           }
-          // warp edges: the left neighbour of lane 0 and the right neighbour of lane 31 live in other warps.  Both
-          // are computed by ONE extra conv1 instruction stream (lane 0: position p-1, lane 31: position p+1; the
-          // other lanes idle through it) instead of two divergent ones; beyond the A-scan conv2 pads with zeros.
-          {
-            const bool hi = lane == 31;
-            const float xe = ldx(hi ? xa + 4 : xa - 4);
-            uint32_t ext[4];
-            conv1(hi ? x0 : xe, hi ? xp : xm, hi ? xe : x0, ext);
-            const bool zl = c_pos == 0, zr = c_pos + 1 >= S;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (lane == 0) lft[j] = zl ? 0u : ext[j];
-              if (hi) rgt[j] = zr ? 0u : ext[j];
-            }
+          // warp edges: the left neighbour of lane 0 and the right neighbour of lane 31 live in other warps; the
+          // edge warp has published their conv1 vectors (zeros beyond the A-scan)
+          if (c_edge) {
+            uint32_t e0, e1, e2, e3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3)
+                         : "r"(eb_base + slot * (uint32_t)(ENC_COMPUTE / 32 * 2 * 16) + c_eoff));
+            if (lane == 0) { lft[0] = e0; lft[1] = e1; lft[2] = e2; lft[3] = e3; }
+            else { rgt[0] = e0; rgt[1] = e1; rgt[2] = e2; rgt[3] = e3; }
           }
           asm volatile(
               "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -317,8 +373,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
         const long long c1b = probe ? clock64() : 0;
         named_sync(1, ENC_COMPUTE);                         // all compute warps: operand rows stored, accumulators drained
         if (tid == 0) {
-          mbar_arrive(&bar_full[buf]);                      // hand the group to the issuer warp
-          mbar_arrive(&bar_xe[G & (XS_SLOTS - 1)]);         // and its x slot back to the loader warp
+          mbar_arrive_a(a_bar_full + buf * 8);              // hand the group to the issuer warp
+          mbar_arrive_a(a_bar_xe + slot * 8);               // and its x slot back to the loader warp
         }
         const long long c2 = probe ? clock64() : 0;
         if (g > 0) epi_finish(g - 1, er);
@@ -485,14 +541,15 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
   p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
   const size_t smem = (size_t)S * 256 + 16384 + (size_t)(S / 8) * A2_LBO + 2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
-  PAUT_CUDA(cudaFuncSetAttribute(k_msc_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool debug = std::getenv("PAUT_ENC_DEBUG") != nullptr;
+  void (*kern)(MscEncArgs) = debug ? k_msc_encoder_tc<true> : k_msc_encoder_tc<false>;
+  PAUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t nblocks = (A + 127) / 128;
   PAUT_CHECK(nblocks < (int64_t(1) << 24), PAUT_ERR_INVALID, "msc encoder: too many A-scans in one launch");
   const int64_t grid = nblocks < c.num_sms ? nblocks : c.num_sms;      // persistent: one CTA per SM
-  static const bool debug = std::getenv("PAUT_ENC_DEBUG") != nullptr;
   p.dbg = nullptr;
   if (debug) PAUT_CUDA(cudaMalloc(&p.dbg, sizeof(unsigned long long) * 8 * (ENC_THREADS / 32)));
-  k_msc_encoder_tc<<<(unsigned)grid, ENC_THREADS, smem, c.stream>>>(p);
+  kern<<<(unsigned)grid, ENC_THREADS, smem, c.stream>>>(p);
   c.launched("msc_encoder_tc");
   if (debug) {
     std::vector<unsigned long long> hbuf(8 * (ENC_THREADS / 32));
