@@ -168,6 +168,8 @@ struct ConvTcLaunch {
   int Lp = 0, H0 = 0;            // explicit row geometry row(a,l) = H0 + a*Lp + l (0: the (L, halo) flat layout)
   int NT = 0, CB = 0;            // tile plan the weights were packed with (conv_tc_plan)
   bool skip_lo = false;          // space-to-depth stride-2 view: tap 0 only multiplies the upper half of Cin
+  int groups = 0;                // > 0: grouped mode (conv_tc_pack_grouped); taps = the largest tap count
+  int gtaps[4] = {0, 0, 0, 0}, goff[4] = {0, 0, 0, 0};
   const void* Wp = nullptr;      // conv_tc_pack() layout
   const float* shift = nullptr;
   int taps = 1, dil = 1, pad = 0;  // pad in taps (PyTorch padding = pad * dil)
@@ -182,6 +184,8 @@ struct ConvTcLaunch {
 };
 bool conv_tc_plan(int Cin, int taps, int Cout, int max_dil, int* NT, int* CB);
 void conv_tc_pack(const float* w, int taps, int Cin, int Cout, int NT, int CB, std::vector<uint16_t>& out);
+void conv_tc_pack_grouped(const float* const* w, const int* taps, int groups, int CB, int GN, std::vector<uint16_t>& out,
+                          int* goff16);
 size_t flat_rows(int64_t A, int L, int halo);
 void op_conv_tc(Ctx& c, const ConvTcLaunch& a);
 void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const float* w, const float* shift, int k,

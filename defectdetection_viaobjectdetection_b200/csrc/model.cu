@@ -549,6 +549,45 @@ void Model::finalize() {
         const std::string p = std::string("signal_encoder.conv_") + n + ".";
         C_(p + "0", p + "1"); C_(p + "3", p + "4");
       }
+      ts_grouped = GroupedConv{};
+      if (cfg.precision == PAUT_PRECISION_BF16 && (d / 4) % 16 == 0 && d <= 128) {
+        // the four second convolutions (q -> q channels, 3/5/7/11 taps) as ONE grouped tcgen05 launch
+        const int q = d / 4;
+        std::vector<std::vector<float>> ws(4);
+        std::vector<float> shift_all;
+        const float* wp[4];
+        int i = 0;
+        for (const char* n : {"small", "medium", "large", "xlarge"}) {
+          const std::string cn = std::string("signal_encoder.conv_") + n + ".3", bn = std::string("signal_encoder.conv_") + n + ".4";
+          const HostTensor& w = H(cn + ".weight");
+          const HostTensor& b = H(cn + ".bias");
+          const HostTensor& g = H(bn + ".weight");
+          const HostTensor& be = H(bn + ".bias");
+          const HostTensor& mu = H(bn + ".running_mean");
+          const HostTensor& var = H(bn + ".running_var");
+          const int taps = (int)w.shape[2];
+          ts_grouped.taps[i] = taps;
+          ws[i].assign((size_t)taps * q * q, 0.f);
+          for (int co = 0; co < q; ++co) {
+            const double sc = (double)g.data[co] / std::sqrt((double)var.data[co] + 1e-5);
+            shift_all.push_back((float)(((double)b.data[co] - (double)mu.data[co]) * sc + (double)be.data[co]));
+            for (int ci = 0; ci < q; ++ci)
+              for (int t = 0; t < taps; ++t)
+                ws[i][((size_t)t * q + ci) * q + co] = w.data[((size_t)co * q + ci) * taps + t] * (float)sc;
+          }
+          wp[i] = ws[i].data();
+          ++i;
+        }
+        std::vector<uint16_t> packed;
+        conv_tc_pack_grouped(wp, ts_grouped.taps, 4, q, q, packed, ts_grouped.goff);
+        void* dptr = nullptr;
+        PAUT_CUDA(cudaMalloc(&dptr, packed.size() * sizeof(uint16_t)));
+        dev_allocs.push_back(dptr);
+        PAUT_CUDA(cudaMemcpy(dptr, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        ts_grouped.Wp = dptr;
+        ts_grouped.shift = upload(shift_all);
+        ts_grouped.ready = true;
+      }
       L("signal_encoder.projection.0"); N_("signal_encoder.projection.1");
       R("sequence_transformer.pos_encoder.pe");
       for (int i = 0; i < 4; ++i)
@@ -855,6 +894,23 @@ void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_ou
   float* feat = c.allocf((size_t)A * d);
   const char* names[4] = {"small", "medium", "large", "xlarge"};
   const bool tcc = g.tc_convs(S) && q % 16 == 0;
+  if (tcc && ts_grouped.ready) {
+    // all four stems write one [rows, 4q] buffer; the four second convolutions + BN + ReLU + mean run as one
+    // grouped tcgen05 launch whose pooled output is the concatenated feature vector (two_stage_model.py:102-118)
+    __nv_bfloat16* a0h = g.alloc_flat(A, S, d);
+    for (int i = 0; i < 4; ++i)
+      g.stem_flat(x, A, S, conv[std::string("signal_encoder.conv_") + names[i] + ".0"], a0h, d, q * i);
+    ConvTcLaunch a;
+    a.in = a0h; a.A = A; a.L = S; a.Cin = d; a.Cout = d; a.Wp = ts_grouped.Wp; a.shift = ts_grouped.shift;
+    a.NT = d; a.CB = q; a.groups = 4;
+    int tmax = 0;
+    for (int i = 0; i < 4; ++i) { a.gtaps[i] = ts_grouped.taps[i]; a.goff[i] = ts_grouped.goff[i]; tmax = std::max(tmax, a.gtaps[i]); }
+    a.taps = tmax; a.dil = 1; a.pad = tmax / 2; a.relu = true;
+    const size_t tiles = (flat_rows(A, S, CONV_HALO) + 127) / 128;
+    a.pool_partial = c.allocf(tiles * 3 * (size_t)d);
+    a.pool_out = feat; a.ldp = d; a.poff = 0;
+    op_conv_tc(c, a);
+  } else {
   float* a0 = tcc ? nullptr : c.allocf((size_t)A * S * q);
   __nv_bfloat16* a0h = tcc ? g.alloc_flat(A, S, q) : nullptr;
   for (int i = 0; i < 4; ++i) {                                                  // two_stage_model.py:102-114
@@ -868,6 +924,7 @@ void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_ou
       op_stem_conv(c, x, A, S, s.w, s.shift, s.taps, s.Cout, true, a0);
       g.conv(a0, A, S, w, 1, 1, w.taps / 2, true, nullptr, nullptr, 0, 0, feat, d, q * i);
     }
+  }
   }
   float* pr = g.linear(feat, d, lin["signal_encoder.projection.0"], A);
   float* seq = g.norm(pr, nullptr, ln["signal_encoder.projection.1"], A);

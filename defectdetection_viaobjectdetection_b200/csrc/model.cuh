@@ -76,6 +76,12 @@ struct Model {
     const void* W2p = nullptr;
     bool ready = false;
   } enc_tc;
+  struct GroupedConv {                         // the two-stage encoder's four second convolutions as one launch
+    const void* Wp = nullptr;
+    const float* shift = nullptr;              // [4 * q]
+    int taps[4] = {0, 0, 0, 0}, goff[4] = {0, 0, 0, 0};
+    bool ready = false;
+  } ts_grouped;
   struct SetTc {                               // plain bf16 [N][K] weights of the fused set-stage kernels
     const void* Wqkv_self = nullptr; const void* Wo_self = nullptr;
     const void* Wqkv_cross = nullptr; const void* Wo_cross = nullptr;

@@ -61,6 +61,8 @@ struct ConvTcArgs {
   float* pool;                  // per-tile column sums [tiles][nseg segments][Cout] (nullable)
   int nseg;                     // A-scans a 128-row tile can touch: 2 (period >= 127 rows) or 3
   int skip_lo;                  // space-to-depth stride-2 view: tap 0 multiplies only the upper half of Cin
+  int grouped;                  // grouped mode: channel block cb is its own conv (gtaps[cb] taps, N = NT / ncb columns)
+  int gtaps[4], goff[4];        // taps and resident-weight offset (16-byte units) of every group
   int L, Lp, H0;                // geometry: valid rows per A-scan, period, leading halo
   int64_t A;
   int wrows;                    // window rows = 128 + (taps-1)*dil
@@ -188,12 +190,33 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
         if (leader) {
           tc_fence_after();
           const uint32_t a_addr = a_ring + (uint32_t)stage * p.a_stage_bytes;
+          const uint64_t a_ks = (uint64_t)(2 * p.wrows), a_t = (uint64_t)p.dil;
+          if (p.grouped) {
+            // branch cb: its own tap count (centred in the common window), its own 32-column block of the accumulator
+            const int GN = NT / ncb, tg = p.gtaps[cb];
+            const uint32_t idesc_g = make_idesc_bf16(128, GN);
+            const uint32_t d = tmem + acc * 128 + cb * GN;
+            uint64_t ad_t = make_desc(a_addr + (uint32_t)((p.pad - tg / 2) * p.dil) * 16, p.wrows * 16, 128);
+            uint64_t bd = make_desc(w_addr + (uint32_t)p.goff[cb] * 16, GN * 16, 128);
+            const uint64_t b_step = (uint64_t)(2 * GN);
+            uint32_t accum = 0u;
+            for (int t = 0; t < tg; ++t) {
+              uint64_t ad = ad_t;
+              for (int ks = 0; ks < chunks / 2; ++ks) {
+                mma_bf16_ss(d, ad, bd, idesc_g, accum);
+                accum = 1u;
+                ad += a_ks;
+                bd += b_step;
+              }
+              ad_t += a_t;
+            }
+          } else {
           const uint32_t b_addr = w_addr + (uint32_t)(cb * p.taps * chunks * NT) * 16;
           const uint32_t d = tmem + acc * 128;
           // descriptors advance by constant amounts in their 14-bit address field (16-byte units)
           uint64_t ad_t = make_desc(a_addr, p.wrows * 16, 128);
           uint64_t bd = make_desc(b_addr, NT * 16, 128);
-          const uint64_t a_ks = (uint64_t)(2 * p.wrows), a_t = (uint64_t)p.dil, b_step = (uint64_t)(2 * NT);
+          const uint64_t b_step = (uint64_t)(2 * NT);
           uint32_t accum = cb ? 1u : 0u;
           for (int t = 0; t < p.taps; ++t) {
             if (p.skip_lo && t == 0 && 2 * cb < ncb) {       // [0 | W0]: the lower channel half of tap 0 is zero
@@ -209,6 +232,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
               bd += b_step;
             }
             ad_t += a_t;
+          }
           }
           mma_commit(&empty[stage]);
           if (cb == ncb - 1) mma_commit(&acc_full[acc]);
@@ -622,6 +646,23 @@ void conv_tc_pack(const float* w, int taps, int Cin, int Cout, int NT, int CB, s
       }
 }
 
+// Grouped variant (the two-stage encoder's four branches in one launch): group g is a conv of CB -> GN channels
+// with taps[g] taps; weights [g][t][CB/8][GN][8] back to back.  w[g] is [taps[g]][CB][GN] fp32 (BN scale folded).
+void conv_tc_pack_grouped(const float* const* w, const int* taps, int groups, int CB, int GN, std::vector<uint16_t>& out,
+                          int* goff16) {
+  const int chunks = CB / 8;
+  size_t total = 0;
+  for (int g = 0; g < groups; ++g) { goff16[g] = (int)(total / 8); total += (size_t)taps[g] * CB * GN; }
+  out.assign(total, 0);
+  for (int g = 0; g < groups; ++g)
+    for (int t = 0; t < taps[g]; ++t)
+      for (int ci = 0; ci < CB; ++ci)
+        for (int co = 0; co < GN; ++co) {
+          const size_t idx = (size_t)goff16[g] * 8 + ((((size_t)t * chunks + ci / 8) * GN + co) * 8 + ci % 8);
+          out[idx] = f2bf_(w[g][((size_t)t * CB + ci) * GN + co]);
+        }
+}
+
 size_t flat_rows(int64_t A, int L, int halo) { return (size_t)halo + (size_t)A * (L + halo); }
 
 void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
@@ -644,12 +685,20 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   PAUT_CHECK(!a.pool_partial || (p.Lp >= 64 && 4 * p.nseg * p.NT <= 1024), PAUT_ERR_UNSUPPORTED,
              "conv_tc: pooled mean needs a row period >= 64 (and N tile <= 64 below 127)");
   p.skip_lo = a.skip_lo ? 1 : 0;
+  p.grouped = a.groups > 0 ? 1 : 0;
+  for (int g = 0; g < 4; ++g) { p.gtaps[g] = a.gtaps[g]; p.goff[g] = a.goff[g]; }
+  PAUT_CHECK(!p.grouped || (a.groups == a.Cin / p.CB && a.groups <= 4 && p.NT == a.Cout && (p.NT / a.groups) % 16 == 0),
+             PAUT_ERR_UNSUPPORTED, "conv_tc: grouped mode needs one channel block and >= 16 output columns per group");
   PAUT_CHECK(!p.skip_lo || (a.Cin / p.CB) % 2 == 0, PAUT_ERR_INVALID, "conv_tc: skip_lo needs an even number of channel blocks");
   p.relu = a.relu ? 1 : 0; p.res = static_cast<const __nv_bfloat16*>(a.res); p.ldr = a.ldr;
   p.out = static_cast<__nv_bfloat16*>(a.out); p.ldc = a.ldc; p.coff = a.coff; p.pool = a.pool_partial;
   p.wrows = 128 + (a.taps - 1) * a.dil;
   p.a_stage_bytes = ((p.CB / 8) * p.wrows * 16 + 127) & ~127;
   p.w_bytes = a.taps * a.Cin * p.NT * 2;                   // all weights of one N tile
+  if (p.grouped) {
+    p.w_bytes = 0;
+    for (int g = 0; g < a.groups; ++g) p.w_bytes += a.gtaps[g] * p.CB * (p.NT / a.groups) * 2;
+  }
   p.num_tiles = (p.R + 127) / 128;
   const size_t smem = (size_t)p.w_bytes + (size_t)CT_STAGES * p.a_stage_bytes;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "conv_tc: weights + ring do not fit shared memory");
