@@ -190,20 +190,23 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
         if (leader) {
           tc_fence_after();
           const uint32_t a_addr = a_ring + (uint32_t)stage * p.a_stage_bytes;
-          const uint64_t a_ks = (uint64_t)(2 * p.wrows), a_t = (uint64_t)p.dil;
+          // descriptors as (lo, hi) words: hi (SBO = 128 B, version 1) is constant; lo = start address | LBO << 16
+          // advances by constant 16-byte-unit amounts with one 32-bit add per MMA
+          const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
+          const uint32_t a_ks = (uint32_t)(2 * p.wrows), a_t = (uint32_t)p.dil;
           if (p.grouped) {
             // branch cb: its own tap count (centred in the common window), its own 32-column block of the accumulator
             const int GN = NT / ncb, tg = p.gtaps[cb];
             const uint32_t idesc_g = make_idesc_bf16(128, GN);
             const uint32_t d = tmem + acc * 128 + cb * GN;
-            uint64_t ad_t = make_desc(a_addr + (uint32_t)((p.pad - tg / 2) * p.dil) * 16, p.wrows * 16, 128);
-            uint64_t bd = make_desc(w_addr + (uint32_t)p.goff[cb] * 16, GN * 16, 128);
-            const uint64_t b_step = (uint64_t)(2 * GN);
+            uint32_t ad_t = (((a_addr >> 4) + (uint32_t)((p.pad - tg / 2) * p.dil)) & 0x3FFFu) | ((uint32_t)p.wrows << 16);
+            uint32_t bd = (((w_addr >> 4) + (uint32_t)p.goff[cb]) & 0x3FFFu) | ((uint32_t)GN << 16);
+            const uint32_t b_step = (uint32_t)(2 * GN);
             uint32_t accum = 0u;
             for (int t = 0; t < tg; ++t) {
-              uint64_t ad = ad_t;
+              uint32_t ad = ad_t;
               for (int ks = 0; ks < chunks / 2; ++ks) {
-                mma_bf16_ss(d, ad, bd, idesc_g, accum);
+                mma_bf16_ss2(d, ad, desc_hi, bd, desc_hi, idesc_g, accum);
                 accum = 1u;
                 ad += a_ks;
                 bd += b_step;
@@ -211,28 +214,26 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
               ad_t += a_t;
             }
           } else {
-          const uint32_t b_addr = w_addr + (uint32_t)(cb * p.taps * chunks * NT) * 16;
-          const uint32_t d = tmem + acc * 128;
-          // descriptors advance by constant amounts in their 14-bit address field (16-byte units)
-          uint64_t ad_t = make_desc(a_addr, p.wrows * 16, 128);
-          uint64_t bd = make_desc(b_addr, NT * 16, 128);
-          const uint64_t b_step = (uint64_t)(2 * NT);
-          uint32_t accum = cb ? 1u : 0u;
-          for (int t = 0; t < p.taps; ++t) {
-            if (p.skip_lo && t == 0 && 2 * cb < ncb) {       // [0 | W0]: the lower channel half of tap 0 is zero
+            const uint32_t d = tmem + acc * 128;
+            uint32_t ad_t = ((a_addr >> 4) & 0x3FFFu) | ((uint32_t)p.wrows << 16);
+            uint32_t bd = (((w_addr >> 4) + (uint32_t)(cb * p.taps * chunks * NT)) & 0x3FFFu) | ((uint32_t)NT << 16);
+            const uint32_t b_step = (uint32_t)(2 * NT);
+            uint32_t accum = cb ? 1u : 0u;
+            for (int t = 0; t < p.taps; ++t) {
+              if (p.skip_lo && t == 0 && 2 * cb < ncb) {     // [0 | W0]: the lower channel half of tap 0 is zero
+                ad_t += a_t;
+                bd += b_step * (uint32_t)(chunks / 2);
+                continue;
+              }
+              uint32_t ad = ad_t;
+              for (int ks = 0; ks < chunks / 2; ++ks) {
+                mma_bf16_ss2(d, ad, desc_hi, bd, desc_hi, idesc, accum);
+                accum = 1u;
+                ad += a_ks;
+                bd += b_step;
+              }
               ad_t += a_t;
-              bd += b_step * (uint64_t)(chunks / 2);
-              continue;
             }
-            uint64_t ad = ad_t;
-            for (int ks = 0; ks < chunks / 2; ++ks) {
-              mma_bf16_ss(d, ad, bd, idesc, accum);
-              accum = 1u;
-              ad += a_ks;
-              bd += b_step;
-            }
-            ad_t += a_t;
-          }
           }
           mma_commit(&empty[stage]);
           if (cb == ncb - 1) mma_commit(&acc_full[acc]);
