@@ -51,7 +51,7 @@ def kernel_work(kind, n_per):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/), per A-scan; None until a capture of the current kernel exists
-NCU_TRAFFIC_PER_ASCAN = {"msc_encoder_tc": None}
+NCU_TRAFFIC_PER_ASCAN = {"msc_encoder_tc": 837.7}   # profiles/r01_s2/ncu_msc_encoder_tc.txt: (230.6 + 70.9) MB / 360 000 A-scans
 
 
 def peaks():
