@@ -22,7 +22,7 @@ namespace {
 
 constexpr int DM = 64, HD = 16, NH = 4, FF = 32;
 constexpr int WS = DM + 8;            // bf16 row stride of K rows and of weight rows with K = 64
-constexpr int AB_WARPS = 10;
+constexpr int AB_WARPS = 20;
 constexpr int KBLK = 64;              // keys per softmax block
 
 struct AttnBlockArgs {
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block(AttnBlockAr
   const int Np = (N + KBLK - 1) / KBLK * KBLK;
   const int vts = Np + 8;
   __nv_bfloat16* Kb = reinterpret_cast<__nv_bfloat16*>(smraw);        // [Np][WS]
-  __nv_bfloat16* Vt = Kb + (size_t)Np * WS;                             // [64][Np + 8]
-  __nv_bfloat16* Wq = Vt + (size_t)DM * vts;                            // [192][WS]
+  __half* Vt = reinterpret_cast<__half*>(Kb + (size_t)Np * WS);           // [64][Np + 8], fp16: the P V product runs in fp16
+  __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(Vt + (size_t)DM * vts);   // [192][WS]
   __nv_bfloat16* Wo = Wq + (size_t)3 * DM * WS;                         // [64][WS]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block(AttnBlockAr
   for (int i = tid; i < (Np - N) * WS; i += AB_WARPS * 32) Kb[(size_t)N * WS + i] = __float2bfloat16_rn(0.f);
   for (int i = tid; i < DM * (vts - N); i += AB_WARPS * 32) {
     const int d = i / (vts - N), j = i - d * (vts - N);
-    Vt[(size_t)d * vts + N + j] = __float2bfloat16_rn(0.f);
+    Vt[(size_t)d * vts + N + j] = __float2half_rn(0.f);
   }
   __syncthreads();
 
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block(AttnBlockAr
         const int r = r0 + g + hh * 8;
         if (r >= N) continue;
         const uint32_t kp = pack_bf16(kc[2 * hh], kc[2 * hh + 1]);
-        const __nv_bfloat16 v0 = __float2bfloat16_rn(vc[2 * hh]), v1 = __float2bfloat16_rn(vc[2 * hh + 1]);
+        const __half v0 = __float2half_rn(vc[2 * hh]), v1 = __float2half_rn(vc[2 * hh + 1]);
         // key slot(s) of source row r: identity, or (shifted sequence) j = r-1 and the repeated last row
         int j0 = r, j1 = -1;
         if (p.kv_shift) { j0 = r - 1; j1 = (r == N - 1) ? N - 1 : -1; }
@@ -189,8 +189,12 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block(AttnBlockAr
       for (int i = 0; i < 4; ++i) { q0[i] *= qscale; q1[i] *= qscale; }
       uint32_t qa[4];
       c_to_a(q0, q1, qa);
-      float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+      float m0 = -INFINITY, m1 = -INFINITY;
       float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      // third output tile = P x [1 0 .. 0]: its column 0 is the row sum of the (rounded) probabilities, so the
+      // softmax denominator costs four MMAs per key block instead of 32 adds; B fragment is a lane constant
+      float osum[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t ones_b = g == 0 ? 0x3C003C00u : 0u;
       for (int kb = 0; kb < Np; kb += KBLK) {
         float s[8][4];
 #pragma unroll
@@ -220,31 +224,28 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block(AttnBlockAr
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
         const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);
         m0 = mn0; m1 = mn1;
-        l0 *= c0; l1 *= c1;
 #pragma unroll
         for (int d = 0; d < 2; ++d) { o[d][0] *= c0; o[d][1] *= c0; o[d][2] *= c1; o[d][3] *= c1; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s[j][0] = fast_exp2(s[j][0] - mn0);
-          s[j][1] = fast_exp2(s[j][1] - mn0);
-          s[j][2] = fast_exp2(s[j][2] - mn1);
-          s[j][3] = fast_exp2(s[j][3] - mn1);
-          l0 += s[j][0] + s[j][1];
-          l1 += s[j][2] + s[j][3];
-        }
+        osum[0] *= c0; osum[1] *= c0; osum[2] *= c1; osum[3] *= c1;
+        // probabilities as packed fp16 pairs: exactly the registers of the A fragment of P (k-step ks = key
+        // tiles 2ks, 2ks+1), one MUFU instruction per pair
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           uint32_t pa[4];
-          c_to_a(s[2 * ks], s[2 * ks + 1], pa);
+          pa[0] = exp2_pair_f16(s[2 * ks][0] - mn0, s[2 * ks][1] - mn0);
+          pa[1] = exp2_pair_f16(s[2 * ks][2] - mn1, s[2 * ks][3] - mn1);
+          pa[2] = exp2_pair_f16(s[2 * ks + 1][0] - mn0, s[2 * ks + 1][1] - mn0);
+          pa[3] = exp2_pair_f16(s[2 * ks + 1][2] - mn1, s[2 * ks + 1][3] - mn1);
 #pragma unroll
           for (int d = 0; d < 2; ++d) {
-            const __nv_bfloat16* vr = Vt + (size_t)(h * HD + d * 8 + g) * vts + kb + ks * 16 + 2 * t;
-            mma_bf16_16816(o[d], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+            const __half* vr = Vt + (size_t)(h * HD + d * 8 + g) * vts + kb + ks * 16 + 2 * t;
+            mma_f16_16816(o[d], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
           }
+          mma_f16_16816(osum, pa, ones_b, ones_b);
         }
       }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      // column 0 of the sum tile lives in the lanes with t == 0: rows g (osum[0]) and g + 8 (osum[2])
+      const float l0 = __shfl_sync(0xffffffffu, osum[0], lane & ~3), l1 = __shfl_sync(0xffffffffu, osum[2], lane & ~3);
       const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
       for (int d = 0; d < 2; ++d) { o[d][0] *= i0; o[d][1] *= i0; o[d][2] *= i1; o[d][3] *= i1; }
