@@ -658,100 +658,138 @@ void op_copy_cols(Ctx& c, const float* src, int lds, float* dst, int ldd, int co
 }
 
 // ------------------------------------------------------------------------------------------ MSC front end
-// CTA = one A-scan.  x row + conv1 output (8 x S) + conv2 output (16 x S, only when the background
-// extractor needs the neighbours) live in shared memory; the channel mean is reduced in registers.
-__global__ void __launch_bounds__(128) k_msc_front(const float* __restrict__ x, int S, const float* __restrict__ w1,
-                                                   const float* __restrict__ b1, const float* __restrict__ w2,
-                                                   const float* __restrict__ b2, const float* __restrict__ wbg,
-                                                   const float* __restrict__ bbg, float* __restrict__ f) {
-  extern __shared__ float sm[];
-  float* xs = sm;                      // [S+2]      zero halo of 1
-  float* a1 = xs + (S + 2);            // [8][S+2]   zero halo of 1
-  float* a2 = a1 + 8 * (S + 2);        // [16][S+10] zero halo of 5 (only with background)
-  __shared__ float W1[8 * 3], B1[8], W2[16 * 8 * 3], B2[16], WB[16 * 11], BB[16];
-  const int64_t a = blockIdx.x;
+// Persistent CTA over A-scans.  x row + conv1 output (8 x S) + conv2 output (16 x S, only when the background
+// extractor needs the neighbours) live in shared memory.  conv2 and the background filter are register-tiled:
+// a thread owns 4 consecutive positions x all 16 channels (64 accumulators), so one 128-bit weight load feeds 16
+// FMAs and the kernel is bound by the FMA pipe instead of by shared-memory loads.  Accumulation order per output
+// (bias, then input channel outer / tap inner; channel sum in channel order) is the reference order.
+__global__ void __launch_bounds__(128) k_msc_front(const float* __restrict__ x, int S, int64_t A,
+                                                   const float* __restrict__ w1, const float* __restrict__ b1,
+                                                   const float* __restrict__ w2, const float* __restrict__ b2,
+                                                   const float* __restrict__ wbg, const float* __restrict__ bbg,
+                                                   float* __restrict__ f) {
+  extern __shared__ __align__(16) float sm[];
+  const int S2 = S + 2 + ((4 - (S + 2) % 4) % 4);      // padded row length (multiple of 4 floats)
+  const int SP = S + 12;                               // conv2 rows: zero halo of 5 on the left, 7 on the right
+  float* xs = sm;                      // [S2]      zero halo of 1
+  float* a1 = xs + S2;                 // [8][S2]   zero halo of 1
+  float* a2 = a1 + 8 * S2;             // [16][SP]  (only with background)
+  __shared__ __align__(16) float W1[8 * 3], B1[8], W2t[24 * 16], B2[16], WB[16 * 12], BB[16];
   const int tid = threadIdx.x;
   for (int i = tid; i < 24; i += 128) W1[i] = w1[i];
   for (int i = tid; i < 8; i += 128) B1[i] = b1[i];
-  for (int i = tid; i < 384; i += 128) W2[i] = w2[i];
+  for (int i = tid; i < 384; i += 128) {               // w2 [co][ci][t] -> W2t [ci*3+t][co]
+    const int co = i / 24, r = i - co * 24;
+    W2t[r * 16 + co] = w2[i];
+  }
   for (int i = tid; i < 16; i += 128) B2[i] = b2[i];
   if (wbg) {
-    for (int i = tid; i < 176; i += 128) WB[i] = wbg[i];
+    for (int i = tid; i < 16 * 12; i += 128) { const int co = i / 12, t = i - co * 12; WB[i] = t < 11 ? wbg[co * 11 + t] : 0.f; }
     for (int i = tid; i < 16; i += 128) BB[i] = bbg[i];
+    for (int i = tid; i < 16 * SP; i += 128) a2[i] = 0.f;           // halos stay zero: only [5, 5+S) is rewritten
   }
-  for (int i = tid; i < S + 2; i += 128) xs[i] = (i >= 1 && i <= S) ? x[a * S + i - 1] : 0.f;
-  __syncthreads();
-  for (int i = tid; i < 8 * (S + 2); i += 128) {
-    const int ch = i / (S + 2), l = i - ch * (S + 2);     // l is the padded index (position l-1)
-    float v = 0.f;
-    if (l >= 1 && l <= S) {
-      v = B1[ch];
-      v = fmaf(W1[ch * 3 + 0], xs[l - 1], v);
-      v = fmaf(W1[ch * 3 + 1], xs[l], v);
-      v = fmaf(W1[ch * 3 + 2], xs[l + 1], v);
-      v = fmaxf(v, 0.f);
-    }
-    a1[i] = v;
-  }
-  __syncthreads();
-  if (!wbg) {
-    for (int l = tid; l < S; l += 128) {
-      float s = 0.f;
-      float av[24];
-#pragma unroll
-      for (int ci = 0; ci < 8; ++ci) {
-        av[ci * 3 + 0] = a1[ci * (S + 2) + l];
-        av[ci * 3 + 1] = a1[ci * (S + 2) + l + 1];
-        av[ci * 3 + 2] = a1[ci * (S + 2) + l + 2];
-      }
-      for (int co = 0; co < 16; ++co) {
-        float v = B2[co];
-#pragma unroll
-        for (int i = 0; i < 24; ++i) v = fmaf(W2[co * 24 + i], av[i], v);
-        s += fmaxf(v, 0.f);
-      }
-      f[a * S + l] = s * (1.f / 16.f);
-    }
-  } else {
-    const int SP = S + 10;
-    for (int i = tid; i < 16 * SP; i += 128) {
-      const int co = i / SP, lp = i - co * SP;
-      const int l = lp - 5;
-      float v = 0.f;
-      if (l >= 0 && l < S) {
-        v = B2[co];
-#pragma unroll
-        for (int ci = 0; ci < 8; ++ci) {
-          const float* ar = a1 + ci * (S + 2) + l;
-          const float* w = W2 + (co * 8 + ci) * 3;
-          v = fmaf(w[0], ar[0], v);
-          v = fmaf(w[1], ar[1], v);
-          v = fmaf(w[2], ar[2], v);
-        }
-        v = fmaxf(v, 0.f);
-      }
-      a2[i] = v;
+  for (int i = tid; i < 9 * S2; i += 128) sm[i] = 0.f;
+  const int l0 = 4 * tid;
+  for (int64_t a = blockIdx.x; a < A; a += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < S; i += 128) xs[i + 1] = x[a * S + i];
+    __syncthreads();
+    for (int i = tid; i < 8 * S; i += 128) {
+      const int ch = i / S, l = i - ch * S;
+      float v = B1[ch];
+      v = fmaf(W1[ch * 3 + 0], xs[l], v);
+      v = fmaf(W1[ch * 3 + 1], xs[l + 1], v);
+      v = fmaf(W1[ch * 3 + 2], xs[l + 2], v);
+      a1[ch * S2 + l + 1] = fmaxf(v, 0.f);
     }
     __syncthreads();
-    for (int l = tid; l < S; l += 128) {
-      float s = 0.f;
-      for (int co = 0; co < 16; ++co) {
-        const float* ar = a2 + co * SP + l;       // ar[t] = position l + t - 5
-        float bg = BB[co];
+    float acc[4][16];
+    if (l0 < S) {
 #pragma unroll
-        for (int t = 0; t < 11; ++t) bg = fmaf(WB[co * 11 + t], ar[t], bg);
-        s += ar[5] - bg;
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int co = 0; co < 16; ++co) acc[p][co] = B2[co];
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        float av[6];                                    // positions l0-1 .. l0+4
+        const float4 v4 = *reinterpret_cast<const float4*>(a1 + ci * S2 + l0);
+        const float2 v2 = *reinterpret_cast<const float2*>(a1 + ci * S2 + l0 + 4);
+        av[0] = v4.x; av[1] = v4.y; av[2] = v4.z; av[3] = v4.w; av[4] = v2.x; av[5] = v2.y;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          float w[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 w4 = *reinterpret_cast<const float4*>(W2t + (ci * 3 + t) * 16 + 4 * j);
+            w[4 * j] = w4.x; w[4 * j + 1] = w4.y; w[4 * j + 2] = w4.z; w[4 * j + 3] = w4.w;
+          }
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int co = 0; co < 16; ++co) acc[p][co] = fmaf(w[co], av[p + t], acc[p][co]);
+        }
       }
-      f[a * S + l] = s * (1.f / 16.f);
+    }
+    if (!wbg) {
+      if (l0 < S) {
+        float s[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          s[p] = 0.f;
+#pragma unroll
+          for (int co = 0; co < 16; ++co) s[p] += fmaxf(acc[p][co], 0.f);
+        }
+        *reinterpret_cast<float4*>(f + a * S + l0) =
+            make_float4(s[0] * (1.f / 16.f), s[1] * (1.f / 16.f), s[2] * (1.f / 16.f), s[3] * (1.f / 16.f));
+      }
+    } else {
+      if (l0 < S) {
+#pragma unroll
+        for (int co = 0; co < 16; ++co)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) a2[co * SP + 5 + l0 + p] = fmaxf(acc[p][co], 0.f);
+      }
+      __syncthreads();
+      if (l0 < S) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int co = 0; co < 16; ++co) {
+          float ar[16];                                 // ar[j] = position l0 + j - 5
+          const float* base = a2 + co * SP + l0;        // (5 + l0 - 5); l0 % 4 == 0 and SP % 4 == 0: 16-byte aligned
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v4 = *reinterpret_cast<const float4*>(base + 4 * j);
+            ar[4 * j] = v4.x; ar[4 * j + 1] = v4.y; ar[4 * j + 2] = v4.z; ar[4 * j + 3] = v4.w;
+          }
+          float wb[12];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float4 w4 = *reinterpret_cast<const float4*>(WB + co * 12 + 4 * j);
+            wb[4 * j] = w4.x; wb[4 * j + 1] = w4.y; wb[4 * j + 2] = w4.z; wb[4 * j + 3] = w4.w;
+          }
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            float bg = BB[co];
+#pragma unroll
+            for (int t = 0; t < 11; ++t) bg = fmaf(wb[t], ar[p + t], bg);
+            s[p] += ar[p + 5] - bg;
+          }
+        }
+        *reinterpret_cast<float4*>(f + a * S + l0) =
+            make_float4(s[0] * (1.f / 16.f), s[1] * (1.f / 16.f), s[2] * (1.f / 16.f), s[3] * (1.f / 16.f));
+      }
     }
   }
 }
 void op_msc_front(Ctx& c, const float* x, int64_t A, int S, const float* w1, const float* b1, const float* w2,
                   const float* b2, const float* wbg, const float* bbg, float* f) {
   if (c.dry) return;
-  const size_t smem = sizeof(float) * ((size_t)(S + 2) * 9 + (wbg ? (size_t)16 * (S + 10) : 0));
+  PAUT_CHECK(S % 4 == 0 && S <= 512, PAUT_ERR_UNSUPPORTED, "msc front: signal length must be a multiple of 4, at most 512");
+  const int S2 = S + 2 + ((4 - (S + 2) % 4) % 4);
+  const size_t smem = sizeof(float) * ((size_t)S2 * 9 + (wbg ? (size_t)16 * (S + 12) : 0));
   PAUT_CHECK(smem <= 48 * 1024, PAUT_ERR_UNSUPPORTED, "msc front: signal too long");
-  k_msc_front<<<(unsigned)A, 128, smem, c.stream>>>(x, S, w1, b1, w2, b2, wbg, bbg, f);
+  int64_t grid = (int64_t)c.num_sms * 6;
+  if (grid > A) grid = A;
+  k_msc_front<<<(unsigned)grid, 128, smem, c.stream>>>(x, S, A, w1, b1, w2, b2, wbg, bbg, f);
   c.launched("msc_front");
 }
 
