@@ -259,7 +259,8 @@ def main():
     # ---- end to end through the public API with host buffers: H2D + forward + post-process + D2H records
     # (VolumeScanner: resident chunks on two streams, H2D / kernels / D2H of kept records overlapped)
     from defectdetection_viaobjectdetection_b200.streaming import VolumeScanner
-    scanner = VolumeScanner(model, chunk_sets=max(1, (76800 // n_per)))
+    scan_chunk = int(os.environ.get("PAUT_BENCH_CHUNK_ASCANS", "76800"))
+    scanner = VolumeScanner(model, chunk_sets=max(1, (scan_chunk // n_per)), lanes=int(os.environ.get("PAUT_BENCH_LANES", "4")))
 
     def step_e2e():
         return scanner.scan(x_host, threshold=0.5)

@@ -496,7 +496,7 @@ __global__ void k_stem_flat(const void* __restrict__ x, int x_dtype, int64_t A, 
 // groups of one row (full 128-byte lines for 64 channels).
 constexpr int STEM_RPT = 4;
 template <int K>
-__global__ void __launch_bounds__(256) k_stem_flat_t(const void* __restrict__ x, int x_dtype, int A, int S,
+__global__ void __launch_bounds__(256, 2) k_stem_flat_t(const void* __restrict__ x, int x_dtype, int A, int S,
                                                      const float* __restrict__ w, const float* __restrict__ shift,
                                                      int Cout, int relu, __nv_bfloat16* __restrict__ out, int ldc,
                                                      int coff, int Lp, int H0, int R) {
