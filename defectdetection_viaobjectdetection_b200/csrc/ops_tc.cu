@@ -10,7 +10,9 @@
 //   * one elected thread of the issuer warp runs the K loop (tcgen05.mma 128 x NT x 16), committing every block
 //     to its ring slot's "empty" barrier and the last block of a tile to the accumulator's "full" barrier;
 //   * 8 epilogue warps read the accumulator (two TMEM buffers: the MMAs of tile i+1 overlap the epilogue of
-//     tile i) with tcgen05.ld, apply bias / activation / residual / row table and write fp32 rows.
+//     tile i) with tcgen05.ld, transpose 32x32 blocks through a swizzled per-warp shared-memory tile and, with
+//     8 lanes per row, apply bias / activation / residual / row table and write fp32 rows as full 128-byte
+//     lines (a row-per-lane store touches 32 lines per instruction and made the epilogue 16x longer than the MMAs).
 #include <cstdlib>
 #include <cstring>
 
@@ -30,6 +32,7 @@ constexpr int GT_EPI_WARPS = 8, GT_LOAD_WARPS = 8;
 constexpr int GT_THREADS = 32 * (GT_EPI_WARPS + 1 + GT_LOAD_WARPS);
 constexpr int GT_ALBO = 2048 + 16;           // chunk stride of the A operand (+16 B: bank skew)
 constexpr int GT_ASTAGE = 8 * GT_ALBO;
+constexpr int GT_TSM_BYTES = GT_EPI_WARPS * 4096;   // per-warp 32x32 fp32 transposition tiles
 constexpr size_t GT_DYN_SMEM = 232448 - 2304;   // opt-in limit minus the static barriers / bias
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
   const int w_bytes = chunks_total * NT * 16;
   unsigned char* Wres = smem;                                       // [chunks_total][NT][16 B]
   unsigned char* Aring = smem + ((w_bytes + 127) & ~127);           // [GT_STAGES][8 chunks][GT_ALBO]
+  unsigned char* tsm = Aring + GT_STAGES * GT_ASTAGE;                // [GT_EPI_WARPS][32 rows][128 B], swizzled
   const uint32_t acc_stride = p.tmem_cols / 2;
 
   if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
@@ -179,45 +183,69 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
       }
     }
   } else {
-    // ================= epilogue: warp w owns TMEM lanes 32*(w%4).. and the 16-column groups w/4, w/4+2, ... ====
-    const int q = warp & 3;
+    // ================= epilogue: warp w owns TMEM lanes 32*(w%4).. and the 32-column passes w/4, w/4+2, ... ====
+    const int q = warp & 3, half = warp >> 2;
+    const int rr = lane >> 3, cg = lane & 7;               // transposed domain: rows rr + 4i, columns 4cg..4cg+3
+    const uint32_t tw = smem_u32(tsm) + (uint32_t)warp * 4096;
+    uint32_t st_addr[8], ld_addr[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      st_addr[c] = tw + (uint32_t)lane * 128 + (uint32_t)((c ^ (lane & 7)) * 16);
+      const int rl = rr + 4 * c;
+      ld_addr[c] = tw + (uint32_t)rl * 128 + (uint32_t)((cg ^ (rl & 7)) * 16);
+    }
+    const int npass = NT > 32 * half ? (NT - 32 * half + 63) / 64 : 0;
     int it = 0;
     for (int64_t tile = tile0; tile < num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int64_t m = tile * BM + q * 32 + lane;
-      const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
-      for (int c0 = (warp >> 2) * 16; c0 < NT; c0 += 32) {
-        float v[16];
-        tmem_ld16(t_row + c0, v);
-        if (m < p.M) {
-          const int n = nt * NT + c0;
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) v[jj] = tc_act(v[jj] + bias_s[c0 + jj], p.act) + p.act_eps;
-          if (p.res) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.res + m * p.ldr + n);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float4 r = __ldg(r4 + jj);
-              v[4 * jj] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
-            }
-          }
-          if (p.table) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.table + (m % p.table_mod) * p.N + n);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float4 r = __ldg(r4 + jj);
-              v[4 * jj] += r.x; v[4 * jj + 1] += r.y; v[4 * jj + 2] += r.z; v[4 * jj + 3] += r.w;
-            }
-          }
-          float4* dst = reinterpret_cast<float4*>(p.C + m * p.ldc + p.coff + n);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) dst[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-        }
+      if (npass == 0) {                                      // narrow N tile: only keep the barrier phases in step
+        tc_fence_before();
+        mbar_arrive(&acc_empty[acc]);
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);                          // accumulator drained: the MMAs of tile it+2 may start
+      const int64_t m0 = tile * BM + q * 32 + rr;
+      const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
+      for (int k = 0; k < npass; ++k) {
+        const int c0 = 32 * half + 64 * k;
+        uint32_t t32[32];
+        tmem_ld32(t_row + c0, t32);
+        if (k == npass - 1) {                                // accumulator drained: the MMAs of tile it+2 may start
+          tc_fence_before();
+          mbar_arrive(&acc_empty[acc]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr[c]), "r"(t32[4 * c]), "r"(t32[4 * c + 1]),
+                       "r"(t32[4 * c + 2]), "r"(t32[4 * c + 3])
+                       : "memory");
+        __syncwarp();
+        const int col = c0 + 4 * cg;                         // this lane's 4 columns inside the N tile
+        if (col < NT) {
+          const int n = nt * NT + col;
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + 4 * i;
+            float4 t;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(ld_addr[i]));
+            if (m < p.M) {
+              t.x = tc_act(t.x + b4.x, p.act) + p.act_eps; t.y = tc_act(t.y + b4.y, p.act) + p.act_eps;
+              t.z = tc_act(t.z + b4.z, p.act) + p.act_eps; t.w = tc_act(t.w + b4.w, p.act) + p.act_eps;
+              if (p.res) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + m * p.ldr + n));
+                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+              }
+              if (p.table) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.table + (m % p.table_mod) * p.N + n));
+                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+              }
+              *reinterpret_cast<float4*>(p.C + m * p.ldc + p.coff + n) = t;
+            }
+          }
+        }
+        __syncwarp();                                        // the tile is rewritten by the next pass
+      }
     }
   }
   tc_fence_before();
@@ -233,7 +261,7 @@ int tc_pick_ntile(int N, int K) {
   if (N % 16 != 0) return 0;
   const size_t Kp = (size_t)(K + 15) / 16 * 16;
   for (int nt = 256; nt >= 16; nt -= 16)
-    if (N % nt == 0 && ((Kp * nt * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE <= GT_DYN_SMEM) return nt;
+    if (N % nt == 0 && ((Kp * nt * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE + GT_TSM_BYTES <= GT_DYN_SMEM) return nt;
   return 0;
 }
 
@@ -271,9 +299,9 @@ void op_linear_tc(Ctx& c, const LinArgs& a) {
   g.A = a.A; g.lda = a.lda; g.Wp = static_cast<const __nv_bfloat16*>(a.Wp); g.bias = a.bias; g.M = a.M; g.K = a.K;
   g.Kp = (a.K + 15) / 16 * 16; g.N = a.N; g.NT = a.NT; g.C = a.C; g.ldc = a.ldc; g.coff = a.coff; g.act = a.act;
   g.act_eps = a.act_eps; g.res = a.res; g.ldr = a.ldr; g.table = a.table; g.table_mod = a.table_mod;
-  g.tmem_cols = 32;
+  g.tmem_cols = 64;                                        // the epilogue reads 32-column blocks: >= 32 columns per accumulator
   while ((int)g.tmem_cols < 2 * a.NT) g.tmem_cols <<= 1;
-  const size_t smem = (((size_t)g.Kp * a.NT * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE;
+  const size_t smem = (((size_t)g.Kp * a.NT * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE + GT_TSM_BYTES;
   PAUT_CHECK(smem <= GT_DYN_SMEM && (int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED,
              "linear_tc: resident weights do not fit shared memory (N tile too wide for this K)");
   if (smem > c.gemm_tc_smem_configured) {
