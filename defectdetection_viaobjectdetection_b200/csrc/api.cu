@@ -316,13 +316,15 @@ int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float*
     a.bias = static_cast<const float*>(up(b.data(), b.size() * 4));
     try {
       if (impl == 1) {
-        const int nt = paut::tc_pick_ntile(N, K);
+        int stream_b = 0;
+        const int nt = paut::tc_pick_ntile(N, K, &stream_b);
         PAUT_CHECK(nt > 0, PAUT_ERR_UNSUPPORTED, "op_linear: tcgen05 path needs N to be a multiple of 16");
         std::vector<uint16_t> packed;
         int Kp = 0;
         paut::tc_pack_weight(w.data(), N, K, nt, packed, &Kp);
         a.Wp = up(packed.data(), packed.size() * 2);
         a.NT = nt;
+        a.stream_b = stream_b;
         paut::op_linear_tc(c, a);
       } else {
         paut::op_linear(c, a);

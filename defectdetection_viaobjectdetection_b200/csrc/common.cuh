@@ -95,6 +95,7 @@ struct LinArgs {
   const float* W = nullptr;    // [N][K]  (original layout, used when N is tiny)
   const void* Wp = nullptr;    // bf16, packed for tcgen05 (ops_tc.cu); null in fp32 mode
   int NT = 0;                  // N tile of the packed weight
+  int stream_b = 0;            // the packed weight is streamed through the ring (tc_pick_ntile)
   const float* bias = nullptr;
   int64_t M = 0;
   int K = 0, N = 0;
@@ -109,7 +110,7 @@ struct LinArgs {
 };
 void op_linear(Ctx& c, const LinArgs& a);
 // tcgen05 path (ops_tc.cu): bf16 operands, fp32 accumulation in TMEM
-int tc_pick_ntile(int N, int K);
+int tc_pick_ntile(int N, int K, int* stream = nullptr);
 void tc_pack_weight(const float* W, int N, int K, int NT, std::vector<uint16_t>& out, int* Kp_out);
 bool linear_tc_supported(const LinArgs& a);
 void op_linear_tc(Ctx& c, const LinArgs& a);

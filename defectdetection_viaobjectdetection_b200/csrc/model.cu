@@ -248,7 +248,7 @@ Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int r
 // bf16 mode: additionally pack the weight for the tcgen05 GEMM (chunked K-major bf16)
 void Model::pack_tc(Lin& l, const std::vector<float>& W) {
   if (cfg.precision != PAUT_PRECISION_BF16) return;
-  const int nt = tc_pick_ntile(l.N, l.K);
+  const int nt = tc_pick_ntile(l.N, l.K, &l.stream_b);
   if (nt == 0) return;
   std::vector<uint16_t> packed;
   int Kp = 0;
@@ -624,7 +624,7 @@ struct G {
     if (!out) { out = c.allocf((size_t)M * L.N); ldc = L.N; coff = 0; }
     a.C = out; a.ldc = ldc; a.coff = coff; a.act = act; a.act_eps = eps; a.res = res; a.ldr = ldr;
     a.table = table; a.table_mod = mod;
-    a.Wp = L.Wp; a.NT = L.NT;
+    a.Wp = L.Wp; a.NT = L.NT; a.stream_b = L.stream_b;
     if (bf16 && linear_tc_supported(a)) op_linear_tc(c, a);
     else op_linear(c, a);
     return out;

@@ -21,6 +21,7 @@ struct Lin {
   const float* b = nullptr;
   const void* Wp = nullptr;   // bf16 packed for tcgen05 (bf16 mode only)
   int NT = 0;
+  int stream_b = 0;              // tcgen05 GEMM mode chosen with NT (weights resident or streamed)
   int K = 0, N = 0;
 };
 struct ConvW {

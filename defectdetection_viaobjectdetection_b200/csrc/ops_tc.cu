@@ -3,6 +3,9 @@
 // Persistent, warp-specialised (544 threads, one CTA per SM):
 //   * a CTA owns ONE N tile (NT <= 256 columns) whose packed weights ([K/8 chunks][NT rows][16 B], K-major, no
 //     swizzle) stay resident in shared memory, and walks a strided set of 128-row M tiles;
+//     (when K * NT bf16 does not fit, e.g. the 2048-deep FFN output layer, the weights' K blocks ride the ring
+//     next to the activation blocks instead -- `stream_b` -- which keeps the N tile wide: re-reading the
+//     activations once per narrow N tile costs more than re-reading L2-resident weights once per M tile);
 //   * 8 loader warps stream the fp32 activations of a [128 x 64] block with fully coalesced 128-bit loads (two
 //     rows per warp instruction), convert to bf16 and store the canonical K-major operand into a 4-stage ring
 //     (chunk stride 2048+16 B so that the 8-byte stores of a half-warp cover all banks); the loads of the next
@@ -62,6 +65,7 @@ struct GemmTcArgs {
   const float* table;
   int table_mod;
   uint32_t tmem_cols;              // power of two >= 2 * NT
+  int stream_b;                    // weights too large to stay resident at this N tile: their K blocks ride the ring
 };
 
 __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
@@ -78,10 +82,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
   const int64_t num_tiles = (p.M + BM - 1) / BM;
   const int chunks_total = p.Kp / 8;
   const int nkb = (p.Kp + BK - 1) / BK;
-  const int w_bytes = chunks_total * NT * 16;
+  const int w_bytes = p.stream_b ? 0 : chunks_total * NT * 16;
+  const uint32_t stage_bytes = GT_ASTAGE + (p.stream_b ? (uint32_t)NT * 128 : 0u);   // A block (+ B block when streaming)
   unsigned char* Wres = smem;                                       // [chunks_total][NT][16 B]
-  unsigned char* Aring = smem + ((w_bytes + 127) & ~127);           // [GT_STAGES][8 chunks][GT_ALBO]
-  unsigned char* tsm = Aring + GT_STAGES * GT_ASTAGE;                // [GT_EPI_WARPS][32 rows][128 B], swizzled
+  unsigned char* Aring = smem + ((w_bytes + 127) & ~127);           // [GT_STAGES][8 chunks][GT_ALBO] (+ [8][NT][16 B])
+  unsigned char* tsm = Aring + GT_STAGES * stage_bytes;              // [GT_EPI_WARPS][32 rows][128 B], swizzled
   const uint32_t acc_stride = p.tmem_cols / 2;
 
   if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
     fence_mbar_init();
   }
   {  // resident weights of this N tile: one contiguous block of the packed layout
-    const uint4* src = reinterpret_cast<const uint4*>(p.Wp) + (size_t)nt * (w_bytes / 16);
+    const uint4* src = reinterpret_cast<const uint4*>(p.Wp) + (size_t)nt * (chunks_total * NT);
     uint4* dst = reinterpret_cast<uint4*>(Wres);
     for (int i = tid; i < w_bytes / 16; i += GT_THREADS) dst[i] = __ldg(src + i);
   }
@@ -107,7 +112,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
     const int lw = warp - (GT_EPI_WARPS + 1);                       // 0..7: rows lw*16 .. lw*16+15 of the tile
     const int j = lane & 15;                                        // K quad of the block: k = k0 + 4j .. 4j+3
     const int r0 = lw * 16 + (lane >> 4);                           // rows r0, r0+2, ..., r0+14
-    const uint32_t dst0 = smem_u32(Aring) + (uint32_t)(j >> 1) * GT_ALBO + (uint32_t)(j & 1) * 8 + (uint32_t)r0 * 16;
+    const uint32_t ring0 = smem_u32(Aring);
+    const uint32_t dst0 = ring0 + (uint32_t)(j >> 1) * GT_ALBO + (uint32_t)(j & 1) * 8 + (uint32_t)r0 * 16;
     auto load = [&](int64_t tile, int kb, float4 (&v)[8]) {
       const int k = kb * BK + 4 * j;
       const bool kok = k + 4 <= p.K;
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
       }
     };
     auto store = [&](int stage, const float4 (&v)[8]) {
-      const uint32_t d = dst0 + (uint32_t)stage * GT_ASTAGE;
+      const uint32_t d = dst0 + (uint32_t)stage * stage_bytes;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i].x, v[i].y), h1 = __floats2bfloat162_rn(v[i].z, v[i].w);
@@ -129,24 +135,54 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
                      : "memory");
       }
     };
+    // weight block of K block kb -> the B half of a ring stage (cp.async, 16 B per request; contiguous in the packed layout)
+    const int lt = tid - (GT_EPI_WARPS + 1) * 32;                   // 0..255
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.Wp) + (size_t)nt * chunks_total * NT * 16;
+    auto load_b = [&](int kb, int stage) {
+      const int nch = min(8, chunks_total - kb * 8);
+      const uint32_t d = ring0 + (uint32_t)stage * stage_bytes + GT_ASTAGE;
+      const unsigned char* src = wsrc + (size_t)kb * 8 * NT * 16;
+      for (int i = lt; i < nch * NT; i += GT_LOAD_WARPS * 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)i * 16), "l"(src + (size_t)i * 16) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     int64_t tile = tile0;
     int kb = 0, stage = 0;
     uint32_t use = 0;
     float4 cur[8], nxt[8];
     bool have = tile < num_tiles;
-    if (have) load(tile, kb, cur);
+    if (have) {
+      if (p.stream_b) load_b(kb, stage);
+      load(tile, kb, cur);
+    }
     while (have) {
       int64_t tile_n = tile;
       int kb_n = kb + 1;
       if (kb_n == nkb) { kb_n = 0; tile_n += tstep; }
       const bool have_n = tile_n < num_tiles;
-      if (have_n) load(tile_n, kb_n, nxt);                          // next block in flight while this one is stored
-      if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);         // MMAs that read this slot are done
-      store(stage, cur);
+      int stage_n = stage + 1;
+      uint32_t use_n = use;
+      if (stage_n == GT_STAGES) { stage_n = 0; ++use_n; }
+      if (p.stream_b) {
+        // the next block's weights are requested now (its slot must be free), so that they land while this
+        // block's activations are converted; this block's slot was waited for one iteration ago
+        if (have_n) {
+          if (use_n > 0) mbar_wait(&empty[stage_n], (use_n - 1) & 1);
+          load_b(kb_n, stage_n);
+          load(tile_n, kb_n, nxt);
+        }
+        store(stage, cur);
+        if (have_n) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else {
+        if (have_n) load(tile_n, kb_n, nxt);                        // next block in flight while this one is stored
+        if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);       // MMAs that read this slot are done
+        store(stage, cur);
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[stage]);
-      if (++stage == GT_STAGES) { stage = 0; ++use; }
+      stage = stage_n; use = use_n;
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
       tile = tile_n; kb = kb_n; have = have_n;
@@ -167,8 +203,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
         if (leader) {
           tc_fence_after();
           const int nch = min(8, chunks_total - kb * 8);             // chunks of this block (even)
-          uint64_t ad = make_desc(a_ring + (uint32_t)stage * GT_ASTAGE, GT_ALBO, 128);
-          uint64_t bd = make_desc(w_addr + (uint32_t)(kb * 8 * NT) * 16, NT * 16, 128);
+          uint64_t ad = make_desc(a_ring + (uint32_t)stage * stage_bytes, GT_ALBO, 128);
+          uint64_t bd = p.stream_b ? make_desc(a_ring + (uint32_t)stage * stage_bytes + GT_ASTAGE, NT * 16, 128)
+                                   : make_desc(w_addr + (uint32_t)(kb * 8 * NT) * 16, NT * 16, 128);
           const uint32_t d = tmem + acc * acc_stride;
           for (int ks = 0; ks < nch / 2; ++ks) {
             mma_bf16_ss(d, ad, bd, idesc, (kb | ks) ? 1u : 0u);
@@ -255,14 +292,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
 
 }  // namespace
 
-// N tile: the largest multiple of 16 that divides N, is <= 256 and whose resident weights (Kp * NT bf16) fit the
-// shared memory beside the activation ring
-int tc_pick_ntile(int N, int K) {
+// N tile and mode.  Resident mode: the largest multiple of 16 that divides N, is <= 256 and whose weights (Kp * NT
+// bf16) fit the shared memory beside the activation ring.  If that forces more N tiles than the widest legal tile
+// would need, the weights are streamed through the ring instead (stream = 1) and the tile stays wide.
+int tc_pick_ntile(int N, int K, int* stream) {
+  if (stream) *stream = 0;
   if (N % 16 != 0) return 0;
   const size_t Kp = (size_t)(K + 15) / 16 * 16;
-  for (int nt = 256; nt >= 16; nt -= 16)
-    if (N % nt == 0 && ((Kp * nt * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE + GT_TSM_BYTES <= GT_DYN_SMEM) return nt;
-  return 0;
+  int wide = 0, resident = 0;
+  for (int nt = 256; nt >= 16; nt -= 16) {
+    if (N % nt != 0) continue;
+    if (!wide && (size_t)GT_STAGES * (GT_ASTAGE + (size_t)nt * 128) + GT_TSM_BYTES <= GT_DYN_SMEM) wide = nt;
+    if (!resident && ((Kp * nt * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE + GT_TSM_BYTES <= GT_DYN_SMEM) resident = nt;
+  }
+  if (stream && wide > resident) {
+    *stream = 1;
+    return wide;
+  }
+  return resident;
 }
 
 // Host-side packing of an nn.Linear weight [N][K] (fp32) into the chunked K-major bf16 layout.
@@ -301,7 +348,9 @@ void op_linear_tc(Ctx& c, const LinArgs& a) {
   g.act_eps = a.act_eps; g.res = a.res; g.ldr = a.ldr; g.table = a.table; g.table_mod = a.table_mod;
   g.tmem_cols = 64;                                        // the epilogue reads 32-column blocks: >= 32 columns per accumulator
   while ((int)g.tmem_cols < 2 * a.NT) g.tmem_cols <<= 1;
-  const size_t smem = (((size_t)g.Kp * a.NT * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE + GT_TSM_BYTES;
+  g.stream_b = a.stream_b ? 1 : 0;
+  const size_t smem = g.stream_b ? (size_t)GT_STAGES * (GT_ASTAGE + (size_t)a.NT * 128) + GT_TSM_BYTES
+                                 : (((size_t)g.Kp * a.NT * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE + GT_TSM_BYTES;
   PAUT_CHECK(smem <= GT_DYN_SMEM && (int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED,
              "linear_tc: resident weights do not fit shared memory (N tile too wide for this K)");
   if (smem > c.gemm_tc_smem_configured) {
