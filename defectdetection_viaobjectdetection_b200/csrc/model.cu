@@ -1169,6 +1169,18 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
     chunk = next;
     need = footprint(chunk);
   }
+  // bf16 conv models: the pooled-mean epilogue sums per 128-row tile of the flat layout, so which rows share a
+  // tile depends on the A-scan's index modulo the layout period (16 / 32 / 64 A-scans for the row periods 328 /
+  // 164 / 82).  Chunks that start on a multiple of 64 A-scans reproduce the unchunked summation order exactly.
+  if (cfg.precision == PAUT_PRECISION_BF16 && kind != PAUT_MODEL_MSC && kind != PAUT_MODEL_MSC_N && chunk < B) {
+    int64_t a = 64, b = N;
+    while (b) { const int64_t t = a % b; a = b; b = t; }         // a = gcd(64, N)
+    const int64_t align = 64 / a;                                  // sets per alignment period
+    if (chunk >= align && chunk % align != 0) {
+      chunk -= chunk % align;
+      need = footprint(chunk);
+    }
+  }
   c.reserve(need + slack);
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     c.reset();

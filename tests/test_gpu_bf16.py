@@ -105,3 +105,43 @@ def test_bf16_attention_weights_and_shift():
         s = w.sum(-1)
         assert torch.allclose(s, torch.ones_like(s), atol=1e-3)      # rows of averaged softmax sum to 1
         assert (w >= 0).all()
+
+
+@pytest.mark.parametrize("kind", ["msc", "two_stage", "ssd", "enhanced"])
+def test_bf16_chunked_matches_unchunked(kind):
+    """bf16 mode in resident chunks.  Every output row is computed independently, so MSC is bit-exact for any
+    chunking.  The pooled-mean epilogue of the flat-row convolutions sums per 128-row tile; the library therefore
+    starts chunks on multiples of the layout period (64 A-scans = 32 sets of 50), which reproduces the unchunked
+    summation order bit for bit.  Chunks too small to be aligned differ only by fp32 summation order before a
+    bf16 rounding, i.e. by less than the bf16 tolerance itself (7e-3 observed on the enhanced logits)."""
+    N = 300 if kind == "msc" else 50
+    B = 24 if kind == "msc" else 96
+    x = torch.from_numpy(synth.synth_paut_sets(B, N, 320, seed=11, defect_frac=0.1)).to(torch.bfloat16).cuda()
+    m = build(kind, dict(signal_length=320), precision="bf16")
+    ctx = paut.get_context(x.device)
+    ctx.set_workspace_limit(64 << 30)
+    full = run_flat(m, kind, x)
+    ctx.set_workspace_limit((96 << 20) if kind == "msc" else (1100 << 20))      # >= 32 sets of every conv model
+    chunked = run_flat(m, kind, x)
+    ctx.set_workspace_limit(96 << 20)                                            # a few sets: cannot be aligned
+    tiny = run_flat(m, kind, x)
+    ctx.set_workspace_limit(16 << 30)
+    for k in full:
+        assert np.array_equal(full[k], chunked[k]), k
+        if kind == "msc":
+            assert np.array_equal(full[k], tiny[k]), k
+        else:
+            assert np.abs(full[k] - tiny[k]).max() <= BF16_ATOL, (k, np.abs(full[k] - tiny[k]).max())
+
+
+@pytest.mark.parametrize("M,K,N", [(100, 2048, 128), (777, 1024, 256), (33, 640, 256)])
+def test_tcgen05_linear_streamed_weights(M, K, N):
+    """Shapes whose weights cannot stay resident at the full N tile take the streamed-weights mode of the GEMM
+    (K blocks of the weight ride the activation ring); GELU epilogue, ragged M."""
+    g = torch.Generator().manual_seed(K + N + M)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = F.gelu(F.linear(a.to(torch.bfloat16).double(), w.to(torch.bfloat16).double(), b.double())).float()
+    got = op_linear(a.cuda(), w, b, 2, 1).cpu()
+    assert (got - ref).abs().max() <= 3e-4 * max(1.0, ref.abs().max().item())
