@@ -15,13 +15,27 @@ import torch.distributed as dist
 from ._lib import DETECTION
 
 
-def shard_range(n_sets, world_size, rank):
-    """Contiguous, near-equal blocks in scan order: the first ``n_sets % world_size`` ranks get one more set."""
+def shard_range(n_sets, world_size, rank, align=1):
+    """Contiguous, near-equal blocks in scan order: the first ranks get one more unit.
+
+    ``align`` (sets): shard boundaries fall on multiples of it (the last shard takes the remainder).  The bf16
+    convolution models pool per 128-row tile of their flat activation layout, whose period is 64 A-scans:
+    ``align = bf16_shard_alignment(n_per_set)`` makes every shard reproduce the single-GPU result bit for bit."""
     if not (0 <= rank < world_size):
         raise ValueError("rank out of range")
-    base, extra = divmod(int(n_sets), int(world_size))
+    align = max(1, int(align))
+    units = -(-int(n_sets) // align)                     # blocks of `align` sets (the last one may be short)
+    base, extra = divmod(units, int(world_size))
     start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    stop = start + base + (1 if rank < extra else 0)
+    return min(start * align, int(n_sets)), min(stop * align, int(n_sets))
+
+
+def bf16_shard_alignment(n_per_set):
+    """Sets per period of the flat-row layout (64 A-scans): shard / chunk boundaries on its multiples keep the
+    pooled sums of the bf16 convolution models in the same order as an unsharded run."""
+    import math
+    return 64 // math.gcd(64, int(n_per_set))
 
 
 def msc_shard_range(n_scans, seq_length, world_size, rank):

@@ -40,6 +40,18 @@ def _worker(rank, world, port, n_sets, out):
     dist.destroy_process_group()
 
 
+def test_shard_range_alignment():
+    """Aligned shards: boundaries on multiples of the layout period, still an exact partition."""
+    assert sharding.bf16_shard_alignment(50) == 32 and sharding.bf16_shard_alignment(300) == 16
+    for n in (0, 1, 31, 32, 33, 1000, 20000):
+        for w in (1, 2, 4, 8):
+            spans = [sharding.shard_range(n, w, r, align=32) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(lo % 32 == 0 for lo, _ in spans if lo < n)
+
+
 def test_shard_range_partitions_exactly():
     for n in (0, 1, 7, 8, 9, 3334, 160000):
         for w in (1, 2, 4, 8):
