@@ -507,8 +507,8 @@ constexpr int RNN_SB = 8;
 template <int G>
 __global__ void k_rnn_bidir(const float* __restrict__ gi, const float* __restrict__ whh_t,
                             const float* __restrict__ bhh, float* __restrict__ out, int64_t B, int T, int H) {
-  extern __shared__ float sm[];
-  float* hs = sm;                       // [SB][H]
+  extern __shared__ __align__(16) float sm[];
+  float* hs = sm;                       // [H][SB] (transposed: see below)
   float* cs = hs + RNN_SB * H;          // [SB][H] (LSTM cell)
   float* gh = cs + RNN_SB * H;          // [SB][G*H]
   const int dir = blockIdx.y;
@@ -517,6 +517,7 @@ __global__ void k_rnn_bidir(const float* __restrict__ gi, const float* __restric
   const int j = threadIdx.x;            // blockDim.x == GH
   const float* wt = whh_t + (size_t)dir * H * GH;
   const float bj = bhh[dir * GH + j];
+  // hs is stored [H][SB]: the 8 hidden states a thread needs for one k are two 128-bit broadcast loads
   for (int i = j; i < RNN_SB * H; i += GH) { hs[i] = 0.f; cs[i] = 0.f; }
   __syncthreads();
   for (int step = 0; step < T; ++step) {
@@ -524,10 +525,13 @@ __global__ void k_rnn_bidir(const float* __restrict__ gi, const float* __restric
     float acc[RNN_SB];
 #pragma unroll
     for (int s = 0; s < RNN_SB; ++s) acc[s] = bj;
+#pragma unroll 4
     for (int k = 0; k < H; ++k) {
       const float w = __ldg(wt + (size_t)k * GH + j);
-#pragma unroll
-      for (int s = 0; s < RNN_SB; ++s) acc[s] = fmaf(w, hs[s * H + k], acc[s]);
+      const float4 h0 = *reinterpret_cast<const float4*>(hs + k * RNN_SB);
+      const float4 h1 = *reinterpret_cast<const float4*>(hs + k * RNN_SB + 4);
+      acc[0] = fmaf(w, h0.x, acc[0]); acc[1] = fmaf(w, h0.y, acc[1]); acc[2] = fmaf(w, h0.z, acc[2]); acc[3] = fmaf(w, h0.w, acc[3]);
+      acc[4] = fmaf(w, h1.x, acc[4]); acc[5] = fmaf(w, h1.y, acc[5]); acc[6] = fmaf(w, h1.z, acc[6]); acc[7] = fmaf(w, h1.w, acc[7]);
     }
 #pragma unroll
     for (int s = 0; s < RNN_SB; ++s) gh[s * GH + j] = acc[s];
@@ -538,12 +542,13 @@ __global__ void k_rnn_bidir(const float* __restrict__ gi, const float* __restric
       if (b < B) {
         const float* g_in = gi + ((b * T + t) * 2 + dir) * (int64_t)GH;
         const float* g_h = gh + s * GH;
+        const float hprev = hs[u * RNN_SB + s];
         float hnew;
         if (G == 3) {   // GRU: r | z | n
           const float r = sigmoidf_(g_in[u] + g_h[u]);
           const float z = sigmoidf_(g_in[H + u] + g_h[H + u]);
           const float n = tanhf(g_in[2 * H + u] + r * g_h[2 * H + u]);
-          hnew = (1.f - z) * n + z * hs[i];
+          hnew = (1.f - z) * n + z * hprev;
         } else {        // LSTM: i | f | g | o
           const float ig = sigmoidf_(g_in[u] + g_h[u]);
           const float fg = sigmoidf_(g_in[H + u] + g_h[H + u]);
@@ -553,7 +558,7 @@ __global__ void k_rnn_bidir(const float* __restrict__ gi, const float* __restric
           cs[i] = cn;
           hnew = og * tanhf(cn);
         }
-        hs[i] = hnew;
+        hs[u * RNN_SB + s] = hnew;
         out[(b * T + t) * (int64_t)(2 * H) + dir * H + u] = hnew;
       }
     }
