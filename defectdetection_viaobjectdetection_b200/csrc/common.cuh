@@ -171,6 +171,8 @@ struct ConvTcLaunch {
   bool skip_lo = false;          // space-to-depth stride-2 view: tap 0 only multiplies the upper half of Cin
   int groups = 0;                // > 0: grouped mode (conv_tc_pack_grouped); taps = the largest tap count
   int gtaps[4] = {0, 0, 0, 0}, goff[4] = {0, 0, 0, 0};
+  bool shared_input = false;     // groups read the same Cin (= CB) channels with dilations gdil[g]; dil = the largest
+  int gdil[4] = {1, 1, 1, 1};
   const void* Wp = nullptr;      // conv_tc_pack() layout
   const float* shift = nullptr;
   int taps = 1, dil = 1, pad = 0;  // pad in taps (PyTorch padding = pad * dil)

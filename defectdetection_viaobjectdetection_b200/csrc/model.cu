@@ -513,6 +513,38 @@ void Model::finalize() {
         C_(q + "0", q + "1", 1 << r); C_(q + "3", q + "4", 1 << r);
       }
       C_(e + "pyramid_1", e + "pyramid_bn1", 1, true); C_(e + "pyramid_2", e + "pyramid_bn2", 1, true);
+      enh_branches = BranchConv{};
+      if (cfg.precision == PAUT_PRECISION_BF16) {
+        // multi_scale.branch1..4 (64 -> 32 channels, 3 taps, dilation 1/2/4/8, no BN): one shared-input grouped launch
+        std::vector<std::vector<float>> ws(4);
+        std::vector<float> shift_all;
+        const float* wp[4];
+        int taps[4] = {3, 3, 3, 3};
+        bool ok = true;
+        for (int b = 0; b < 4; ++b) {
+          const HostTensor& w = H(e + "multi_scale.branch" + istr(b + 1) + ".weight");
+          const HostTensor& bi = H(e + "multi_scale.branch" + istr(b + 1) + ".bias");
+          ok = ok && w.shape[0] == 32 && w.shape[1] == 64 && w.shape[2] == 3;
+          ws[b].assign((size_t)3 * 64 * 32, 0.f);
+          for (int co = 0; co < 32 && ok; ++co) {
+            shift_all.push_back(bi.data[co]);
+            for (int ci = 0; ci < 64; ++ci)
+              for (int t = 0; t < 3; ++t) ws[b][((size_t)t * 64 + ci) * 32 + co] = w.data[((size_t)co * 64 + ci) * 3 + t];
+          }
+          wp[b] = ws[b].data();
+        }
+        if (ok) {
+          std::vector<uint16_t> packed;
+          conv_tc_pack_grouped(wp, taps, 4, 64, 32, packed, enh_branches.goff);
+          void* dptr = nullptr;
+          PAUT_CUDA(cudaMalloc(&dptr, packed.size() * sizeof(uint16_t)));
+          dev_allocs.push_back(dptr);
+          PAUT_CUDA(cudaMemcpy(dptr, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          enh_branches.Wp = dptr;
+          enh_branches.shift = upload(shift_all);
+          enh_branches.ready = true;
+        }
+      }
       L(e + "fc.0"); N_(e + "fc.1");
       R("sequence_transformer.pos_encoder.pe");
       for (int i = 0; i < cfg.num_layers; ++i)
@@ -969,9 +1001,20 @@ void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_out
     __nv_bfloat16* bufA = g.alloc_flat(A, S, 128);
     __nv_bfloat16* bufB = g.alloc_flat(A, S, 128);
     __nv_bfloat16* bufC = g.alloc_flat(A, S, 128);
-    for (int b = 0; b < 4; ++b)
-      g.convtc(s0, A, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, false, nullptr, 0, bufA, 128, 32 * b,
-               nullptr, 0, 0);
+    if (enh_branches.ready) {
+      // the four dilated branches read the same 64 channels: one launch, one staged window (dilation 8 wide),
+      // one 128-column accumulator = the concatenated output (enhanced_model.py:82-89)
+      ConvTcLaunch a;
+      a.in = s0; a.A = A; a.L = S; a.Cin = 64; a.Cout = 128; a.Wp = enh_branches.Wp; a.shift = enh_branches.shift;
+      a.NT = 128; a.CB = 64; a.groups = 4; a.shared_input = true;
+      for (int b = 0; b < 4; ++b) { a.gtaps[b] = 3; a.goff[b] = enh_branches.goff[b]; a.gdil[b] = 1 << b; }
+      a.taps = 3; a.dil = 8; a.pad = 1; a.relu = false; a.out = bufA; a.ldc = 128; a.coff = 0;
+      op_conv_tc(c, a);
+    } else {
+      for (int b = 0; b < 4; ++b)
+        g.convtc(s0, A, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, false, nullptr, 0, bufA, 128, 32 * b,
+                 nullptr, 0, 0);
+    }
     g.convtc(bufA, A, S, conv[e + "multi_scale.combine.0"], 1, true, nullptr, 0, bufB, 128, 0, nullptr, 0, 0);
     __nv_bfloat16* h = bufB;
     __nv_bfloat16* spare = bufC;

@@ -83,6 +83,12 @@ struct Model {
     int taps[4] = {0, 0, 0, 0}, goff[4] = {0, 0, 0, 0};
     bool ready = false;
   } ts_grouped;
+  struct BranchConv {                          // the enhanced encoder's four dilated branches as one launch
+    const void* Wp = nullptr;
+    const float* shift = nullptr;              // [128] (the conv biases)
+    int goff[4] = {0, 0, 0, 0};
+    bool ready = false;
+  } enh_branches;
   struct SetTc {                               // plain bf16 [N][K] weights of the fused set-stage kernels
     const void* Wqkv_self = nullptr; const void* Wo_self = nullptr;
     const void* Wqkv_cross = nullptr; const void* Wo_cross = nullptr;

@@ -61,8 +61,10 @@ struct ConvTcArgs {
   float* pool;                  // per-tile column sums [tiles][nseg segments][Cout] (nullable)
   int nseg;                     // A-scans a 128-row tile can touch: 2 (period >= 127 rows) or 3
   int skip_lo;                  // space-to-depth stride-2 view: tap 0 multiplies only the upper half of Cin
-  int grouped;                  // grouped mode: channel block cb is its own conv (gtaps[cb] taps, N = NT / ncb columns)
-  int gtaps[4], goff[4];        // taps and resident-weight offset (16-byte units) of every group
+  int grouped;                  // 1: channel block cb is its own conv (gtaps[cb] taps, N = NT / ncb columns);
+                                // 2: ngroups convs share the ONE channel block and differ in dilation gdil[g]
+  int ngroups;
+  int gtaps[4], goff[4], gdil[4];   // taps, resident-weight offset (16-byte units), dilation of every group
   int L, Lp, H0;                // geometry: valid rows per A-scan, period, leading halo
   int64_t A;
   int wrows;                    // window rows = 128 + (taps-1)*dil
@@ -194,7 +196,30 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
           // advances by constant 16-byte-unit amounts with one 32-bit add per MMA
           const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
           const uint32_t a_ks = (uint32_t)(2 * p.wrows), a_t = (uint32_t)p.dil;
-          if (p.grouped) {
+          if (p.grouped == 2) {
+            // multi-dilation branches over the same input block: branch g = taps at (t - pad) * gdil[g] around the
+            // centre of the common window, output columns [g * GN, (g + 1) * GN)
+            const int GN = NT / p.ngroups;
+            const uint32_t idesc_g = make_idesc_bf16(128, GN);
+            const uint32_t b_step = (uint32_t)(2 * GN);
+            for (int g = 0; g < p.ngroups; ++g) {
+              const uint32_t d = tmem + acc * 128 + g * GN;
+              const uint32_t gd = (uint32_t)p.gdil[g];
+              uint32_t ad_t = (((a_addr >> 4) + (uint32_t)(p.pad * (p.dil - p.gdil[g]))) & 0x3FFFu) | ((uint32_t)p.wrows << 16);
+              uint32_t bd = (((w_addr >> 4) + (uint32_t)p.goff[g]) & 0x3FFFu) | ((uint32_t)GN << 16);
+              uint32_t accum = 0u;
+              for (int t = 0; t < p.gtaps[g]; ++t) {
+                uint32_t ad = ad_t;
+                for (int ks = 0; ks < chunks / 2; ++ks) {
+                  mma_bf16_ss2(d, ad, desc_hi, bd, desc_hi, idesc_g, accum);
+                  accum = 1u;
+                  ad += a_ks;
+                  bd += b_step;
+                }
+                ad_t += gd;
+              }
+            }
+          } else if (p.grouped) {
             // branch cb: its own tap count (centred in the common window), its own 32-column block of the accumulator
             const int GN = NT / ncb, tg = p.gtaps[cb];
             const uint32_t idesc_g = make_idesc_bf16(128, GN);
@@ -686,10 +711,13 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   PAUT_CHECK(!a.pool_partial || (p.Lp >= 64 && 4 * p.nseg * p.NT <= 1024), PAUT_ERR_UNSUPPORTED,
              "conv_tc: pooled mean needs a row period >= 64 (and N tile <= 64 below 127)");
   p.skip_lo = a.skip_lo ? 1 : 0;
-  p.grouped = a.groups > 0 ? 1 : 0;
-  for (int g = 0; g < 4; ++g) { p.gtaps[g] = a.gtaps[g]; p.goff[g] = a.goff[g]; }
-  PAUT_CHECK(!p.grouped || (a.groups == a.Cin / p.CB && a.groups <= 4 && p.NT == a.Cout && (p.NT / a.groups) % 16 == 0),
+  p.grouped = a.groups > 0 ? (a.shared_input ? 2 : 1) : 0;
+  p.ngroups = a.groups;
+  for (int g = 0; g < 4; ++g) { p.gtaps[g] = a.gtaps[g]; p.goff[g] = a.goff[g]; p.gdil[g] = a.gdil[g]; }
+  PAUT_CHECK(p.grouped != 1 || (a.groups == a.Cin / p.CB && a.groups <= 4 && p.NT == a.Cout && (p.NT / a.groups) % 16 == 0),
              PAUT_ERR_UNSUPPORTED, "conv_tc: grouped mode needs one channel block and >= 16 output columns per group");
+  PAUT_CHECK(p.grouped != 2 || (a.Cin == p.CB && a.groups <= 4 && p.NT == a.Cout && (p.NT / a.groups) % 16 == 0),
+             PAUT_ERR_UNSUPPORTED, "conv_tc: shared-input groups need a single channel block");
   PAUT_CHECK(!p.skip_lo || (a.Cin / p.CB) % 2 == 0, PAUT_ERR_INVALID, "conv_tc: skip_lo needs an even number of channel blocks");
   p.relu = a.relu ? 1 : 0; p.res = static_cast<const __nv_bfloat16*>(a.res); p.ldr = a.ldr;
   p.out = static_cast<__nv_bfloat16*>(a.out); p.ldc = a.ldc; p.coff = a.coff; p.pool = a.pool_partial;
