@@ -43,7 +43,6 @@ constexpr int CT_EPI_WARPS = 8;          // warps 0-7 epilogue (2 per TMEM lane 
 constexpr int CT_EPI = CT_EPI_WARPS * 32;
 constexpr int CT_THREADS = CT_EPI + 32 + 128;
 constexpr int CT_LOADERS = 128;
-constexpr int CT_LAG = 4;                // loader arrives on stage j-LAG after issuing stage j
 
 struct ConvTcArgs {
   const __nv_bfloat16* in;      // flat rows [R, Cin]
@@ -118,16 +117,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   unsigned long long pt[4] = {0, 0, 0, 0};
 
   if (warp > CT_EPI_WARPS) {
-    // ================= loaders: cp.async of the A windows, CT_LAG stages of look-ahead =================
+    // ================= loaders: cp.async of the A windows, up to CT_STAGES stages of look-ahead =================
     const int l = tid - (CT_EPI_WARPS + 1) * 32;            // 0..127
     const int ch = l & 7;                                   // fixed chunk (8 lanes cover one 128-byte row)
     const int rsub = l >> 3;                                // rows rsub, rsub+16, ...
     const uint32_t a_ring = smem_u32(Aring);
-    int stage = 0, issued = 0;
+    int stage = 0;
     uint32_t use = 0;
-    auto arrive_stage = [&](int j) {                        // stage index of the j-th issued block
-      mbar_arrive(&full[j % CT_STAGES]);
-    };
     for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep) {
       const int64_t wr0 = tile * 128 - (int64_t)p.pad * p.dil;
       for (int cb = 0; cb < ncb; ++cb) {
@@ -158,21 +154,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
             }
           }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        ++issued;
-        if (issued > CT_LAG) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(CT_LAG) : "memory");
-          fence_async_smem();
-          arrive_stage(issued - 1 - CT_LAG);
-        }
+        // the slot's "full" barrier counts this thread in as soon as ITS copies have landed -- no wait here, and no
+        // coupling of the hand-over to the request of a later stage (a wait_group-based hand-over of stage j only
+        // happens once stage j + LAG can be requested, i.e. after the MMAs of stage j - 1 have completed: that
+        // serialised consecutive stages and left the tensor pipe idle between them)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
         if (probe) { const long long q2 = clock64(); pt[0] += q1 - q0; pt[1] += q2 - q1; pt[2] += 1; }
         if (++stage == CT_STAGES) { stage = 0; ++use; }
       }
     }
     if (probe) { p.dbg[0] = pt[0]; p.dbg[1] = pt[1]; p.dbg[2] = pt[2]; }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    fence_async_smem();
-    for (int j = (issued > CT_LAG ? issued - CT_LAG : 0); j < issued; ++j) arrive_stage(j);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing may be in flight when the CTA retires
   } else if (warp == CT_EPI_WARPS) {
     // ================= MMA issuer (one elected lane) =================
     const bool leader = elect_one();
@@ -191,6 +183,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
         const long long m2 = probe ? clock64() : 0;
         if (leader) {
           tc_fence_after();
+          fence_async_smem();                                // cp.async (generic proxy) writes -> tensor-core operand reads
           const uint32_t a_addr = a_ring + (uint32_t)stage * p.a_stage_bytes;
           // descriptors as (lo, hi) words: hi (SBO = 128 B, version 1) is constant; lo = start address | LBO << 16
           // advances by constant 16-byte-unit amounts with one 32-bit add per MMA
