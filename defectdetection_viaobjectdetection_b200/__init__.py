@@ -1,10 +1,14 @@
 """B200-native (sm_100a) batched inference for the PAUT A-scan signal models of
 CSMaus/DefectDetection_viaObjectDetection: drop-in nn.Modules over the libpaut.so C ABI."""
-from .modules import (DETECTION, DefectDetectionModel, EnhancedSignalSequenceDetector, MultiSignalClassifier,
-                      MultiSignalClassifier_N, SignalSequenceDetector, TwoStageDefectDetector,
-                      load_checkpoint_state, sample_indices)
-from .runtime import NativeModel, gather_windows, get_context, window_table
+from .modules import (DETECTION, ComplexDetectionModel, DefectDetectionModel, EnhancedSignalSequenceDetector,
+                      HybridBinaryModel, ImprovedMultiSignalClassifier, MultiSignalClassifier,
+                      MultiSignalClassifier_N, MultiSignalClassifierLegacy, SignalSequenceDetector,
+                      TwoStageDefectDetector, load_checkpoint_state, sample_indices)
+from .runtime import (NativeModel, difference_matrix, gather_windows, get_context, metrics_confusion, metrics_match,
+                      window_table)
 
 __all__ = ["MultiSignalClassifier", "MultiSignalClassifier_N", "DefectDetectionModel", "SignalSequenceDetector",
-           "EnhancedSignalSequenceDetector", "TwoStageDefectDetector", "NativeModel", "get_context",
-           "gather_windows", "window_table", "sample_indices", "load_checkpoint_state", "DETECTION"]
+           "EnhancedSignalSequenceDetector", "TwoStageDefectDetector", "MultiSignalClassifierLegacy",
+           "ImprovedMultiSignalClassifier", "HybridBinaryModel", "ComplexDetectionModel", "NativeModel", "get_context",
+           "gather_windows", "window_table", "difference_matrix", "metrics_match", "metrics_confusion",
+           "sample_indices", "load_checkpoint_state", "DETECTION"]

@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(HERE, "libpaut.so")
 PAUT_MAX_OUTPUTS = 12
 F32, BF16, I64 = 0, 1, 2
 PRECISION = {"fp32": 0, "bf16": 1}
-KINDS = {"msc": 0, "msc_n": 1, "conv1d_msc": 2, "ssd": 3, "enhanced": 4, "two_stage": 5}
+KINDS = {"msc": 0, "msc_n": 1, "conv1d_msc": 2, "ssd": 3, "enhanced": 4, "two_stage": 5,
+         "msc_legacy": 6, "improved": 7, "hybrid": 8, "complex": 9}
 
 # every symbol include/paut.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = (
@@ -21,6 +22,7 @@ SYMBOLS = (
     "paut_model_finalize", "paut_model_num_keys", "paut_model_key", "paut_forward", "paut_postprocess",
     "paut_window_gather", "paut_window_table_host", "paut_ctx_launch_count", "paut_ctx_profile_begin",
     "paut_ctx_profile_end", "paut_op_linear", "paut_debug_mma",
+    "paut_difference_matrix", "paut_metrics_match", "paut_metrics_confusion",
 )
 
 
@@ -30,6 +32,12 @@ class ModelCfg(C.Structure):
         ("d_model", C.c_int32), ("num_classes", C.c_int32), ("num_layers", C.c_int32),
         ("dim_feedforward", C.c_int32), ("precision", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
+
+
+class Metrics(C.Structure):
+    """paut_metrics"""
+    _fields_ = [("tp", C.c_int64), ("fp", C.c_int64), ("fn", C.c_int64), ("tn", C.c_int64),
+                ("sum_iou", C.c_double), ("sum_position_error", C.c_double)]
 
 
 class Outputs(C.Structure):
@@ -86,6 +94,9 @@ def load():
         "paut_ctx_profile_end": (i32, [vp, C.c_char_p, i64]),
         "paut_op_linear": (i32, [vp, vp, i64, i32, vp, vp, i32, vp, i32, i32]),
         "paut_debug_mma": (i32, [vp, i32, i32, i32, i32, i32, vp]),
+        "paut_difference_matrix": (i32, [vp, vp, i32, vp, i64, i64, i64, C.c_double, vp, vp, vp]),
+        "paut_metrics_match": (i32, [vp, i32, vp, vp, i64, i64, vp, vp, C.c_double, vp]),
+        "paut_metrics_confusion": (i32, [vp, vp, vp, i64, C.c_double, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -54,9 +54,10 @@ class _Spec(list):
                 self.append((f"{n}.bias_hh_l{layer}{suf}", (gates * hidden,), "b"))
 
 
-def state_spec(kind, signal_length=320, hidden_sizes=(128, 64, 32), d_model=None, num_classes=2,
-               num_layers=None, dim_feedforward=None):
+def state_spec(kind, signal_length=320, hidden_sizes=None, d_model=None, num_classes=2,
+               num_layers=None, dim_feedforward=None, num_heads=None):
     s = _Spec()
+    hidden_sizes = tuple(hidden_sizes or ((256, 128, 48) if kind == "hybrid" else (128, 64, 32)))
     if kind in ("msc", "msc_n"):                      # signals/multisignalNN/NN_models.py:45-128, :198-246
         h0, h1, h2 = hidden_sizes
         s.conv("conv1d.0", 8, 1, 3)
@@ -191,6 +192,58 @@ def state_spec(kind, signal_length=320, hidden_sizes=(128, 64, 32), d_model=None
             s.lin(m + ".0", 64, d)
             s.ln(m + ".1", 64)
             s.lin(m + ".4", 2, 64)
+    elif kind == "msc_legacy":                        # signals/resaveModelOnnx.py:7-22
+        h0, h1, h2 = hidden_sizes
+        s.lin("shared_layer.0", h0, signal_length)
+        s.lin("shared_layer.2", h1, h0)
+        s.mha("attention", h1)
+        s.lin("classifier.0", h2, h1)
+        s.lin("classifier.2", 1, h2)
+    elif kind in ("improved", "hybrid"):              # improved_model.py:69-121, hybrid_binary.py:83-134
+        hyb = kind == "hybrid"
+        h0, h1, h2 = hidden_sizes
+        if not hyb:
+            s.conv("conv1d.0", 16, 1, 3)
+            s.bn("conv1d.1", 16)
+            s.conv("conv1d.3", 32, 16, 3)
+            s.bn("conv1d.4", 32)
+            s.conv("background_extractor", 32, 1, 15)
+            s.lin("shared_layer.0", h0, signal_length)
+        else:
+            s.conv("conv_layers.0", 32, 1, 3)
+            s.bn("conv_layers.1", 32)
+            s.conv("conv_layers.3", 64, 32, 3)
+            s.bn("conv_layers.4", 64)
+            s.conv("conv_layers.6", 64, 64, 5)
+            s.bn("conv_layers.7", 64)
+            s.lin("shared_layer.0", h0, 256)
+        s.lin("shared_layer.3", h1, h0)
+        s.append(("position_encoding.encoding", (1200 if hyb else 300, h1), "randn"))
+        for i in range(num_layers or 4):
+            t = f"transformer_layers.{i}."
+            s.mha(t + "self_attn", h1)
+            s.conv(t + "local_attn.local_conv", h1, 1, 11 if hyb else 9)
+            if hyb:
+                s.conv(t + "local_attn.local_conv2", h1, 1, 5)
+            s.lin(t + "ffn.0", h2, h1)
+            s.lin(t + "ffn.3", h1, h2)
+            for j in (1, 2, 3):
+                s.ln(f"{t}norm{j}", h1)
+        s.lin("classifier", 1 if hyb else 3, h1)
+    elif kind == "complex":                           # detection_models/complex_detection_model.py:6-61
+        d = d_model or 64
+        s.append(("positional_encoding", (300, d), "randn"))
+        s.conv("conv_layers.0", 32, 1, 3)
+        s.bn("conv_layers.1", 32)
+        s.conv("conv_layers.3", 64, 32, 7)
+        s.bn("conv_layers.4", 64)
+        s.conv("conv_layers.6", 64, 64, 15)
+        s.bn("conv_layers.7", 64)
+        s.lin("feature_projection.0", d, 128)
+        for i in range(num_layers or 4):
+            s.tel(f"transformer.layers.{i}", d, 2 * d)
+        s.lin("detection_head.0", d // 2, d)
+        s.lin("detection_head.3", 1, d // 2)
     else:
         raise ValueError(f"unknown model kind {kind!r}")
     return list(s)

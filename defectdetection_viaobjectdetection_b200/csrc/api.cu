@@ -173,13 +173,17 @@ int paut_model_create(paut_ctx* ctx, int model_kind, const paut_model_cfg* cfg, 
   return guarded(&ctx->c, [&] {
     PAUT_CHECK(out != nullptr, PAUT_ERR_INVALID, "model_create: out is null");
     *out = nullptr;
-    PAUT_CHECK(model_kind >= PAUT_MODEL_MSC && model_kind <= PAUT_MODEL_TWO_STAGE, PAUT_ERR_INVALID,
+    PAUT_CHECK(model_kind >= PAUT_MODEL_MSC && model_kind <= PAUT_MODEL_COMPLEX, PAUT_ERR_INVALID,
                "model_create: unknown model kind");
     paut_model_cfg c{};
     if (cfg) c = *cfg;
     // reference constructor defaults
-    if (c.signal_length <= 0) c.signal_length = (model_kind <= PAUT_MODEL_CONV1D_MSC) ? 320 : 100;
-    if (c.hidden_sizes[0] <= 0) { c.hidden_sizes[0] = 128; c.hidden_sizes[1] = 64; c.hidden_sizes[2] = 32; }
+    const bool seq_kind = model_kind >= PAUT_MODEL_SSD && model_kind <= PAUT_MODEL_TWO_STAGE;
+    if (c.signal_length <= 0) c.signal_length = seq_kind ? 100 : 320;
+    if (c.hidden_sizes[0] <= 0) {
+      if (model_kind == PAUT_MODEL_HYBRID) { c.hidden_sizes[0] = 256; c.hidden_sizes[1] = 128; c.hidden_sizes[2] = 48; }
+      else { c.hidden_sizes[0] = 128; c.hidden_sizes[1] = 64; c.hidden_sizes[2] = 32; }
+    }
     if (c.num_classes <= 0) c.num_classes = 2;
     switch (model_kind) {
       case PAUT_MODEL_MSC:
@@ -205,11 +209,25 @@ int paut_model_create(paut_ctx* ctx, int model_kind, const paut_model_cfg* cfg, 
         if (c.d_model <= 0) c.d_model = 128;
         c.num_heads = 8; c.num_layers = 4; c.dim_feedforward = 512; c.num_classes = 2;
         break;
+      case PAUT_MODEL_MSC_LEGACY:
+        c.num_heads = 4;
+        break;
+      case PAUT_MODEL_IMPROVED:
+      case PAUT_MODEL_HYBRID:
+        if (c.num_heads <= 0) c.num_heads = 8;
+        if (c.num_layers <= 0) c.num_layers = 4;
+        break;
+      case PAUT_MODEL_COMPLEX:
+        if (c.d_model <= 0) c.d_model = 64;
+        if (c.num_heads <= 0) c.num_heads = 8;
+        if (c.num_layers <= 0) c.num_layers = 4;
+        c.dim_feedforward = 2 * c.d_model;
+        break;
     }
     PAUT_CHECK(c.num_classes <= 16, PAUT_ERR_UNSUPPORTED, "num_classes must be <= 16");
     PAUT_CHECK(c.precision == PAUT_PRECISION_FP32 || c.precision == PAUT_PRECISION_BF16, PAUT_ERR_INVALID,
                "precision must be PAUT_PRECISION_FP32 or PAUT_PRECISION_BF16");
-    if (model_kind >= PAUT_MODEL_SSD) {
+    if (seq_kind || model_kind == PAUT_MODEL_COMPLEX) {
       PAUT_CHECK(c.d_model % 32 == 0 && c.d_model <= 1024, PAUT_ERR_UNSUPPORTED,
                  "d_model must be a multiple of 32 and <= 1024");
       PAUT_CHECK(c.dim_feedforward % 4 == 0, PAUT_ERR_UNSUPPORTED, "dim_feedforward must be a multiple of 4");
@@ -285,6 +303,51 @@ int paut_window_gather(paut_ctx* ctx, const void* volume, int src_dtype, int64_t
     PAUT_CHECK(G >= 0 && n > 0 && S > 0 && W >= 0 && L > 0, PAUT_ERR_INVALID, "window_gather: bad sizes");
     PAUT_CUDA(cudaSetDevice(ctx->c.device));
     paut::op_window_gather(ctx->c, volume, src_dtype, G, n, (int)S, table_dev, W, (int)L, sets_dev, dst_dtype);
+  });
+}
+
+int paut_difference_matrix(paut_ctx* ctx, const void* x, int x_dtype, const float* prob, int64_t B, int64_t N,
+                           int64_t S, double threshold, float* reference, float* diff, int32_t* healthy_count) {
+  if (!ctx) return PAUT_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    Ctx& c = ctx->c;
+    PAUT_CHECK(x && prob && B > 0 && N > 0 && S > 0, PAUT_ERR_INVALID, "difference_matrix: bad arguments");
+    PAUT_CHECK(x_dtype == PAUT_F32 || x_dtype == PAUT_BF16, PAUT_ERR_INVALID, "difference_matrix: dtype must be F32 or BF16");
+    PAUT_CHECK(B < 65536, PAUT_ERR_UNSUPPORTED, "difference_matrix: at most 65535 sets per call");
+    PAUT_CUDA(cudaSetDevice(c.device));
+    c.reset();
+    c.reserve((size_t)B * S * sizeof(double) + (size_t)B * sizeof(int32_t) + 1024);
+    paut::op_difference_matrix(c, x, x_dtype, prob, B, (int)N, (int)S, threshold, reference, diff, healthy_count);
+  });
+}
+
+int paut_metrics_match(paut_ctx* ctx, int rule, const paut_detection* det, const int32_t* count_dev, int64_t B,
+                       int64_t N, const int32_t* target_label, const float* target_pos, double iou_threshold,
+                       paut_metrics* out_dev) {
+  if (!ctx) return PAUT_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    Ctx& c = ctx->c;
+    PAUT_CHECK(det && count_dev && target_label && target_pos && out_dev && B > 0 && N > 0, PAUT_ERR_INVALID,
+               "metrics_match: bad arguments");
+    PAUT_CHECK(iou_threshold >= 0.0, PAUT_ERR_INVALID, "metrics_match: iou_threshold must be >= 0");
+    PAUT_CHECK(B < (int64_t(1) << 26), PAUT_ERR_UNSUPPORTED, "metrics_match: too many sets");
+    PAUT_CUDA(cudaSetDevice(c.device));
+    c.reset();
+    c.reserve((size_t)B * 32 + 1024);
+    paut::op_metrics_match(c, rule, det, count_dev, B, (int)N, target_label, target_pos, iou_threshold, out_dev);
+  });
+}
+
+int paut_metrics_confusion(paut_ctx* ctx, const float* prob, const float* label, int64_t M, double threshold, int ge,
+                           paut_metrics* out_dev) {
+  if (!ctx) return PAUT_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    Ctx& c = ctx->c;
+    PAUT_CHECK(prob && label && out_dev && M > 0, PAUT_ERR_INVALID, "metrics_confusion: bad arguments");
+    PAUT_CUDA(cudaSetDevice(c.device));
+    c.reset();
+    c.reserve(4096);
+    paut::op_metrics_confusion(c, prob, label, M, threshold, ge, out_dev);
   });
 }
 

@@ -225,9 +225,34 @@ struct PostArgs {
   int64_t B = 0;
   int N = 0, S = 0;
   double threshold = 0.5;
+  int cmp = 0;                        // MSC-family keep rule: 0 fp64 '>', 1 fp64 '>=', 2 fp32 '>=', 3 fp32 '>'
 };
 void op_postprocess(Ctx& c, const PostArgs& a, paut_detection* det, int32_t* count_dev);
 void op_window_gather(Ctx& c, const void* volume, int src_dtype, int64_t G, int64_t n, int S,
                       const int32_t* table, int64_t W, int L, void* sets, int dst_dtype);
+
+
+// ---------------------------------------------------------------------------------------------
+// SURVEY section 8 "next" rows (ops_next.cu)
+// ---------------------------------------------------------------------------------------------
+// improved_model.py:126-133: f[a,l] = mean_c(x - depthwise_conv_k(x)); in [A,L,C] fp32, w [C][k]
+void op_bgsub_chanmean(Ctx& c, const float* in, int64_t A, int L, int C, int k, const float* w, const float* bias,
+                       float* f);
+// channel mean + (mode 0: AvgPool1d(pk) -> linear interpolate to P | mode 1: AdaptiveAvgPool1d(P)); rows
+// row(a,l) = H0 + a*Lp + l of a [rows, C] fp32 or bf16 buffer -> out [A, P]
+void op_chanmean_resample(Ctx& c, const void* in, int in_dtype, int64_t A, int L, int C, int Lp, int H0, int mode,
+                          int pk, int P, float* out);
+// hybrid_binary.py:147-149: out [B,N,2D] = cat(seq, seq - mean over N)
+void op_seqmean_concat(Ctx& c, const float* seq, int64_t B, int N, int D, float* out);
+// improved_model.py:147-156: sigmoid / clamp / clamp of o [M,3]
+void op_improved_head(Ctx& c, const float* o, int64_t M, float* prob, float* start, float* end);
+// teststtt.py:54-69
+void op_difference_matrix(Ctx& c, const void* x, int x_dtype, const float* prob, int64_t B, int N, int S, double thr,
+                          float* ref, float* diff, int32_t* healthy);
+// two_stage_train.py:284-375 (rule 0), train.py:279-361 (rule 1), acc_metrics_hybrid_binary_dynamic_.py:73-94
+void op_metrics_match(Ctx& c, int rule, const paut_detection* det, const int32_t* count_dev, int64_t B, int N,
+                      const int32_t* tlabel, const float* tpos, double thr, paut_metrics* out);
+void op_metrics_confusion(Ctx& c, const float* prob, const float* label, int64_t M, double thr, int ge,
+                          paut_metrics* out);
 
 }  // namespace paut

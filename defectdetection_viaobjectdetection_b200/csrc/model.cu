@@ -163,6 +163,54 @@ void Model::build_spec() {
       }
       break;
     }
+    case PAUT_MODEL_MSC_LEGACY: {                     // resaveModelOnnx.py:8-22
+      const int h0 = cfg.hidden_sizes[0], h1 = cfg.hidden_sizes[1], h2 = cfg.hidden_sizes[2];
+      b.lin("shared_layer.0", h0, S);
+      b.lin("shared_layer.2", h1, h0);
+      b.mha("attention", h1);
+      b.lin("classifier.0", h2, h1);
+      b.lin("classifier.2", 1, h2);
+      break;
+    }
+    case PAUT_MODEL_IMPROVED:                         // improved_model.py:70-121
+    case PAUT_MODEL_HYBRID: {                         // hybrid_binary.py:88-134
+      const int h0 = cfg.hidden_sizes[0], h1 = cfg.hidden_sizes[1], h2 = cfg.hidden_sizes[2];
+      const bool hyb = kind == PAUT_MODEL_HYBRID;
+      if (!hyb) {
+        b.conv("conv1d.0", 16, 1, 3); b.bn("conv1d.1", 16);
+        b.conv("conv1d.3", 32, 16, 3); b.bn("conv1d.4", 32);
+        b.conv("background_extractor", 32, 1, 15);
+        b.lin("shared_layer.0", h0, S);
+      } else {
+        b.conv("conv_layers.0", 32, 1, 3); b.bn("conv_layers.1", 32);
+        b.conv("conv_layers.3", 64, 32, 3); b.bn("conv_layers.4", 64);
+        b.conv("conv_layers.6", 64, 64, 5); b.bn("conv_layers.7", 64);
+        b.lin("shared_layer.0", h0, 256);
+      }
+      b.lin("shared_layer.3", h1, h0);
+      b.add("position_encoding.encoding", {hyb ? 1200 : 300, h1});
+      for (int i = 0; i < cfg.num_layers; ++i) {
+        const std::string t = "transformer_layers." + istr(i) + ".";
+        b.mha(t + "self_attn", h1);
+        b.conv(t + "local_attn.local_conv", h1, 1, hyb ? 11 : 9);
+        if (hyb) b.conv(t + "local_attn.local_conv2", h1, 1, 5);
+        b.lin(t + "ffn.0", h2, h1);
+        b.lin(t + "ffn.3", h1, h2);
+        for (int j = 1; j <= 3; ++j) b.ln(t + "norm" + istr(j), h1);
+      }
+      b.lin("classifier", hyb ? 1 : 3, h1);
+      break;
+    }
+    case PAUT_MODEL_COMPLEX:                          // complex_detection_model.py:11-61
+      b.add("positional_encoding", {300, d});
+      b.conv("conv_layers.0", 32, 1, 3); b.bn("conv_layers.1", 32);
+      b.conv("conv_layers.3", 64, 32, 7); b.bn("conv_layers.4", 64);
+      b.conv("conv_layers.6", 64, 64, 15); b.bn("conv_layers.7", 64);
+      b.lin("feature_projection.0", d, 128);
+      for (int i = 0; i < cfg.num_layers; ++i) b.tel("transformer.layers." + istr(i), d, 2 * d);
+      b.lin("detection_head.0", d / 2, d);
+      b.lin("detection_head.3", 1, d / 2);
+      break;
     default:
       throw Error(PAUT_ERR_INVALID, "unknown model kind");
   }
@@ -631,6 +679,42 @@ void Model::finalize() {
       }
       break;
     }
+    case PAUT_MODEL_MSC_LEGACY:
+      L("shared_layer.0"); L("shared_layer.2");
+      mha["attention"] = pack_mha("attention", 4);
+      L("classifier.0"); L("classifier.2");
+      break;
+    case PAUT_MODEL_IMPROVED:
+    case PAUT_MODEL_HYBRID: {
+      const bool hyb = kind == PAUT_MODEL_HYBRID;
+      PAUT_CHECK(cfg.hidden_sizes[1] % cfg.num_heads == 0, PAUT_ERR_INVALID,
+                 "embed_dim must be divisible by num_heads");
+      if (!hyb) {
+        C_("conv1d.0", "conv1d.1"); C_("conv1d.3", "conv1d.4");
+        R("background_extractor.weight"); R("background_extractor.bias");
+      } else {
+        C_("conv_layers.0", "conv_layers.1"); C_("conv_layers.3", "conv_layers.4"); C_("conv_layers.6", "conv_layers.7");
+      }
+      L("shared_layer.0"); L("shared_layer.3");
+      R("position_encoding.encoding");
+      for (int i = 0; i < cfg.num_layers; ++i) {
+        const std::string t = "transformer_layers." + istr(i) + ".";
+        mha[t + "self_attn"] = pack_mha(t + "self_attn", cfg.num_heads);
+        R(t + "local_attn.local_conv.weight"); R(t + "local_attn.local_conv.bias");
+        if (hyb) { R(t + "local_attn.local_conv2.weight"); R(t + "local_attn.local_conv2.bias"); }
+        L(t + "ffn.0"); L(t + "ffn.3");
+        for (int j2 = 1; j2 <= 3; ++j2) N_(t + "norm" + istr(j2));
+      }
+      L("classifier");
+      break;
+    }
+    case PAUT_MODEL_COMPLEX:
+      C_("conv_layers.0", "conv_layers.1"); C_("conv_layers.3", "conv_layers.4"); C_("conv_layers.6", "conv_layers.7");
+      L("feature_projection.0");
+      R("positional_encoding");
+      for (int i = 0; i < cfg.num_layers; ++i) tel.push_back(pack_tel("transformer.layers." + istr(i), cfg.num_heads));
+      L("detection_head.0"); L("detection_head.3");
+      break;
   }
   PAUT_CUDA(cudaDeviceSynchronize());
   finalized = true;
@@ -1150,6 +1234,127 @@ void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_out
   if (out.slot[3]) shallow("position_uncertainty", 2, slot_at<float>(out, 3, b0 * N * 2));
 }
 
+// ------------------------------------------------------------------------------------------ section 8 "next" rows
+// f3: the legacy no-conv MultiSignalClassifier (resaveModelOnnx.py:24-33): MLP per A-scan, one self-attention over
+// the set WITHOUT residual or norm, MLP head + sigmoid.
+void Model::fwd_msc_legacy(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+  Ctx& c = *ctx;
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
+  const int64_t A = B * N;
+  const Lin& l0 = lin["shared_layer.0"];
+  const Lin& l2 = lin["shared_layer.2"];
+  float* h0 = g.linear(x, S, l0, A, ACT_RELU);
+  float* h = g.linear(h0, l0.N, l2, A, ACT_RELU);
+  float* att = g.self_attention(h, mha["attention"], B, N, nullptr);
+  float* h1 = g.linear(att, l2.N, lin["classifier.0"], A, ACT_RELU);
+  if (out.slot[0])
+    g.linear(h1, lin["classifier.0"].N, lin["classifier.2"], A, ACT_SIGMOID, nullptr, 0, slot_at<float>(out, 0, b0 * N), 1, 0);
+}
+
+namespace {
+// Three-layer conv stack (1 -> C0 -> C1 -> C2, BN folded, ReLU) followed by channel mean + resampling to 128 values
+// per A-scan (hybrid_binary.py:139-145, complex_detection_model.py:68-75).  bf16 mode: stem into flat rows and the two
+// channel-mixing convolutions on the tcgen05 implicit-GEMM kernel when their weights were packed for it.
+void conv_stack_pooled(Model& m, G& g, const float* x, int64_t A, int S, const char* n0, const char* n1, const char* n2,
+                       int mode, int pk, float* pooled) {
+  Ctx& c = g.c;
+  const ConvW& c0 = m.conv[n0];
+  const ConvW& c1 = m.conv[n1];
+  const ConvW& c2 = m.conv[n2];
+  if (g.tc_convs(S) && c1.Wp && c2.Wp && c1.taps / 2 <= CONV_HALO && c2.taps / 2 <= CONV_HALO) {
+    __nv_bfloat16* a0 = g.alloc_flat(A, S, c0.Cout);
+    g.stem_flat(x, A, S, c0, a0, c0.Cout, 0);
+    __nv_bfloat16* a1 = g.alloc_flat(A, S, c1.Cout);
+    g.convtc(a0, A, S, c1, 1, true, nullptr, 0, a1, c1.Cout, 0, nullptr, 0, 0);
+    __nv_bfloat16* a2 = g.alloc_flat(A, S, c2.Cout);
+    g.convtc(a1, A, S, c2, 1, true, nullptr, 0, a2, c2.Cout, 0, nullptr, 0, 0);
+    op_chanmean_resample(c, a2, PAUT_BF16, A, S, c2.Cout, S + CONV_HALO, CONV_HALO, mode, pk, 128, pooled);
+  } else {
+    float* a0 = c.allocf((size_t)A * S * c0.Cout);
+    op_stem_conv(c, x, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
+    float* a1 = c.allocf((size_t)A * S * c1.Cout);
+    g.conv(a0, A, S, c1, 1, 1, c1.taps / 2, true, nullptr, a1, c1.Cout, 0, nullptr, 0, 0);
+    float* a2 = c.allocf((size_t)A * S * c2.Cout);
+    g.conv(a1, A, S, c2, 1, 1, c2.taps / 2, true, nullptr, a2, c2.Cout, 0, nullptr, 0, 0);
+    op_chanmean_resample(c, a2, PAUT_F32, A, S, c2.Cout, S, 0, mode, pk, 128, pooled);
+  }
+}
+}  // namespace
+
+// f2: ImprovedMultiSignalClassifier (improved_model.py:123-157) and HybridBinaryModel (hybrid_binary.py:136-168):
+// a per-A-scan conv front end, the shared MLP, a learned position table and num_layers encoder layers of the
+// MSC_N type (self-attention -> LN -> depthwise local convolution(s) over the set axis -> LN -> FFN -> LN).
+void Model::fwd_improved(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+  Ctx& c = *ctx;
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
+  const int64_t A = B * N;
+  const bool hyb = kind == PAUT_MODEL_HYBRID;
+  const int D = cfg.hidden_sizes[1];
+  float* feat = nullptr;      // input of shared_layer.0: [A, S] (improved) or [A, 256] (hybrid)
+  int featK = 0;
+  if (!hyb) {
+    const ConvW& c0 = conv["conv1d.0"];
+    const ConvW& c1 = conv["conv1d.3"];
+    float* a0 = c.allocf((size_t)A * S * c0.Cout);
+    op_stem_conv(c, x, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
+    float* a1 = c.allocf((size_t)A * S * c1.Cout);
+    g.conv(a0, A, S, c1, 1, 1, 1, true, nullptr, a1, c1.Cout, 0, nullptr, 0, 0);
+    feat = c.allocf((size_t)A * S);
+    op_bgsub_chanmean(c, a1, A, S, c1.Cout, 15, raw["background_extractor.weight"], raw["background_extractor.bias"], feat);
+    featK = S;
+  } else {
+    float* pooled = c.allocf((size_t)A * 128);
+    const int pk = std::max(1, S / 128);                                       // hybrid_binary.py:108-111
+    conv_stack_pooled(*this, g, x, A, S, "conv_layers.0", "conv_layers.3", "conv_layers.6", /*mode=*/0, pk, pooled);
+    feat = c.allocf((size_t)A * 256);
+    op_seqmean_concat(c, pooled, B, N, 128, feat);
+    featK = 256;
+  }
+  float* h0 = g.linear(feat, featK, lin["shared_layer.0"], A, ACT_RELU);
+  const Lin& l3 = lin["shared_layer.3"];
+  float* h = g.linear(h0, l3.K, l3, A, ACT_RELU, nullptr, 0, nullptr, 0, 0, 0.f, raw["position_encoding.encoding"], N);
+  for (int i = 0; i < cfg.num_layers; ++i) {
+    const std::string t = "transformer_layers." + istr(i) + ".";
+    float* y = g.self_attention(h, mha[t + "self_attn"], B, N, h);
+    h = g.norm(y, nullptr, ln[t + "norm1"], A);
+    float* loc = c.allocf((size_t)A * D);
+    op_dwconv_seq(c, h, raw[t + "local_attn.local_conv.weight"], raw[t + "local_attn.local_conv.bias"], loc, B, N, D,
+                  hyb ? 11 : 9);
+    if (hyb) {
+      float* loc2 = c.allocf((size_t)A * D);
+      op_dwconv_seq(c, loc, raw[t + "local_attn.local_conv2.weight"], raw[t + "local_attn.local_conv2.bias"], loc2, B,
+                    N, D, 5);
+      loc = loc2;
+    }
+    h = g.norm(h, loc, ln[t + "norm2"], A);
+    float* f1 = g.linear(h, D, lin[t + "ffn.0"], A, ACT_RELU);
+    y = g.linear(f1, lin[t + "ffn.0"].N, lin[t + "ffn.3"], A, ACT_NONE, h, D);
+    h = g.norm(y, nullptr, ln[t + "norm3"], A);
+  }
+  if (hyb) {
+    if (out.slot[0]) g.linear(h, D, lin["classifier"], A, ACT_SIGMOID, nullptr, 0, slot_at<float>(out, 0, b0 * N), 1, 0);
+  } else {
+    float* o = g.linear(h, D, lin["classifier"], A);
+    op_improved_head(c, o, A, slot_at<float>(out, 0, b0 * N), slot_at<float>(out, 1, b0 * N), slot_at<float>(out, 2, b0 * N));
+  }
+}
+
+// f2: ComplexDetectionModel (complex_detection_model.py:63-96)
+void Model::fwd_complex(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+  Ctx& c = *ctx;
+  G g{c, cfg.precision == PAUT_PRECISION_BF16};
+  const int64_t A = B * N;
+  const int d = cfg.d_model;
+  float* pooled = c.allocf((size_t)A * 128);
+  conv_stack_pooled(*this, g, x, A, S, "conv_layers.0", "conv_layers.3", "conv_layers.6", /*mode=*/1, 1, pooled);
+  float* h = g.linear(pooled, 128, lin["feature_projection.0"], A, ACT_RELU, nullptr, 0, nullptr, 0, 0, 0.f,
+                      raw["positional_encoding"], N);
+  for (const TELW& t : tel) h = g.encoder_layer(h, t, B, N, ACT_RELU);
+  float* h1 = g.linear(h, d, lin["detection_head.0"], A, ACT_RELU);
+  if (out.slot[0])
+    g.linear(h1, d / 2, lin["detection_head.3"], A, ACT_SIGMOID, nullptr, 0, slot_at<float>(out, 0, b0 * N), 1, 0);
+}
+
 // ------------------------------------------------------------------------------------------ driver
 void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S, const paut_outputs& out) {
   PAUT_CHECK(finalized, PAUT_ERR_STATE, "forward before paut_model_finalize");
@@ -1161,6 +1366,16 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
     PAUT_CHECK(S == cfg.signal_length, PAUT_ERR_INVALID,
                "forward: signal length differs from the model's signal_length (shared_layer.0 in_features)");
     PAUT_CHECK(N <= 300, PAUT_ERR_INVALID, "forward: more than 300 signals per set (position table has 300 rows)");
+  } else if (kind == PAUT_MODEL_MSC_LEGACY) {
+    PAUT_CHECK(S == cfg.signal_length, PAUT_ERR_INVALID,
+               "forward: signal length differs from the model's signal_length (shared_layer.0 in_features)");
+  } else if (kind == PAUT_MODEL_IMPROVED || kind == PAUT_MODEL_HYBRID || kind == PAUT_MODEL_COMPLEX) {
+    PAUT_CHECK(kind != PAUT_MODEL_IMPROVED || S == cfg.signal_length, PAUT_ERR_INVALID,
+               "forward: signal length differs from the model's signal_length (shared_layer.0 in_features)");
+    PAUT_CHECK(kind == PAUT_MODEL_IMPROVED || S >= 128, PAUT_ERR_UNSUPPORTED,
+               "forward: signals shorter than 128 samples are not supported for this model");
+    PAUT_CHECK(N <= (kind == PAUT_MODEL_HYBRID ? 1200 : 300), PAUT_ERR_INVALID,
+               "forward: more signals per set than rows in the position table");
   } else if (kind != PAUT_MODEL_CONV1D_MSC) {
     PAUT_CHECK(N <= 5000, PAUT_ERR_INVALID, "forward: sequence longer than the positional-encoding table");
   }
@@ -1188,6 +1403,10 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
       case PAUT_MODEL_SSD: fwd_ssd(xf, nb, (int)N, (int)S, out, b0, B); break;
       case PAUT_MODEL_ENHANCED: fwd_enhanced(xf, nb, (int)N, (int)S, out, b0, B); break;
       case PAUT_MODEL_TWO_STAGE: fwd_two_stage(xf, nb, (int)N, (int)S, out, b0); break;
+      case PAUT_MODEL_MSC_LEGACY: fwd_msc_legacy(xf, nb, (int)N, (int)S, out, b0); break;
+      case PAUT_MODEL_IMPROVED:
+      case PAUT_MODEL_HYBRID: fwd_improved(xf, nb, (int)N, (int)S, out, b0); break;
+      case PAUT_MODEL_COMPLEX: fwd_complex(xf, nb, (int)N, (int)S, out, b0); break;
       default: throw Error(PAUT_ERR_INVALID, "unknown model kind");
     }
   };
@@ -1245,6 +1464,10 @@ void Model::postprocess(const paut_outputs& o, int64_t B, int64_t N, int64_t S, 
     case PAUT_MODEL_MSC:
     case PAUT_MODEL_MSC_N: a.score_src = need(0); a.start = need(1); a.end = need(2); break;
     case PAUT_MODEL_CONV1D_MSC: a.score_src = need(0); break;
+    case PAUT_MODEL_MSC_LEGACY: a.score_src = need(0); a.cmp = 1; break;
+    case PAUT_MODEL_IMPROVED: a.score_src = need(0); a.start = need(1); a.end = need(2); a.cmp = 1; break;
+    case PAUT_MODEL_HYBRID: a.score_src = need(0); a.cmp = 2; break;
+    case PAUT_MODEL_COMPLEX: a.score_src = need(0); a.cmp = 3; break;
     case PAUT_MODEL_SSD: a.score_src = need(0); a.pos = need(1); a.anomaly = need(2); break;
     case PAUT_MODEL_ENHANCED: a.score_src = need(0); a.unc = need(1); a.pos = need(2); a.anomaly = need(4); break;
     case PAUT_MODEL_TWO_STAGE: a.score_src = need(1); a.unc = need(2); a.pos = need(3); break;

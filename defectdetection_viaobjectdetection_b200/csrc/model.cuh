@@ -122,6 +122,10 @@ struct Model {
   void fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
   void fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
   void fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  // SURVEY section 8 "next" rows f2 / f3
+  void fwd_msc_legacy(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_improved(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_complex(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
 };
 
 }  // namespace paut

@@ -53,7 +53,12 @@ __device__ __forceinline__ Decision decide(const PostArgs& p, int64_t m) {
   } else {  // MSC family
     d.score = p.score_src[m];
     d.conf = (double)d.score;
-    d.keep = d.conf > p.threshold;
+    switch (p.cmp) {                                   // include/paut.h "Keep rule"
+      case 1: d.keep = d.conf >= p.threshold; break;
+      case 2: d.keep = d.score >= (float)p.threshold; break;
+      case 3: d.keep = d.score > (float)p.threshold; break;
+      default: d.keep = d.conf > p.threshold; break;
+    }
     d.start = p.start ? p.start[m] : 0.f;
     d.end = p.end ? p.end[m] : 0.f;
   }

@@ -279,6 +279,92 @@ class TwoStageDefectDetector(PautModule):
                 for b, rows in enumerate(_group_by_set(rec, B))]
 
 
+# ------------------------------------------------------------------------------------------------ SURVEY section 8 "next" rows
+class MultiSignalClassifierLegacy(PautModule):
+    """The no-conv ``MultiSignalClassifier`` of signals/resaveModelOnnx.py:7-33 (same class in
+    GNN_testing_multi_v2_MAP.py:16-36, teststtt.py) -- the one the repository's MultiSignalClassifier_model*.pth
+    checkpoints load into.  forward(x[B,N,S]) -> outputs[B,N]."""
+
+    _kind = "msc_legacy"
+
+    def __init__(self, signal_length, hidden_sizes):
+        super().__init__(dict(signal_length=signal_length, hidden_sizes=tuple(list(hidden_sizes)[:3])))
+
+    @torch.no_grad()
+    def forward(self, x):
+        _, (o, _, _) = self._run(x)
+        return o["defect_prob"]
+
+    @torch.no_grad()
+    def difference_matrix(self, x, threshold=0.5):
+        """teststtt.py:54-69 for every set of x: (outputs [B,N], reference [B,S], diff [B,N,S], healthy_count [B])."""
+        from .runtime import difference_matrix
+        prob = self.forward(x)
+        ref, diff, healthy = difference_matrix(x, prob, threshold)
+        return prob, ref, diff, healthy
+
+
+class ImprovedMultiSignalClassifier(PautModule):
+    """signals/improved_multisignal/improved_model.py:69-197."""
+
+    _kind = "improved"
+
+    def __init__(self, signal_length, hidden_sizes, num_heads=8, dropout=0.1, num_transformer_layers=4):
+        hidden_sizes = list(hidden_sizes)
+        if hidden_sizes[1] % num_heads != 0:
+            raise AssertionError("embed_dim must be divisible by num_heads")
+        super().__init__(dict(signal_length=signal_length, hidden_sizes=tuple(hidden_sizes[:3]), num_heads=num_heads,
+                              num_layers=num_transformer_layers))
+
+    @torch.no_grad()
+    def forward(self, x):
+        _, (o, _, _) = self._run(x)
+        return o["defect_prob"], o["defect_start"], o["defect_end"]
+
+    def predict(self, x, threshold=0.5):
+        """improved_model.py:160-197: keep iff prob >= threshold."""
+        B = x.shape[0]
+        rec = self.predict_records(x, threshold)
+        return [[{"position": int(r["position"]), "defect_prob": float(r["score"]),
+                  "defect_position": [float(r["start"]), float(r["end"])]} for r in rows]
+                for rows in _group_by_set(rec, B)]
+
+
+class HybridBinaryModel(PautModule):
+    """signals/improved_multisignal/detection_models/hybrid_binary.py:83-168.  forward(x[B,N,S]) -> defect_prob[B,N]."""
+
+    _kind = "hybrid"
+
+    def __init__(self, signal_length=320, hidden_sizes=(256, 128, 48), num_heads=8, dropout=0.15,
+                 num_transformer_layers=4):
+        hidden_sizes = list(hidden_sizes)
+        if hidden_sizes[1] % num_heads != 0:
+            raise AssertionError("embed_dim must be divisible by num_heads")
+        super().__init__(dict(signal_length=signal_length, hidden_sizes=tuple(hidden_sizes[:3]), num_heads=num_heads,
+                              num_layers=num_transformer_layers))
+
+    @torch.no_grad()
+    def forward(self, x):
+        _, (o, _, _) = self._run(x)
+        return o["defect_prob"]
+
+
+class ComplexDetectionModel(PautModule):
+    """signals/improved_multisignal/detection_models/complex_detection_model.py:6-96.  forward -> detection_prob[B,N]."""
+
+    _kind = "complex"
+
+    def __init__(self, signal_length=320, d_model=64, num_heads=8, num_layers=4, dropout=0.1):
+        if d_model % num_heads != 0:
+            raise AssertionError("embed_dim must be divisible by num_heads")
+        super().__init__(dict(signal_length=signal_length, d_model=d_model, num_heads=num_heads, num_layers=num_layers))
+
+    @torch.no_grad()
+    def forward(self, x):
+        _, (o, _, _) = self._run(x)
+        return o["defect_prob"]
+
+
 def sample_indices(defect_position, signal_length):
     """predict.py:111-113 / signal_visualizer.py:409-410: int(start * len(signal)) with the float32 product."""
     p = np.asarray(defect_position, dtype=np.float32) * np.float32(signal_length)
@@ -291,5 +377,6 @@ def load_checkpoint_state(ckpt):
 
 
 __all__ = ["MultiSignalClassifier", "MultiSignalClassifier_N", "DefectDetectionModel", "SignalSequenceDetector",
-           "EnhancedSignalSequenceDetector", "TwoStageDefectDetector", "sample_indices", "load_checkpoint_state",
-           "DETECTION"]
+           "EnhancedSignalSequenceDetector", "TwoStageDefectDetector", "MultiSignalClassifierLegacy",
+           "ImprovedMultiSignalClassifier", "HybridBinaryModel", "ComplexDetectionModel", "sample_indices",
+           "load_checkpoint_state", "DETECTION"]

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DETECTION, KINDS, PRECISION, ModelCfg, Outputs, check
+from ._lib import DETECTION, KINDS, PRECISION, Metrics, ModelCfg, Outputs, check
 
 _contexts = {}
 _contexts_lock = threading.Lock()
@@ -27,6 +27,11 @@ OUTPUT_SLOTS = {
                  ("attention_weights", "LNN"), ("context_attention", "N"), ("cross_attention", "NN")],
     "two_stage": [("defect_logits", "N2"), ("defect_probs", "N2"), ("defect_uncertainty", "N2"),
                   ("position_preds", "N2"), ("position_uncertainty", "N2")],
+    # SURVEY section 8 "next" rows f2 / f3
+    "msc_legacy": [("defect_prob", "N")],
+    "improved": [("defect_prob", "N"), ("defect_start", "N"), ("defect_end", "N")],
+    "hybrid": [("defect_prob", "N")],
+    "complex": [("defect_prob", "N")],
 }
 
 
@@ -231,3 +236,67 @@ def gather_windows(volume, rule, seq_length=50, out_dtype=None, keep_groups=None
                                      C.c_void_p(table_dev.data_ptr()), len(table), seq_length,
                                      C.c_void_p(sets.data_ptr()), dt[out_dtype]), ctx.handle)
     return sets, table
+
+
+# ------------------------------------------------------------------------------------------------ section 8 rows f3 / f4
+def _f32c(t, name):
+    if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+        raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor")
+    return t
+
+
+def difference_matrix(x, prob, threshold=0.5, want_diff=True):
+    """signals/teststtt.py:54-69 on device for a batch of sets: x [B,N,S] (fp32/bf16), prob [B,N] fp32 ->
+    (reference [B,S], diff [B,N,S] or None, healthy_count int32 [B]).  Sets without a healthy A-scan
+    (the reference returns None) have healthy_count 0 and zero rows."""
+    if not (x.is_cuda and x.is_contiguous() and x.dim() == 3):
+        raise RuntimeError("x must be a contiguous CUDA tensor [B,N,S]")
+    B, N, S = x.shape
+    _f32c(prob, "prob")
+    dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[x.dtype]
+    ctx = get_context(x.device)
+    ref = torch.empty((B, S), dtype=torch.float32, device=x.device)
+    diff = torch.empty((B, N, S), dtype=torch.float32, device=x.device) if want_diff else None
+    healthy = torch.empty(B, dtype=torch.int32, device=x.device)
+    check(ctx.lib.paut_difference_matrix(ctx.handle, C.c_void_p(x.data_ptr()), dt, C.c_void_p(prob.data_ptr()), B, N, S,
+                                         float(threshold), C.c_void_p(ref.data_ptr()),
+                                         C.c_void_p(diff.data_ptr()) if want_diff else None,
+                                         C.c_void_p(healthy.data_ptr())), ctx.handle)
+    return ref, diff, healthy
+
+
+def _metrics_out(device):
+    return torch.zeros(C.sizeof(Metrics), dtype=torch.uint8, device=device)
+
+
+def _metrics_read(buf):
+    m = Metrics.from_buffer_copy(buf.cpu().numpy().tobytes())
+    return dict(tp=m.tp, fp=m.fp, fn=m.fn, tn=m.tn, sum_iou=m.sum_iou, sum_position_error=m.sum_position_error)
+
+
+def metrics_match(rule, det, count, B, N, target_label, target_pos, iou_threshold=0.5):
+    """Detection-level matching on device.  rule 'position' = two_stage_train.py:284-375, 'class' =
+    train.py:279-361.  det/count: what NativeModel.postprocess returned; target_label int32 [B,N],
+    target_pos fp32 [B,N,2].  Returns the paut_metrics fields as a dict."""
+    r = {"position": 0, "class": 1}[rule]
+    if not (target_label.is_cuda and target_label.dtype == torch.int32 and target_label.is_contiguous()):
+        raise RuntimeError("target_label must be a contiguous int32 CUDA tensor")
+    _f32c(target_pos, "target_pos")
+    ctx = get_context(det.device)
+    out = _metrics_out(det.device)
+    check(ctx.lib.paut_metrics_match(ctx.handle, r, C.c_void_p(det.data_ptr()), C.c_void_p(count.data_ptr()), B, N,
+                                     C.c_void_p(target_label.data_ptr()), C.c_void_p(target_pos.data_ptr()),
+                                     float(iou_threshold), C.c_void_p(out.data_ptr())), ctx.handle)
+    return _metrics_read(out)
+
+
+def metrics_confusion(prob, label, threshold=0.5, ge=True):
+    """acc_metrics_hybrid_binary_dynamic_.py:73-94 on device: TP / FP / FN / TN of (prob >= thr) vs (label > 0.5)."""
+    _f32c(prob, "prob")
+    _f32c(label, "label")
+    ctx = get_context(prob.device)
+    out = _metrics_out(prob.device)
+    check(ctx.lib.paut_metrics_confusion(ctx.handle, C.c_void_p(prob.data_ptr()), C.c_void_p(label.data_ptr()),
+                                         prob.numel(), float(threshold), 1 if ge else 0, C.c_void_p(out.data_ptr())),
+          ctx.handle)
+    return _metrics_read(out)

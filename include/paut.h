@@ -50,7 +50,13 @@ typedef enum {
   PAUT_MODEL_CONV1D_MSC = 2, /* signals/MSC_Conv1D_training.py:50-89        DefectDetectionModel    */
   PAUT_MODEL_SSD = 3,        /* SignalSequenceDetection/model.py:230-343    SignalSequenceDetector  */
   PAUT_MODEL_ENHANCED = 4,   /* SignalSequenceDetection/enhanced_model.py:449-566                   */
-  PAUT_MODEL_TWO_STAGE = 5   /* SignalSequenceDetection/two_stage_model.py:254-312                  */
+  PAUT_MODEL_TWO_STAGE = 5,  /* SignalSequenceDetection/two_stage_model.py:254-312                  */
+  /* SURVEY section 8 "next" rows f2 / f3 */
+  PAUT_MODEL_MSC_LEGACY = 6, /* signals/resaveModelOnnx.py:7-33 (= GNN_testing_multi_v2_MAP.py:16-36): the no-conv
+                                MultiSignalClassifier the repository ships trained .pth weights for             */
+  PAUT_MODEL_IMPROVED = 7,   /* signals/improved_multisignal/improved_model.py:69-157 ImprovedMultiSignalClassifier */
+  PAUT_MODEL_HYBRID = 8,     /* signals/improved_multisignal/detection_models/hybrid_binary.py:83-168 HybridBinaryModel */
+  PAUT_MODEL_COMPLEX = 9     /* .../detection_models/complex_detection_model.py:6-96 ComplexDetectionModel       */
 } paut_model_kind;
 
 typedef enum { PAUT_F32 = 0, PAUT_BF16 = 1, PAUT_I64 = 2 } paut_dtype;
@@ -66,6 +72,10 @@ typedef enum { PAUT_PRECISION_FP32 = 0, PAUT_PRECISION_BF16 = 1 } paut_precision
  *   SSD         : (signal_length, d_model, num_classes, nhead, num_layers, dim_feedforward) model.py:234-243
  *   ENHANCED    : same six, enhanced_model.py:453-462 (cross-attention heads fixed at 8, :491)
  *   TWO_STAGE   : (signal_length, d_model, num_classes)  two_stage_model.py:258 (nhead 8, 4 layers, ff 512)
+ *   MSC_LEGACY  : (signal_length, hidden_sizes[3])  resaveModelOnnx.py:8 (4 heads, fixed)
+ *   IMPROVED    : (signal_length, hidden_sizes[3], num_heads=8, num_layers=num_transformer_layers=4) improved_model.py:70
+ *   HYBRID      : (signal_length=320, hidden_sizes={256,128,48}, num_heads=8, num_layers=4)  hybrid_binary.py:88
+ *   COMPLEX     : (signal_length=320, d_model=64, num_heads=8, num_layers=4)  complex_detection_model.py:11
  * A zero field selects the reference default. */
 typedef struct {
   int32_t signal_length;
@@ -90,7 +100,11 @@ typedef struct {
  *                 6 attention_weights[L,B,N,N] (layer-major) 7 context_attention[B,N]
  *                 8 cross_attention[B,N,N]                                   enhanced_model.py:556-566
  *   TWO_STAGE   : 0 defect_logits[B,N,2] 1 defect_probs[B,N,2] 2 defect_uncertainty[B,N,2]
- *                 3 position_preds[B,N,2] 4 position_uncertainty[B,N,2]      two_stage_model.py:305-312 */
+ *                 3 position_preds[B,N,2] 4 position_uncertainty[B,N,2]      two_stage_model.py:305-312
+ *   MSC_LEGACY  : 0 outputs[B,N] (sigmoid)                                       resaveModelOnnx.py:33
+ *   IMPROVED    : 0 defect_prob[B,N] 1 defect_start[B,N] 2 defect_end[B,N] (clamped) improved_model.py:147-157
+ *   HYBRID      : 0 defect_prob[B,N]                                             hybrid_binary.py:165-168
+ *   COMPLEX     : 0 detection_prob[B,N]                                complex_detection_model.py:93-96 */
 #define PAUT_MAX_OUTPUTS 12
 typedef struct {
   void* slot[PAUT_MAX_OUTPUTS];
@@ -157,6 +171,13 @@ int paut_forward(paut_model* m, const void* x, int x_dtype, int64_t B, int64_t N
 int paut_postprocess(paut_model* m, const paut_outputs* outs, int64_t B, int64_t N, int64_t S,
                      double threshold, paut_detection* det, int32_t* count_dev);
 
+/* Keep rule of paut_postprocess for the single-probability kinds (start/end are 0 where the model has none):
+ *   MSC, MSC_N, CONV1D_MSC : float64(prob) >  threshold   model_pred.py:84, evalMSC.py:91
+ *   MSC_LEGACY             : float64(prob) >= threshold   teststtt.py:60,66 (tolist() -> Python floats)
+ *   IMPROVED               : float64(prob) >= threshold   improved_model.py:178-181 (.item())
+ *   HYBRID                 : prob >= float32(threshold)   acc_metrics_hybrid_binary_dynamic_.py:84 (tensor compare)
+ *   COMPLEX                : prob >  float32(threshold)   test_detection.py:77 (tensor compare) */
+
 /* Windowing + cast (a0): gathers fixed-length sets from a resident volume [G, n, S]
  * (json_dataset.py:84-103, dataset_preparation.py:222-282, cast json_dataset.py:112-116).
  * table_dev is int32 [W,3] = (group, start, valid_len) rows; rows >= valid_len are zero.
@@ -166,6 +187,35 @@ int paut_window_gather(paut_ctx* ctx, const void* volume, int src_dtype, int64_t
 /* Host-side window tables for the two reference rules (rule 0 = signals/ json_dataset rule,
  * 1 = SignalSequenceDetection rule).  Writes up to cap (start, valid_len) pairs, returns the count. */
 int paut_window_table_host(int rule, int64_t n, int64_t L, int32_t* pairs_host, int cap);
+
+/* f3 -- reference signal and difference matrix (signals/teststtt.py:54-69).  Per set b: reference[b,:] = mean of
+ * the A-scans with prob < threshold (fp64 accumulation in set order, like np.mean(axis=0) of the float64 rows),
+ * diff[b,i,:] = |x[b,i,:] - reference[b,:]| where prob >= threshold, zeros elsewhere.  A set without a healthy
+ * A-scan (the reference returns None and skips it) gets healthy_count 0 and zero rows.  x is [B,N,S] F32 or BF16;
+ * reference [B,S], diff [B,N,S] fp32 (either may be NULL), healthy_count int32 [B] (may be NULL). */
+int paut_difference_matrix(paut_ctx* ctx, const void* x, int x_dtype, const float* prob, int64_t B, int64_t N,
+                           int64_t S, double threshold, float* reference, float* diff, int32_t* healthy_count);
+
+/* f4 -- detection-level metrics on device.  The fp64 sums are accumulated in a fixed order (reproducible);
+ * precision / recall / F1 / means are three divisions the caller does on these numbers. */
+typedef struct {
+  int64_t tp, fp, fn, tn;          /* tn only from paut_metrics_confusion                            */
+  double sum_iou;                  /* rule 1: sum of the matched IoUs (mean_iou = sum_iou / tp)      */
+  double sum_position_error;       /* rule 0: sum of (|ds| + |de|) / 2 over the matches              */
+} paut_metrics;
+/* det/count_dev: the records paut_postprocess wrote ((set, position) order).  Targets are dense:
+ * target_label int32 [B,N] (> 0 = defect, the class for rule 1), target_pos fp32 [B,N,2] = (start, end).
+ *   rule 0: two_stage_train.py:284-375 calculate_metrics -- match on the same position, TP iff IoU > iou_threshold
+ *   rule 1: train.py:279-361 calculate_metrics -- greedy first match in target order on equal class, IoU > iou_threshold
+ *           (0.5 in the reference)
+ * IoU arithmetic is fp32, as in the reference (numpy float32 scalars on both sides).  out_dev: one paut_metrics. */
+int paut_metrics_match(paut_ctx* ctx, int rule, const paut_detection* det, const int32_t* count_dev, int64_t B,
+                       int64_t N, const int32_t* target_label, const float* target_pos, double iou_threshold,
+                       paut_metrics* out_dev);
+/* acc_metrics_hybrid_binary_dynamic_.py:73-94: preds = prob >= float32(threshold) (ge = 1; ge = 0: '>',
+ * test_detection.py:77), y = label > 0.5; TP / FP / FN / TN over M values. */
+int paut_metrics_confusion(paut_ctx* ctx, const float* prob, const float* label, int64_t M, double threshold, int ge,
+                           paut_metrics* out_dev);
 
 /* One fused linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) on device buffers A, C (fp32, contiguous);
  * W and bias may be host or device memory and are packed on every call (a unit-test / stand-alone entry,

@@ -368,7 +368,92 @@ def two_stage_forward(sd, x, nhead=8, precision="fp32"):
             "attention_weights": None}
 
 
+# --------------------------------------------------------------------------- SURVEY section 8 "next" rows
+def msc_legacy_forward(sd, x, precision="fp32"):
+    """Legacy no-conv MultiSignalClassifier.forward, signals/resaveModelOnnx.py:24-33 (identical copies in
+    GNN_testing_multi_v2_MAP.py:16-36, teststtt.py): MLP, one self-attention (4 heads) with no residual, MLP head."""
+    sd, x = _prep(sd, x, precision)
+    h = F.relu(linear(sd, "shared_layer.0", x))
+    h = F.relu(linear(sd, "shared_layer.2", h))
+    a, _ = mha(sd, "attention", h, h, 4)
+    o = torch.sigmoid(linear(sd, "classifier.2", F.relu(linear(sd, "classifier.0", a))))
+    return o.squeeze(-1)
+
+
+def _local_encoder_layer(sd, t, h, num_heads, kernels):
+    """improved_model.py:55-67 / hybrid_binary.py:65-80: self-attention -> LN -> depthwise conv(s) along the set
+    axis (LocalAttention) -> LN -> FFN -> LN, dropout = identity."""
+    a, _ = mha(sd, t + "self_attn", h, h, num_heads)
+    h = layer_norm(sd, t + "norm1", h + a)
+    loc = h.permute(0, 2, 1)
+    for name, k in kernels:
+        loc = conv1d(sd, t + "local_attn." + name, loc, padding=k // 2, groups=loc.shape[1])
+    h = layer_norm(sd, t + "norm2", h + loc.permute(0, 2, 1))
+    f = linear(sd, t + "ffn.3", F.relu(linear(sd, t + "ffn.0", h)))
+    return layer_norm(sd, t + "norm3", h + f)
+
+
+def improved_forward(sd, x, num_heads=8, precision="fp32"):
+    """ImprovedMultiSignalClassifier.forward, improved_model.py:123-157."""
+    sd, x = _prep(sd, x, precision)
+    B, N, S = x.shape
+    h = x.reshape(B * N, 1, S)
+    h = F.relu(bn_eval(sd, "conv1d.1", conv1d(sd, "conv1d.0", h, padding=1)))
+    h = F.relu(bn_eval(sd, "conv1d.4", conv1d(sd, "conv1d.3", h, padding=1)))
+    h = h - conv1d(sd, "background_extractor", h, padding=7, groups=32)          # :130-131
+    h = h.mean(dim=1)
+    h = F.relu(linear(sd, "shared_layer.0", h))
+    h = F.relu(linear(sd, "shared_layer.3", h)).view(B, N, -1)
+    h = h + sd["position_encoding.encoding"][:N][None]
+    for i in range(_n_layers(sd, "transformer_layers.")):
+        h = _local_encoder_layer(sd, f"transformer_layers.{i}.", h, num_heads, (("local_conv", 9),))
+    o = linear(sd, "classifier", h)
+    return torch.sigmoid(o[..., 0]), torch.clamp(o[..., 1], 0.0, 1.0), torch.clamp(o[..., 2], 0.0, 1.0)
+
+
+def _conv_stack3(sd, h, pads):
+    for idx, pad in zip((0, 3, 6), pads):
+        h = F.relu(bn_eval(sd, f"conv_layers.{idx + 1}", conv1d(sd, f"conv_layers.{idx}", h, padding=pad)))
+    return h
+
+
+def hybrid_forward(sd, x, num_heads=8, precision="fp32"):
+    """HybridBinaryModel.forward, hybrid_binary.py:136-168."""
+    sd, x = _prep(sd, x, precision)
+    B, N, S = x.shape
+    h = _conv_stack3(sd, x.reshape(B * N, 1, S), (1, 1, 2))
+    k = max(S // 128, 1)                                                         # :108-111
+    h = F.avg_pool1d(h, kernel_size=k, stride=k)
+    h = F.interpolate(h, size=128, mode="linear", align_corners=False)           # :145
+    seq = h.mean(dim=1).view(B, N, -1)
+    seq = torch.cat([seq, seq - seq.mean(dim=1, keepdim=True)], dim=-1)          # :147-149
+    h = F.relu(linear(sd, "shared_layer.0", seq))
+    h = F.relu(linear(sd, "shared_layer.3", h))
+    h = h + sd["position_encoding.encoding"][:N][None]
+    for i in range(_n_layers(sd, "transformer_layers.")):
+        h = _local_encoder_layer(sd, f"transformer_layers.{i}.", h, num_heads, (("local_conv", 11), ("local_conv2", 5)))
+    return torch.sigmoid(linear(sd, "classifier", h).squeeze(-1))
+
+
+def complex_forward(sd, x, num_heads=8, precision="fp32"):
+    """ComplexDetectionModel.forward, complex_detection_model.py:63-96."""
+    sd, x = _prep(sd, x, precision)
+    B, N, S = x.shape
+    h = _conv_stack3(sd, x.reshape(B * N, 1, S), (1, 3, 7))
+    h = F.adaptive_avg_pool1d(h, 128).mean(dim=1)                                # :71-75
+    h = F.relu(linear(sd, "feature_projection.0", h)).view(B, N, -1)
+    h = h + sd["positional_encoding"][:N][None]
+    for i in range(_n_layers(sd, "transformer.layers.")):
+        h, _ = encoder_layer(sd, f"transformer.layers.{i}", h, num_heads)
+    h = F.relu(linear(sd, "detection_head.0", h))
+    return torch.sigmoid(linear(sd, "detection_head.3", h).squeeze(-1))
+
+
 FORWARD = {
+    "msc_legacy": msc_legacy_forward,
+    "improved": improved_forward,
+    "hybrid": hybrid_forward,
+    "complex": complex_forward,
     "msc": msc_forward,
     "msc_n": msc_n_forward,
     "conv1d_msc": conv1d_msc_forward,

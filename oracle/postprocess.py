@@ -96,12 +96,33 @@ def two_stage_postprocess(defect_probs, defect_uncertainty, position_preds, thre
                  np.asarray(position_preds, np.float32), signal_length)
 
 
-def msc_postprocess(defect_prob, defect_start, defect_end, threshold, signal_length):
+def keep_rule(score_f32, threshold, cmp):
+    """The four ways the reference thresholds a single probability:
+    'gt64' model_pred.py:84 / evalMSC.py:91 (`.item()`-style fp64 `>`); 'ge64' improved_model.py:178-181,
+    teststtt.py:60,66 (Python floats, `>=`); 'ge32' acc_metrics_hybrid_binary_dynamic_.py:84 and 'gt32'
+    test_detection.py:77 (tensor comparison: the Python scalar is rounded to fp32 first)."""
+    s = np.asarray(score_f32, np.float32)
+    if cmp == "gt64":
+        return s.astype(np.float64) > threshold
+    if cmp == "ge64":
+        return s.astype(np.float64) >= threshold
+    if cmp == "ge32":
+        return s >= np.float32(threshold)
+    if cmp == "gt32":
+        return s > np.float32(threshold)
+    raise ValueError(cmp)
+
+
+KEEP_RULE = {"msc": "gt64", "msc_n": "gt64", "conv1d_msc": "gt64", "msc_legacy": "ge64", "improved": "ge64",
+             "hybrid": "ge32", "complex": "gt32"}
+
+
+def msc_postprocess(defect_prob, defect_start, defect_end, threshold, signal_length, cmp="gt64"):
     """MSC callers: model_pred.py:82-85 / evalMSC.py:91 -- `prob > 0.5` (strict) marks the A-scan
-    defective; start/end are the model's fractional positions."""
+    defective; start/end are the model's fractional positions.  Other single-probability models: keep_rule."""
     score = np.asarray(defect_prob, np.float32)
     conf = score.astype(np.float64)
-    keep = conf > threshold
+    keep = keep_rule(score, threshold, cmp)
     pos = np.stack([np.asarray(defect_start, np.float32), np.asarray(defect_end, np.float32)], axis=-1)
     return _emit(keep, np.ones(score.shape, np.int32), score, np.zeros_like(score), np.zeros_like(score),
                  conf, pos, signal_length)
@@ -111,12 +132,14 @@ def postprocess(kind, outputs, threshold, signal_length):
     """Dispatch on model kind; ``outputs`` is what oracle.models.FORWARD[kind] returns."""
     def npy(t):
         return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
-    if kind in ("msc", "msc_n"):
-        return msc_postprocess(*(npy(o) for o in outputs), threshold, signal_length)
-    if kind == "conv1d_msc":
-        p = npy(outputs)
+    if kind in ("msc", "msc_n", "improved"):
+        if isinstance(outputs, dict):
+            outputs = (outputs["defect_prob"], outputs["defect_start"], outputs["defect_end"])
+        return msc_postprocess(*(npy(o) for o in outputs), threshold, signal_length, KEEP_RULE[kind])
+    if kind in ("conv1d_msc", "msc_legacy", "hybrid", "complex"):
+        p = npy(outputs["defect_prob"] if isinstance(outputs, dict) else outputs)
         z = np.zeros_like(p)
-        return msc_postprocess(p, z, z, threshold, signal_length)
+        return msc_postprocess(p, z, z, threshold, signal_length, KEEP_RULE[kind])
     if kind == "ssd":
         return ssd_postprocess(npy(outputs["class_preds"]), npy(outputs["position_preds"]),
                                npy(outputs["anomaly_scores"]), threshold, signal_length)

@@ -17,6 +17,11 @@ Reference classes (paths relative to the reference root):
   ssd        SignalSequenceDetection/model.py:230-285    SignalSequenceDetector
   enhanced   SignalSequenceDetection/enhanced_model.py:449-500
   two_stage  SignalSequenceDetection/two_stage_model.py:254-271
+SURVEY section 8 "next" rows:
+  msc_legacy signals/resaveModelOnnx.py:7-22 (the class the shipped MultiSignalClassifier_model*.pth belong to)
+  improved   signals/improved_multisignal/improved_model.py:69-121   ImprovedMultiSignalClassifier
+  hybrid     signals/improved_multisignal/detection_models/hybrid_binary.py:83-134   HybridBinaryModel
+  complex    signals/improved_multisignal/detection_models/complex_detection_model.py:6-61
 """
 from __future__ import annotations
 
@@ -26,7 +31,8 @@ from collections import OrderedDict
 
 import numpy as np
 
-KINDS = ("msc", "msc_n", "conv1d_msc", "ssd", "enhanced", "two_stage")
+KINDS = ("msc", "msc_n", "conv1d_msc", "ssd", "enhanced", "two_stage",
+         "msc_legacy", "improved", "hybrid", "complex")
 
 # role -> how the tensor is filled
 #   w   : U(-1/sqrt(fan_in), 1/sqrt(fan_in))   (fan_in = prod(shape[1:]))
@@ -85,10 +91,11 @@ def _rnn(spec, name, gates, in0, hidden, layers=2):
             spec[f"{name}.bias_hh_l{layer}{suffix}"] = ((gates * hidden,), "b", hidden)
 
 
-def state_spec(kind, signal_length=320, hidden_sizes=(128, 64, 32), d_model=None,
-               num_classes=2, num_layers=None, dim_feedforward=None):
+def state_spec(kind, signal_length=320, hidden_sizes=None, d_model=None,
+               num_classes=2, num_layers=None, dim_feedforward=None, num_heads=None):
     """Ordered {key: (shape, role, fan)} following the reference's registration order."""
     s = OrderedDict()
+    hidden_sizes = tuple(hidden_sizes or ((256, 128, 48) if kind == "hybrid" else (128, 64, 32)))
     if kind in ("msc", "msc_n"):
         h0, h1, h2 = hidden_sizes
         _conv(s, "conv1d.0", 8, 1, 3)
@@ -222,6 +229,60 @@ def state_spec(kind, signal_length=320, hidden_sizes=(128, 64, 32), d_model=None
             _lin(s, f"{mod}.{sub}.0", 64, d)
             _ln(s, f"{mod}.{sub}.1", 64)
             _lin(s, f"{mod}.{sub}.4", 2, 64)
+    elif kind == "msc_legacy":
+        h0, h1, h2 = hidden_sizes
+        _lin(s, "shared_layer.0", h0, signal_length)
+        _lin(s, "shared_layer.2", h1, h0)
+        _mha(s, "attention", h1)
+        _lin(s, "classifier.0", h2, h1)
+        _lin(s, "classifier.2", 1, h2)
+    elif kind in ("improved", "hybrid"):
+        hyb = kind == "hybrid"
+        h0, h1, h2 = hidden_sizes
+        nl = num_layers or 4
+        if not hyb:
+            _conv(s, "conv1d.0", 16, 1, 3)
+            _bn(s, "conv1d.1", 16)
+            _conv(s, "conv1d.3", 32, 16, 3)
+            _bn(s, "conv1d.4", 32)
+            _conv(s, "background_extractor", 32, 1, 15)
+            _lin(s, "shared_layer.0", h0, signal_length)
+        else:
+            _conv(s, "conv_layers.0", 32, 1, 3)
+            _bn(s, "conv_layers.1", 32)
+            _conv(s, "conv_layers.3", 64, 32, 3)
+            _bn(s, "conv_layers.4", 64)
+            _conv(s, "conv_layers.6", 64, 64, 5)
+            _bn(s, "conv_layers.7", 64)
+            _lin(s, "shared_layer.0", h0, 256)
+        _lin(s, "shared_layer.3", h1, h0)
+        s["position_encoding.encoding"] = ((1200 if hyb else 300, h1), "randn", 0)
+        for i in range(nl):
+            t = f"transformer_layers.{i}."
+            _mha(s, t + "self_attn", h1)
+            _conv(s, t + "local_attn.local_conv", h1, 1, 11 if hyb else 9)
+            if hyb:
+                _conv(s, t + "local_attn.local_conv2", h1, 1, 5)
+            _lin(s, t + "ffn.0", h2, h1)
+            _lin(s, t + "ffn.3", h1, h2)
+            for j in (1, 2, 3):
+                _ln(s, f"{t}norm{j}", h1)
+        _lin(s, "classifier", 1 if hyb else 3, h1)
+    elif kind == "complex":
+        d = d_model or 64
+        nl = num_layers or 4
+        s["positional_encoding"] = ((300, d), "randn", 0)
+        _conv(s, "conv_layers.0", 32, 1, 3)
+        _bn(s, "conv_layers.1", 32)
+        _conv(s, "conv_layers.3", 64, 32, 7)
+        _bn(s, "conv_layers.4", 64)
+        _conv(s, "conv_layers.6", 64, 64, 15)
+        _bn(s, "conv_layers.7", 64)
+        _lin(s, "feature_projection.0", d, 128)
+        for i in range(nl):
+            _tel(s, f"transformer.layers.{i}", d, 2 * d)
+        _lin(s, "detection_head.0", d // 2, d)
+        _lin(s, "detection_head.3", 1, d // 2)
     else:
         raise ValueError(f"unknown model kind {kind!r}")
     return s

@@ -1,6 +1,7 @@
 """Generate the golden fixtures by running the REFERENCE classes (build container only).
 
     python tests/golden/make_golden.py            # needs /root/reference
+    python tests/golden/make_golden.py --only msc_legacy,improved,hybrid,complex   # add kinds, keep the rest
 
 For every hot-path model it imports the reference class from /root/reference,
 loads the synthetic weights of oracle/synth.py with a strict load_state_dict,
@@ -50,7 +51,25 @@ CASES = [
     ("two_stage", "u2x50", dict(), dict(gen="uniform", B=2, N=50, S=320, seed=1234)),
     ("two_stage", "p3x37", dict(), dict(gen="paut", B=3, N=37, S=320, seed=7)),
     ("two_stage", "s100", dict(signal_length=100), dict(gen="uniform", B=2, N=50, S=100, seed=5)),
+    # SURVEY section 8 "next" rows f2 / f3
+    ("msc_legacy", "u2x300", dict(), dict(gen="uniform", B=2, N=300, S=320, seed=1234)),
+    # the shipped checkpoints saturate at 0 on [0,1] synthetic volumes (they were trained on other amplitudes), which
+    # would make parity trivial: the inputs are scaled into the range where each checkpoint's sigmoid is informative
+    ("msc_legacy", "real4p2x300", dict(weights="MultiSignalClassifier_model4.pth"),
+     dict(gen="paut", B=2, N=300, S=320, seed=7, scale=-0.5)),
+    ("msc_legacy", "realOPDp1x298", dict(weights="MultiSignalClassifier_modelOPD.pth"),
+     dict(gen="paut", B=1, N=298, S=320, seed=11, scale=0.25)),
+    ("msc_legacy", "realFPDp2x170", dict(weights="MultiSignalClassifier_modelFPD.pth", signal_length=360),
+     dict(gen="paut", B=2, N=170, S=360, seed=9, scale=0.1)),
+    ("improved", "u2x300", dict(), dict(gen="uniform", B=2, N=300, S=320, seed=1234)),
+    ("improved", "p1x37", dict(), dict(gen="paut", B=1, N=37, S=320, seed=7)),
+    ("hybrid", "u2x300", dict(), dict(gen="uniform", B=2, N=300, S=320, seed=1234)),
+    ("hybrid", "p1x37", dict(), dict(gen="paut", B=1, N=37, S=320, seed=7)),
+    ("hybrid", "h192p3x50", dict(hidden_sizes=[256, 192, 64]), dict(gen="paut", B=3, N=50, S=320, seed=13)),
+    ("complex", "u2x300", dict(), dict(gen="uniform", B=2, N=300, S=320, seed=1234)),
+    ("complex", "p1x37", dict(), dict(gen="paut", B=1, N=37, S=320, seed=7)),
 ]
+SPEC_KEYS = ("num_classes", "signal_length", "hidden_sizes", "d_model", "num_layers")
 
 
 def make_input(spec):
@@ -60,6 +79,8 @@ def make_input(spec):
         x = synth.synth_paut_sets(spec["B"], spec["N"], spec["S"], seed=spec["seed"], defect_frac=0.2)
     if spec.get("transpose"):
         x = np.ascontiguousarray(x.transpose(0, 2, 1))
+    if "scale" in spec:
+        x = (x * np.float32(spec["scale"])).astype(np.float32)
     return x
 
 
@@ -73,7 +94,18 @@ def reference_classes():
     src = open(os.path.join(REF, "signals", "MSC_Conv1D_training.py")).read().split("\n")
     ns = {}
     exec("import torch\nimport torch.nn as nn\n" + "\n".join(src[49:89]), ns)
+    legacy_src = open(os.path.join(REF, "signals", "resaveModelOnnx.py")).read().split("\n")
+    ns2 = {}
+    exec("import torch\nimport torch.nn as nn\n" + "\n".join(legacy_src[6:33]), ns2)   # class only: the script exports at import
+    sys.path.insert(0, os.path.join(REF, "signals", "improved_multisignal"))
+    from improved_model import ImprovedMultiSignalClassifier
+    from detection_models.hybrid_binary import HybridBinaryModel
+    from detection_models.complex_detection_model import ComplexDetectionModel
     return {
+        "msc_legacy": lambda **c: ns2["MultiSignalClassifier"](c.get("signal_length", 320), [128, 64, 32]),
+        "improved": lambda **c: ImprovedMultiSignalClassifier(c.get("signal_length", 320), [128, 64, 32], 8),
+        "hybrid": lambda **c: HybridBinaryModel(**{k: v for k, v in c.items() if k in ("signal_length", "hidden_sizes")}),
+        "complex": lambda **c: ComplexDetectionModel(),
         "msc": lambda **c: MultiSignalClassifier(c.get("signal_length", 320), [128, 64, 32], 4),
         "msc_n": lambda **c: MultiSignalClassifier_N(c.get("signal_length", 320), [128, 64, 32], 4),
         "conv1d_msc": lambda **c: ns["DefectDetectionModel"](320, 300),
@@ -93,7 +125,10 @@ def records_to_array(kind, preds, S):
             rec["start"], rec["end"] = start, end
             rec["start_index"] = int(start * S)            # predict.py:111-113 verbatim expression
             rec["end_index"] = int(end * S)
-            if kind == "two_stage":
+            if kind == "improved":
+                rec["cls"] = 1
+                rec["score"] = rec["confidence"] = r["defect_prob"]
+            elif kind == "two_stage":
                 rec["cls"] = 1
                 rec["score"], rec["uncertainty"] = r["defect_prob"], r["defect_uncertainty"]
                 rec["confidence"] = r["adjusted_confidence"]
@@ -109,9 +144,9 @@ def records_to_array(kind, preds, S):
 
 
 def flatten_outputs(kind, out):
-    if kind in ("msc", "msc_n"):
+    if kind in ("msc", "msc_n", "improved"):
         return {"defect_prob": out[0], "defect_start": out[1], "defect_end": out[2]}
-    if kind == "conv1d_msc":
+    if kind in ("conv1d_msc", "msc_legacy", "hybrid", "complex"):
         return {"defect_prob": out}
     flat = {}
     for k, v in out.items():
@@ -166,15 +201,128 @@ def windowing_vectors():
     return vec
 
 
+def _ref_functions(path, names, extra=None):
+    """exec only the named top-level functions of a reference script (the scripts train / plot at import)."""
+    import ast
+    import math
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "torch": torch, "math": math}
+    ns.update(extra or {})
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns
+
+
+def metrics_vectors():
+    """f4 / f3 known answers from the reference's own functions: two_stage_train.calculate_metrics,
+    train.calculate_metrics, acc_metrics_hybrid_binary_dynamic_.evaluate, teststtt.calculate_*."""
+    from oracle import metrics as om
+    rng = np.random.default_rng(2024)
+    B, N = 23, 50
+    # predictions: records as paut_postprocess would emit them ((set, position) order, unique positions)
+    keep = rng.random((B, N)) < 0.4
+    label = (rng.random((B, N)) < 0.35).astype(np.int32) * rng.integers(1, 3, size=(B, N)).astype(np.int32)
+    tpos = np.sort(rng.random((B, N, 2), dtype=np.float32), axis=-1)
+    ppos = tpos + rng.normal(0, 0.08, size=(B, N, 2)).astype(np.float32)        # some overlap well, some do not
+    ppos[rng.random((B, N)) < 0.1] = np.float32(0.25)                           # zero-length predictions (union may be 0)
+    tpos[rng.random((B, N)) < 0.05] = np.float32(0.25)
+    ppos = ppos.astype(np.float32)
+    b, i = np.nonzero(keep)
+    rec = np.zeros(b.size, dtype=DETECTION)
+    rec["set_index"], rec["position"] = b, i
+    rec["cls"] = rng.integers(1, 3, size=b.size)
+    rec["start"], rec["end"] = ppos[b, i, 0], ppos[b, i, 1]
+    preds = om.records_to_predictions(rec, B)
+    ssd = os.path.join(REF, "SignalSequenceDetection")
+    f_ts = _ref_functions(os.path.join(ssd, "two_stage_train.py"), {"calculate_metrics"})["calculate_metrics"]
+    f_tr = _ref_functions(os.path.join(ssd, "train.py"), {"calculate_metrics"})["calculate_metrics"]
+    out = {"rec": rec, "label": label, "tpos": tpos}
+    # rule 0: targets as two_stage_train.py:249-262 builds them
+    targets0 = om.targets_from_dense(label, tpos)
+    thr0 = [0.5, 0.3, 0.0, 0.75]
+    res0 = [f_ts(preds, targets0, iou_threshold=t) for t in thr0]
+    out["rule0_thr"] = np.asarray(thr0)
+    out["rule0_counts"] = np.asarray([[r["true_positives"], r["false_positives"], r["false_negatives"]] for r in res0])
+    out["rule0_mean_err"] = np.asarray([float(r["mean_position_error"]) for r in res0])
+    # rule 1: targets as the SSD dataset yields them (dict with label + bbox tensor; train.py:300-307)
+    targets1 = [[{"label": int(label[bb, ii]), "position": ii,
+                  "bbox": torch.tensor([0.0, 1.0, tpos[bb, ii, 0], tpos[bb, ii, 1]])} for ii in range(N)]
+                for bb in range(B)]
+    r1 = f_tr(preds, targets1)
+    out["rule1_counts"] = np.asarray([r1["true_positives"], r1["false_positives"], r1["false_negatives"]])
+    out["rule1_mean_iou"] = np.asarray(float(r1["mean_iou"]))
+    # confusion counts: evaluate() of the hybrid accuracy script on a fake loader
+    acc = os.path.join(REF, "signals", "improved_multisignal", "acc_metrics_hybrid_binary_dynamic_.py")
+    fns = _ref_functions(acc, {"evaluate", "safe_div", "mcc"})
+    prob = rng.random((7, 300), dtype=np.float32)
+    prob[0, :5] = np.float32(0.7)                                 # == float32(0.7) but < 0.7 in fp64
+    lab = (rng.random((7, 300)) < 0.3).astype(np.float32)
+
+    class _M:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return x
+
+    conf = []
+    for thr in (0.5, 0.7):
+        counts, _ = fns["evaluate"](_M(), [(torch.from_numpy(prob), torch.from_numpy(lab), None)], "cpu", threshold=thr)
+        conf.append([counts["TP"], counts["FP"], counts["FN"], counts["TN"]])
+    out.update(conf_prob=prob, conf_label=lab, conf_thr=np.asarray([0.5, 0.7]), conf_counts=np.asarray(conf))
+    # f3: teststtt.py:54-69 on float64 rows (np.loadtxt), three sets incl. one without a healthy A-scan
+    fd = _ref_functions(os.path.join(REF, "signals", "teststtt.py"),
+                        {"calculate_reference_signal", "calculate_difference_matrix"})
+    x = synth.synth_paut_sets(3, 40, 320, seed=77, defect_frac=0.3)
+    p = rng.random((3, 40), dtype=np.float32)
+    p[2] = np.float32(0.9)                                        # no healthy A-scan -> reference None
+    p[0, 3] = np.float32(0.5)                                     # boundary: >= 0.5 is defective
+    refs, diffs, healthy = [], [], []
+    for s in range(3):
+        sig = [row.astype(np.float64) for row in x[s]]
+        pl = [float(v) for v in p[s]]
+        r = fd["calculate_reference_signal"](pl, sig)
+        healthy.append(sum(v < 0.5 for v in pl))
+        if r is None:
+            refs.append(np.zeros(320))
+            diffs.append(np.zeros((40, 320)))
+        else:
+            refs.append(r)
+            diffs.append(fd["calculate_difference_matrix"](r, pl, sig))
+    out.update(diff_x_seed=np.asarray(77), diff_prob=p, diff_ref=np.asarray(refs), diff_mat=np.asarray(diffs),
+               diff_healthy=np.asarray(healthy, np.int32))
+    np.savez_compressed(os.path.join(HERE, "metrics_vectors.npz"), **out)
+    print("wrote metrics_vectors.npz", out["rule0_counts"].tolist(), out["rule1_counts"].tolist(), conf, healthy)
+
+
 def main():
+    if "--metrics" in sys.argv:
+        metrics_vectors()
+        return
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     classes = reference_classes()
     manifest = {}
+    only = None                                     # --only kind[,kind]: add cases without touching the other fixtures
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
+        with open(os.path.join(HERE, "state_manifest.json")) as f:
+            manifest = json.load(f)
     for kind, case, cfg, spec in CASES:
+        if only is not None and kind not in only:
+            continue
         model = classes[kind](**cfg)
-        spec_cfg = {k: v for k, v in cfg.items() if k in ("num_classes", "signal_length")}
-        sd = synth.synth_state_dict(kind, seed=0, **spec_cfg)
+        spec_cfg = {k: v for k, v in cfg.items() if k in SPEC_KEYS}
+        if "weights" in cfg:
+            # f3: the trained checkpoints the reference ships (signals/MultiSignalClassifier_model*.pth); stored as a
+            # test fixture so that the GPU box (no /root/reference) can run the real-weights parity case
+            sd = torch.load(os.path.join(REF, "signals", cfg["weights"]), map_location="cpu", weights_only=True)
+            np.savez_compressed(os.path.join(HERE, "weights_" + cfg["weights"][:-4] + ".npz"),
+                                **{k: v.numpy() for k, v in sd.items()})
+        else:
+            sd = synth.synth_state_dict(kind, seed=0, **spec_cfg)
         ref_keys = list(model.state_dict().keys())
         assert ref_keys == list(sd.keys()), f"{kind}: state_dict key/order mismatch"
         for k, v in model.state_dict().items():
@@ -193,7 +341,9 @@ def main():
                     torch=torch.__version__, numpy=np.__version__)
         if hasattr(model, "predict"):
             S = spec["S"]
-            if kind == "two_stage":
+            if kind == "improved":
+                conf = flat["defect_prob"].astype(np.float64)
+            elif kind == "two_stage":
                 conf = flat["defect_probs"][..., 1].astype(np.float64) / (1.0 + flat["defect_uncertainty"][..., 1].astype(np.float64))
             elif kind == "enhanced":
                 p = torch.softmax(torch.from_numpy(flat["class_preds"]), -1).numpy()
@@ -212,8 +362,9 @@ def main():
               + (f" records {[len(save[f'rec{i}']) for i in range(3)]}" if "rec0" in save else ""))
     with open(os.path.join(HERE, "state_manifest.json"), "w") as f:
         json.dump(manifest, f, indent=0, sort_keys=True)
-    with open(os.path.join(HERE, "windowing.json"), "w") as f:
-        json.dump(windowing_vectors(), f, sort_keys=True)
+    if only is None:
+        with open(os.path.join(HERE, "windowing.json"), "w") as f:
+            json.dump(windowing_vectors(), f, sort_keys=True)
     print("ok")
 
 

@@ -55,6 +55,10 @@ MODELS = {
     "ssd": lambda cfg: paut.SignalSequenceDetector(**cfg),
     "enhanced": lambda cfg: paut.EnhancedSignalSequenceDetector(**cfg),
     "two_stage": lambda cfg: paut.TwoStageDefectDetector(cfg.get("signal_length", 320)),
+    "msc_legacy": lambda cfg: paut.MultiSignalClassifierLegacy(cfg.get("signal_length", 320), [128, 64, 32]),
+    "improved": lambda cfg: paut.ImprovedMultiSignalClassifier(cfg.get("signal_length", 320), [128, 64, 32], 8),
+    "hybrid": lambda cfg: paut.HybridBinaryModel(**{k: v for k, v in cfg.items() if k in ("signal_length", "hidden_sizes")}),
+    "complex": lambda cfg: paut.ComplexDetectionModel(),
 }
 
 
@@ -87,6 +91,8 @@ def test_constructor_errors_match_reference():
         paut.MultiSignalClassifier_N(320, [128, 64, 32], 9)          # training_01.py:116 num_heads=9
     with pytest.raises(AssertionError):
         paut.SignalSequenceDetector(d_model=128, nhead=7)
+    with pytest.raises(AssertionError):
+        paut.ImprovedMultiSignalClassifier(320, [128, 64, 32], num_heads=9)
 
 
 def test_window_table_host_matches_oracle():

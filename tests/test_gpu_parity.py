@@ -12,7 +12,7 @@ from defectdetection_viaobjectdetection_b200._lib import Outputs
 from oracle import models as om
 from oracle import postprocess as opp
 from oracle import synth, windowing
-from tests._golden import case_id, flatten, golden_files, load_case
+from tests._golden import case_id, case_state_dict, flatten, golden_files, load_case
 from tests.test_abi import MODELS
 
 pytestmark = pytest.mark.gpu
@@ -21,9 +21,9 @@ FP32_ATOL = 1e-4     # north_star: fp32 mode within 1e-4 absolute
 BF16_ATOL = 1e-2     # north_star: bf16 I/O within 1e-2 absolute
 
 
-def build(kind, cfg, precision="fp32"):
+def build(kind, cfg, precision="fp32", sd=None):
     m = MODELS[kind](cfg)
-    m.load_state_dict(synth.synth_state_dict(kind, seed=0, **cfg), strict=True)
+    m.load_state_dict(sd if sd is not None else synth.synth_state_dict(kind, seed=0, **cfg), strict=True)
     m = m.cuda().eval()
     m.precision = precision
     return m
@@ -38,7 +38,7 @@ def run_flat(m, kind, x):
 @pytest.mark.parametrize("path", FILES, ids=case_id)
 def test_forward_fp32_matches_reference_golden(path):
     c = load_case(path)
-    m = build(c["kind"], c["cfg"])
+    m = build(c["kind"], c["cfg"], sd=case_state_dict(c))
     got = run_flat(m, c["kind"], torch.from_numpy(c["x"]).cuda())
     assert set(got) == set(c["outs"])
     for k, ref in c["outs"].items():
@@ -50,15 +50,19 @@ def test_forward_fp32_matches_reference_golden(path):
 @pytest.mark.parametrize("kind,shape", [
     ("msc", (3, 300, 320)), ("msc_n", (2, 170, 320)), ("conv1d_msc", (2, 298, 320)),
     ("ssd", (5, 50, 320)), ("enhanced", (3, 50, 320)), ("two_stage", (7, 50, 320)),
+    ("msc_legacy", (3, 298, 320)), ("msc_legacy", (2, 170, 360)), ("improved", (3, 300, 320)),
+    ("hybrid", (2, 300, 320)), ("hybrid", (3, 50, 384)), ("complex", (2, 300, 320)), ("complex", (3, 61, 200)),
 ])
 def test_forward_fp32_matches_oracle_fresh_inputs(kind, shape):
     B, N, S = shape
     x = synth.synth_paut_sets(B, N, S, seed=99, defect_frac=0.1)
-    sd = synth.synth_state_dict(kind, seed=0, signal_length=S)
+    # hybrid / complex: the conv stack is length-agnostic (shared_layer.0 sees the 128 resampled values)
+    cfg = dict(signal_length=S) if kind not in ("hybrid", "complex") else {}
+    sd = synth.synth_state_dict(kind, seed=0, **cfg)
     xin = np.ascontiguousarray(x.transpose(0, 2, 1)) if kind == "conv1d_msc" else x
     with torch.no_grad():
         ref = flatten(kind, om.FORWARD[kind](sd, torch.from_numpy(xin)))
-    m = build(kind, dict(signal_length=S))
+    m = build(kind, cfg)
     got = run_flat(m, kind, torch.from_numpy(xin).cuda())
     for k in ref:
         err = np.abs(got[k] - ref[k]).max()
@@ -103,7 +107,7 @@ def _struct_from(kind, outs, device):
 def test_postprocess_bit_exact_on_reference_outputs(path):
     """Integer stage fed the reference's forward outputs: records identical to the reference predict()."""
     c = load_case(path)
-    m = build(c["kind"], c["cfg"])
+    m = build(c["kind"], c["cfg"], sd=case_state_dict(c))
     x = torch.from_numpy(c["x"]).cuda()
     native = m._native_for(x)
     B, N, S = c["x"].shape

@@ -9,19 +9,19 @@ import torch
 from oracle import models as om
 from oracle import postprocess as opp
 from oracle import synth, windowing
-from tests._golden import GOLDEN_DIR, case_id, flatten, golden_files, load_case
+from tests._golden import GOLDEN_DIR, case_id, case_state_dict, flatten, golden_files, load_case
 
 FILES = golden_files()
 
 
 def test_golden_files_present():
-    assert len(FILES) >= 15
+    assert len(FILES) >= 26
 
 
 @pytest.mark.parametrize("path", FILES, ids=case_id)
 def test_oracle_forward_matches_reference(path):
     c = load_case(path)
-    sd = synth.synth_state_dict(c["kind"], seed=0, **c["cfg"])
+    sd = case_state_dict(c)
     with torch.no_grad():
         out = om.FORWARD[c["kind"]](sd, torch.from_numpy(c["x"]))
     flat = flatten(c["kind"], out)
@@ -53,7 +53,7 @@ def test_oracle_postprocess_bit_exact_on_reference_outputs(path):
 def test_state_manifest_matches_spec():
     with open(os.path.join(GOLDEN_DIR, "state_manifest.json")) as f:
         manifest = json.load(f)
-    assert len(manifest) >= 6
+    assert len(manifest) >= 11
     for key, shapes in manifest.items():
         kind, cfg = key.split(":", 1)
         spec = synth.state_spec(kind, **json.loads(cfg))
