@@ -26,7 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SETS = {"msc": (3334, 300), "msc_n": (3334, 300), "conv1d_msc": (3334, 300),
-        "ssd": (20000, 50), "enhanced": (20000, 50), "two_stage": (20000, 50)}
+        "ssd": (20000, 50), "enhanced": (20000, 50), "two_stage": (20000, 50),
+        # SURVEY section 8 "next" rows (f2 / f3): same volume as the MSC config
+        "msc_legacy": (3334, 300), "improved": (3334, 300), "hybrid": (3334, 300), "complex": (3334, 300)}
 S = 320
 
 # Algorithmic work per A-scan of the fused kernels: (FLOPs = 2*MAC, HBM bytes, bound).
@@ -41,7 +43,10 @@ def kernel_work(kind, n_per):
             "msc_ffn_head": (2 * 2 * 64 * 32 + 2 * 64 * 3, 4 * 64 + 12, "hbm"),
             "msc_front": (2 * (8 * 3 + 16 * 24) * S, 2 * 4 * S, "hbm"),
         }
-    conv = {"two_stage": 2 * 32 * 32 * (3 + 5 + 7 + 11) * S, "ssd": 2 * (64 * 128 * 5 + 128 * 256 * 3) * S,
+    if kind in ("msc_legacy", "improved"):
+        return {}                                   # CUDA-core front end + library-shaped linears: no fused-kernel figure yet
+    conv = {"hybrid": 2 * (32 * 64 * 3 + 64 * 64 * 5) * S, "complex": 2 * (32 * 64 * 7 + 64 * 64 * 15) * S,
+            "two_stage": 2 * 32 * 32 * (3 + 5 + 7 + 11) * S, "ssd": 2 * (64 * 128 * 5 + 128 * 256 * 3) * S,
             "conv1d_msc": 2 * (64 * 128 * 3 + 128 * 128) * S,
             # branches + combine + six residual convs at full length; the stride-2 pyramid at S/2 and S/4 outputs
             "enhanced": 2 * (4 * 64 * 32 * 3 + 128 * 128 + 6 * 128 * 128 * 3) * S +

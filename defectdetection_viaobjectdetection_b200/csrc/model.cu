@@ -270,19 +270,10 @@ const float* Model::upload(const std::vector<float>& v) {
   return static_cast<const float*>(p);
 }
 
-Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int row0, int rows) {
-  const HostTensor& w = H(wkey);
-  const HostTensor& b = H(bkey);
-  const int K = (int)w.shape[1];
-  std::vector<float> W((size_t)rows * K), Wt((size_t)rows * K), bias(rows);
-  for (int n = 0; n < rows; ++n) {
-    bias[n] = b.data[row0 + n];
-    for (int k = 0; k < K; ++k) {
-      const float v = w.data[(size_t)(row0 + n) * K + k];
-      W[(size_t)n * K + k] = v;
-      Wt[(size_t)k * rows + n] = v;
-    }
-  }
+Lin Model::make_lin(const std::vector<float>& W, const std::vector<float>& bias, int rows, int K) {
+  std::vector<float> Wt((size_t)rows * K);
+  for (int n = 0; n < rows; ++n)
+    for (int k = 0; k < K; ++k) Wt[(size_t)k * rows + n] = W[(size_t)n * K + k];
   Lin l;
   l.K = K;
   l.N = rows;
@@ -291,6 +282,15 @@ Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int r
   l.b = upload(bias);
   pack_tc(l, W);
   return l;
+}
+
+Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int row0, int rows) {
+  const HostTensor& w = H(wkey);
+  const HostTensor& b = H(bkey);
+  const int K = (int)w.shape[1];
+  std::vector<float> W(w.data.begin() + (size_t)row0 * K, w.data.begin() + (size_t)(row0 + rows) * K);
+  std::vector<float> bias(b.data.begin() + row0, b.data.begin() + row0 + rows);
+  return make_lin(W, bias, rows, K);
 }
 
 // bf16 mode: additionally pack the weight for the tcgen05 GEMM (chunked K-major bf16)
@@ -386,6 +386,37 @@ MHAW Model::pack_mha(const std::string& name, int heads) {
   m.H = heads;
   PAUT_CHECK(heads > 0 && m.D % heads == 0, PAUT_ERR_INVALID, "embed_dim must be divisible by num_heads");
   PAUT_CHECK(m.D / heads <= 64, PAUT_ERR_UNSUPPORTED, "attention head_dim must be <= 64");
+  m.hd = m.D / heads;
+  m.Dp = m.D;
+  if (cfg.precision == PAUT_PRECISION_BF16 && m.hd == 8) {
+    // bf16 mode, head_dim 8 (d_model 64 with 8 heads: improved_model.py:70, complex_detection_model.py:11): the
+    // tensor-core attention kernel works on head_dim 16 / 32, so every head is zero-padded to 16 through the
+    // weights -- in_proj emits [q | 0], [k | 0], [v | 0] per head (q.k and P.v are unchanged by zero columns),
+    // out_proj gets zero columns for the padding.  The kernel's 1/sqrt(16) becomes the 1/sqrt(8) of the model by
+    // scaling the q rows (and q bias) by sqrt(2).
+    const HostTensor& w = H(name + ".in_proj_weight");
+    const HostTensor& b = H(name + ".in_proj_bias");
+    const HostTensor& wo = H(name + ".out_proj.weight");
+    const int D = m.D, Dp = 2 * D;
+    std::vector<float> W((size_t)3 * Dp * D, 0.f), bias((size_t)3 * Dp, 0.f), Wo((size_t)D * Dp, 0.f);
+    const float qs = std::sqrt(2.0f);
+    for (int part = 0; part < 3; ++part)
+      for (int h = 0; h < heads; ++h)
+        for (int j = 0; j < 8; ++j) {
+          const int src = part * D + h * 8 + j, dst = part * Dp + h * 16 + j;
+          const float sc = part == 0 ? qs : 1.f;
+          bias[dst] = b.data[src] * sc;
+          for (int k = 0; k < D; ++k) W[(size_t)dst * D + k] = w.data[(size_t)src * D + k] * sc;
+        }
+    for (int n = 0; n < D; ++n)
+      for (int h = 0; h < heads; ++h)
+        for (int j = 0; j < 8; ++j) Wo[(size_t)n * Dp + h * 16 + j] = wo.data[(size_t)n * D + h * 8 + j];
+    m.in_proj = make_lin(W, bias, 3 * Dp, D);
+    m.out_proj = make_lin(Wo, H(name + ".out_proj.bias").data, D, Dp);
+    m.hd = 16;
+    m.Dp = Dp;
+    return m;
+  }
   m.in_proj = pack_lin_rows(name + ".in_proj_weight", name + ".in_proj_bias", 0, 3 * m.D);
   m.out_proj = pack_lin(name + ".out_proj");
   return m;
@@ -754,11 +785,11 @@ struct G {
   float* self_attention(const float* x, const MHAW& m, int64_t B, int N, const float* res, bool kv_shift = false,
                         float* avgw = nullptr) {
     const int64_t M = B * N;
-    const int D = m.D;
+    const int D = m.D, Dp = m.Dp;                      // Dp > D: heads zero-padded through the weights (pack_mha)
     float* qkv = linear(x, D, m.in_proj, M);
-    float* att = c.allocf((size_t)M * D);
-    attention(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, att, D, B, N, N, m.H, D / m.H, kv_shift, avgw);
-    return linear(att, D, m.out_proj, M, ACT_NONE, res, D);
+    float* att = c.allocf((size_t)M * Dp);
+    attention(qkv, 3 * Dp, qkv + Dp, 3 * Dp, qkv + 2 * Dp, 3 * Dp, att, Dp, B, N, N, m.H, m.hd, kv_shift, avgw);
+    return linear(att, Dp, m.out_proj, M, ACT_NONE, res, D);
   }
   // post-norm encoder layer (nn.TransformerEncoderLayer / SelfAttentionBlock)
   float* encoder_layer(const float* x, const TELW& t, int64_t B, int N, int act, float* avgw = nullptr) {

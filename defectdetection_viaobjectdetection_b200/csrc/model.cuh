@@ -41,6 +41,7 @@ struct LNW {
 struct MHAW {
   Lin in_proj, out_proj;
   int D = 0, H = 0;
+  int hd = 0, Dp = 0;            // head_dim / width the attention kernel sees (padded in bf16 mode when head_dim = 8)
 };
 struct TELW {  // post-norm transformer encoder layer
   MHAW attn;
@@ -108,6 +109,7 @@ struct Model {
   const HostTensor& H(const std::string& key) const;
   const float* upload(const std::vector<float>& v);
   Lin pack_lin(const std::string& name);
+  Lin make_lin(const std::vector<float>& W, const std::vector<float>& bias, int rows, int K);
   void pack_tc(Lin& l, const std::vector<float>& W);
   Lin pack_lin_rows(const std::string& wkey, const std::string& bkey, int row0, int rows);
   ConvW pack_conv(const std::string& conv_name, const std::string& bn_name, int max_dil = 1, bool stride2 = false);

@@ -14,53 +14,113 @@ inline unsigned grid_cap(int64_t n, int threads, int64_t cap = 148 * 16) {
 }
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+// sum of the 4 fp32 / 8 bf16 values of one 128-bit load
+__device__ __forceinline__ float sum128(const uint4* p, const float*) {
+  const uint4 u = __ldg(p);
+  return (__uint_as_float(u.x) + __uint_as_float(u.y)) + (__uint_as_float(u.z) + __uint_as_float(u.w));
+}
+__device__ __forceinline__ float sum128(const uint4* p, const __nv_bfloat16*) {
+  const uint4 u = __ldg(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += __uint_as_float(w[i] << 16) + __uint_as_float(w[i] & 0xffff0000u);
+  return s;
+}
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ f2: front ends
 // ImprovedMultiSignalClassifier (improved_model.py:126-133): bg = depthwise Conv1d(C, C, k, pad k/2, groups C);
 // x = x - bg; f = mean over channels.  in [A, L, C] channels-last fp32, w [C][k], bias [C] -> f [A, L].
-// One CTA per A-scan: the [L, C] tile is staged in shared memory (row stride C+1: conflict-free column walks).
-__global__ void __launch_bounds__(256) k_bgsub_chanmean(const float* __restrict__ in, int L, int C, int k,
+// Folded: f[l] = (1/C) sum_c sum_o w''_c[o] x_c[l + o - 7] - mean(bias) with w'' = delta - w centred in a 15-wide
+// window.  One CTA per A-scan: the tile is staged TRANSPOSED in shared memory ([C][L + halo], zero halos, so the
+// taps need no bounds checks); a thread owns 4 consecutive positions of one channel group, reads its 20-sample
+// window as five 128-bit loads and does 60 FMAs per channel (the first version did one LDS per FMA and was
+// shared-memory bound); the channel groups' partial sums meet in shared memory.
+constexpr int BG_HALO = 8;         // left halo (>= k/2, multiple of 4)
+constexpr int BG_MAXCG = 8;
+__global__ void __launch_bounds__(256) k_bgsub_chanmean(const float* __restrict__ in, int L, int C, int k, int CG,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ f) {
-  extern __shared__ float sm[];
-  const int ldc = C + 1;
-  float* tile = sm;                    // [L][C+1]
-  float* ws = tile + (size_t)L * ldc;  // [C][k]
-  float* bs = ws + C * k;              // [C]
+  extern __shared__ __align__(16) float sm[];
+  const int Lp = L + 20;               // 8 left + 12 right zero samples; Lp % 32 = 4 * odd for L % 32 == 0
+  float* tile = sm;                    // [C][Lp]
+  float* ws = tile + (size_t)C * Lp;   // [C][16]: centred folded taps, ws[c][15] = 0
+  float* part = ws + C * 16;           // [CG][L]
+  __shared__ float meanb;
   const int64_t a = blockIdx.x;
   const float* src = in + a * (int64_t)L * C;
-  for (int i = threadIdx.x; i < L * C; i += blockDim.x) tile[(i / C) * ldc + (i % C)] = src[i];
-  for (int i = threadIdx.x; i < C * k; i += blockDim.x) ws[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
-  __syncthreads();
+  for (int i = threadIdx.x; i < C * 20; i += blockDim.x) {
+    const int c = i / 20, j = i % 20;
+    tile[c * Lp + (j < BG_HALO ? j : L + j)] = 0.f;
+  }
+  for (int i = threadIdx.x; i < L * C; i += blockDim.x) tile[(i % C) * Lp + BG_HALO + i / C] = src[i];
   const int half = k >> 1;
+  for (int i = threadIdx.x; i < C * 16; i += blockDim.x) {
+    const int c = i >> 4, o = i & 15, t = o - 7 + half;          // o = t - half + 7
+    float v = 0.f;
+    if (o < 15 && t >= 0 && t < k) v = (t == half ? 1.f : 0.f) - w[c * k + t];
+    ws[i] = v;
+  }
+  if (threadIdx.x < 32) {
+    float b = 0.f;
+    for (int c = threadIdx.x; c < C; c += 32) b += bias[c];
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (threadIdx.x == 0) meanb = b / (float)C;
+  }
+  __syncthreads();
+  const int PG = L >> 2;
+  for (int item = threadIdx.x; item < PG * CG; item += blockDim.x) {
+    const int pg = item % PG, cg = item / PG;
+    const int l0 = pg * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = cg; c < C; c += CG) {
+      float v[20], wv[16];
+      const float4* tp = reinterpret_cast<const float4*>(tile + c * Lp + l0);      // samples l0 - 8 .. l0 + 11
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const float4 t4 = tp[i];
+        v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+      }
+      const float4* wp = reinterpret_cast<const float4*>(ws + c * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t4 = wp[i];
+        wv[4 * i] = t4.x; wv[4 * i + 1] = t4.y; wv[4 * i + 2] = t4.z; wv[4 * i + 3] = t4.w;
+      }
+#pragma unroll
+      for (int o = 0; o < 15; ++o) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv[o], v[j + o + 1], acc[j]);   // sample l0 + j + o - 7
+      }
+    }
+    *reinterpret_cast<float4*>(part + cg * L + l0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+  __syncthreads();
   const float inv = 1.f / (float)C;
   for (int l = threadIdx.x; l < L; l += blockDim.x) {
-    float acc = 0.f;
-    for (int c = 0; c < C; ++c) {
-      float bg = bs[c];
-      for (int t = 0; t < k; ++t) {
-        const int ll = l + t - half;
-        if (ll >= 0 && ll < L) bg = fmaf(ws[c * k + t], tile[ll * ldc + c], bg);
-      }
-      acc += tile[l * ldc + c] - bg;
-    }
-    f[a * L + l] = acc * inv;
+    float s = 0.f;
+    for (int cg = 0; cg < CG; ++cg) s += part[cg * L + l];
+    f[a * L + l] = s * inv - meanb;
   }
 }
 
 void op_bgsub_chanmean(Ctx& c, const float* in, int64_t A, int L, int C, int k, const float* w, const float* bias,
                        float* f) {
   if (c.dry) return;
-  const size_t smem = ((size_t)L * (C + 1) + (size_t)C * k + C) * sizeof(float);
+  PAUT_CHECK(L % 4 == 0 && k % 2 == 1 && k <= 15, PAUT_ERR_UNSUPPORTED,
+             "bgsub_chanmean: L must be a multiple of 4 and the kernel size odd and <= 15");
+  int CG = 256 / (L / 4);
+  CG = CG < 1 ? 1 : (CG > BG_MAXCG ? BG_MAXCG : CG);
+  if (CG > C) CG = C;
+  const size_t smem = ((size_t)C * (L + 20) + (size_t)C * 16 + (size_t)CG * L) * sizeof(float);
   PAUT_CHECK(smem <= (size_t)c.smem_optin, PAUT_ERR_UNSUPPORTED, "bgsub_chanmean: A-scan tile exceeds shared memory");
   static thread_local size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     PAUT_CUDA(cudaFuncSetAttribute(k_bgsub_chanmean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_bgsub_chanmean<<<(unsigned)A, 256, smem, c.stream>>>(in, L, C, k, w, bias, f);
+  k_bgsub_chanmean<<<(unsigned)A, 256, smem, c.stream>>>(in, L, C, k, CG, w, bias, f);
   c.launched("bgsub_chanmean");
 }
 
@@ -81,11 +141,25 @@ __global__ void __launch_bounds__(256) k_chanmean_resample(const T* __restrict__
   const T* src = in + ((int64_t)H0 + a * Lp) * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float inv = 1.f / (float)C;
-  for (int l = warp; l < L; l += nw) {
-    float s = 0.f;
-    for (int ch = lane; ch < C; ch += 32) s += ldf(src + (int64_t)l * C + ch);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) m[l] = s * inv;
+  constexpr int EPV = 16 / (int)sizeof(T);            // elements per 128-bit load
+  const int V = C / EPV;                              // 128-bit loads per row
+  if (C % EPV == 0 && V <= 32 && (V & (V - 1)) == 0) {
+    // V lanes share a row (one 128-bit load each), 32 / V rows per warp instruction, log2(V) shuffles per row group
+    const int rpw = 32 / V, sub = lane / V, part = lane % V;
+    for (int l0 = warp * rpw; l0 < L; l0 += nw * rpw) {
+      const int l = l0 + sub;
+      float s = 0.f;
+      if (l < L) s = sum128(reinterpret_cast<const uint4*>(src + (int64_t)l * C) + part, static_cast<const T*>(nullptr));
+      for (int o = V >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (part == 0 && l < L) m[l] = s * inv;
+    }
+  } else {
+    for (int l = warp; l < L; l += nw) {
+      float s = 0.f;
+      for (int ch = lane; ch < C; ch += 32) s += ldf(src + (int64_t)l * C + ch);
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) m[l] = s * inv;
+    }
   }
   __syncthreads();
   if (mode == 0) {

@@ -146,8 +146,13 @@ def test_legacy_real_weights_end_to_end():
     p = prob.cpu().numpy()
     for s in range(2):
         r, d = omx.difference_matrix(c["x"][s], [float(v) for v in p[s]], 0.5)
+        assert int(healthy[s]) == int((p[s].astype(np.float64) < 0.5).sum())
+        if r is None:                                          # no healthy A-scan in the set: the reference skips it
+            assert int(healthy[s]) == 0 and not ref[s].any() and not diff[s].any()
+            continue
         np.testing.assert_array_equal(ref[s].cpu().numpy(), r.astype(np.float32))
         np.testing.assert_array_equal(diff[s].cpu().numpy(), d.astype(np.float32))
+    assert int(healthy.sum()) > 0
     rec = m.predict_records(x, 0.5)
     want = opp.postprocess("msc_legacy", p, 0.5, 360)
     np.testing.assert_array_equal(rec["position"], want["position"])
