@@ -23,6 +23,8 @@ SYMBOLS = (
     "paut_window_gather", "paut_window_table_host", "paut_ctx_launch_count", "paut_ctx_profile_begin",
     "paut_ctx_profile_end", "paut_op_linear", "paut_debug_mma",
     "paut_difference_matrix", "paut_metrics_match", "paut_metrics_confusion",
+    "paut_json_load_host", "paut_json_free", "paut_json_last_error", "paut_json_num_beams", "paut_json_beam_info",
+    "paut_json_beam_copy_host", "paut_group_nonzero",
 )
 
 
@@ -97,6 +99,13 @@ def load():
         "paut_difference_matrix": (i32, [vp, vp, i32, vp, i64, i64, i64, C.c_double, vp, vp, vp]),
         "paut_metrics_match": (i32, [vp, i32, vp, vp, i64, i64, vp, vp, C.c_double, vp]),
         "paut_metrics_confusion": (i32, [vp, vp, vp, i64, C.c_double, i32, vp]),
+        "paut_group_nonzero": (i32, [vp, vp, i32, i64, i64, i64, vp]),
+        "paut_json_load_host": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "paut_json_free": (None, [vp]),
+        "paut_json_last_error": (C.c_char_p, []),
+        "paut_json_num_beams": (i32, [vp]),
+        "paut_json_beam_info": (i32, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i64)]),
+        "paut_json_beam_copy_host": (i32, [vp, i32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -306,6 +306,17 @@ int paut_window_gather(paut_ctx* ctx, const void* volume, int src_dtype, int64_t
   });
 }
 
+int paut_group_nonzero(paut_ctx* ctx, const void* volume, int dtype, int64_t G, int64_t n, int64_t S, int32_t* flags_dev) {
+  if (!ctx) return PAUT_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    PAUT_CHECK(volume && flags_dev && G > 0 && n > 0 && S > 0, PAUT_ERR_INVALID, "group_nonzero: bad arguments");
+    PAUT_CHECK(dtype == PAUT_F32 || dtype == PAUT_BF16, PAUT_ERR_INVALID, "group_nonzero: dtype must be F32 or BF16");
+    PAUT_CHECK(G < (int64_t(1) << 31), PAUT_ERR_UNSUPPORTED, "group_nonzero: too many groups");
+    PAUT_CUDA(cudaSetDevice(ctx->c.device));
+    paut::op_group_nonzero(ctx->c, volume, dtype, G, n * S, flags_dev);
+  });
+}
+
 int paut_difference_matrix(paut_ctx* ctx, const void* x, int x_dtype, const float* prob, int64_t B, int64_t N,
                            int64_t S, double threshold, float* reference, float* diff, int32_t* healthy_count) {
   if (!ctx) return PAUT_ERR_INVALID;

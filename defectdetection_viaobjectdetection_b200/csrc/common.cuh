@@ -246,6 +246,8 @@ void op_chanmean_resample(Ctx& c, const void* in, int in_dtype, int64_t A, int L
 void op_seqmean_concat(Ctx& c, const float* seq, int64_t B, int N, int D, float* out);
 // improved_model.py:147-156: sigmoid / clamp / clamp of o [M,3]
 void op_improved_head(Ctx& c, const float* o, int64_t M, float* prob, float* start, float* end);
+// dataset_preparation.py:205: flags[g] = any(volume[g] != 0)
+void op_group_nonzero(Ctx& c, const void* vol, int dtype, int64_t G, int64_t per_group, int32_t* flags);
 // teststtt.py:54-69
 void op_difference_matrix(Ctx& c, const void* x, int x_dtype, const float* prob, int64_t B, int N, int S, double thr,
                           float* ref, float* diff, int32_t* healthy);

@@ -243,6 +243,44 @@ void op_improved_head(Ctx& c, const float* o, int64_t M, float* prob, float* sta
   c.launched("improved_head");
 }
 
+// ------------------------------------------------------------------------------------------ f1: all-zero-run drop
+// dataset_preparation.py:205 skips a run whose signals are all zero (np.all(signals == 0)).  flags[g] = 1 iff
+// any sample of volume[g] is non-zero (-0.0 counts as zero, NaN as non-zero, like the numpy comparison).
+// One CTA per group, 128-bit loads, block-uniform early exit (__syncthreads_or).
+template <typename T>
+__global__ void __launch_bounds__(256) k_group_nonzero(const T* __restrict__ vol, int64_t per_group,
+                                                        int32_t* __restrict__ flags) {
+  int found = 0;
+  constexpr int EPV = 16 / (int)sizeof(T);
+  const uint4* src = reinterpret_cast<const uint4*>(vol + blockIdx.x * per_group);
+  const int64_t nvec = per_group / EPV;
+  constexpr uint32_t M = sizeof(T) == 4 ? 0x7fffffffu : 0x7fff7fffu;      // drop the sign bit(s): -0.0 == 0
+  for (int64_t i0 = 0; i0 < nvec; i0 += 256 * 8) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t i = i0 + j * 256 + threadIdx.x;
+      if (i < nvec) {
+        const uint4 u = __ldg(src + i);
+        acc |= (u.x & M) | (u.y & M) | (u.z & M) | (u.w & M);
+      }
+    }
+    found = __syncthreads_or(acc != 0);               // block-uniform: every thread leaves the loop together
+    if (found) break;
+  }
+  if (threadIdx.x == 0) flags[blockIdx.x] = found;
+}
+void op_group_nonzero(Ctx& c, const void* vol, int dtype, int64_t G, int64_t per_group, int32_t* flags) {
+  if (c.dry) return;
+  const int epv = dtype == PAUT_F32 ? 4 : 8;
+  PAUT_CHECK(per_group % epv == 0, PAUT_ERR_UNSUPPORTED, "group_nonzero: group size must be a multiple of 16 bytes");
+  if (dtype == PAUT_F32)
+    k_group_nonzero<float><<<(unsigned)G, 256, 0, c.stream>>>(static_cast<const float*>(vol), per_group, flags);
+  else
+    k_group_nonzero<__nv_bfloat16><<<(unsigned)G, 256, 0, c.stream>>>(static_cast<const __nv_bfloat16*>(vol), per_group, flags);
+  c.launched("group_nonzero");
+}
+
 // ------------------------------------------------------------------------------------------ f3: difference matrix
 // teststtt.py:54-69.  Per set: reference signal = mean of the A-scans with pred < thr (fp64, ascending order, like
 // np.mean(axis=0) over the float64 rows), difference row = |signal - reference| where pred >= thr, zeros elsewhere.

@@ -1,0 +1,85 @@
+"""On-disk volume format -> resident sets.
+
+``load_json_volume`` parses one JSON file of the reference's format with the native host loader
+(csrc/host_json.cu); ``json_signal_sets`` restates ``JsonSignalDataset`` (signals/improved_multisignal/
+json_dataset.py:9-160): the same sequences, labels and defect positions in the same order, with the windows
+gathered on the device by ``paut_window_gather`` when a CUDA device is given.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+def load_json_volume(path):
+    """One file -> list of beams in file order: dict(key, signals float32 [n,S] or None if ragged, labels int32 [n],
+    defects float32 [n,2], scan_order int64 [n]) with the scans in the reference's sorted order."""
+    lib = _lib.load()
+    h = C.c_void_p()
+    if lib.paut_json_load_host(os.fsencode(path), C.byref(h)) != 0:
+        raise ValueError(lib.paut_json_last_error().decode())
+    try:
+        beams = []
+        key, n, S = C.c_char_p(), C.c_int64(), C.c_int64()
+        for b in range(lib.paut_json_num_beams(h)):
+            lib.paut_json_beam_info(h, b, C.byref(key), C.byref(n), C.byref(S))
+            labels = np.empty(n.value, np.int32)
+            defects = np.empty((n.value, 2), np.float32)
+            order = np.empty(n.value, np.int64)
+            signals = np.empty((n.value, S.value), np.float32) if S.value >= 0 else None
+            rc = lib.paut_json_beam_copy_host(h, b, signals.ctypes.data if signals is not None else None,
+                                              labels.ctypes.data, defects.ctypes.data, order.ctypes.data)
+            if rc != 0:
+                raise ValueError(lib.paut_json_last_error().decode())
+            beams.append(dict(key=key.value.decode(), signals=signals, labels=labels, defects=defects, scan_order=order))
+        return beams
+    finally:
+        lib.paut_json_free(h)
+
+
+def json_signal_sets(json_dir_or_files, seq_length=50, device=None, dtype=None):
+    """JsonSignalDataset(json_dir, seq_length) without the Python loops: returns (signal_sets [W, L, S],
+    labels float32 [W, L], defect_positions float32 [W, L, 2]) in the dataset's order.  ``signal_sets`` is a CUDA
+    tensor gathered on the device when ``device`` is a CUDA device (dtype fp32, or bf16 on request), else numpy.
+    Files that fail to parse are skipped, like the reference's per-file try/except (json_dataset.py:38,158)."""
+    import torch
+    from .runtime import gather_windows, window_table
+    if isinstance(json_dir_or_files, (str, os.PathLike)) and os.path.isdir(json_dir_or_files):
+        files = [os.path.join(json_dir_or_files, f) for f in os.listdir(json_dir_or_files) if f.endswith(".json")]
+    else:
+        files = list(json_dir_or_files)
+    on_gpu = device is not None and torch.device(device).type == "cuda"
+    sets, labels, defects = [], [], []
+    for path in files:
+        try:
+            beams = load_json_volume(path)
+        except ValueError as e:
+            print(f"Error loading {os.path.basename(path)}: {e}")
+            continue
+        for beam in beams:
+            n = len(beam["labels"])
+            wins = window_table("msc", n, seq_length)               # json_dataset.py:51-52, 84-103
+            if not wins or beam["signals"] is None or beam["signals"].shape[1] == 0:
+                continue                                            # too short, or ragged (json_dataset.py:136-146)
+            idx = np.array([np.arange(s, s + seq_length) for s, _ in wins])
+            labels.append(beam["labels"][idx].astype(np.float32))
+            defects.append(beam["defects"][idx])
+            if on_gpu:
+                vol = torch.from_numpy(beam["signals"]).to(device)[None]
+                out, _ = gather_windows(vol, "msc", seq_length, out_dtype=dtype or torch.float32)
+                sets.append(out)
+            else:
+                sets.append(beam["signals"][idx])
+    if not sets:
+        return (torch.empty(0) if on_gpu else np.zeros((0, seq_length, 0), np.float32),
+                np.zeros((0, seq_length), np.float32), np.zeros((0, seq_length, 2), np.float32))
+    lengths = {s.shape[-1] for s in sets}
+    if len(lengths) != 1:
+        raise ValueError(f"beams with different signal lengths {sorted(lengths)} cannot form one batch "
+                         "(the reference's DataLoader fails at collation)")
+    cat = torch.cat(sets, 0) if on_gpu else np.concatenate(sets, 0)
+    return cat, np.concatenate(labels, 0), np.concatenate(defects, 0)

@@ -216,12 +216,28 @@ def window_table(rule, n, seq_length=50):
     return [(buf[2 * i], buf[2 * i + 1]) for i in range(cnt)]
 
 
-def gather_windows(volume, rule, seq_length=50, out_dtype=None, keep_groups=None):
+def group_nonzero(volume):
+    """dataset_preparation.py:205 on device: bool numpy mask [G], False where volume[g] is all zero."""
+    if not volume.is_cuda or not volume.is_contiguous() or volume.dim() != 3:
+        raise RuntimeError("volume must be a contiguous CUDA tensor [G, n, S]")
+    G, n, S = volume.shape
+    ctx = get_context(volume.device)
+    dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[volume.dtype]
+    flags = torch.empty(G, dtype=torch.int32, device=volume.device)
+    check(ctx.lib.paut_group_nonzero(ctx.handle, C.c_void_p(volume.data_ptr()), dt, G, n, S,
+                                     C.c_void_p(flags.data_ptr())), ctx.handle)
+    return flags.cpu().numpy().astype(bool)
+
+
+def gather_windows(volume, rule, seq_length=50, out_dtype=None, keep_groups=None, drop_all_zero=False):
     """Device windowing: volume [G, n, S] (CUDA, fp32/bf16) -> (sets [W, L, S], table int32 [W,3] on host).
-    keep_groups: optional bool mask [G] (e.g. the all-zero-run drop of dataset_preparation.py:205)."""
+    keep_groups: optional bool mask [G]; drop_all_zero: compute it on the device with the all-zero-run rule of
+    dataset_preparation.py:205."""
     if not volume.is_cuda or not volume.is_contiguous():
         raise RuntimeError("volume must be a contiguous CUDA tensor")
     G, n, S = volume.shape
+    if drop_all_zero and keep_groups is None:
+        keep_groups = group_nonzero(volume)
     wins = window_table(rule, n, seq_length)
     groups = range(G) if keep_groups is None else [g for g in range(G) if bool(keep_groups[g])]
     table = np.array([(g, s, v) for g in groups for (s, v) in wins], dtype=np.int32).reshape(-1, 3)

@@ -184,9 +184,30 @@ int paut_postprocess(paut_model* m, const paut_outputs* outs, int64_t B, int64_t
  * sets_dev is [W, L, S] in dst_dtype. */
 int paut_window_gather(paut_ctx* ctx, const void* volume, int src_dtype, int64_t G, int64_t n, int64_t S,
                        const int32_t* table_dev, int64_t W, int64_t L, void* sets_dev, int dst_dtype);
+/* The all-zero-run drop of dataset_preparation.py:205 on a resident volume [G, n, S] (F32 or BF16):
+ * flags_dev[g] = 1 iff any sample of group g is non-zero (np.all(signals == 0) is False). */
+int paut_group_nonzero(paut_ctx* ctx, const void* volume, int dtype, int64_t G, int64_t n, int64_t S, int32_t* flags_dev);
 /* Host-side window tables for the two reference rules (rule 0 = signals/ json_dataset rule,
  * 1 = SignalSequenceDetection rule).  Writes up to cap (start, valid_len) pairs, returns the count. */
 int paut_window_table_host(int rule, int64_t n, int64_t L, int32_t* pairs_host, int cap);
+
+/* f1 -- host-side loader of the reference's on-disk volume format (improved_multisignal/README.md:67-89):
+ *   {"<beam>": {"<scan>_<label>[_<start>-<end>]": [S numbers] | {"signal": [...]}, ...}, ...}
+ * Restates the parsing half of JsonSignalDataset._load_all_json_files (json_dataset.py:36-81): beams in file order,
+ * scans stably sorted by int(key.split('_')[0]), label 0 iff the second field is "Health", defect range from the
+ * third field ("<start>-<end>", [0, 0] on any parse failure), samples as float32(float64(text)).  The windowing
+ * half (json_dataset.py:84-160) is paut_window_table_host(rule 0) + paut_window_gather.  Pure host calls. */
+typedef struct paut_json_volume paut_json_volume;
+int paut_json_load_host(const char* path, paut_json_volume** out);
+void paut_json_free(paut_json_volume* v);
+const char* paut_json_last_error(void);
+int paut_json_num_beams(const paut_json_volume* v);
+/* signal_length is -1 when the scans of the beam differ in length */
+int paut_json_beam_info(const paut_json_volume* v, int beam, const char** key, int64_t* n_scans, int64_t* signal_length);
+/* sorted scans of one beam: signals float32 [n,S], labels int32 [n], defects float32 [n,2], scan_order int64 [n]
+ * (the integer prefix of the key); any pointer may be NULL */
+int paut_json_beam_copy_host(const paut_json_volume* v, int beam, float* signals, int32_t* labels, float* defects,
+                             int64_t* scan_order);
 
 /* f3 -- reference signal and difference matrix (signals/teststtt.py:54-69).  Per set b: reference[b,:] = mean of
  * the A-scans with prob < threshold (fp64 accumulation in set order, like np.mean(axis=0) of the float64 rows),

@@ -159,3 +159,26 @@ def test_legacy_real_weights_end_to_end():
     m16 = build("msc_legacy", c["cfg"], precision="bf16", sd=sd)
     p16 = m16(x.to(torch.bfloat16)).cpu().numpy()
     assert np.abs(p16 - c["outs"]["defect_prob"]).max() <= 2e-2
+
+
+def test_all_zero_run_drop_on_device():
+    """dataset_preparation.py:205 (np.all(signals == 0)) as a device reduction, then the SSD windowing."""
+    from oracle import windowing
+    rng = np.random.default_rng(3)
+    vol = rng.random((9, 120, 320), dtype=np.float32)
+    vol[2] = 0
+    vol[5] = -0.0                                    # -0.0 == 0
+    vol[7] = 0
+    vol[7, 119, 319] = 1e-30                         # one non-zero sample at the very end keeps the run
+    vol[8] = 0
+    vol[8, 0, 0] = np.nan                            # nan != 0
+    want = ~np.all(vol.reshape(9, -1) == 0, axis=1)
+    for dt in (torch.float32, torch.bfloat16):
+        v = torch.from_numpy(vol).to(dt)
+        want_dt = ~np.all(v.float().numpy().reshape(9, -1) == 0, axis=1)
+        np.testing.assert_array_equal(paut.group_nonzero(v.cuda()), want_dt)
+    ref_sets, ref_table = windowing.gather_windows(vol, "ssd", 50)
+    sets, table = paut.gather_windows(torch.from_numpy(vol).cuda(), "ssd", 50, drop_all_zero=True)
+    np.testing.assert_array_equal(table, ref_table)
+    np.testing.assert_array_equal(sets.cpu().numpy(), ref_sets)
+    assert want.sum() == 6

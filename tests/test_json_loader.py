@@ -1,0 +1,67 @@
+"""the native host loader of the reference's JSON volume format against the reference's
+own JsonSignalDataset (fixtures and expected arrays in tests/golden/json_volume, made by running
+signals/improved_multisignal/json_dataset.py in the build container)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from defectdetection_viaobjectdetection_b200 import dataio
+from tests._golden import GOLDEN_DIR
+
+JDIR = os.path.join(GOLDEN_DIR, "json_volume")
+
+
+@pytest.fixture(scope="module")
+def expected():
+    return np.load(os.path.join(JDIR, "expected.npz"))
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_host_loader_matches_reference_dataset(name, expected):
+    sets, labels, defects = dataio.json_signal_sets([os.path.join(JDIR, name + ".json")], seq_length=5)
+    np.testing.assert_array_equal(sets, expected[name + "_sets"])            # float32(float64(text)): bit-exact
+    np.testing.assert_array_equal(labels, expected[name + "_labels"])
+    np.testing.assert_array_equal(defects, expected[name + "_defects"])      # nan == nan positionally
+
+
+def test_parser_details():
+    beams = dataio.load_json_volume(os.path.join(JDIR, "a.json"))
+    assert [b["key"] for b in beams] == ["beam_0", "beam_1", "beam_2"]
+    assert beams[0]["scan_order"].tolist() == list(range(13))
+    # stable sort: "3_Defect_0.125-0.875" was written before "3_Defect_0.5-0.75"
+    order = beams[2]["scan_order"].tolist()
+    assert order == sorted(order) and order.count(3) == 2
+    i = order.index(3)
+    assert beams[2]["defects"][i].tolist() == [0.125, 0.875] and beams[2]["defects"][i + 1].tolist() == [0.5, 0.75]
+    with open(os.path.join(JDIR, "a.json")) as f:
+        raw = json.load(f)
+    first_key = sorted(raw["beam_0"], key=lambda k: int(k.split("_")[0]))[0]
+    np.testing.assert_array_equal(beams[0]["signals"][0], np.array(raw["beam_0"][first_key], dtype=np.float32))
+
+
+def test_parser_errors(tmp_path):
+    for text in ('{"b": {"x_Health": [1, 2]}}',          # int('x') fails -> the reference aborts the file
+                 '{"b": {"3": [1, 2]}}',                 # no label field
+                 '{"b": {"3_Health": [1, 2,]}}',         # invalid JSON
+                 '{"b": {"3_Health": [0x10]}}'):
+        p = tmp_path / "bad.json"
+        p.write_text(text)
+        with pytest.raises(ValueError):
+            dataio.load_json_volume(str(p))
+    with pytest.raises(ValueError):
+        dataio.load_json_volume(str(tmp_path / "missing.json"))
+
+
+@pytest.mark.gpu
+def test_device_windowing_matches_reference_dataset(expected):
+    for name in ("a", "b"):
+        sets, labels, defects = dataio.json_signal_sets([os.path.join(JDIR, name + ".json")], seq_length=5, device="cuda")
+        assert sets.is_cuda
+        np.testing.assert_array_equal(sets.cpu().numpy(), expected[name + "_sets"])
+        np.testing.assert_array_equal(labels, expected[name + "_labels"])
+    sets16, _, _ = dataio.json_signal_sets([os.path.join(JDIR, "b.json")], seq_length=5, device="cuda", dtype=torch.bfloat16)
+    np.testing.assert_array_equal(sets16.float().cpu().numpy(),
+                                  torch.from_numpy(expected["b_sets"]).to(torch.bfloat16).float().numpy())
