@@ -16,9 +16,10 @@
 //  two Linear layers are tcgen05.mma on operands that never left shared memory; their accumulators live
 //  in TMEM, reusing the columns of the double-buffered conv stage once it is over.
 //
-//  Pipeline per group of 2 A-scans (= S/64 M tiles): conv1(g) on all warps -> the issuer warp issues the MMAs
-//  of group g and commits them to an mbarrier -> all warps run the epilogue of group g-1 while those MMAs
-//  execute (TMEM operand rows and accumulators are double-buffered).  The CTA is persistent over blocks of 128
+//  Pipeline per group of 2 A-scans (= S/64 M tiles), per TEAM of four compute warps (= one M tile): conv1(g) ->
+//  the issuer warp issues the two MMAs of that tile and commits them to the tile's mbarrier -> the team runs the
+//  epilogue of its tile of group g-1 while those MMAs execute (TMEM operand rows and accumulators are
+//  double-buffered).  Teams only meet at the block-level Linear stages, so their latency chains interleave.  The CTA is persistent over blocks of 128
 //  A-scans; the weights of both Linear layers stay resident in shared memory.
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +42,8 @@ constexpr int ENC_THREADS = ENC_COMPUTE + 96;   // + MMA issuer warp (20) + x lo
 constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
 constexpr int D1_COL = 0, D2_COL = 128;     // alias the conv accumulators (dead by then)
 constexpr int XS_PAD = 16;
+constexpr int MAX_TILES = 5;             // M tiles (teams of 4 compute warps) per group: S / 64 <= 5
+constexpr int BAR_BLOCK = 6;             // named barrier of all compute warps (ids 1..5 belong to the teams)
 constexpr int XS_SLOTS = 4;              // x staging ring: cp.async prefetch runs ~3 groups ahead of conv1
 
 struct MscEncArgs {
@@ -106,7 +109,7 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
 template <bool PROBE>
 __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_conv[2], bar_full[2], bar_x[XS_SLOTS], bar_xe[XS_SLOTS], bar_e[XS_SLOTS], bar_l1, bar_l2;
+  __shared__ __align__(8) uint64_t bar_conv[2][MAX_TILES], bar_full[2][MAX_TILES], bar_x[XS_SLOTS], bar_xe[XS_SLOTS], bar_e[XS_SLOTS], bar_l1, bar_l2;
   __shared__ __align__(16) uint4 EB[XS_SLOTS][ENC_COMPUTE / 32 * 2];   // conv1 vectors just outside every warp's 32 positions
   __shared__ uint32_t tmem_slot;
 
@@ -128,9 +131,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   // ---- one-time setup
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
-    mbar_init(&bar_conv[0], 1); mbar_init(&bar_conv[1], 1);
-    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
-    for (int i = 0; i < XS_SLOTS; ++i) { mbar_init(&bar_x[i], 32); mbar_init(&bar_xe[i], 1); mbar_init(&bar_e[i], 1); }
+    for (int b = 0; b < 2; ++b)
+      for (int t = 0; t < MAX_TILES; ++t) { mbar_init(&bar_conv[b][t], 1); mbar_init(&bar_full[b][t], 1); }
+    // an x slot is released by every team (one arrival each) once its conv1 of the group is done
+    for (int i = 0; i < XS_SLOTS; ++i) { mbar_init(&bar_x[i], 32); mbar_init(&bar_xe[i], tiles); mbar_init(&bar_e[i], 1); }
     mbar_init(&bar_l1, 1);
     mbar_init(&bar_l2, 1);
     fence_mbar_init();
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   const uint32_t xs_base = smem_u32(XS), eb_base = smem_u32(&EB[0][0]);
   const uint32_t slot_bytes = (uint32_t)(2 * xs_stride * 2);
   const uint32_t a_bar_x = smem_u32(&bar_x[0]), a_bar_xe = smem_u32(&bar_xe[0]), a_bar_e = smem_u32(&bar_e[0]),
-                 a_bar_conv = smem_u32(&bar_conv[0]), a_bar_full = smem_u32(&bar_full[0]);
+                 a_bar_conv = smem_u32(&bar_conv[0][0]), a_bar_full = smem_u32(&bar_full[0][0]);
 
   // Groups are numbered globally over the blocks this CTA walks: G = it * 64 + g.  Every ring / double buffer
   // (conv1 buffers, TMEM accumulators, x slots) and every barrier parity is a function of G only, so the three
@@ -193,26 +197,23 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       for (int g = 0; g < ngroups; ++g, ++G) {
         const uint32_t buf = G & 1;
         const long long i0 = probe ? clock64() : 0;
-        mbar_wait_a(a_bar_full + buf * 8, (G >> 1) & 1);  // operand rows of group G are in tensor memory
-        const long long i1 = probe ? clock64() : 0;
-        if (leader) {
-          tc_fence_after();
-          const uint32_t a0t = tmem + buf * tbuf, d0 = a0t + tiles * 16;
+        const uint32_t a0t = tmem + buf * tbuf, d0 = a0t + tiles * 16;
+        // every M tile is handed over by its own team of four compute warps and committed to its own barrier:
+        // the teams drift apart instead of meeting at a 640-thread barrier once per group
 #pragma unroll
-          for (int T = 0; T < 5; ++T) {
-            if (T < tiles) {
+        for (int T = 0; T < MAX_TILES; ++T) {
+          if (T < tiles) {
+            mbar_wait_a(a_bar_full + (buf * MAX_TILES + T) * 8, (G >> 1) & 1);  // operand rows of tile T are in tensor memory
+            if (leader) {
+              tc_fence_after();
               mma_f16_ts(d0 + T * 32, a0t + T * 16, bd0, idesc_conv, 0u);
               mma_f16_ts(d0 + T * 32, a0t + T * 16 + 8, bd1, idesc_conv, 1u);
+              mma_commit(&bar_conv[buf][T]);
             }
+            __syncwarp();
           }
-          mma_commit(&bar_conv[buf]);
         }
-        __syncwarp();
-        if (probe) {
-          const long long i2 = clock64();
-          tsum[0] += i1 - i0;    // waiting for the operand
-          tsum[2] += i2 - i1;    // MMA issue + commit
-        }
+        if (probe) tsum[0] += clock64() - i0;    // waiting for the operands + MMA issue
       }
     }
     if (probe) {
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     // epilogue of one conv group: f[pos] = sum_c relu(y_c) (the 1/32 lives in W1) -> bf16 K-major operand of L1
     auto epi_issue = [&](uint32_t G, uint32_t (&r)[18]) {   // wait for the MMAs of group G, request this lane's row
       const uint32_t buf = G & 1;
-      mbar_wait_a(a_bar_conv + buf * 8, (G >> 1) & 1);
+      mbar_wait_a(a_bar_conv + (buf * MAX_TILES + T) * 8, (G >> 1) & 1);
       tc_fence_after();
       if (c_active) tmem_issue18(tmem + t_lane + buf * tbuf + tiles * 16 + T * 32, r);
     };
@@ -328,11 +329,14 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       }
     };
 
+    const bool team_active = T < tiles;                 // whole teams are active or idle (2 * S is a multiple of 128)
+    const uint32_t team_bars = (uint32_t)T * 8;
     uint32_t G = 0;
     int it = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
       const int64_t a0 = blk * 128;
-      for (int g = 0; g < ngroups; ++g, ++G) {
+      if (!team_active) G += ngroups;
+      for (int g = 0; team_active && g < ngroups; ++g, ++G) {
         const uint32_t buf = G & 1, slot = G & (XS_SLOTS - 1);
         const long long c0 = probe ? clock64() : 0;
         mbar_wait_a(a_bar_e + slot * 8, (G / XS_SLOTS) & 1);          // x has landed and the edge vectors are published
@@ -371,10 +375,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
         const long long c1 = probe ? clock64() : 0;
         tc_fence_before();
         const long long c1b = probe ? clock64() : 0;
-        named_sync(1, ENC_COMPUTE);                         // all compute warps: operand rows stored, accumulators drained
-        if (tid == 0) {
-          mbar_arrive_a(a_bar_full + buf * 8);              // hand the group to the issuer warp
-          mbar_arrive_a(a_bar_xe + slot * 8);               // and its x slot back to the loader warp
+        named_sync(1 + T, 128);                             // the team's four warps: operand rows of tile T stored
+        if ((tid & 127) == 0) {
+          mbar_arrive_a(a_bar_full + buf * (MAX_TILES * 8) + team_bars);   // hand the tile to the issuer warp
+          mbar_arrive_a(a_bar_xe + slot * 8);               // and the team's share of the x slot back to the loader warp
         }
         const long long c2 = probe ? clock64() : 0;
         if (g > 0) epi_finish(g - 1, er);
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
           tsum[4] += c4 - c2;    // barrier release + epilogue of the previous group (incl. mbarrier wait)
         }
       }
-      {
+      if (team_active) {
         uint32_t er[18];
         epi_issue(G - 1, er);
         epi_finish(ngroups - 1, er);
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       // ---- Linear S -> 128 (+ReLU): A = A2, B = W1S, both resident; accumulator D1 reuses the conv columns
       fence_async_smem();
       tc_fence_before();
-      named_sync(1, ENC_COMPUTE);
+      named_sync(BAR_BLOCK, ENC_COMPUTE);
       if (warp == 0) {
         if (elect_one()) {
           tc_fence_after();
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       }
       fence_async_smem();
       tc_fence_before();
-      named_sync(1, ENC_COMPUTE);
+      named_sync(BAR_BLOCK, ENC_COMPUTE);
       // ---- Linear 128 -> 64
       if (warp == 0) {
         if (elect_one()) {
@@ -464,8 +468,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
           }
         }
       }
-      // the next block's conv epilogues rewrite A2 and its MMAs rewrite the TMEM columns of D1 / D2: both are
-      // ordered behind this point by the group hand-off (proxy fence + tcgen05 fence + named barrier + arrive)
+      // the next block's conv epilogues rewrite A2 and its MMAs rewrite the TMEM columns of D1 / D2.  A team hands
+      // its first tile over without waiting for the other teams, so every warp must have finished reading D2
+      // before any team moves on: one block-wide barrier per 128 A-scans (the hand-off itself then orders the
+      // MMAs behind it: tcgen05 fence + team barrier + arrive)
+      tc_fence_before();
+      named_sync(BAR_BLOCK, ENC_COMPUTE);
       if (probe) tsum[5] += clock64() - l0;
     }
     if (probe) {
