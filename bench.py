@@ -56,7 +56,7 @@ def kernel_work(kind, n_per):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/), per A-scan; None until a capture of the current kernel exists
-NCU_TRAFFIC_PER_ASCAN = {"msc_encoder_tc": 837.7}   # profiles/r01_s2/ncu_msc_encoder_tc.txt: (230.6 + 70.9) MB / 360 000 A-scans
+NCU_TRAFFIC_PER_ASCAN = {"msc_encoder_tc": 827.0}   # profiles/r01_s3/ncu_msc_encoder_tc_team_handoff.txt: (230.6 + 67.1) MB / 360 000 A-scans
 
 
 def peaks():

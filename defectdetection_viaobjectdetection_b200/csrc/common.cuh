@@ -235,9 +235,10 @@ void op_window_gather(Ctx& c, const void* volume, int src_dtype, int64_t G, int6
 // ---------------------------------------------------------------------------------------------
 // SURVEY section 8 "next" rows (ops_next.cu)
 // ---------------------------------------------------------------------------------------------
-// improved_model.py:126-133: f[a,l] = mean_c(x - depthwise_conv_k(x)); in [A,L,C] fp32, w [C][k]
-void op_bgsub_chanmean(Ctx& c, const float* in, int64_t A, int L, int C, int k, const float* w, const float* bias,
-                       float* f);
+// improved_model.py:126-133: f[a,l] = mean_c(x - depthwise_conv_k(x)); rows row(a,l) = H0 + a*Lrow + l of a
+// [rows, C] fp32 or bf16 buffer, w [C][k]
+void op_bgsub_chanmean(Ctx& c, const void* in, int in_dtype, int64_t A, int L, int C, int Lrow, int H0, int k,
+                       const float* w, const float* bias, float* f);
 // channel mean + (mode 0: AvgPool1d(pk) -> linear interpolate to P | mode 1: AdaptiveAvgPool1d(P)); rows
 // row(a,l) = H0 + a*Lp + l of a [rows, C] fp32 or bf16 buffer -> out [A, P]
 void op_chanmean_resample(Ctx& c, const void* in, int in_dtype, int64_t A, int L, int C, int Lp, int H0, int mode,

@@ -1326,12 +1326,23 @@ void Model::fwd_improved(const float* x, int64_t B, int N, int S, const paut_out
   if (!hyb) {
     const ConvW& c0 = conv["conv1d.0"];
     const ConvW& c1 = conv["conv1d.3"];
-    float* a0 = c.allocf((size_t)A * S * c0.Cout);
-    op_stem_conv(c, x, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
-    float* a1 = c.allocf((size_t)A * S * c1.Cout);
-    g.conv(a0, A, S, c1, 1, 1, 1, true, nullptr, a1, c1.Cout, 0, nullptr, 0, 0);
     feat = c.allocf((size_t)A * S);
-    op_bgsub_chanmean(c, a1, A, S, c1.Cout, 15, raw["background_extractor.weight"], raw["background_extractor.bias"], feat);
+    const float* wbg = raw["background_extractor.weight"];
+    const float* bbg = raw["background_extractor.bias"];
+    if (g.tc_convs(S) && c1.Wp) {
+      // bf16 mode: stem into flat rows, the 16 -> 32 convolution on the tcgen05 implicit-GEMM kernel
+      __nv_bfloat16* a0 = g.alloc_flat(A, S, c0.Cout);
+      g.stem_flat(x, A, S, c0, a0, c0.Cout, 0);
+      __nv_bfloat16* a1 = g.alloc_flat(A, S, c1.Cout);
+      g.convtc(a0, A, S, c1, 1, true, nullptr, 0, a1, c1.Cout, 0, nullptr, 0, 0);
+      op_bgsub_chanmean(c, a1, PAUT_BF16, A, S, c1.Cout, S + CONV_HALO, CONV_HALO, 15, wbg, bbg, feat);
+    } else {
+      float* a0 = c.allocf((size_t)A * S * c0.Cout);
+      op_stem_conv(c, x, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
+      float* a1 = c.allocf((size_t)A * S * c1.Cout);
+      g.conv(a0, A, S, c1, 1, 1, 1, true, nullptr, a1, c1.Cout, 0, nullptr, 0, 0);
+      op_bgsub_chanmean(c, a1, PAUT_F32, A, S, c1.Cout, S, 0, 15, wbg, bbg, feat);
+    }
     featK = S;
   } else {
     float* pooled = c.allocf((size_t)A * 128);

@@ -39,9 +39,10 @@ __device__ __forceinline__ float sum128(const uint4* p, const __nv_bfloat16*) {
 // shared-memory bound); the channel groups' partial sums meet in shared memory.
 constexpr int BG_HALO = 8;         // left halo (>= k/2, multiple of 4)
 constexpr int BG_MAXCG = 8;
-__global__ void __launch_bounds__(256) k_bgsub_chanmean(const float* __restrict__ in, int L, int C, int k, int CG,
-                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                         float* __restrict__ f) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_bgsub_chanmean(const T* __restrict__ in, int L, int C, int k, int CG, int Lrow,
+                                                         int H0, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ f) {
   extern __shared__ __align__(16) float sm[];
   const int Lp = L + 20;               // 8 left + 12 right zero samples; Lp % 32 = 4 * odd for L % 32 == 0
   float* tile = sm;                    // [C][Lp]
@@ -49,12 +50,34 @@ __global__ void __launch_bounds__(256) k_bgsub_chanmean(const float* __restrict_
   float* part = ws + C * 16;           // [CG][L]
   __shared__ float meanb;
   const int64_t a = blockIdx.x;
-  const float* src = in + a * (int64_t)L * C;
+  const T* src = in + ((int64_t)H0 + a * Lrow) * C;     // rows row(a, l) = H0 + a*Lrow + l (dense: H0 = 0, Lrow = L)
   for (int i = threadIdx.x; i < C * 20; i += blockDim.x) {
     const int c = i / 20, j = i % 20;
     tile[c * Lp + (j < BG_HALO ? j : L + j)] = 0.f;
   }
-  for (int i = threadIdx.x; i < L * C; i += blockDim.x) tile[(i % C) * Lp + BG_HALO + i / C] = src[i];
+  constexpr int EPV = 16 / (int)sizeof(T);                 // 128-bit global loads: EPV channels of one row each
+  if (C % EPV == 0) {
+    const int vpr = C / EPV;
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    for (int i = threadIdx.x; i < L * vpr; i += blockDim.x) {
+      const int l = i / vpr, c0 = (i - l * vpr) * EPV;
+      const uint4 u = __ldg(src4 + i);
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+      float* dst = tile + c0 * Lp + BG_HALO + l;
+      if (sizeof(T) == 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j * Lp] = __uint_as_float(wv[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dst[(2 * j) * Lp] = __uint_as_float(wv[j] << 16);
+          dst[(2 * j + 1) * Lp] = __uint_as_float(wv[j] & 0xffff0000u);
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < L * C; i += blockDim.x) tile[(i % C) * Lp + BG_HALO + i / C] = ldf(src + i);
+  }
   const int half = k >> 1;
   for (int i = threadIdx.x; i < C * 16; i += blockDim.x) {
     const int c = i >> 4, o = i & 15, t = o - 7 + half;          // o = t - half + 7
@@ -105,8 +128,8 @@ __global__ void __launch_bounds__(256) k_bgsub_chanmean(const float* __restrict_
   }
 }
 
-void op_bgsub_chanmean(Ctx& c, const float* in, int64_t A, int L, int C, int k, const float* w, const float* bias,
-                       float* f) {
+void op_bgsub_chanmean(Ctx& c, const void* in, int in_dtype, int64_t A, int L, int C, int Lrow, int H0, int k,
+                       const float* w, const float* bias, float* f) {
   if (c.dry) return;
   PAUT_CHECK(L % 4 == 0 && k % 2 == 1 && k <= 15, PAUT_ERR_UNSUPPORTED,
              "bgsub_chanmean: L must be a multiple of 4 and the kernel size odd and <= 15");
@@ -115,12 +138,16 @@ void op_bgsub_chanmean(Ctx& c, const float* in, int64_t A, int L, int C, int k, 
   if (CG > C) CG = C;
   const size_t smem = ((size_t)C * (L + 20) + (size_t)C * 16 + (size_t)CG * L) * sizeof(float);
   PAUT_CHECK(smem <= (size_t)c.smem_optin, PAUT_ERR_UNSUPPORTED, "bgsub_chanmean: A-scan tile exceeds shared memory");
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    PAUT_CUDA(cudaFuncSetAttribute(k_bgsub_chanmean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  if (smem > 48 * 1024) {
+    PAUT_CUDA(cudaFuncSetAttribute(k_bgsub_chanmean<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PAUT_CUDA(cudaFuncSetAttribute(k_bgsub_chanmean<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  k_bgsub_chanmean<<<(unsigned)A, 256, smem, c.stream>>>(in, L, C, k, CG, w, bias, f);
+  if (in_dtype == PAUT_F32)
+    k_bgsub_chanmean<float><<<(unsigned)A, 256, smem, c.stream>>>(static_cast<const float*>(in), L, C, k, CG, Lrow, H0, w,
+                                                                   bias, f);
+  else
+    k_bgsub_chanmean<__nv_bfloat16><<<(unsigned)A, 256, smem, c.stream>>>(static_cast<const __nv_bfloat16*>(in), L, C, k,
+                                                                           CG, Lrow, H0, w, bias, f);
   c.launched("bgsub_chanmean");
 }
 

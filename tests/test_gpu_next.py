@@ -181,4 +181,4 @@ def test_all_zero_run_drop_on_device():
     sets, table = paut.gather_windows(torch.from_numpy(vol).cuda(), "ssd", 50, drop_all_zero=True)
     np.testing.assert_array_equal(table, ref_table)
     np.testing.assert_array_equal(sets.cpu().numpy(), ref_sets)
-    assert want.sum() == 6
+    assert want.sum() == 7
