@@ -125,7 +125,7 @@ class ClockSampler:
 
 
 def make_volume(kind, n_sets, n_per_set, seed):
-    from oracle import synth
+    from defectdetection_viaobjectdetection_b200 import synthetic as synth
     x = synth.synth_paut_sets(n_sets, n_per_set, S, seed=seed, defect_frac=0.01)     # [sets, N, S] fp32 in [0,1]
     if kind == "conv1d_msc":
         x = np.ascontiguousarray(x.transpose(0, 2, 1))
@@ -133,6 +133,7 @@ def make_volume(kind, n_sets, n_per_set, seed):
 
 
 def oracle_forward(kind, sd, x, threshold=0.5):
+    # the ONLY use of oracle/ in this file: the CPU legs (cpu_baseline and --impl reference)
     from oracle import models as om
     from oracle import postprocess as opp
     with torch.no_grad():
@@ -178,7 +179,7 @@ def main():
     n_sets, n_per = SETS[kind]
     if args.sets:
         n_sets = args.sets
-    from oracle import synth
+    from defectdetection_viaobjectdetection_b200 import synthetic as synth      # data + weights: not oracle code
     sd = synth.synth_state_dict(kind, seed=0)
     workload = f"{kind} over {n_sets * n_per} A-scans per GPU ({n_sets} sets x {n_per} x {S}), synthetic PAUT volume"
 
@@ -213,7 +214,7 @@ def main():
     # ------------------------------------------------------------------ our arm
     import defectdetection_viaobjectdetection_b200 as paut
     from defectdetection_viaobjectdetection_b200 import runtime
-    from tests.test_abi import MODELS
+    from defectdetection_viaobjectdetection_b200.modules import FACTORIES as MODELS
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

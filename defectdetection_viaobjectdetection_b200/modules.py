@@ -365,6 +365,21 @@ class ComplexDetectionModel(PautModule):
         return o["defect_prob"]
 
 
+# kind -> constructor from a cfg dict (bench.py and the tests build every model through this table)
+FACTORIES = {
+    "msc": lambda cfg: MultiSignalClassifier(cfg.get("signal_length", 320), [128, 64, 32], 4),
+    "msc_n": lambda cfg: MultiSignalClassifier_N(cfg.get("signal_length", 320), [128, 64, 32], 4),
+    "conv1d_msc": lambda cfg: DefectDetectionModel(320, 300),
+    "ssd": lambda cfg: SignalSequenceDetector(**cfg),
+    "enhanced": lambda cfg: EnhancedSignalSequenceDetector(**cfg),
+    "two_stage": lambda cfg: TwoStageDefectDetector(cfg.get("signal_length", 320)),
+    "msc_legacy": lambda cfg: MultiSignalClassifierLegacy(cfg.get("signal_length", 320), [128, 64, 32]),
+    "improved": lambda cfg: ImprovedMultiSignalClassifier(cfg.get("signal_length", 320), [128, 64, 32], 8),
+    "hybrid": lambda cfg: HybridBinaryModel(**{k: v for k, v in cfg.items() if k in ("signal_length", "hidden_sizes")}),
+    "complex": lambda cfg: ComplexDetectionModel(),
+}
+
+
 def sample_indices(defect_position, signal_length):
     """predict.py:111-113 / signal_visualizer.py:409-410: int(start * len(signal)) with the float32 product."""
     p = np.asarray(defect_position, dtype=np.float32) * np.float32(signal_length)

@@ -48,18 +48,7 @@ def test_no_cpu_fallback():
         m(torch.rand(1, 50, 320))
 
 
-MODELS = {
-    "msc": lambda cfg: paut.MultiSignalClassifier(cfg.get("signal_length", 320), [128, 64, 32], 4),
-    "msc_n": lambda cfg: paut.MultiSignalClassifier_N(cfg.get("signal_length", 320), [128, 64, 32], 4),
-    "conv1d_msc": lambda cfg: paut.DefectDetectionModel(320, 300),
-    "ssd": lambda cfg: paut.SignalSequenceDetector(**cfg),
-    "enhanced": lambda cfg: paut.EnhancedSignalSequenceDetector(**cfg),
-    "two_stage": lambda cfg: paut.TwoStageDefectDetector(cfg.get("signal_length", 320)),
-    "msc_legacy": lambda cfg: paut.MultiSignalClassifierLegacy(cfg.get("signal_length", 320), [128, 64, 32]),
-    "improved": lambda cfg: paut.ImprovedMultiSignalClassifier(cfg.get("signal_length", 320), [128, 64, 32], 8),
-    "hybrid": lambda cfg: paut.HybridBinaryModel(**{k: v for k, v in cfg.items() if k in ("signal_length", "hidden_sizes")}),
-    "complex": lambda cfg: paut.ComplexDetectionModel(),
-}
+from defectdetection_viaobjectdetection_b200.modules import FACTORIES as MODELS  # noqa: E402
 
 
 def test_modules_expose_reference_state_dict_contract():
