@@ -245,8 +245,8 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step_resident()
-    barrier()
+        det, count = step_resident()     # same reference pattern as the timed loop: the caching allocator reaches its
+    barrier()                            # steady state (two record buffers alive) before the timed region
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = ctx.launch_count
@@ -267,13 +267,15 @@ def main():
     # ---- end to end through the public API with host buffers: H2D + forward + post-process + D2H records
     # (VolumeScanner: resident chunks on two streams, H2D / kernels / D2H of kept records overlapped)
     from defectdetection_viaobjectdetection_b200.streaming import VolumeScanner
-    scan_chunk = int(os.environ.get("PAUT_BENCH_CHUNK_ASCANS", "76800"))
-    scanner = VolumeScanner(model, chunk_sets=max(1, (scan_chunk // n_per)), lanes=int(os.environ.get("PAUT_BENCH_LANES", "4")))
+    scan_chunk = int(os.environ.get("PAUT_BENCH_CHUNK_ASCANS", "38400"))
+    scanner = VolumeScanner(model, chunk_sets=max(1, (scan_chunk // n_per)), lanes=int(os.environ.get("PAUT_BENCH_LANES", "4")),
+                            reuse_output=True)
 
     def step_e2e():
         return scanner.scan(x_host, threshold=0.5)
 
-    step_e2e()
+    for _ in range(3):                   # warm-up: lanes, both record arenas, allocator steady state
+        rec = step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -322,7 +324,7 @@ def main():
                        "threshold": 0.5, "detections_last_step": n_found},
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "A-scans/s", "h2d_bytes_per_step": scanner.h2d_bytes,
-                    "d2h_bytes_per_step": scanner.d2h_bytes, "api": "VolumeScanner.scan(pinned host tensor)"},
+                    "d2h_bytes_per_step": scanner.d2h_bytes, "api": "VolumeScanner(reuse_output=True).scan(pinned host tensor)"},
             "roofline": roof,
             "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
         }

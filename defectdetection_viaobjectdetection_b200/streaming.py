@@ -34,8 +34,13 @@ class VolumeScanner:
     makes the copies asynchronous.  Returns a numpy structured array (dtype ``DETECTION``) whose
     ``set_index`` is the index into ``x_host``."""
 
-    def __init__(self, model, chunk_sets=256, device=None, lanes=4):
+    def __init__(self, model, chunk_sets=256, device=None, lanes=4, reuse_output=False):
+        """reuse_output: keep the host record arena between scans (two arenas, used alternately) instead of
+        allocating -- and page-faulting -- a fresh one per scan; the array returned by scan() is then only valid
+        until the second next scan() of this scanner (copy it to keep it)."""
         self.model = model
+        self.reuse_output = bool(reuse_output)
+        self._arenas, self._arena_turn = [None, None], 0
         self.chunk_sets = int(chunk_sets)
         self.num_lanes = max(2, int(lanes))
         self.device = torch.device(device) if device is not None else next(iter(model.state_dict().values())).device
@@ -71,9 +76,11 @@ class VolumeScanner:
                     lane.host[copied:nbytes].copy_(det[copied:nbytes], non_blocking=True)
                 lane.stream.synchronize()
                 self.d2h_bytes += nbytes - copied
-            # raw byte memcpy out of the pinned buffer (a structured-dtype copy would go field by field)
+            # raw byte memcpy out of the pinned buffer (a structured-dtype copy would go field by field), then the
+            # chunk-local set indices -> volume indices while the later chunks are still in flight
             self._raw[self._off:self._off + nbytes] = lane.host[:nbytes].numpy()
-            self._chunks.append((self._off // DETECTION.itemsize, n, first))
+            if first:
+                self._raw[self._off:self._off + nbytes].view(DETECTION)["set_index"] += first
             self._off += nbytes
             self._spec_bytes = max(self._spec_bytes, int(nbytes * 1.25) // 48 * 48 + 48)
         self.d2h_bytes += 4 + copied
@@ -93,8 +100,15 @@ class VolumeScanner:
         out = None
         n_total = x_host.shape[0]
         n_per = x_host.shape[2] if self.model._kind == "conv1d_msc" else x_host.shape[1]
-        self._raw = np.empty(n_total * n_per * DETECTION.itemsize, dtype=np.uint8)   # worst case, touched lazily
-        self._off, self._chunks = 0, []
+        need = n_total * n_per * DETECTION.itemsize                                  # worst case
+        if self.reuse_output:
+            self._arena_turn ^= 1
+            if self._arenas[self._arena_turn] is None or self._arenas[self._arena_turn].size < need:
+                self._arenas[self._arena_turn] = np.empty(need, dtype=np.uint8)
+            self._raw = self._arenas[self._arena_turn]
+        else:
+            self._raw = np.empty(need, dtype=np.uint8)                               # touched lazily
+        self._off = 0
         main = torch.cuda.current_stream(self.device)
         for lane in self._lanes:
             lane.stream.wait_stream(main)
@@ -123,8 +137,6 @@ class VolumeScanner:
         for lane in self._lanes:
             main.wait_stream(lane.stream)
         rec = self._raw[:self._off].view(DETECTION)
-        for start, n, first in self._chunks:                   # chunk-local set indices -> volume indices
-            rec["set_index"][start:start + n] += first
         self._raw = None
         return rec
 

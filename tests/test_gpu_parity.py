@@ -206,6 +206,12 @@ def test_volume_scanner_equals_resident_run(kind, precision):
     thr = float(np.median(everything["confidence"]))          # keeps about half of the A-scans
     whole = m.predict_records(x.cuda(), threshold=thr)
     scanner = VolumeScanner(m, chunk_sets=8)
+    reusing = VolumeScanner(m, chunk_sets=8, reuse_output=True)
+    first = reusing.scan(x, threshold=thr).copy()
+    again = reusing.scan(x, threshold=thr)
+    for f in whole.dtype.names:                               # the arena of the previous scan is not clobbered
+        np.testing.assert_array_equal(first[f], whole[f], err_msg=f)
+        np.testing.assert_array_equal(again[f], whole[f], err_msg=f)
     for host in (x.pin_memory(), x):
         got = scanner.scan(host, threshold=thr)
         assert len(got) == len(whole) > 0
