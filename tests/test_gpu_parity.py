@@ -220,3 +220,42 @@ def test_volume_scanner_equals_resident_run(kind, precision):
     assert scanner.h2d_bytes == x.numel() * x.element_size()
     preds = to_predictions(got, B)
     assert sum(len(p) for p in preds) == len(got)
+
+
+@pytest.mark.parametrize("n_sets,kind", [(3334, "msc"), (26667, "msc"), (20000, "two_stage")])
+def test_full_size_volume_invariants(n_sets, kind):
+    """BASELINE.json's full sizes (1 M A-scans of configs[1] / configs[3], the 8 M-A-scan whole-weld volume of
+    configs[4]) through size-independent properties: the volume is a 256-set block repeated, so every repetition
+    must reproduce the block's outputs bit for bit wherever it falls relative to the resident chunks (sets are
+    independent); records of the whole volume == two half-volume shards concatenated; and, at 1 M A-scans, == the
+    records streamed from host memory by VolumeScanner.  The block itself is checked against the oracle."""
+    from defectdetection_viaobjectdetection_b200.streaming import VolumeScanner
+    N = 300 if kind == "msc" else 50
+    block = synth.synth_paut_sets(256, N, 320, seed=17, defect_frac=0.05)
+    sd = synth.synth_state_dict(kind, seed=0)
+    xb = torch.from_numpy(block).to(torch.bfloat16)
+    reps = (n_sets + 255) // 256
+    x = xb.cuda().repeat(reps, 1, 1)[:n_sets].contiguous()
+    m = build(kind, dict(signal_length=320), precision="bf16")
+    key = "defect_prob" if kind == "msc" else "defect_logits"
+    out = run_flat(m, kind, x)[key]
+    head = out[:256]
+    with torch.no_grad():
+        ref = flatten(kind, om.FORWARD[kind](sd, xb[:16].float(), precision="bf16"))[key]
+    assert np.abs(head[:16] - ref).max() <= BF16_ATOL
+    for k in range(1, reps):
+        part = out[k * 256:(k + 1) * 256]
+        assert np.array_equal(part, head[:len(part)]), f"repetition {k} differs from the first block"
+    thr = float(np.median(m.predict_records(x[:256].contiguous(), threshold=-1.0)["confidence"]))   # keeps about half
+    whole = m.predict_records(x, threshold=thr)
+    h = (n_sets // 2) // 256 * 256                              # shard boundary on a block (and chunk-alignment) boundary
+    lo, hi = m.predict_records(x[:h].contiguous(), thr), m.predict_records(x[h:].contiguous(), thr)
+    hi["set_index"] += h
+    both = np.concatenate([lo, hi])
+    assert len(both) == len(whole) > 0
+    for f in whole.dtype.names:
+        np.testing.assert_array_equal(both[f], whole[f], err_msg=f)
+    if n_sets <= 3334:
+        got = VolumeScanner(m, chunk_sets=128).scan(x.cpu(), threshold=thr)
+        for f in whole.dtype.names:
+            np.testing.assert_array_equal(got[f], whole[f], err_msg=f)
