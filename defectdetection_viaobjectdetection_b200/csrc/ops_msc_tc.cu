@@ -163,10 +163,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   // conv1 + ReLU at the sample x1 with neighbours x0, x2: 8 channels as 4 fp16 pairs
   auto conv1 = [&](float x0, float x1, float x2, uint32_t (&o)[4]) {
     const __half2 h0 = __float2half2_rn(x0), h1 = __float2half2_rn(x1), h2 = __float2half2_rn(x2);
-    const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const __half2 v = __hmax2(__hfma2(cw[j][2], h2, __hfma2(cw[j][1], h1, __hfma2(cw[j][0], h0, cb[j]))), zero);
+      const __half2 v = __hfma2_relu(cw[j][2], h2, __hfma2(cw[j][1], h1, __hfma2(cw[j][0], h0, cb[j])));   // fma.rn.relu
       o[j] = *reinterpret_cast<const uint32_t*>(&v);
     }
   };
@@ -304,18 +303,26 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     const int c_al = tid >= S ? 1 : 0, c_pos = tid - c_al * S;
     const uint32_t c_xoff = (uint32_t)(c_al * xs_stride + 8 + c_pos) * 2;
     const uint32_t c_eoff = (uint32_t)(2 * warp + (lane == 31 ? 1 : 0)) * 16;
-    const bool c_edge = lane == 0 || lane == 31;
     const int q = warp & 3, T = warp >> 2;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    // loop-invariant addresses, pinned in registers (the empty asm makes them opaque: otherwise every use
+    // re-derives them from the warp index and the kernel arguments, ~25 of the loop's issue slots)
+    uint32_t tm_st[2] = {tmem + t_lane + (uint32_t)(T * 16), tmem + t_lane + (uint32_t)(tbuf + T * 16)};
+    uint32_t tm_ld[2] = {tmem + t_lane + (uint32_t)(tiles * 16 + T * 32), tmem + t_lane + (uint32_t)(tbuf + tiles * 16 + T * 32)};
+    uint32_t bar_conv_t = a_bar_conv + (uint32_t)T * 8, bar_full_t = a_bar_full + (uint32_t)T * 8;
+    uint32_t xs_addr = xs_base + c_xoff, eb_addr = eb_base + c_eoff;
+    asm volatile("" : "+r"(tm_st[0]), "+r"(tm_st[1]), "+r"(tm_ld[0]), "+r"(tm_ld[1]), "+r"(bar_conv_t), "+r"(bar_full_t),
+                      "+r"(xs_addr), "+r"(eb_addr));
+    const bool is_first = lane == 0, is_last = lane == 31;
     // this lane's output element of the conv epilogue (row q*32 + lane of tile T)
     const uint32_t e_off = (uint32_t)(c_pos >> 3) * A2_LBO + (uint32_t)c_al * 16 + (uint32_t)(c_pos & 7) * 2;
 
     // epilogue of one conv group: f[pos] = sum_c relu(y_c) (the 1/32 lives in W1) -> bf16 K-major operand of L1
     auto epi_issue = [&](uint32_t G, uint32_t (&r)[18]) {   // wait for the MMAs of group G, request this lane's row
       const uint32_t buf = G & 1;
-      mbar_wait_a(a_bar_conv + (buf * MAX_TILES + T) * 8, (G >> 1) & 1);
+      mbar_wait_a(bar_conv_t + buf * (MAX_TILES * 8), (G >> 1) & 1);
       tc_fence_after();
-      if (c_active) tmem_issue18(tmem + t_lane + buf * tbuf + tiles * 16 + T * 32, r);
+      if (c_active) tmem_issue18(tm_ld[buf], r);
     };
     auto epi_finish = [&](int g, uint32_t (&r)[18]) {
       if (c_active) {
@@ -330,20 +337,23 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     };
 
     const bool team_active = T < tiles;                 // whole teams are active or idle (2 * S is a multiple of 128)
-    const uint32_t team_bars = (uint32_t)T * 8;
     uint32_t G = 0;
     int it = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
       const int64_t a0 = blk * 128;
-      if (!team_active) G += ngroups;
-      for (int g = 0; team_active && g < ngroups; ++g, ++G) {
-        const uint32_t buf = G & 1, slot = G & (XS_SLOTS - 1);
+      G += ngroups;
+      // G = it * 64 + g and 64 is a multiple of every ring length, so buffer / slot indices and barrier parities
+      // depend on g alone: unrolled by four they are compile-time constants of each copy of the body
+      if (team_active) {
+#pragma unroll 4
+      for (int g = 0; g < ngroups; ++g) {
+        const uint32_t buf = g & 1, slot = g & (XS_SLOTS - 1);
         const long long c0 = probe ? clock64() : 0;
-        mbar_wait_a(a_bar_e + slot * 8, (G / XS_SLOTS) & 1);          // x has landed and the edge vectors are published
+        mbar_wait_a(a_bar_e + slot * 8, (g / XS_SLOTS) & 1);          // x has landed and the edge vectors are published
         // ---- conv1 + ReLU -> im2col row in tensor memory.  The operand columns are free: the MMAs of group G-2
         // completed before the epilogue of group G-2 ran.
         if (c_active) {
-          const uint32_t xa = xs_base + slot * slot_bytes + c_xoff;
+          const uint32_t xa = xs_addr + slot * slot_bytes;
           const float xm = ldx(xa - 2), x0 = ldx(xa), xp = ldx(xa + 2);
           uint32_t mid[4], lft[4], rgt[4];
           conv1(xm, x0, xp, mid);
@@ -354,30 +364,34 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
           }
           // warp edges: the left neighbour of lane 0 and the right neighbour of lane 31 live in other warps; the
           // edge warp has published their conv1 vectors (zeros beyond the A-scan)
-          if (c_edge) {
+          // branch-free: every lane loads one edge vector (its own warp's left one, lane 31 the right one) and
+          // only lanes 0 / 31 select it -- a divergent branch for two lanes cost the whole warp ~20 issue slots
+          {
             uint32_t e0, e1, e2, e3;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3)
-                         : "r"(eb_base + slot * (uint32_t)(ENC_COMPUTE / 32 * 2 * 16) + c_eoff));
-            if (lane == 0) { lft[0] = e0; lft[1] = e1; lft[2] = e2; lft[3] = e3; }
-            else { rgt[0] = e0; rgt[1] = e1; rgt[2] = e2; rgt[3] = e3; }
+                         : "r"(eb_addr + slot * (uint32_t)(ENC_COMPUTE / 32 * 2 * 16)));
+            lft[0] = is_first ? e0 : lft[0]; lft[1] = is_first ? e1 : lft[1];
+            lft[2] = is_first ? e2 : lft[2]; lft[3] = is_first ? e3 : lft[3];
+            rgt[0] = is_last ? e0 : rgt[0]; rgt[1] = is_last ? e1 : rgt[1];
+            rgt[2] = is_last ? e2 : rgt[2]; rgt[3] = is_last ? e3 : rgt[3];
           }
           asm volatile(
               "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-              ::"r"(tmem + t_lane + buf * tbuf + T * 16), "r"(lft[0]), "r"(lft[1]), "r"(lft[2]), "r"(lft[3]), "r"(mid[0]),
+              ::"r"(tm_st[buf]), "r"(lft[0]), "r"(lft[1]), "r"(lft[2]), "r"(lft[3]), "r"(mid[0]),
               "r"(mid[1]), "r"(mid[2]), "r"(mid[3]), "r"(rgt[0]), "r"(rgt[1]), "r"(rgt[2]), "r"(rgt[3]), "r"(0x3C003C00u), "r"(0u),
               "r"(0u), "r"(0u)
               : "memory");
         }
         // the accumulator rows of the previous group are requested while the operand store drains
         uint32_t er[18];
-        if (g > 0) epi_issue(G - 1, er);
+        if (g > 0) epi_issue(g - 1, er);
         if (c_active) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         const long long c1 = probe ? clock64() : 0;
         tc_fence_before();
         const long long c1b = probe ? clock64() : 0;
         named_sync(1 + T, 128);                             // the team's four warps: operand rows of tile T stored
         if ((tid & 127) == 0) {
-          mbar_arrive_a(a_bar_full + buf * (MAX_TILES * 8) + team_bars);   // hand the tile to the issuer warp
+          mbar_arrive_a(bar_full_t + buf * (MAX_TILES * 8));   // hand the tile to the issuer warp
           mbar_arrive_a(a_bar_xe + slot * 8);               // and the team's share of the x slot back to the loader warp
         }
         const long long c2 = probe ? clock64() : 0;
@@ -390,10 +404,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
           tsum[4] += c4 - c2;    // barrier release + epilogue of the previous group (incl. mbarrier wait)
         }
       }
-      if (team_active) {
+      {
         uint32_t er[18];
-        epi_issue(G - 1, er);
+        epi_issue(ngroups - 1, er);
         epi_finish(ngroups - 1, er);
+      }
       }
       const long long l0 = probe ? clock64() : 0;
       // ---- Linear S -> 128 (+ReLU): A = A2, B = W1S, both resident; accumulator D1 reuses the conv columns
