@@ -157,7 +157,8 @@ void op_msc_front(Ctx& c, const float* x, int64_t A, int S, const float* w1, con
 // Fused tcgen05 encoder of MultiSignalClassifier (ops_msc_tc.cu): x -> h [A,64] (bf16 mode)
 bool msc_encoder_tc_supported(int S, int h0, int h1);
 void msc_pack_conv2(const float* w2, const float* b2, std::vector<uint16_t>& out);
-void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1, const float* b1,
+// w1_host / b1_host: conv1d.0 weight [8][3] and bias [8] in HOST memory (they travel as kernel parameters)
+void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1_host, const float* b1_host,
                        const void* Bc, const void* W1p, const float* bl1, const void* W2p, const float* bl2,
                        const float* pos, float* h);
 // ---- tcgen05 implicit-GEMM Conv1d on "flat rows" (ops_conv_tc.cu), bf16 mode

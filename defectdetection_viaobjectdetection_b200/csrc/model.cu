@@ -876,7 +876,7 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
       xin = xb;
       x_dtype = PAUT_BF16;
     }
-    op_msc_encoder_tc(c, xin, x_dtype, A, S, N, raw["conv1d.0.weight"], raw["conv1d.0.bias"], enc_tc.Bc, enc_tc.W1p,
+    op_msc_encoder_tc(c, xin, x_dtype, A, S, N, H("conv1d.0.weight").data.data(), H("conv1d.0.bias").data.data(), enc_tc.Bc, enc_tc.W1p,
                       lin["shared_layer.0"].b, enc_tc.W2p, l2.b, raw["position_encoding.encoding"], h);
   } else {
     const float* x = static_cast<const float*>(xin);

@@ -51,8 +51,8 @@ struct MscEncArgs {
   int x_dtype;
   int64_t A;
   int S, Nset;
-  const float* w1;                 // conv1d.0.weight [8][3]
-  const float* b1;                 // conv1d.0.bias   [8]
+  uint32_t cw[12];                 // conv1d.0.weight as fp16 pairs: [j][t] = channels (2j, 2j+1), tap t -- passed BY VALUE so
+  uint32_t cb[4];                  // that the HFMA2s read them from the constant bank instead of 16 registers
   const __nv_bfloat16* Bc;         // conv2 operand [4 chunks][32 rows][8], fp16 bit patterns
   const __nv_bfloat16* W1p;        // shared_layer.0 / 32, packed [S/8][128][8]
   const float* bl1;
@@ -143,14 +143,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   for (int i = tid; i < S * 16; i += ENC_THREADS) reinterpret_cast<uint4*>(W1S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W1p) + i);
   for (int i = tid; i < 1024; i += ENC_THREADS) reinterpret_cast<uint4*>(W2S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2p) + i);
   for (int i = tid; i < XS_SLOTS * 2 * xs_stride; i += ENC_THREADS) XS[i] = __float2bfloat16_rn(0.f);
-  // per-thread conv1 weights as fp16 pairs: channels (2j, 2j+1), taps 0..2
-  __half2 cw[4][3], cb[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    cb[j] = __floats2half2_rn(p.b1[2 * j], p.b1[2 * j + 1]);
-#pragma unroll
-    for (int t = 0; t < 3; ++t) cw[j][t] = __floats2half2_rn(p.w1[(2 * j) * 3 + t], p.w1[(2 * j + 1) * 3 + t]);
-  }
+  // conv1 weights as fp16 pairs, channels (2j, 2j+1), taps 0..2: kernel parameters (constant bank)
+  auto cwh = [&](int j, int t) { return *reinterpret_cast<const __half2*>(&p.cw[j * 3 + t]); };
+  auto cbh = [&](int j) { return *reinterpret_cast<const __half2*>(&p.cb[j]); };
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -165,7 +160,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     const __half2 h0 = __float2half2_rn(x0), h1 = __float2half2_rn(x1), h2 = __float2half2_rn(x2);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const __half2 v = __hfma2_relu(cw[j][2], h2, __hfma2(cw[j][1], h1, __hfma2(cw[j][0], h0, cb[j])));   // fma.rn.relu
+      const __half2 v = __hfma2_relu(cwh(j, 2), h2, __hfma2(cwh(j, 1), h1, __hfma2(cwh(j, 0), h0, cbh(j))));   // fma.rn.relu
       o[j] = *reinterpret_cast<const uint32_t*>(&v);
     }
   };
@@ -552,14 +547,24 @@ void msc_pack_conv2(const float* w2 /*[16][8][3]*/, const float* b2 /*[16]*/, st
   at(3, 16, 1) = f2h(bsum - h2f(bhi));
 }
 
-void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1, const float* b1,
+void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int Nset, const float* w1_host, const float* b1_host,
                        const void* Bc, const void* W1p, const float* bl1, const void* W2p, const float* bl2,
                        const float* pos, float* h) {
   if (c.dry) return;
   PAUT_CHECK(msc_encoder_tc_supported(S, H0, H1), PAUT_ERR_UNSUPPORTED, "msc encoder: unsupported signal length");
   PAUT_CHECK(x_dtype == PAUT_BF16, PAUT_ERR_INVALID, "msc encoder: input must be bf16 (cast fp32 first)");
   MscEncArgs p;
-  p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset; p.w1 = w1; p.b1 = b1;
+  p.x = x; p.x_dtype = x_dtype; p.A = A; p.S = S; p.Nset = Nset;
+  for (int j = 0; j < 4; ++j) {
+    auto pack = [](float lo, float hi) {
+      const __half2 h = __floats2half2_rn(lo, hi);
+      uint32_t u;
+      memcpy(&u, &h, 4);
+      return u;
+    };
+    p.cb[j] = pack(b1_host[2 * j], b1_host[2 * j + 1]);
+    for (int t = 0; t < 3; ++t) p.cw[j * 3 + t] = pack(w1_host[(2 * j) * 3 + t], w1_host[(2 * j + 1) * 3 + t]);
+  }
   p.Bc = static_cast<const __nv_bfloat16*>(Bc); p.W1p = static_cast<const __nv_bfloat16*>(W1p); p.bl1 = bl1;
   p.W2p = static_cast<const __nv_bfloat16*>(W2p); p.bl2 = bl2; p.pos = pos; p.h = h;
   const size_t smem = (size_t)S * 256 + 16384 + (size_t)(S / 8) * A2_LBO + 2048 + (size_t)XS_SLOTS * 2 * (S + XS_PAD) * 2;
