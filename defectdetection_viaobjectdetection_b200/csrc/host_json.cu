@@ -294,6 +294,12 @@ int paut_json_beam_info(const paut_json_volume* v, int beam, const char** key, i
   return PAUT_OK;
 }
 
+const char* paut_json_scan_key(const paut_json_volume* v, int beam, int64_t i) {
+  if (!v || beam < 0 || beam >= (int)v->beams.size()) return nullptr;
+  const Beam& b = v->beams[beam];
+  return i >= 0 && i < (int64_t)b.scans.size() ? b.scans[i].key.c_str() : nullptr;
+}
+
 int paut_json_beam_copy_host(const paut_json_volume* v, int beam, float* signals, int32_t* labels, float* defects,
                              int64_t* scan_order) {
   if (!v || beam < 0 || beam >= (int)v->beams.size()) return PAUT_ERR_INVALID;

@@ -35,7 +35,9 @@ def load_json_volume(path):
                                               labels.ctypes.data, defects.ctypes.data, order.ctypes.data)
             if rc != 0:
                 raise ValueError(lib.paut_json_last_error().decode())
-            beams.append(dict(key=key.value.decode(), signals=signals, labels=labels, defects=defects, scan_order=order))
+            keys = [lib.paut_json_scan_key(h, b, i).decode() for i in range(n.value)]
+            beams.append(dict(key=key.value.decode(), signals=signals, labels=labels, defects=defects, scan_order=order,
+                              scan_keys=keys))
         return beams
     finally:
         lib.paut_json_free(h)
@@ -83,3 +85,26 @@ def json_signal_sets(json_dir_or_files, seq_length=50, device=None, dtype=None):
                          "(the reference's DataLoader fails at collation)")
     cat = torch.cat(sets, 0) if on_gpu else np.concatenate(sets, 0)
     return cat, np.concatenate(labels, 0), np.concatenate(defects, 0)
+
+
+def json_scan_sequences(path):
+    """The signal half of SignalSequencePreparation.get_datafile_sequences (SignalSequenceDetection/
+    dataset_preparation.py:36-116) -- the SSD-family layout, where one sequence runs ACROSS the beams at a fixed
+    scan position: beams sorted by float(beam_key.split('_')[1]), signals grouped by the scan key's first field (the
+    string: '07' and '7' are different keys), groups sorted by int(key).  Returns an ordered dict
+    {scan_key: float32 [n_beams_with_that_scan, S]} (the reference holds float64 there and casts to float32 in its
+    dataset class).  Windows: ``gather_windows(torch.from_numpy(seq)[None].cuda(), "ssd", 50, drop_all_zero=True)``."""
+    from collections import OrderedDict
+    beams = load_json_volume(path)
+    order = sorted(range(len(beams)), key=lambda i: float(beams[i]["key"].split("_")[1]))      # stable, like sorted()
+    groups = OrderedDict()
+    for b in order:
+        beam = beams[b]
+        if beam["signals"] is None:
+            raise ValueError(f"beam {beam['key']!r}: scans of different lengths")
+        for i, full_key in enumerate(beam["scan_keys"]):
+            groups.setdefault(full_key.split("_")[0], []).append(beam["signals"][i])
+    out = OrderedDict()
+    for k in sorted(groups, key=lambda k: int(k)):                                               # stable
+        out[k] = np.stack(groups[k]).astype(np.float32)
+    return out

@@ -32,6 +32,19 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().paut_abi_version() == 1
 
 
+def test_header_is_valid_c(tmp_path):
+    """include/paut.h is a C header: a C99 translation unit includes it, binds the entry points with dlsym and
+    runs the host-only calls (window tables, JSON loader, the no-GPU failure of ctx_create)."""
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    src = os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                    "-ldl"], check=True)
+    r = subprocess.run([exe, _lib.LIB_PATH, os.path.join(GOLDEN_DIR, "json_volume", "a.json")], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "c abi ok" in r.stdout
+
+
 def test_detection_record_layout():
     assert _lib.DETECTION.itemsize == 48
     assert _lib.DETECTION.fields["confidence"][1] == 40

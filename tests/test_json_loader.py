@@ -65,3 +65,14 @@ def test_device_windowing_matches_reference_dataset(expected):
     sets16, _, _ = dataio.json_signal_sets([os.path.join(JDIR, "b.json")], seq_length=5, device="cuda", dtype=torch.bfloat16)
     np.testing.assert_array_equal(sets16.float().cpu().numpy(),
                                   torch.from_numpy(expected["b_sets"]).to(torch.bfloat16).float().numpy())
+
+
+def test_scan_sequences_match_reference_grouping():
+    """SSD-family layout: SignalSequencePreparation.get_datafile_sequences (dataset_preparation.py:36-116) run in the
+    build container on c_ssd.json -> expected_ssd.npz; beams out of order (one float index), one beam lacking scans."""
+    z = np.load(os.path.join(JDIR, "expected_ssd.npz"))
+    got = dataio.json_scan_sequences(os.path.join(JDIR, "c_ssd.json"))
+    assert list(got.keys()) == [str(k) for k in z["keys"]]
+    for k, v in got.items():
+        np.testing.assert_array_equal(v, z["seq_" + k])
+    assert [v.shape[0] for v in got.values()] == [3, 4, 3, 4, 3, 4]
