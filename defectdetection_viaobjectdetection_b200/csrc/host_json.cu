@@ -300,6 +300,15 @@ const char* paut_json_scan_key(const paut_json_volume* v, int beam, int64_t i) {
   return i >= 0 && i < (int64_t)b.scans.size() ? b.scans[i].key.c_str() : nullptr;
 }
 
+int64_t paut_json_scan_copy_host(const paut_json_volume* v, int beam, int64_t i, float* out, int64_t cap) {
+  if (!v || beam < 0 || beam >= (int)v->beams.size()) return PAUT_ERR_INVALID;
+  const Beam& b = v->beams[beam];
+  if (i < 0 || i >= (int64_t)b.scans.size()) return PAUT_ERR_INVALID;
+  const Scan& s = b.scans[i];
+  if (out && cap > 0) std::memcpy(out, b.data.data() + s.off, (size_t)std::min<int64_t>(cap, (int64_t)s.len) * sizeof(float));
+  return (int64_t)s.len;
+}
+
 int paut_json_beam_copy_host(const paut_json_volume* v, int beam, float* signals, int32_t* labels, float* defects,
                              int64_t* scan_order) {
   if (!v || beam < 0 || beam >= (int)v->beams.size()) return PAUT_ERR_INVALID;

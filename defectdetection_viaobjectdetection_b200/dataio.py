@@ -16,8 +16,9 @@ from . import _lib
 
 
 def load_json_volume(path):
-    """One file -> list of beams in file order: dict(key, signals float32 [n,S] or None if ragged, labels int32 [n],
-    defects float32 [n,2], scan_order int64 [n]) with the scans in the reference's sorted order."""
+    """One file -> list of beams in file order: dict(key, signals float32 [n,S] (None if the scans differ in length:
+    then ``ragged`` is the list of per-scan arrays), labels int32 [n], defects float32 [n,2], scan_order int64 [n],
+    scan_keys) with the scans in the reference's sorted order."""
     lib = _lib.load()
     h = C.c_void_p()
     if lib.paut_json_load_host(os.fsencode(path), C.byref(h)) != 0:
@@ -35,9 +36,17 @@ def load_json_volume(path):
                                               labels.ctypes.data, defects.ctypes.data, order.ctypes.data)
             if rc != 0:
                 raise ValueError(lib.paut_json_last_error().decode())
+            ragged = None
+            if signals is None:                                  # scans of different lengths: keep them one by one
+                ragged = []
+                for i in range(n.value):
+                    ln = lib.paut_json_scan_copy_host(h, b, i, None, 0)
+                    row = np.empty(ln, np.float32)
+                    lib.paut_json_scan_copy_host(h, b, i, row.ctypes.data, ln)
+                    ragged.append(row)
             keys = [lib.paut_json_scan_key(h, b, i).decode() for i in range(n.value)]
             beams.append(dict(key=key.value.decode(), signals=signals, labels=labels, defects=defects, scan_order=order,
-                              scan_keys=keys))
+                              scan_keys=keys, ragged=ragged))
         return beams
     finally:
         lib.paut_json_free(h)
@@ -65,8 +74,20 @@ def json_signal_sets(json_dir_or_files, seq_length=50, device=None, dtype=None):
         for beam in beams:
             n = len(beam["labels"])
             wins = window_table("msc", n, seq_length)               # json_dataset.py:51-52, 84-103
-            if not wins or beam["signals"] is None or beam["signals"].shape[1] == 0:
-                continue                                            # too short, or ragged (json_dataset.py:136-146)
+            if not wins:
+                continue                                            # fewer scans than seq_length
+            if beam["signals"] is None:
+                # scans of different lengths: a window is kept iff all its scans are as long as its first one
+                # (json_dataset.py:136-146); such beams are rare, so they take the host path
+                for s0, _ in wins:
+                    rows = beam["ragged"][s0:s0 + seq_length]
+                    if any(len(r) != len(rows[0]) for r in rows):
+                        continue
+                    w = np.stack(rows)
+                    sets.append(torch.from_numpy(w).to(device=device, dtype=dtype or torch.float32)[None] if on_gpu else w[None])
+                    labels.append(beam["labels"][s0:s0 + seq_length].astype(np.float32)[None])
+                    defects.append(beam["defects"][s0:s0 + seq_length][None])
+                continue
             idx = np.array([np.arange(s, s + seq_length) for s, _ in wins])
             labels.append(beam["labels"][idx].astype(np.float32))
             defects.append(beam["defects"][idx])

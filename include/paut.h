@@ -206,6 +206,9 @@ int paut_json_num_beams(const paut_json_volume* v);
 int paut_json_beam_info(const paut_json_volume* v, int beam, const char** key, int64_t* n_scans, int64_t* signal_length);
 /* full key ("<scan>_<label>[_<start>-<end>]") of the i-th sorted scan of a beam; NULL when out of range */
 const char* paut_json_scan_key(const paut_json_volume* v, int beam, int64_t i);
+/* samples of the i-th sorted scan of a beam (for beams whose scans differ in length): copies min(cap, length)
+ * values into out (may be NULL) and returns the scan's length, or a negative paut_status */
+int64_t paut_json_scan_copy_host(const paut_json_volume* v, int beam, int64_t i, float* out, int64_t cap);
 /* sorted scans of one beam: signals float32 [n,S], labels int32 [n], defects float32 [n,2], scan_order int64 [n]
  * (the integer prefix of the key); any pointer may be NULL */
 int paut_json_beam_copy_host(const paut_json_volume* v, int beam, float* signals, int32_t* labels, float* defects,

@@ -76,3 +76,21 @@ def test_scan_sequences_match_reference_grouping():
     for k, v in got.items():
         np.testing.assert_array_equal(v, z["seq_" + k])
     assert [v.shape[0] for v in got.values()] == [3, 4, 3, 4, 3, 4]
+
+
+def test_ragged_beam_is_filtered_window_by_window(tmp_path):
+    """A beam whose scans differ in length: the reference drops only the windows that contain the odd scan
+    (json_dataset.py:136-146); expected arrays from JsonSignalDataset on each beam of d_ragged.json."""
+    z = np.load(os.path.join(JDIR, "expected_ragged.npz"))
+    with open(os.path.join(JDIR, "d_ragged.json")) as f:
+        data = json.load(f)
+    for beam in ("r0", "r1"):
+        p = tmp_path / f"{beam}.json"
+        p.write_text(json.dumps({beam: data[beam]}))
+        sets, labels, defects = dataio.json_signal_sets([str(p)], seq_length=5)
+        np.testing.assert_array_equal(sets, z[beam + "_sets"])
+        np.testing.assert_array_equal(labels, z[beam + "_labels"])
+        np.testing.assert_array_equal(defects, z[beam + "_defects"])
+    assert z["r0_sets"].shape[0] == 2                       # windows [0,5) and [8,13); [5,10) holds the short scan
+    with pytest.raises(ValueError):                          # both beams at once: S = 8 and S = 6 cannot be one batch
+        dataio.json_signal_sets([os.path.join(JDIR, "d_ragged.json")], seq_length=5)
