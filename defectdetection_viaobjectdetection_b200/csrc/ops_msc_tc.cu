@@ -38,7 +38,10 @@ namespace {
 
 constexpr int H0 = 128, H1 = 64;
 constexpr int ENC_COMPUTE = 640;        // 20 compute warps: 2 conv1 items per thread, 1 epilogue unit (tile, quarter) per warp
-constexpr int ENC_THREADS = ENC_COMPUTE + 96;   // + MMA issuer warp (20) + x loader warp (21) + edge warp (22)
+constexpr int ENC_THREADS = ENC_COMPUTE + 128;  // + MMA issuer warp (20) + x loader warp (21) + idle warp (22) + edge warp (23):
+                                                // warp w issues on scheduler w % 4, and the edge warp's ~60 instructions per
+                                                // group are better placed on the scheduler that has no other helper
+constexpr int EDGE_WARP = ENC_COMPUTE / 32 + 3;
 constexpr int A2_LBO = 2048 + 16;       // chunk stride of the f operand: +16 B skews the chunks across banks
 constexpr int D1_COL = 0, D2_COL = 128;     // alias the conv accumulators (dead by then)
 constexpr int XS_PAD = 16;
@@ -254,6 +257,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       }
     }
   } else if (warp == ENC_COMPUTE / 32 + 2) {
+    // idle: only there to put the edge warp on the fourth scheduler
+  } else if (warp == EDGE_WARP) {
     // ================= edge warp =================
     // A compute warp owns 32 consecutive positions and needs the conv1 vectors of the two positions just outside
     // (conv2 taps -1 / +1 of its first / last row).  Computing them inside the compute warps costs a full
@@ -268,11 +273,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
       epos[j] = e < 2 * (ENC_COMPUTE / 32) && P0 < 2 * S ? (side ? first + 32 : first - 1) : -2;   // -2: no entry
       exoff[j] = (al * xs_stride + 8 + (epos[j] > -2 ? epos[j] : 0)) * 2;
     }
-    uint32_t G = 0;
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-      for (int g = 0; g < ngroups; ++g, ++G) {
-        const uint32_t slot = G & (XS_SLOTS - 1);
-        mbar_wait_a(a_bar_x + slot * 8, (G / XS_SLOTS) & 1);         // x of the group has landed
+#pragma unroll 4
+      for (int g = 0; g < ngroups; ++g) {                             // slot and parity depend on g alone (64 % 4 == 0)
+        const uint32_t slot = g & (XS_SLOTS - 1);
+        mbar_wait_a(a_bar_x + slot * 8, (g / XS_SLOTS) & 1);         // x of the group has landed
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (epos[j] > -2) {
