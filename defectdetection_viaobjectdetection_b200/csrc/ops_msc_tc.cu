@@ -525,7 +525,7 @@ bool msc_encoder_tc_supported(int S, int h0, int h1) { return h0 == H0 && h1 == 
 void msc_pack_conv2(const float* w2 /*[16][8][3]*/, const float* b2 /*[16]*/, std::vector<uint16_t>& out) {
   out.assign(4 * 32 * 8, 0);
   auto f2h = [](float f) -> uint16_t { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; };
-  auto h2f = [](uint16_t u) -> float { __half h; memcpy(&h, &u, 2); return __half2float(h); };
+  auto h2f = [](uint16_t u) -> float { __half_raw r; r.x = u; return __half2float(__half(r)); };
   auto at = [&](int chunk, int row, int e) -> uint16_t& { return out[((size_t)chunk * 32 + row) * 8 + e]; };
   float wsum[3][8] = {}, bsum = 0.f;
   for (int n = 0; n < 16; ++n) {

@@ -296,6 +296,13 @@ class MultiSignalClassifierLegacy(PautModule):
         return o["defect_prob"]
 
     @torch.no_grad()
+    def prediction_map(self, volume, num_signals_per_set):
+        """GNN_testing_multi_v2_MAP.py:38-67 (load_and_predict + generate_prediction_map): one row per A-scan-index
+        folder, computed from the folder's first ``num_signals_per_set`` signals.  volume [folders, n, S] -> [folders,
+        num_signals_per_set] probabilities (the reference plots ``map * 100``)."""
+        return self.forward(volume[:, :num_signals_per_set].contiguous())
+
+    @torch.no_grad()
     def difference_matrix(self, x, threshold=0.5):
         """teststtt.py:54-69 for every set of x: (outputs [B,N], reference [B,S], diff [B,N,S], healthy_count [B])."""
         from .runtime import difference_matrix

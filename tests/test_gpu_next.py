@@ -153,6 +153,11 @@ def test_legacy_real_weights_end_to_end():
         np.testing.assert_array_equal(ref[s].cpu().numpy(), r.astype(np.float32))
         np.testing.assert_array_equal(diff[s].cpu().numpy(), d.astype(np.float32))
     assert int(healthy.sum()) > 0
+    pmap = m.prediction_map(x, 100)                             # GNN_testing_multi_v2_MAP.py:38-67: first 100 signals per folder
+    with torch.no_grad():
+        from oracle import models as om
+        want_map = om.msc_legacy_forward(sd, torch.from_numpy(c["x"][:, :100]))
+    assert pmap.shape == (2, 100) and np.abs(pmap.cpu().numpy() - want_map.numpy()).max() <= 1e-4
     rec = m.predict_records(x, 0.5)
     want = opp.postprocess("msc_legacy", p, 0.5, 360)
     np.testing.assert_array_equal(rec["position"], want["position"])
