@@ -10,7 +10,13 @@ pass and post-processing of the reference models (citations in each function
 are relative to the reference repository root).  It is pinned against the
 reference itself: ``tests/golden/make_golden.py`` imports the reference
 classes from ``/root/reference`` (possible only in the build container), runs
-them on the synthetic weights/inputs of ``oracle/synth.py`` and commits the
-outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks the
+them on the synthetic weights/inputs of ``oracle/synth.py`` (re-exported from the
+package's ``synthetic.py``: data generators, no reference arithmetic) and commits
+the outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks the
 restatement against those files everywhere.
+
+Modules: ``models`` (forwards of the ten model kinds), ``postprocess`` (predict()
+loops, keep rules, integer sample indices), ``windowing`` (the two window rules),
+``metrics`` (detection-level metrics and the difference matrix, pinned on known
+answers from the reference's own functions: ``tests/test_oracle_next.py``).
 """
