@@ -5,11 +5,11 @@ from .modules import (DETECTION, ComplexDetectionModel, DefectDetectionModel, En
                       MultiSignalClassifier_N, MultiSignalClassifierLegacy, SignalSequenceDetector,
                       TwoStageDefectDetector, load_checkpoint_state, sample_indices)
 from .dataio import json_signal_sets, load_json_volume
-from .runtime import (NativeModel, difference_matrix, gather_windows, get_context, group_nonzero, metrics_confusion,
+from .runtime import (NativeModel, detection_metrics, difference_matrix, gather_windows, get_context, group_nonzero, metrics_confusion,
                       metrics_match, window_table)
 
 __all__ = ["MultiSignalClassifier", "MultiSignalClassifier_N", "DefectDetectionModel", "SignalSequenceDetector",
            "EnhancedSignalSequenceDetector", "TwoStageDefectDetector", "MultiSignalClassifierLegacy",
            "ImprovedMultiSignalClassifier", "HybridBinaryModel", "ComplexDetectionModel", "NativeModel", "get_context",
-           "gather_windows", "group_nonzero", "window_table", "json_signal_sets", "load_json_volume", "difference_matrix", "metrics_match", "metrics_confusion",
+           "gather_windows", "group_nonzero", "window_table", "json_signal_sets", "load_json_volume", "difference_matrix", "detection_metrics", "metrics_match", "metrics_confusion",
            "sample_indices", "load_checkpoint_state", "DETECTION"]

@@ -316,3 +316,24 @@ def metrics_confusion(prob, label, threshold=0.5, ge=True):
                                          prob.numel(), float(threshold), 1 if ge else 0, C.c_void_p(out.data_ptr())),
           ctx.handle)
     return _metrics_read(out)
+
+
+def detection_metrics(rule, m):
+    """paut_metrics counts -> the dict the reference's calculate_metrics returns (same keys, same formulas).
+    rule 'position': two_stage_train.py:361-375; rule 'class': train.py:343-361."""
+    tp, fp, fn = m["tp"], m["fp"], m["fn"]
+    if rule == "position":
+        precision = tp / max(tp + fp, 1)
+        recall = tp / max(tp + fn, 1)
+        return {"precision": precision, "recall": recall,
+                "f1_score": 2 * precision * recall / max(precision + recall, 1e-8),
+                "mean_position_error": m["sum_position_error"] / tp if tp else 0,
+                "true_positives": tp, "false_positives": fp, "false_negatives": fn}
+    if rule == "class":
+        precision = tp / (tp + fp) if tp + fp > 0 else 0
+        recall = tp / (tp + fn) if tp + fn > 0 else 0
+        return {"precision": precision, "recall": recall,
+                "f1": 2 * precision * recall / (precision + recall) if precision + recall > 0 else 0,
+                "mean_iou": m["sum_iou"] / tp if tp else 0,
+                "true_positives": tp, "false_positives": fp, "false_negatives": fn}
+    raise ValueError(rule)

@@ -61,3 +61,25 @@ def test_keep_rules():
     assert opp.keep_rule(s, 0.7, "ge64").tolist() == [False, False, False, True]    # float32(0.7) < 0.7
     assert opp.keep_rule(s, 0.5, "gt32").tolist() == [True, False, False, True]
     assert opp.keep_rule(s, 0.5, "ge64").tolist() == [True, True, False, True]
+
+
+def test_detection_metrics_formulas_match_reference(vec):
+    """The host-side summary of the device counts uses the reference's formulas and key names."""
+    from defectdetection_viaobjectdetection_b200.runtime import detection_metrics
+    B = vec["label"].shape[0]
+    preds = omx.records_to_predictions(vec["rec"], B)
+    targets = omx.targets_from_dense(vec["label"], vec["tpos"])
+    r0 = omx.match_same_position(preds, targets, 0.5)
+    got0 = detection_metrics("position", dict(tp=r0["true_positives"], fp=r0["false_positives"], fn=r0["false_negatives"],
+                                              sum_position_error=r0["sum_position_error"], sum_iou=0.0))
+    for k in ("precision", "recall", "f1_score", "true_positives", "false_positives", "false_negatives"):
+        assert got0[k] == r0[k], k
+    assert got0["mean_position_error"] == pytest.approx(r0["mean_position_error"], abs=1e-6)
+    r1 = omx.match_first_class(preds, targets)
+    got1 = detection_metrics("class", dict(tp=r1["true_positives"], fp=r1["false_positives"], fn=r1["false_negatives"],
+                                           sum_iou=r1["sum_iou"], sum_position_error=0.0))
+    for k in ("precision", "recall", "f1", "true_positives", "false_positives", "false_negatives"):
+        assert got1[k] == r1[k], k
+    assert got1["mean_iou"] == pytest.approx(r1["mean_iou"], abs=1e-6)
+    empty = detection_metrics("class", dict(tp=0, fp=0, fn=0, sum_iou=0.0, sum_position_error=0.0))
+    assert empty["precision"] == 0 and empty["f1"] == 0 and empty["mean_iou"] == 0
