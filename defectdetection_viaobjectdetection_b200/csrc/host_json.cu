@@ -6,16 +6,25 @@
 // [0.0, 0.0] on any failure.  Pure host code (no CUDA calls): the parsed beams are handed to the device windowing
 // (paut_window_gather) by the caller.
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cerrno>
 #include <charconv>
+#include <chrono>
 #include <cmath>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/paut.h"
 
@@ -181,6 +190,63 @@ bool py_float(const std::string& raw, double* out) {
   return true;
 }
 
+// one beam's object "{ "<scan key>": [..] | {"signal": [..]}, ... }" -> sorted scans (json_dataset.py:44-81)
+void parse_beam(Parser& ps, Beam& beam) {
+  ps.expect('{');
+  if (!ps.eat('}')) {
+    do {
+      Scan sc;
+      sc.key = ps.str();
+      ps.expect(':');
+      sc.off = beam.data.size();
+      ps.ws();
+      if (ps.p < ps.end && *ps.p == '{') {            // {"signal": [...], ...}   json_dataset.py:113-114
+        ++ps.p;
+        bool found = false;
+        if (!ps.eat('}')) {
+          do {
+            const std::string k = ps.str();
+            ps.expect(':');
+            if (k == "signal") { beam.data.resize(sc.off); ps.numbers(beam.data); found = true; }
+            else ps.skip_value();
+          } while (ps.eat(','));
+          ps.expect('}');
+        }
+        if (!found) throw std::runtime_error("scan '" + sc.key + "' is an object without a 'signal' list");
+      } else {
+        ps.numbers(beam.data);
+      }
+      sc.len = beam.data.size() - sc.off;
+      // key parsing, json_dataset.py:48,69-79
+      const std::vector<std::string> parts = split(sc.key, '_');
+      if (!py_int(parts[0], &sc.order))
+        throw std::runtime_error("scan key '" + sc.key + "': int(key.split('_')[0]) fails");
+      if (parts.size() < 2) throw std::runtime_error("scan key '" + sc.key + "' has no label field");
+      if (parts[1] == "Health") {
+        sc.label = 0;
+      } else {
+        sc.label = 1;
+        double a = 0.0, b = 0.0;
+        bool ok = parts.size() >= 3;
+        if (ok) {
+          const std::vector<std::string> r = split(parts[2], '-');
+          ok = r.size() >= 2 && py_float(r[0], &a) && py_float(r[1], &b);
+        }
+        sc.d0 = ok ? (float)a : 0.f;
+        sc.d1 = ok ? (float)b : 0.f;
+      }
+      beam.scans.push_back(std::move(sc));
+    } while (ps.eat(','));
+    ps.expect('}');
+  }
+  ps.ws();
+  if (ps.p != ps.end) ps.fail("trailing data in beam object");
+  std::stable_sort(beam.scans.begin(), beam.scans.end(), [](const Scan& x, const Scan& y) { return x.order < y.order; });
+  beam.S = beam.scans.empty() ? 0 : (int64_t)beam.scans[0].len;
+  for (const Scan& s : beam.scans)
+    if ((int64_t)s.len != beam.S) beam.S = -1;
+}
+
 }  // namespace
 
 struct paut_json_volume {
@@ -194,84 +260,134 @@ const char* paut_json_last_error(void) { return g_json_error.c_str(); }
 int paut_json_load_host(const char* path, paut_json_volume** out) {
   if (!path || !out) return PAUT_ERR_INVALID;
   *out = nullptr;
-  std::string text;
+  // The file is mapped, not copied: the page faults then happen inside the (parallel) parse.  The span scan needs a
+  // NUL after the last byte; a file mapping is zero-filled up to the end of its last page, so only a size that is an
+  // exact multiple of the page size takes the read-into-a-string path.
+  struct Text {
+    const char* ptr = nullptr;
+    size_t len = 0;
+    void* map = nullptr;
+    size_t map_len = 0;
+    std::string owned;
+    ~Text() { if (map) munmap(map, map_len); }
+    const char* data() const { return ptr; }
+    size_t size() const { return len; }
+  } text;
   {
-    FILE* f = std::fopen(path, "rb");
-    if (!f) { g_json_error = std::string("cannot open ") + path; return PAUT_ERR_INVALID; }
-    std::fseek(f, 0, SEEK_END);
-    const long n = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    text.resize(n > 0 ? (size_t)n : 0);
-    const size_t got = text.empty() ? 0 : std::fread(&text[0], 1, text.size(), f);
-    std::fclose(f);
-    if (got != text.size()) { g_json_error = std::string("short read of ") + path; return PAUT_ERR_INVALID; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { g_json_error = std::string("cannot open ") + path; return PAUT_ERR_INVALID; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); g_json_error = std::string("not a regular file: ") + path; return PAUT_ERR_INVALID; }
+    const size_t n = (size_t)st.st_size, page = (size_t)sysconf(_SC_PAGESIZE);
+    const char* mode = std::getenv("PAUT_JSON_IO");                    // "read" | "mmap" | "populate" (experiment switch)
+    const bool use_map = !(mode && !std::strcmp(mode, "read"));
+    const int map_flags = MAP_PRIVATE | ((mode && !std::strcmp(mode, "populate")) ? MAP_POPULATE : 0);
+    if (use_map && n > 0 && n % page != 0) {
+      void* m = mmap(nullptr, n, PROT_READ, map_flags, fd, 0);
+      if (m != MAP_FAILED) {
+        madvise(m, n, MADV_WILLNEED);
+        text.map = m; text.map_len = n; text.ptr = static_cast<const char*>(m); text.len = n;
+      }
+    }
+    if (!text.map) {
+      text.owned.resize(n);
+      size_t got = 0;
+      while (got < n) {
+        const ssize_t r = read(fd, &text.owned[got], n - got);
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      if (got != n) { close(fd); g_json_error = std::string("short read of ") + path; return PAUT_ERR_INVALID; }
+      text.ptr = text.owned.c_str(); text.len = n;
+    }
+    close(fd);
   }
+  const bool timing = std::getenv("PAUT_JSON_TIMING") != nullptr;
+  const auto t_read = std::chrono::steady_clock::now();
   paut_json_volume* vol = new paut_json_volume();
   try {
+    // pass 1 (one thread, byte scan): the spans of the beams' objects.  Beams are independent, so pass 2 parses them
+    // on several threads; the result is the same as a sequential parse (beams stay in file order).
+    struct Span { std::string key; const char* b; const char* e; };
+    std::vector<Span> spans;
     Parser ps{text.data(), text.data() + text.size(), text.data()};
     ps.expect('{');
     if (!ps.eat('}')) {
       do {
-        Beam beam;
-        beam.key = ps.str();
+        Span sp;
+        sp.key = ps.str();
         ps.expect(':');
-        ps.expect('{');
-        if (!ps.eat('}')) {
-          do {
-            Scan sc;
-            sc.key = ps.str();
-            ps.expect(':');
-            sc.off = beam.data.size();
-            ps.ws();
-            if (ps.p < ps.end && *ps.p == '{') {            // {"signal": [...], ...}   json_dataset.py:113-114
-              ++ps.p;
-              bool found = false;
-              if (!ps.eat('}')) {
-                do {
-                  const std::string k = ps.str();
-                  ps.expect(':');
-                  if (k == "signal") { beam.data.resize(sc.off); ps.numbers(beam.data); found = true; }
-                  else ps.skip_value();
-                } while (ps.eat(','));
-                ps.expect('}');
-              }
-              if (!found) throw std::runtime_error("scan '" + sc.key + "' is an object without a 'signal' list");
-            } else {
-              ps.numbers(beam.data);
-            }
-            sc.len = beam.data.size() - sc.off;
-            // key parsing, json_dataset.py:48,69-79
-            const std::vector<std::string> parts = split(sc.key, '_');
-            if (!py_int(parts[0], &sc.order))
-              throw std::runtime_error("scan key '" + sc.key + "': int(key.split('_')[0]) fails");
-            if (parts.size() < 2) throw std::runtime_error("scan key '" + sc.key + "' has no label field");
-            if (parts[1] == "Health") {
-              sc.label = 0;
-            } else {
-              sc.label = 1;
-              double a = 0.0, b = 0.0;
-              bool ok = parts.size() >= 3;
-              if (ok) {
-                const std::vector<std::string> r = split(parts[2], '-');
-                ok = r.size() >= 2 && py_float(r[0], &a) && py_float(r[1], &b);
-              }
-              sc.d0 = ok ? (float)a : 0.f;
-              sc.d1 = ok ? (float)b : 0.f;
-            }
-            beam.scans.push_back(std::move(sc));
-          } while (ps.eat(','));
-          ps.expect('}');
+        ps.ws();
+        if (ps.p >= ps.end || *ps.p != '{') ps.fail("expected '{'");
+        sp.b = ps.p;
+        // only quotes and brackets matter here; strcspn (vectorised in glibc) jumps over the number lists, which
+        // are ~99 % of the bytes (the text is NUL-terminated: it lives in a std::string)
+        int depth = 0;
+        const char* q = ps.p;
+        for (;;) {
+          q += std::strcspn(q, "\"{}[]");
+          if (q >= ps.end) break;
+          const char ch = *q;
+          if (ch == '\0') { ++q; continue; }                        // stray NUL inside the file: not a delimiter
+          if (ch == '"') {                                           // skip the string, honouring escapes
+            for (++q; q < ps.end && *q != '"'; ++q)
+              if (*q == '\\') ++q;
+            if (q >= ps.end) break;
+            ++q;
+            continue;
+          }
+          if (ch == '{' || ch == '[') ++depth;
+          else if (--depth == 0) break;
+          ++q;
         }
-        std::stable_sort(beam.scans.begin(), beam.scans.end(), [](const Scan& x, const Scan& y) { return x.order < y.order; });
-        beam.S = beam.scans.empty() ? 0 : (int64_t)beam.scans[0].len;
-        for (const Scan& s : beam.scans)
-          if ((int64_t)s.len != beam.S) beam.S = -1;
-        vol->beams.push_back(std::move(beam));
+        if (q >= ps.end) ps.fail("unterminated beam object");
+        sp.e = q + 1;
+        ps.p = sp.e;
+        spans.push_back(std::move(sp));
       } while (ps.eat(','));
       ps.expect('}');
     }
     ps.ws();
     if (ps.p != ps.end) ps.fail("trailing data");
+
+    const auto t_pass1 = std::chrono::steady_clock::now();
+    vol->beams.resize(spans.size());
+    std::atomic<size_t> next{0};
+    std::mutex err_mu;
+    std::string first_error;
+    size_t first_error_beam = spans.size();
+    auto worker = [&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= spans.size()) return;
+        try {
+          Parser bp{spans[i].b, spans[i].e, text.data()};
+          vol->beams[i].key = spans[i].key;
+          parse_beam(bp, vol->beams[i]);
+        } catch (const std::exception& e) {
+          std::lock_guard<std::mutex> lk(err_mu);
+          if (i < first_error_beam) { first_error_beam = i; first_error = e.what(); }   // the error a sequential parse hits first
+        }
+      }
+    };
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (const char* env = std::getenv("PAUT_JSON_THREADS")) nthreads = (unsigned)std::max(1, std::atoi(env));
+    nthreads = (unsigned)std::min<size_t>({(size_t)std::max(1u, nthreads), spans.size(), (size_t)16});
+    if (text.size() < (size_t(1) << 20)) nthreads = 1;                  // small files: not worth the thread start-up
+    if (nthreads <= 1) {
+      worker();
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+      for (auto& th : pool) th.join();
+    }
+    if (timing) {
+      const auto t_end = std::chrono::steady_clock::now();
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      std::fprintf(stderr, "[paut_json] %zu bytes, %zu beams, %u threads: span scan %.1f ms, parse %.1f ms\n", text.size(),
+                   spans.size(), nthreads, ms(t_read, t_pass1), ms(t_pass1, t_end));
+    }
+    if (!first_error.empty()) throw std::runtime_error(first_error);
   } catch (const std::exception& e) {
     g_json_error = std::string(path) + ": " + e.what();
     delete vol;

@@ -15,10 +15,11 @@ import numpy as np
 from . import _lib
 
 
-def load_json_volume(path):
+def load_json_volume(path, with_keys=False):
     """One file -> list of beams in file order: dict(key, signals float32 [n,S] (None if the scans differ in length:
     then ``ragged`` is the list of per-scan arrays), labels int32 [n], defects float32 [n,2], scan_order int64 [n],
-    scan_keys) with the scans in the reference's sorted order."""
+    scan_keys (the full key strings, only with ``with_keys=True``)) with the scans in the reference's sorted order.
+    Beams are parsed on several threads (PAUT_JSON_THREADS, default: all cores up to 16) from a memory-mapped file."""
     lib = _lib.load()
     h = C.c_void_p()
     if lib.paut_json_load_host(os.fsencode(path), C.byref(h)) != 0:
@@ -44,7 +45,7 @@ def load_json_volume(path):
                     row = np.empty(ln, np.float32)
                     lib.paut_json_scan_copy_host(h, b, i, row.ctypes.data, ln)
                     ragged.append(row)
-            keys = [lib.paut_json_scan_key(h, b, i).decode() for i in range(n.value)]
+            keys = [lib.paut_json_scan_key(h, b, i).decode() for i in range(n.value)] if with_keys else None
             beams.append(dict(key=key.value.decode(), signals=signals, labels=labels, defects=defects, scan_order=order,
                               scan_keys=keys, ragged=ragged))
         return beams
@@ -116,7 +117,7 @@ def json_scan_sequences(path):
     {scan_key: float32 [n_beams_with_that_scan, S]} (the reference holds float64 there and casts to float32 in its
     dataset class).  Windows: ``gather_windows(torch.from_numpy(seq)[None].cuda(), "ssd", 50, drop_all_zero=True)``."""
     from collections import OrderedDict
-    beams = load_json_volume(path)
+    beams = load_json_volume(path, with_keys=True)
     order = sorted(range(len(beams)), key=lambda i: float(beams[i]["key"].split("_")[1]))      # stable, like sorted()
     groups = OrderedDict()
     for b in order:

@@ -42,6 +42,35 @@ def test_parser_details():
     np.testing.assert_array_equal(beams[0]["signals"][0], np.array(raw["beam_0"][first_key], dtype=np.float32))
 
 
+def test_parallel_parse_equals_sequential(tmp_path, monkeypatch):
+    """Files above 1 MB are parsed beam-parallel from a mapped file; the result (and the error a sequential parse
+    would report first) does not depend on the thread count or on the I/O mode."""
+    rng = np.random.default_rng(4)
+    data = {f"beam_{b}": {f"{i}_{'Health' if i % 3 else 'Defect_0.1-0.9'}": [float(x) for x in rng.random(64)]
+                          for i in rng.permutation(120)} for b in range(12)}
+    p = tmp_path / "big.json"
+    p.write_text(json.dumps(data))
+    assert p.stat().st_size > (1 << 20)
+    results = []
+    for threads, io in (("1", "read"), ("3", "mmap"), ("8", "populate")):
+        monkeypatch.setenv("PAUT_JSON_THREADS", threads)
+        monkeypatch.setenv("PAUT_JSON_IO", io)
+        results.append(dataio.load_json_volume(str(p), with_keys=True))
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert a["key"] == b["key"] and a["scan_keys"] == b["scan_keys"]
+            for f in ("signals", "labels", "defects", "scan_order"):
+                np.testing.assert_array_equal(a[f], b[f])
+    want = np.array([data["beam_5"][k] for k in sorted(data["beam_5"], key=lambda k: int(k.split("_")[0]))], np.float32)
+    np.testing.assert_array_equal(results[1][5]["signals"], want)
+    bad = dict(data)
+    bad["beam_4"] = {"x_Health": [1.0]}
+    bad["beam_9"] = {"y_Health": [1.0]}
+    p.write_text(json.dumps(bad))
+    with pytest.raises(ValueError, match="x_Health"):
+        dataio.load_json_volume(str(p))
+
+
 def test_parser_errors(tmp_path):
     for text in ('{"b": {"x_Health": [1, 2]}}',          # int('x') fails -> the reference aborts the file
                  '{"b": {"3": [1, 2]}}',                 # no label field
