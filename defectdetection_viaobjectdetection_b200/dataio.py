@@ -130,3 +130,42 @@ def json_scan_sequences(path):
     for k in sorted(groups, key=lambda k: int(k)):                                               # stable
         out[k] = np.stack(groups[k]).astype(np.float32)
     return out
+
+
+def load_sequences_pickle(path):
+    """The prepared-sequence file of the SSD family (SignalSequenceDataset.__init__, dataset_preparation.py:417-427):
+    a pickled list of dicts {signals [L,S], annotations [{bbox, label}], file_name, scan_key[, start_idx, end_idx,
+    original_length]}.  Plain pickle.load -- load only files you trust, as with the reference."""
+    import pickle
+    with open(path, "rb") as f:
+        return pickle.load(f)
+
+
+def sequence_targets(sequences):
+    """SignalSequenceDataset.__getitem__ for every sequence at once (dataset_preparation.py:429-476): returns
+    (signals float32 [W,L,S], label int32 [W,L], defect_position float32 [W,L,2], label_map, file_names, scan_keys).
+    label / defect_position are the dense targets paut_metrics_match takes.  Kept quirks of the reference: 'Health'
+    is the LAST class id (so a defect class can have id 0), a signal takes the first annotation whose beam range
+    contains (start_idx + i) / L, and sequences without 'start_idx' (zero-padded ones) get no defect targets."""
+    labels = sorted({a["label"] for s in sequences for a in s["annotations"]})
+    label_map = {lab: i for i, lab in enumerate(labels)}
+    label_map["Health"] = len(label_map)
+    W = len(sequences)
+    if W == 0:
+        return (np.zeros((0, 0, 0), np.float32), np.zeros((0, 0), np.int32), np.zeros((0, 0, 2), np.float32), label_map, [], [])
+    L = len(sequences[0]["signals"])
+    signals = np.stack([np.asarray(s["signals"], dtype=np.float32) for s in sequences])
+    label = np.full((W, L), label_map["Health"], np.int32)
+    pos = np.zeros((W, L, 2), np.float32)
+    for w, s in enumerate(sequences):
+        if "start_idx" not in s:
+            continue
+        n = len(s["signals"])
+        for i in range(n):
+            beam_position = (s["start_idx"] + i) / n
+            for a in s["annotations"]:
+                if a["bbox"][0] <= beam_position <= a["bbox"][1]:
+                    label[w, i] = label_map[a["label"]]
+                    pos[w, i] = (a["bbox"][2], a["bbox"][3])
+                    break
+    return signals, label, pos, label_map, [s["file_name"] for s in sequences], [s["scan_key"] for s in sequences]

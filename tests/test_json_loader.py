@@ -123,3 +123,18 @@ def test_ragged_beam_is_filtered_window_by_window(tmp_path):
     assert z["r0_sets"].shape[0] == 2                       # windows [0,5) and [8,13); [5,10) holds the short scan
     with pytest.raises(ValueError):                          # both beams at once: S = 8 and S = 6 cannot be one batch
         dataio.json_signal_sets([os.path.join(JDIR, "d_ragged.json")], seq_length=5)
+
+
+def test_sequence_targets_match_reference_dataset():
+    """Prepared-sequence pickle -> dense targets: SignalSequenceDataset.__getitem__ (dataset_preparation.py:429-476)
+    over sequences.pkl, run in the build container -> expected_sequences.npz (incl. a padded sequence without
+    start_idx and the reference's 'Health is the last class id' mapping)."""
+    z = np.load(os.path.join(JDIR, "expected_sequences.npz"))
+    signals, label, pos, label_map, files, keys = dataio.sequence_targets(
+        dataio.load_sequences_pickle(os.path.join(JDIR, "sequences.pkl")))
+    np.testing.assert_array_equal(signals, z["signals"])
+    np.testing.assert_array_equal(label, z["label"])
+    np.testing.assert_array_equal(pos, z["pos"])
+    assert [f"{k}={v}" for k, v in label_map.items()] == [str(s) for s in z["label_map"]]
+    assert label_map["Health"] == len(label_map) - 1 and (label[3] == label_map["Health"]).all()
+    assert keys == [str(i) for i in range(7)] and files[:2] == ["f0", "f1"]
