@@ -70,3 +70,23 @@ def all_gather_records(records, first_set=0, group=None, device=None):
     dist.all_gather(gathered, payload, group=group)
     parts = [g[: c * DETECTION.itemsize].cpu().numpy().view(DETECTION) for g, c in zip(gathered, counts)]
     return np.concatenate(parts) if parts else np.zeros(0, dtype=DETECTION)
+
+
+def all_reduce_metrics(m, group=None, device=None):
+    """Sum the per-shard detection metrics (the dict of ``metrics_match`` / ``metrics_confusion``) over the ranks:
+    sets are independent, so the counts and the fp64 sums of a sharded evaluation add up to those of the whole
+    volume (integer counts exactly; the fp64 sums in rank order).  One small all-reduce, off the data path."""
+    backend = dist.get_backend(group)
+    dev = torch.device(device) if device is not None else (
+        torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    counts = torch.tensor([m["tp"], m["fp"], m["fn"], m["tn"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    # gather (not reduce) the fp64 sums so that they are added in rank order on every rank: reproducible
+    sums = torch.tensor([m["sum_iou"], m["sum_position_error"]], dtype=torch.float64, device=dev)
+    parts = [torch.zeros_like(sums) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, sums, group=group)
+    total = torch.zeros(2, dtype=torch.float64)
+    for p in parts:
+        total += p.cpu()
+    tp, fp, fn, tn = (int(v) for v in counts.cpu())
+    return dict(tp=tp, fp=fp, fn=fn, tn=tn, sum_iou=float(total[0]), sum_position_error=float(total[1]))

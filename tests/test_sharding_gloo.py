@@ -34,6 +34,15 @@ def _worker(rank, world, port, n_sets, out):
     lo, hi = sharding.shard_range(n_sets, world, rank)
     rec = _fake_records(lo, hi, seed=lo)
     full = sharding.all_gather_records(rec, first_set=lo)
+    # sharded evaluation: per-shard metrics add up (counts exactly, fp64 sums in rank order)
+    mine = dict(tp=10 + rank, fp=3 * rank, fn=7, tn=100 * (rank + 1), sum_iou=0.1 * (rank + 1), sum_position_error=1e-3 + rank)
+    tot = sharding.all_reduce_metrics(mine)
+    assert (tot["tp"], tot["fp"], tot["fn"], tot["tn"]) == (sum(10 + r for r in range(world)), sum(3 * r for r in range(world)),
+                                                            7 * world, sum(100 * (r + 1) for r in range(world)))
+    want_iou = 0.0
+    for r in range(world):
+        want_iou += 0.1 * (r + 1)
+    assert tot["sum_iou"] == want_iou and abs(tot["sum_position_error"] - sum(1e-3 + r for r in range(world))) < 1e-12
     if rank == 0:
         np.save(out, full)
     dist.barrier()
