@@ -21,7 +21,7 @@ SYMBOLS = (
     "paut_ctx_set_workspace_limit", "paut_model_create", "paut_model_destroy", "paut_model_set_tensor",
     "paut_model_finalize", "paut_model_num_keys", "paut_model_key", "paut_forward", "paut_postprocess",
     "paut_window_gather", "paut_window_table_host", "paut_ctx_launch_count", "paut_ctx_profile_begin",
-    "paut_ctx_profile_end", "paut_op_linear", "paut_debug_mma",
+    "paut_ctx_profile_end", "paut_op_linear", "paut_debug_mma", "paut_debug_stage",
     "paut_difference_matrix", "paut_metrics_match", "paut_metrics_confusion",
     "paut_json_load_host", "paut_json_free", "paut_json_last_error", "paut_json_num_beams", "paut_json_beam_info",
     "paut_json_beam_copy_host", "paut_json_scan_key", "paut_json_scan_copy_host", "paut_group_nonzero",
@@ -96,6 +96,7 @@ def load():
         "paut_ctx_profile_end": (i32, [vp, C.c_char_p, i64]),
         "paut_op_linear": (i32, [vp, vp, i64, i32, vp, vp, i32, vp, i32, i32]),
         "paut_debug_mma": (i32, [vp, i32, i32, i32, i32, i32, vp]),
+        "paut_debug_stage": (i32, [vp, i32, vp, i32, i64, i64, i64, vp]),
         "paut_difference_matrix": (i32, [vp, vp, i32, vp, i64, i64, i64, C.c_double, vp, vp, vp]),
         "paut_metrics_match": (i32, [vp, i32, vp, vp, i64, i64, vp, vp, C.c_double, vp]),
         "paut_metrics_confusion": (i32, [vp, vp, vp, i64, C.c_double, i32, vp]),

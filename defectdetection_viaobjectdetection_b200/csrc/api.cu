@@ -2,7 +2,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <set>
 
 #include "model.cuh"
 
@@ -27,6 +29,19 @@ void* Ctx::alloc(size_t bytes) {
   ws_off = off + bytes;
   if (!dry && ws_off > ws_cap) throw Error(PAUT_ERR_STATE, "internal: activation workspace overflow");
   return ws + off;
+}
+
+void smem_optin_once(Ctx& c, const void* kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({c.device, kernel})) return;
+  cudaFuncAttributes fa;
+  PAUT_CUDA(cudaFuncGetAttributes(&fa, kernel));
+  const int dyn = c.smem_optin - (int)fa.sharedSizeBytes;
+  PAUT_CHECK(dyn > 0, PAUT_ERR_UNSUPPORTED, "kernel's static shared memory exceeds the device limit");
+  PAUT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  done.insert({c.device, kernel});
 }
 
 void Ctx::launched(const char* what) {
@@ -409,6 +424,16 @@ int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float*
       throw;
     }
     for (void* p : tmp) cudaFree(p);
+  });
+}
+
+// intermediate tensors of the fused kernels (kernel-level parity tests); not part of the product path
+int paut_debug_stage(paut_model* m, int stage, const void* x, int x_dtype, int64_t B, int64_t N, int64_t S, float* out_dev) {
+  if (!m) return PAUT_ERR_INVALID;
+  return guarded(m->m.ctx, [&] {
+    PAUT_CHECK(x && out_dev && B > 0 && N > 0 && S > 0, PAUT_ERR_INVALID, "debug_stage: bad arguments");
+    m->m.debug_stage(stage, x, x_dtype, B, N, S, out_dev);
+    PAUT_CUDA(cudaStreamSynchronize(m->m.ctx->stream));
   });
 }
 

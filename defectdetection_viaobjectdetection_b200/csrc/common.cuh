@@ -42,9 +42,6 @@ struct Ctx {
   int64_t launches = 0;
   int num_sms = 148;
   int smem_optin = 0;
-  size_t att_smem_configured = 0;
-  size_t gemm_tc_smem_configured = 0;
-  size_t conv_tc_smem_configured[4] = {0, 0, 0, 0};
   bool profiling = false;                // per-kernel CUDA-event timing (paut_ctx_profile_*)
   std::vector<std::pair<std::string, cudaEvent_t>> prof_events;
   bool dry = false;                      // allocation-only pass used to size chunks: ops do nothing
@@ -55,6 +52,14 @@ struct Ctx {
   void reset() { ws_off = 0; }
   void launched(const char* what);       // counts the launch and checks cudaGetLastError
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (device, kernel), not of a context: every kernel that
+// needs more than 48 KB is opted in ONCE per device to everything the device allows beside the kernel's static
+// shared memory (process-wide table behind a mutex, api.cu), so that contexts with different shapes on different
+// streams can never lower each other's limit.
+void smem_optin_once(Ctx& c, const void* kernel);
+template <typename K>
+inline void smem_optin(Ctx& c, K kernel) { smem_optin_once(c, reinterpret_cast<const void*>(kernel)); }
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SOFTPLUS = 4, ACT_TANH_HALF = 5 };
 
@@ -196,6 +201,13 @@ void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const fl
                   int Cout, bool relu, void* out, int ldc, int coff, int halo);
 // bf16 flat rows [R, C] -> dense fp32 [A, L, C]
 void op_unflatten(Ctx& c, const void* flat, int64_t A, int L, int halo, int C, float* out);
+// Fused encoder of TwoStageDefectDetector (ops_ts_enc.cu, bf16 mode): x [A,S] bf16 -> feat [A,128] (mean over the signal
+// length of the four conv branches), TMA input staging + stem on HFMA2 + tcgen05 second convolutions + pooled epilogue
+bool ts_encoder_supported(int S, int d_model);
+void ts_encoder_pack(const float* const* w1, const float* const* sh1, const float* const* w2, std::vector<uint32_t>& sw,
+                     std::vector<uint32_t>& sb, std::vector<uint16_t>& W2);
+void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t* sw_host, const uint32_t* sb_host,
+                   const void* W2, const float* shift2, float* feat);
 // Fused per-set stage of MSC / MSC_N (ops_set_tc.cu, bf16 mode): attention block and FFN + head
 bool msc_set_tc_supported(int N, int d, int heads, int ff);
 void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bqkv, const void* Wo, const float* bo,

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <utility>
+#include <cstdlib>
 #include <cstring>
 
 namespace paut {
@@ -699,6 +700,65 @@ void Model::finalize() {
         ts_grouped.shift = upload(shift_all);
         ts_grouped.ready = true;
       }
+      ts_enc = TsEnc{};
+      if (cfg.precision == PAUT_PRECISION_BF16 && d == 128) {
+        // operands of the fused encoder kernel: BatchNorm folded on the host in fp64, everything in fp16 (stem weights
+        // and shifts as channel pairs for HFMA2, second convolutions in the K-major operand layout)
+        std::vector<std::vector<float>> w1(4), s1(4), w2(4);
+        std::vector<float> shift2;
+        const float* w1p[4];
+        const float* s1p[4];
+        const float* w2p[4];
+        const int ks[4] = {3, 5, 7, 11};
+        bool ok = true;
+        int i = 0;
+        for (const char* n : {"small", "medium", "large", "xlarge"}) {
+          const std::string base = std::string("signal_encoder.conv_") + n + ".";
+          auto fold = [&](const std::string& cn, const std::string& bn, std::vector<float>& scale, std::vector<float>& shift) {
+            const HostTensor& b = H(cn + ".bias");
+            const HostTensor& g = H(bn + ".weight");
+            const HostTensor& be = H(bn + ".bias");
+            const HostTensor& mu = H(bn + ".running_mean");
+            const HostTensor& var = H(bn + ".running_var");
+            const int C = (int)b.data.size();
+            scale.resize(C); shift.resize(C);
+            for (int co = 0; co < C; ++co) {
+              const double sc = (double)g.data[co] / std::sqrt((double)var.data[co] + 1e-5);
+              scale[co] = (float)sc;
+              shift[co] = (float)(((double)b.data[co] - (double)mu.data[co]) * sc + (double)be.data[co]);
+            }
+          };
+          const HostTensor& wa = H(base + "0.weight");
+          const HostTensor& wb = H(base + "3.weight");
+          ok = ok && wa.shape[0] == 32 && wa.shape[2] == ks[i] && wb.shape[0] == 32 && wb.shape[1] == 32 && wb.shape[2] == ks[i];
+          if (!ok) break;
+          std::vector<float> sc1, sc2, sh2;
+          fold(base + "0", base + "1", sc1, s1[i]);
+          fold(base + "3", base + "4", sc2, sh2);
+          shift2.insert(shift2.end(), sh2.begin(), sh2.end());
+          w1[i].assign((size_t)ks[i] * 32, 0.f);
+          w2[i].assign((size_t)ks[i] * 32 * 32, 0.f);
+          for (int co = 0; co < 32; ++co)
+            for (int t = 0; t < ks[i]; ++t) {
+              w1[i][(size_t)t * 32 + co] = wa.data[(size_t)co * ks[i] + t] * sc1[co];
+              for (int ci = 0; ci < 32; ++ci)
+                w2[i][((size_t)t * 32 + ci) * 32 + co] = wb.data[((size_t)co * 32 + ci) * ks[i] + t] * sc2[co];
+            }
+          w1p[i] = w1[i].data(); s1p[i] = s1[i].data(); w2p[i] = w2[i].data();
+          ++i;
+        }
+        if (ok) {
+          std::vector<uint16_t> W2h;
+          ts_encoder_pack(w1p, s1p, w2p, ts_enc.sw, ts_enc.sb, W2h);
+          void* dptr = nullptr;
+          PAUT_CUDA(cudaMalloc(&dptr, W2h.size() * sizeof(uint16_t)));
+          dev_allocs.push_back(dptr);
+          PAUT_CUDA(cudaMemcpy(dptr, W2h.data(), W2h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          ts_enc.W2 = dptr;
+          ts_enc.shift2 = upload(shift2);
+          ts_enc.ready = true;
+        }
+      }
       L("signal_encoder.projection.0"); N_("signal_encoder.projection.1");
       R("sequence_transformer.pos_encoder.pe");
       for (int i = 0; i < 4; ++i)
@@ -816,6 +876,10 @@ struct G {
   bool tc_convs(int S) const { return bf16 && S % 8 == 0 && S + CONV_HALO >= 128; }
   __nv_bfloat16* alloc_flat(int64_t A, int L, int C) {
     return static_cast<__nv_bfloat16*>(c.alloc(flat_rows(A, L, CONV_HALO) * (size_t)C * sizeof(__nv_bfloat16)));
+  }
+  // the stem reads the caller's dtype directly (no fp32 expansion of a bf16 volume)
+  void stem_flat(const XIn& x, int64_t A, int S, const ConvW& w, __nv_bfloat16* out, int ldc, int coff) {
+    op_stem_flat(c, x.p, x.dtype, A, S, w.w, w.shift, w.taps, w.Cout, true, out, ldc, coff, CONV_HALO);
   }
   void stem_flat(const float* x, int64_t A, int S, const ConvW& w, __nv_bfloat16* out, int ldc, int coff) {
     op_stem_flat(c, x, PAUT_F32, A, S, w.w, w.shift, w.taps, w.Cout, true, out, ldc, coff, CONV_HALO);
@@ -965,7 +1029,7 @@ void Model::fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, 
 }
 
 // ------------------------------------------------------------------------------------------ SignalSequenceDetector
-void Model::fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t) {
+void Model::fwd_ssd(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t) {
   Ctx& c = *ctx;
   G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
@@ -980,7 +1044,7 @@ void Model::fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs&
     g.convtc(a1, A, S, conv["signal_encoder.conv3"], 1, true, nullptr, 0, nullptr, 0, 0, feat, 256, 0);
   } else {
     float* a0 = c.allocf((size_t)A * S * 64);
-    op_stem_conv(c, x, A, S, c1.w, c1.shift, c1.taps, c1.Cout, true, a0);
+    op_stem_conv(c, x.as_f32(c), A, S, c1.w, c1.shift, c1.taps, c1.Cout, true, a0);
     float* a1 = c.allocf((size_t)A * S * 128);
     g.conv(a0, A, S, conv["signal_encoder.conv2"], 1, 1, 2, true, nullptr, a1, 128, 0, nullptr, 0, 0);
     g.conv(a1, A, S, conv["signal_encoder.conv3"], 1, 1, 1, true, nullptr, nullptr, 0, 0, feat, 256, 0);
@@ -1033,7 +1097,7 @@ void Model::fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs&
 }
 
 // ------------------------------------------------------------------------------------------ TwoStageDefectDetector
-void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+void Model::fwd_two_stage(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
   G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
@@ -1041,7 +1105,12 @@ void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_ou
   float* feat = c.allocf((size_t)A * d);
   const char* names[4] = {"small", "medium", "large", "xlarge"};
   const bool tcc = g.tc_convs(S) && q % 16 == 0;
-  if (tcc && ts_grouped.ready) {
+  static const bool no_fused = std::getenv("PAUT_TS_UNFUSED") != nullptr;     // A/B switch for the per-layer schedule
+  if (g.bf16 && ts_enc.ready && ts_encoder_supported(S, d) && !no_fused) {
+    // one persistent kernel: TMA input staging, stems on HFMA2, the four second convolutions on tcgen05, BN shift +
+    // ReLU + mean over the signal length in the epilogue (two_stage_model.py:102-118); no activation touches HBM
+    op_ts_encoder(c, x.as_bf16(c), A, S, ts_enc.sw.data(), ts_enc.sb.data(), ts_enc.W2, ts_enc.shift2, feat);
+  } else if (tcc && ts_grouped.ready) {
     // all four stems write one [rows, 4q] buffer; the four second convolutions + BN + ReLU + mean run as one
     // grouped tcgen05 launch whose pooled output is the concatenated feature vector (two_stage_model.py:102-118)
     __nv_bfloat16* a0h = g.alloc_flat(A, S, d);
@@ -1068,7 +1137,7 @@ void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_ou
       g.stem_flat(x, A, S, s, a0h, q, 0);
       g.convtc(a0h, A, S, w, 1, true, nullptr, 0, nullptr, 0, 0, feat, d, q * i);
     } else {
-      op_stem_conv(c, x, A, S, s.w, s.shift, s.taps, s.Cout, true, a0);
+      op_stem_conv(c, x.as_f32(c), A, S, s.w, s.shift, s.taps, s.Cout, true, a0);
       g.conv(a0, A, S, w, 1, 1, w.taps / 2, true, nullptr, nullptr, 0, 0, feat, d, q * i);
     }
   }
@@ -1099,7 +1168,7 @@ void Model::fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_ou
 }
 
 // ------------------------------------------------------------------------------------------ EnhancedSignalSequenceDetector
-void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot) {
+void Model::fwd_enhanced(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot) {
   Ctx& c = *ctx;
   G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
@@ -1160,7 +1229,7 @@ void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_out
     }
   } else {
     float* s0 = c.allocf((size_t)A * S * 64);
-    op_stem_conv(c, x, A, S, ci.w, ci.shift, ci.taps, ci.Cout, true, s0);
+    op_stem_conv(c, x.as_f32(c), A, S, ci.w, ci.shift, ci.taps, ci.Cout, true, s0);
     float* bufA = c.allocf((size_t)A * S * 128);
     float* bufB = c.allocf((size_t)A * S * 128);
     float* bufC = c.allocf((size_t)A * S * 128);
@@ -1268,12 +1337,13 @@ void Model::fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_out
 // ------------------------------------------------------------------------------------------ section 8 "next" rows
 // f3: the legacy no-conv MultiSignalClassifier (resaveModelOnnx.py:24-33): MLP per A-scan, one self-attention over
 // the set WITHOUT residual or norm, MLP head + sigmoid.
-void Model::fwd_msc_legacy(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+void Model::fwd_msc_legacy(XIn& xin, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
   G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
   const Lin& l0 = lin["shared_layer.0"];
   const Lin& l2 = lin["shared_layer.2"];
+  const float* x = xin.as_f32(c);
   float* h0 = g.linear(x, S, l0, A, ACT_RELU);
   float* h = g.linear(h0, l0.N, l2, A, ACT_RELU);
   float* att = g.self_attention(h, mha["attention"], B, N, nullptr);
@@ -1286,7 +1356,7 @@ namespace {
 // Three-layer conv stack (1 -> C0 -> C1 -> C2, BN folded, ReLU) followed by channel mean + resampling to 128 values
 // per A-scan (hybrid_binary.py:139-145, complex_detection_model.py:68-75).  bf16 mode: stem into flat rows and the two
 // channel-mixing convolutions on the tcgen05 implicit-GEMM kernel when their weights were packed for it.
-void conv_stack_pooled(Model& m, G& g, const float* x, int64_t A, int S, const char* n0, const char* n1, const char* n2,
+void conv_stack_pooled(Model& m, G& g, XIn& x, int64_t A, int S, const char* n0, const char* n1, const char* n2,
                        int mode, int pk, float* pooled) {
   Ctx& c = g.c;
   const ConvW& c0 = m.conv[n0];
@@ -1302,7 +1372,7 @@ void conv_stack_pooled(Model& m, G& g, const float* x, int64_t A, int S, const c
     op_chanmean_resample(c, a2, PAUT_BF16, A, S, c2.Cout, S + CONV_HALO, CONV_HALO, mode, pk, 128, pooled);
   } else {
     float* a0 = c.allocf((size_t)A * S * c0.Cout);
-    op_stem_conv(c, x, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
+    op_stem_conv(c, x.as_f32(c), A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
     float* a1 = c.allocf((size_t)A * S * c1.Cout);
     g.conv(a0, A, S, c1, 1, 1, c1.taps / 2, true, nullptr, a1, c1.Cout, 0, nullptr, 0, 0);
     float* a2 = c.allocf((size_t)A * S * c2.Cout);
@@ -1315,7 +1385,7 @@ void conv_stack_pooled(Model& m, G& g, const float* x, int64_t A, int S, const c
 // f2: ImprovedMultiSignalClassifier (improved_model.py:123-157) and HybridBinaryModel (hybrid_binary.py:136-168):
 // a per-A-scan conv front end, the shared MLP, a learned position table and num_layers encoder layers of the
 // MSC_N type (self-attention -> LN -> depthwise local convolution(s) over the set axis -> LN -> FFN -> LN).
-void Model::fwd_improved(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+void Model::fwd_improved(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
   G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
@@ -1338,7 +1408,7 @@ void Model::fwd_improved(const float* x, int64_t B, int N, int S, const paut_out
       op_bgsub_chanmean(c, a1, PAUT_BF16, A, S, c1.Cout, S + CONV_HALO, CONV_HALO, 15, wbg, bbg, feat);
     } else {
       float* a0 = c.allocf((size_t)A * S * c0.Cout);
-      op_stem_conv(c, x, A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
+      op_stem_conv(c, x.as_f32(c), A, S, c0.w, c0.shift, c0.taps, c0.Cout, true, a0);
       float* a1 = c.allocf((size_t)A * S * c1.Cout);
       g.conv(a0, A, S, c1, 1, 1, 1, true, nullptr, a1, c1.Cout, 0, nullptr, 0, 0);
       op_bgsub_chanmean(c, a1, PAUT_F32, A, S, c1.Cout, S, 0, 15, wbg, bbg, feat);
@@ -1382,7 +1452,7 @@ void Model::fwd_improved(const float* x, int64_t B, int N, int S, const paut_out
 }
 
 // f2: ComplexDetectionModel (complex_detection_model.py:63-96)
-void Model::fwd_complex(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
+void Model::fwd_complex(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0) {
   Ctx& c = *ctx;
   G g{c, cfg.precision == PAUT_PRECISION_BF16};
   const int64_t A = B * N;
@@ -1435,12 +1505,8 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
       fwd_msc(xc, x_dtype, nb, (int)N, (int)S, out, b0);
       return;
     }
-    const float* xf = reinterpret_cast<const float*>(xc);
-    if (x_dtype != PAUT_F32) {
-      float* t = c.allocf((size_t)nb * N * S);
-      op_to_f32(c, xc, x_dtype, t, nb * N * S);
-      xf = t;
-    }
+    XIn xf;                                   // fp32 / bf16 copies are made lazily by the paths that need them
+    xf.p = xc; xf.dtype = x_dtype; xf.n = nb * N * S;
     switch (kind) {
       case PAUT_MODEL_SSD: fwd_ssd(xf, nb, (int)N, (int)S, out, b0, B); break;
       case PAUT_MODEL_ENHANCED: fwd_enhanced(xf, nb, (int)N, (int)S, out, b0, B); break;
@@ -1489,6 +1555,26 @@ void Model::forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S,
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     c.reset();
     run(b0, std::min<int64_t>(chunk, B - b0));
+  }
+}
+
+// Intermediate tensors of the fused kernels (paut_debug_stage): one resident chunk, no chunking logic
+void Model::debug_stage(int stage, const void* x, int x_dtype, int64_t B, int64_t N, int64_t S, float* out_dev) {
+  PAUT_CHECK(finalized, PAUT_ERR_STATE, "debug_stage before paut_model_finalize");
+  PAUT_CHECK(x_dtype == PAUT_F32 || x_dtype == PAUT_BF16, PAUT_ERR_INVALID, "debug_stage: x dtype must be F32 or BF16");
+  PAUT_CUDA(cudaSetDevice(ctx->device));
+  Ctx& c = *ctx;
+  const int64_t A = B * N;
+  c.reset();
+  c.reserve((size_t)A * S * 4 + (size_t(1) << 20));
+  XIn xin;
+  xin.p = x; xin.dtype = x_dtype; xin.n = A * S;
+  if (stage == 1) {
+    PAUT_CHECK(kind == PAUT_MODEL_TWO_STAGE && ts_enc.ready && ts_encoder_supported((int)S, cfg.d_model), PAUT_ERR_UNSUPPORTED,
+               "debug_stage 1: the fused two-stage encoder is not available for this model / precision / length");
+    op_ts_encoder(c, xin.as_bf16(c), A, (int)S, ts_enc.sw.data(), ts_enc.sb.data(), ts_enc.W2, ts_enc.shift2, out_dev);
+  } else {
+    throw Error(PAUT_ERR_INVALID, "debug_stage: unknown stage");
   }
 }
 

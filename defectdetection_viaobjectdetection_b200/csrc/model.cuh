@@ -55,6 +55,26 @@ struct RNNW {  // one bidirectional layer
   int H = 0, G = 0;
 };
 
+// Input of one resident chunk in the caller's dtype; the fp32 / bf16 copies are made lazily, only by the paths
+// that need them (the bf16-mode stems and the fused encoders read bf16 directly)
+struct XIn {
+  const void* p = nullptr;
+  int dtype = PAUT_F32;
+  int64_t n = 0;
+  const float* f32 = nullptr;
+  const void* bf16 = nullptr;
+  const float* as_f32(Ctx& c) {
+    if (dtype == PAUT_F32) return static_cast<const float*>(p);
+    if (!f32) { float* t = c.allocf((size_t)n); op_to_f32(c, p, dtype, t, n); f32 = t; }
+    return f32;
+  }
+  const void* as_bf16(Ctx& c) {
+    if (dtype == PAUT_BF16) return p;
+    if (!bf16) { void* t = c.alloc((size_t)n * 2); op_to_bf16(c, static_cast<const float*>(p), t, n); bf16 = t; }
+    return bf16;
+  }
+};
+
 struct Model {
   Ctx* ctx = nullptr;
   int kind = 0;
@@ -84,6 +104,12 @@ struct Model {
     int taps[4] = {0, 0, 0, 0}, goff[4] = {0, 0, 0, 0};
     bool ready = false;
   } ts_grouped;
+  struct TsEnc {                               // operands of the fused two-stage encoder (ops_ts_enc.cu, bf16 mode)
+    std::vector<uint32_t> sw, sb;              // stem weights / shifts as fp16 pairs: kernel parameters (host memory)
+    const void* W2 = nullptr;                  // second convolutions, fp16, packed
+    const float* shift2 = nullptr;             // [128]
+    bool ready = false;
+  } ts_enc;
   struct BranchConv {                          // the enhanced encoder's four dilated branches as one launch
     const void* Wp = nullptr;
     const float* shift = nullptr;              // [128] (the conv biases)
@@ -102,6 +128,7 @@ struct Model {
   void set_tensor(const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim);
   void finalize();
   void forward(const void* x, int x_dtype, int64_t B, int64_t N, int64_t S, const paut_outputs& out);
+  void debug_stage(int stage, const void* x, int x_dtype, int64_t B, int64_t N, int64_t S, float* out_dev);
   void postprocess(const paut_outputs& outs, int64_t B, int64_t N, int64_t S, double thr, paut_detection* det,
                    int32_t* count_dev);
 
@@ -121,13 +148,13 @@ struct Model {
   // forward graphs (one chunk of whole sets)
   void fwd_msc(const void* x, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
   void fwd_conv1d_msc(const void* x, int x_dtype, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
-  void fwd_ssd(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
-  void fwd_enhanced(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
-  void fwd_two_stage(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_ssd(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
+  void fwd_enhanced(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0, int64_t Btot);
+  void fwd_two_stage(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
   // SURVEY section 8 "next" rows f2 / f3
-  void fwd_msc_legacy(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
-  void fwd_improved(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
-  void fwd_complex(const float* x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_msc_legacy(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_improved(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
+  void fwd_complex(XIn& x, int64_t B, int N, int S, const paut_outputs& out, int64_t b0);
 };
 
 }  // namespace paut

@@ -217,8 +217,7 @@ void launch_attn(Ctx& c, const float* q, int ldq, const float* k, int ldk, const
   smem = (smem + 15) & ~size_t(15);
   if (W) smem += sizeof(float) * (size_t)Nq16 * KB;
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "attention: set too long for shared memory");
-  if (smem > 48 * 1024)
-    PAUT_CUDA(cudaFuncSetAttribute(k_attn_mma<HD, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) smem_optin(c, k_attn_mma<HD, W>);
   PAUT_CHECK(B < (int64_t(1) << 31), PAUT_ERR_INVALID, "attention: too many sets");
   k_attn_mma<HD, W><<<(unsigned)B, 128, smem, c.stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, Nq, Nk, H,
                                                           kv_shift ? 1 : 0, avgw);

@@ -730,11 +730,7 @@ void op_conv_tc(Ctx& c, const ConvTcLaunch& a) {
   PAUT_CHECK(!v_res || v_out, PAUT_ERR_UNSUPPORTED, "conv_tc: residual without an output tensor");
   void (*kern)(ConvTcArgs) = v_pool ? (v_out ? k_conv_tc<true, true, true> : k_conv_tc<false, true, false>)
                                     : (v_res ? k_conv_tc<true, false, true> : k_conv_tc<true, false, false>);
-  const int variant = v_pool ? (v_out ? 3 : 2) : (v_res ? 1 : 0);
-  if (smem > c.conv_tc_smem_configured[variant]) {
-    PAUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    c.conv_tc_smem_configured[variant] = smem;
-  }
+  smem_optin(c, kern);
   const int ntn = a.Cout / p.NT;
   int grid = (c.num_sms / ntn) * ntn;                       // every N tile gets the same number of CTAs
   if ((int64_t)grid > p.num_tiles * ntn) grid = (int)(p.num_tiles * ntn);

@@ -461,10 +461,7 @@ void op_attention(Ctx& c, const float* q, int ldq, const float* k, int ldk, cons
   size_t smem = sizeof(float) * ((size_t)Nk * (hd + 1) + (size_t)Nk * hd + ATT_QT * hd + (size_t)ATT_QT * Nk +
                                  (avgw ? (size_t)ATT_QT * Nk : 0));
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "attention: set too long for shared memory");
-  if (smem > c.att_smem_configured) {
-    PAUT_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    c.att_smem_configured = smem;
-  }
+  smem_optin(c, k_attention);
   for (int64_t b0 = 0; b0 < B; b0 += 65535) {
     const int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
     dim3 grid((Nq + ATT_QT - 1) / ATT_QT, (unsigned)nb);

@@ -576,7 +576,7 @@ void op_msc_encoder_tc(Ctx& c, const void* x, int x_dtype, int64_t A, int S, int
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "msc encoder: shared memory budget exceeded");
   static const bool debug = std::getenv("PAUT_ENC_DEBUG") != nullptr;
   void (*kern)(MscEncArgs) = debug ? k_msc_encoder_tc<true> : k_msc_encoder_tc<false>;
-  PAUT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  smem_optin(c, kern);
   const int64_t nblocks = (A + 127) / 128;
   PAUT_CHECK(nblocks < (int64_t(1) << 24), PAUT_ERR_INVALID, "msc encoder: too many A-scans in one launch");
   const int64_t grid = nblocks < c.num_sms ? nblocks : c.num_sms;      // persistent: one CTA per SM

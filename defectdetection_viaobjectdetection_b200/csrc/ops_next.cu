@@ -139,8 +139,8 @@ void op_bgsub_chanmean(Ctx& c, const void* in, int in_dtype, int64_t A, int L, i
   const size_t smem = ((size_t)C * (L + 20) + (size_t)C * 16 + (size_t)CG * L) * sizeof(float);
   PAUT_CHECK(smem <= (size_t)c.smem_optin, PAUT_ERR_UNSUPPORTED, "bgsub_chanmean: A-scan tile exceeds shared memory");
   if (smem > 48 * 1024) {
-    PAUT_CUDA(cudaFuncSetAttribute(k_bgsub_chanmean<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PAUT_CUDA(cudaFuncSetAttribute(k_bgsub_chanmean<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_optin(c, k_bgsub_chanmean<float>);
+    smem_optin(c, k_bgsub_chanmean<__nv_bfloat16>);
   }
   if (in_dtype == PAUT_F32)
     k_bgsub_chanmean<float><<<(unsigned)A, 256, smem, c.stream>>>(static_cast<const float*>(in), L, C, k, CG, Lrow, H0, w,

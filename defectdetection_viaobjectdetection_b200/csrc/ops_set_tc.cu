@@ -408,7 +408,7 @@ void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bq
   const int Np = (N + KBLK - 1) / KBLK * KBLK;
   const size_t smem = sizeof(__nv_bfloat16) * ((size_t)Np * WS + (size_t)DM * (Np + 8) + (size_t)4 * DM * WS);
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "attn block: set too long for shared memory");
-  PAUT_CUDA(cudaFuncSetAttribute(k_msc_attn_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  smem_optin(c, k_msc_attn_block);
   PAUT_CHECK(B < (int64_t(1) << 31), PAUT_ERR_INVALID, "attn block: too many sets");
   k_msc_attn_block<<<(unsigned)B, AB_WARPS * 32, smem, c.stream>>>(p);
   c.launched("msc_attn_block");

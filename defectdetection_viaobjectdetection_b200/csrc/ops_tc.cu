@@ -353,10 +353,7 @@ void op_linear_tc(Ctx& c, const LinArgs& a) {
                                  : (((size_t)g.Kp * a.NT * 2 + 127) & ~(size_t)127) + (size_t)GT_STAGES * GT_ASTAGE + GT_TSM_BYTES;
   PAUT_CHECK(smem <= GT_DYN_SMEM && (int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED,
              "linear_tc: resident weights do not fit shared memory (N tile too wide for this K)");
-  if (smem > c.gemm_tc_smem_configured) {
-    PAUT_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    c.gemm_tc_smem_configured = smem;
-  }
+  smem_optin(c, k_gemm_tc);
   const int ntn = a.N / a.NT;
   const int64_t tiles = (a.M + BM - 1) / BM;
   int64_t grid = (int64_t)(c.num_sms / ntn) * ntn;          // every N tile gets the same number of CTAs

@@ -134,6 +134,10 @@ class NativeModel:
                 t, dt = t.contiguous(), _lib.I64
             else:
                 t, dt = t.to(torch.float32).contiguous(), _lib.F32
+            if t.is_cuda:
+                # set_tensor copies with a blocking cudaMemcpy on the legacy stream, which is NOT ordered behind a
+                # conversion / contiguous kernel enqueued on a non-blocking torch stream (scanner lanes)
+                torch.cuda.current_stream(t.device).synchronize()
             shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
             check(self.lib.paut_model_set_tensor(self.handle, key.encode(), C.c_void_p(t.data_ptr()), dt, shape,
                                                  t.dim()), self.ctx.handle)
@@ -174,6 +178,17 @@ class NativeModel:
         check(self.lib.paut_forward(self.handle, C.c_void_p(x.data_ptr()), dt, B, N, S, C.byref(struct)),
               self.ctx.handle)
         return outs, struct, (B, N, S)
+
+    def debug_stage(self, stage, x, width):
+        """Intermediate tensor of a fused kernel (paut_debug_stage) for kernel-level parity tests: fp32 [B*N, width]."""
+        if not (x.is_cuda and x.is_contiguous() and x.dim() == 3):
+            raise RuntimeError("x must be a contiguous CUDA tensor [B,N,S]")
+        B, N, S = x.shape
+        dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[x.dtype]
+        out = torch.full((B * N, width), float("nan"), dtype=torch.float32, device=x.device)
+        check(self.lib.paut_debug_stage(self.handle, stage, C.c_void_p(x.data_ptr()), dt, B, N, S,
+                                        C.c_void_p(out.data_ptr())), self.ctx.handle)
+        return out
 
     def postprocess(self, struct, B, N, S, threshold, device):
         """Device post-processing; returns (records tensor [B*N*48] uint8 on device, count tensor int32)."""

@@ -253,6 +253,12 @@ int paut_op_linear(paut_ctx* ctx, const float* A, int64_t M, int K, const float*
 /* Micro-benchmark of tcgen05.mma shapes and descriptor experiments (tools/mma_probe.py); debugging aid. */
 int paut_debug_mma(paut_ctx* ctx, int mode, int N, int reps, int lbo, int alt, float* out_dev);
 
+/* Intermediate tensor of one fused kernel, for kernel-level parity tests (tests/test_gpu_fused.py); x as in
+ * paut_forward, one resident chunk, synchronises.  stage 1: pooled encoder features of the two-stage model
+ * (MultiScaleSignalEncoder before the projection, two_stage_model.py:102-115), out_dev fp32 [B*N, 128]. */
+int paut_debug_stage(paut_model* model, int stage, const void* x_dev, int x_dtype, int64_t B, int64_t N, int64_t S,
+                     float* out_dev);
+
 /* Instrumentation: number of kernels this ctx launched since creation (bench.py's gpu_launches). */
 int64_t paut_ctx_launch_count(const paut_ctx* ctx);
 /* Per-kernel device timing: between begin and end every launch on the ctx is followed by a CUDA event
