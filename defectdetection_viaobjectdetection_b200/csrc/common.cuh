@@ -212,6 +212,11 @@ void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t*
 bool msc_set_tc_supported(int N, int d, int heads, int ff);
 void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bqkv, const void* Wo, const float* bo,
                        const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift);
+// the same attention block with every product on tcgen05 (ops_attn_tc.cu): S and P in tensor memory
+bool msc_attn_tc_supported(int N, int d, int heads);
+void msc_attn_tc_pack(const float* W, int row0, int rows, std::vector<uint16_t>& out);
+void op_msc_attn_tc(Ctx& c, const float* x, const void* Wqk, const void* Wv, const void* Wo, const float* bqkv, const float* bo,
+                    const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift);
 void op_msc_ffn_head(Ctx& c, const float* x, const float* pre, const float* pre_g, const float* pre_b, const void* W1,
                      const float* b1, const void* W2, const float* b2, const float* ln_g, const float* ln_b,
                      const void* Wc, const float* bc, float* prob, float* start, float* end, int64_t M);

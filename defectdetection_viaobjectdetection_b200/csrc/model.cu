@@ -555,6 +555,25 @@ void Model::finalize() {
           set_tc.Wqkv_cross = up_bf16(H(te + "cross_attn.in_proj_weight").data);
           set_tc.Wo_cross = up_bf16(H(te + "cross_attn.out_proj.weight").data);
         }
+        auto up_u16 = [&](const std::vector<uint16_t>& hb) {
+          void* p = nullptr;
+          PAUT_CUDA(cudaMalloc(&p, hb.size() * sizeof(uint16_t)));
+          dev_allocs.push_back(p);
+          PAUT_CUDA(cudaMemcpy(p, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          return p;
+        };
+        int ai = 0;
+        for (const char* an : {"self_attn", "cross_attn"}) {
+          if (ai == 1 && kind != PAUT_MODEL_MSC) break;
+          std::vector<uint16_t> pk;
+          msc_attn_tc_pack(H(te + an + ".in_proj_weight").data.data(), 0, 128, pk);
+          set_tc.tc_w[ai][0] = up_u16(pk);
+          msc_attn_tc_pack(H(te + an + ".in_proj_weight").data.data(), 128, 64, pk);
+          set_tc.tc_w[ai][1] = up_u16(pk);
+          msc_attn_tc_pack(H(te + an + ".out_proj.weight").data.data(), 0, 64, pk);
+          set_tc.tc_w[ai][2] = up_u16(pk);
+          ++ai;
+        }
         set_tc.W1 = up_bf16(H(te + "ffn.0.weight").data);
         set_tc.W2 = up_bf16(H(te + "ffn.2.weight").data);
         set_tc.Wc = up_bf16(H("classifier.weight").data, 8 * 64);        // rows 3..7 zero
@@ -961,8 +980,14 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
     const std::string te = "transformer_encoder.";
     const MHAW& sa = mha["self"];
     float* x1 = c.allocf((size_t)A * D);
-    op_msc_attn_block(c, h, set_tc.Wqkv_self, sa.in_proj.b, set_tc.Wo_self, sa.out_proj.b, ln[te + "norm1"].g,
-                      ln[te + "norm1"].b, x1, B, N, false);
+    static const bool attn_mma = std::getenv("PAUT_ATTN_MMA") != nullptr;      // A/B switch: the mma.sync attention block
+    const bool attn_tc = !attn_mma && msc_attn_tc_supported(N, D, cfg.num_heads) && set_tc.tc_w[0][0] != nullptr;
+    if (attn_tc)
+      op_msc_attn_tc(c, h, set_tc.tc_w[0][0], set_tc.tc_w[0][1], set_tc.tc_w[0][2], sa.in_proj.b, sa.out_proj.b,
+                     ln[te + "norm1"].g, ln[te + "norm1"].b, x1, B, N, false);
+    else
+      op_msc_attn_block(c, h, set_tc.Wqkv_self, sa.in_proj.b, set_tc.Wo_self, sa.out_proj.b, ln[te + "norm1"].g,
+                        ln[te + "norm1"].b, x1, B, N, false);
     const float* pre = nullptr;
     const float* pre_g = nullptr;
     const float* pre_b = nullptr;
@@ -970,8 +995,12 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
     if (!isn) {
       const MHAW& ca = mha["cross"];
       x2 = c.allocf((size_t)A * D);
-      op_msc_attn_block(c, x1, set_tc.Wqkv_cross, ca.in_proj.b, set_tc.Wo_cross, ca.out_proj.b, ln[te + "norm2"].g,
-                        ln[te + "norm2"].b, x2, B, N, true);                     // NN_models.py:35-37
+      if (attn_tc)
+        op_msc_attn_tc(c, x1, set_tc.tc_w[1][0], set_tc.tc_w[1][1], set_tc.tc_w[1][2], ca.in_proj.b, ca.out_proj.b,
+                       ln[te + "norm2"].g, ln[te + "norm2"].b, x2, B, N, true);  // NN_models.py:35-37
+      else
+        op_msc_attn_block(c, x1, set_tc.Wqkv_cross, ca.in_proj.b, set_tc.Wo_cross, ca.out_proj.b, ln[te + "norm2"].g,
+                          ln[te + "norm2"].b, x2, B, N, true);
     } else {
       float* loc = c.allocf((size_t)A * D);
       op_dwconv_seq(c, x1, raw[te + "local_attn.local_conv.weight"], raw[te + "local_attn.local_conv.bias"], loc, B, N, D, 5);
@@ -1573,6 +1602,23 @@ void Model::debug_stage(int stage, const void* x, int x_dtype, int64_t B, int64_
     PAUT_CHECK(kind == PAUT_MODEL_TWO_STAGE && ts_enc.ready && ts_encoder_supported((int)S, cfg.d_model), PAUT_ERR_UNSUPPORTED,
                "debug_stage 1: the fused two-stage encoder is not available for this model / precision / length");
     op_ts_encoder(c, xin.as_bf16(c), A, (int)S, ts_enc.sw.data(), ts_enc.sb.data(), ts_enc.W2, ts_enc.shift2, out_dev);
+  } else if (stage >= 2 && stage <= 5) {
+    // MSC attention block on an fp32 [B, N, 64] input: stage 2 / 3 = tcgen05 kernel (self / shifted keys and values),
+    // stage 4 / 5 = the mma.sync kernel
+    PAUT_CHECK(kind == PAUT_MODEL_MSC && set_tc.ready && x_dtype == PAUT_F32 && S == 64, PAUT_ERR_UNSUPPORTED,
+               "debug_stage 2-5: MSC model in bf16 mode and an fp32 [B, N, 64] input");
+    const bool cross = (stage & 1) != 0;
+    const std::string te = "transformer_encoder.";
+    const MHAW& a = mha[cross ? "cross" : "self"];
+    const LNW& n = ln[te + (cross ? "norm2" : "norm1")];
+    if (stage <= 3) {
+      PAUT_CHECK(msc_attn_tc_supported((int)N, 64, cfg.num_heads), PAUT_ERR_UNSUPPORTED, "debug_stage: set too long");
+      op_msc_attn_tc(c, static_cast<const float*>(x), set_tc.tc_w[cross][0], set_tc.tc_w[cross][1], set_tc.tc_w[cross][2],
+                     a.in_proj.b, a.out_proj.b, n.g, n.b, out_dev, B, (int)N, cross);
+    } else {
+      op_msc_attn_block(c, static_cast<const float*>(x), cross ? set_tc.Wqkv_cross : set_tc.Wqkv_self, a.in_proj.b,
+                        cross ? set_tc.Wo_cross : set_tc.Wo_self, a.out_proj.b, n.g, n.b, out_dev, B, (int)N, cross);
+    }
   } else {
     throw Error(PAUT_ERR_INVALID, "debug_stage: unknown stage");
   }

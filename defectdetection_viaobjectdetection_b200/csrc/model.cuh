@@ -120,6 +120,8 @@ struct Model {
     const void* Wqkv_self = nullptr; const void* Wo_self = nullptr;
     const void* Wqkv_cross = nullptr; const void* Wo_cross = nullptr;
     const void* W1 = nullptr; const void* W2 = nullptr; const void* Wc = nullptr;
+    // K-major operand packing of the tcgen05 attention block: [self | cross][Wqk, Wv, Wo]
+    const void* tc_w[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     bool ready = false;
   } set_tc;
 

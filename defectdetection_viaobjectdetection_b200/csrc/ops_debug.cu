@@ -82,6 +82,45 @@ __global__ void __launch_bounds__(128) k_debug_mma(int mode, int N, int reps, in
       }
       __syncwarp();
     }
+  } else if (mode >= 6 && mode <= 9) {
+    // descriptors that CHANGE between consecutive MMAs (a_from_far = mask, i & mask selects the variant; the descriptor
+    // low words are precomputed so that the issuing thread does one AND + one add per MMA):
+    //   mode 6: A start advances by 16 B (convolution taps);  mode 7: A start advances by 8 KB (different tiles);
+    //   mode 8: B start advances by 2 KB;  mode 9: both A (16 B) and B (2 KB) advance
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint32_t hi = (uint32_t)(128 >> 4) | (1u << 14);
+        const uint32_t a_lo = ((smem_u32(A) >> 4) & 0x3FFFu) | ((uint32_t)(lbo >> 4) << 16);
+        const uint32_t b_lo = ((smem_u32(B) >> 4) & 0x3FFFu) | ((uint32_t)N << 16);
+        const uint32_t a_step = mode == 6 || mode == 9 ? 1u : (mode == 7 ? 512u : 0u);
+        const uint32_t b_step = mode == 8 || mode == 9 ? 128u : 0u;
+        t0 = clock64();
+        for (int i = 0; i < reps; ++i) {
+          const uint32_t v = (uint32_t)i & (uint32_t)a_from_far;
+          mma_bf16_ss2(tmem, a_lo + v * a_step, hi, b_lo + v * b_step, hi, idesc, 1u);
+        }
+        mma_commit(&bar);
+      }
+      __syncwarp();
+    }
+  } else if (mode == 4 || mode == 5) {
+    // mode 4: cycles per SS-form MMA whose A descriptor starts `a_from_far` rows (16 B each) into the tile, chunk
+    //         stride `lbo` bytes -- the convolution taps' shifted views (is a start that is not 128-byte aligned slower?)
+    // mode 5: the same, cycling through the shifts 0 .. a_from_far (a convolution's tap loop)
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint64_t bd = make_desc(smem_u32(B), N * 16, 128);
+        t0 = clock64();
+        for (int i = 0; i < reps; ++i) {
+          const int sh = mode == 4 ? a_from_far : (a_from_far > 0 ? i % (a_from_far + 1) : 0);
+          mma_bf16_ss(tmem, make_desc(smem_u32(A) + sh * 16, lbo, 128), bd, idesc, 1u);
+        }
+        mma_commit(&bar);
+      }
+      __syncwarp();
+    }
   } else
   if (warp == 0) {
     if (elect_one()) {
@@ -97,7 +136,7 @@ __global__ void __launch_bounds__(128) k_debug_mma(int mode, int N, int reps, in
   mbar_wait(&bar, 0);
   if (tid == 0) { t1 = clock64(); }
   tc_fence_after();
-  if (mode == 0 || mode == 3) {
+  if (mode == 0 || mode == 3 || mode >= 4) {
     if (tid == 0) out[0] = (float)(t1 - t0) / (float)reps;
   } else {
     float v[16];

@@ -78,3 +78,46 @@ def test_two_stage_fused_is_deterministic_and_position_independent():
     a = a.view(9, 48, 128)
     for r in range(1, 9):
         assert torch.equal(a[0], a[r]), f"repetition {r} differs"
+
+
+def msc_attn_block_ref(sd, cross, x):
+    """TransformerEncoder.forward's attention sub-block (NN_models.py:31-37) in fp64: LN(x + MHA(x, kv)) with
+    kv = x (self) or x shifted left by one with the last row repeated (cross)."""
+    te = "transformer_encoder."
+    name = te + ("cross_attn" if cross else "self_attn")
+    norm = te + ("norm2" if cross else "norm1")
+    x = x.double()
+    kv = torch.cat([x[:, 1:], x[:, -1:]], dim=1) if cross else x
+    B, N, D = x.shape
+    w, b = sd[name + ".in_proj_weight"].double(), sd[name + ".in_proj_bias"].double()
+    q = F.linear(x, w[:D], b[:D]).view(B, N, 4, 16).transpose(1, 2)
+    k = F.linear(kv, w[D:2 * D], b[D:2 * D]).view(B, N, 4, 16).transpose(1, 2)
+    v = F.linear(kv, w[2 * D:], b[2 * D:]).view(B, N, 4, 16).transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) / 4.0, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(B, N, D)
+    o = F.linear(o, sd[name + ".out_proj.weight"].double(), sd[name + ".out_proj.bias"].double())
+    return F.layer_norm(x + o, (D,), sd[norm + ".weight"].double(), sd[norm + ".bias"].double(), 1e-5).float()
+
+
+@pytest.mark.parametrize("B,N", [(1, 300), (3, 300), (2, 37), (2, 128), (2, 129), (1, 16), (2, 170), (1, 298), (1, 320),
+                                 (300, 300)])
+@pytest.mark.parametrize("cross", [False, True])
+def test_msc_attention_block_tcgen05(B, N, cross):
+    """k_msc_attn_tc (all products on tcgen05, S and P in tensor memory) against fp64 and against the mma.sync block:
+    bf16 operands / fp16 probabilities give ~1e-2 after the LayerNorm; the new kernel must not be worse than the old."""
+    sd = synth.synth_state_dict("msc", seed=0, signal_length=320)
+    g = torch.Generator().manual_seed(100 * B + N + (7 if cross else 0))
+    x = torch.randn(B, N, 64, generator=g) * 1.5
+    ref = msc_attn_block_ref(sd, cross, x).view(B * N, 64)
+    m = build("msc", dict(signal_length=320), precision="bf16")
+    native = m._native_for(torch.zeros(1, 4, 320, dtype=torch.bfloat16, device="cuda"))
+    xc = x.cuda()
+    got = native.debug_stage(3 if cross else 2, xc, 64).cpu()
+    old = native.debug_stage(5 if cross else 4, xc, 64).cpu()
+    assert torch.isfinite(got).all(), "non-finite output (unwritten rows?)"
+    err, err_old = (got - ref).abs(), (old - ref).abs()
+    if err.max() > max(3e-2, 1.5 * err_old.max().item()):
+        rows = torch.nonzero(err.max(dim=1).values > 3e-2).flatten().tolist()
+        per_head_cols = [float(err[:, 16 * h:16 * h + 16].max()) for h in range(4)]
+        pytest.fail(f"max abs err {err.max():.3e} (mma.sync block: {err_old.max():.3e}); per 16 columns {per_head_cols}; "
+                    f"{len(rows)} bad rows, first {rows[:16]}, row mod N: {sorted(set(r % N for r in rows))[:24]}")
