@@ -206,7 +206,7 @@ void op_unflatten(Ctx& c, const void* flat, int64_t A, int L, int halo, int C, f
 bool ts_encoder_supported(int S, int d_model);
 void ts_encoder_pack(const float* const* w1, const float* const* sh1, const float* const* w2, std::vector<uint32_t>& sw,
                      std::vector<uint32_t>& sb, std::vector<uint16_t>& W2);
-void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t* sw_host, const uint32_t* sb_host,
+void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t* sw_dev, const uint32_t* sb_dev,
                    const void* W2, const float* shift2, float* feat);
 // Fused per-set stage of MSC / MSC_N (ops_set_tc.cu, bf16 mode): attention block and FFN + head
 bool msc_set_tc_supported(int N, int d, int heads, int ff);

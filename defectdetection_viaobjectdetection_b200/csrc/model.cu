@@ -774,6 +774,15 @@ void Model::finalize() {
           dev_allocs.push_back(dptr);
           PAUT_CUDA(cudaMemcpy(dptr, W2h.data(), W2h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
           ts_enc.W2 = dptr;
+          auto up32 = [&](const std::vector<uint32_t>& v) {
+            void* q = nullptr;
+            PAUT_CUDA(cudaMalloc(&q, v.size() * sizeof(uint32_t)));
+            dev_allocs.push_back(q);
+            PAUT_CUDA(cudaMemcpy(q, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            return static_cast<const uint32_t*>(q);
+          };
+          ts_enc.sw_dev = up32(ts_enc.sw);
+          ts_enc.sb_dev = up32(ts_enc.sb);
           ts_enc.shift2 = upload(shift2);
           ts_enc.ready = true;
         }
@@ -1138,7 +1147,7 @@ void Model::fwd_two_stage(XIn& x, int64_t B, int N, int S, const paut_outputs& o
   if (g.bf16 && ts_enc.ready && ts_encoder_supported(S, d) && !no_fused) {
     // one persistent kernel: TMA input staging, stems on HFMA2, the four second convolutions on tcgen05, BN shift +
     // ReLU + mean over the signal length in the epilogue (two_stage_model.py:102-118); no activation touches HBM
-    op_ts_encoder(c, x.as_bf16(c), A, S, ts_enc.sw.data(), ts_enc.sb.data(), ts_enc.W2, ts_enc.shift2, feat);
+    op_ts_encoder(c, x.as_bf16(c), A, S, ts_enc.sw_dev, ts_enc.sb_dev, ts_enc.W2, ts_enc.shift2, feat);
   } else if (tcc && ts_grouped.ready) {
     // all four stems write one [rows, 4q] buffer; the four second convolutions + BN + ReLU + mean run as one
     // grouped tcgen05 launch whose pooled output is the concatenated feature vector (two_stage_model.py:102-118)
@@ -1601,7 +1610,7 @@ void Model::debug_stage(int stage, const void* x, int x_dtype, int64_t B, int64_
   if (stage == 1) {
     PAUT_CHECK(kind == PAUT_MODEL_TWO_STAGE && ts_enc.ready && ts_encoder_supported((int)S, cfg.d_model), PAUT_ERR_UNSUPPORTED,
                "debug_stage 1: the fused two-stage encoder is not available for this model / precision / length");
-    op_ts_encoder(c, xin.as_bf16(c), A, (int)S, ts_enc.sw.data(), ts_enc.sb.data(), ts_enc.W2, ts_enc.shift2, out_dev);
+    op_ts_encoder(c, xin.as_bf16(c), A, (int)S, ts_enc.sw_dev, ts_enc.sb_dev, ts_enc.W2, ts_enc.shift2, out_dev);
   } else if (stage >= 2 && stage <= 5) {
     // MSC attention block on an fp32 [B, N, 64] input: stage 2 / 3 = tcgen05 kernel (self / shifted keys and values),
     // stage 4 / 5 = the mma.sync kernel

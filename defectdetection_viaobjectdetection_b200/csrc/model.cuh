@@ -105,7 +105,9 @@ struct Model {
     bool ready = false;
   } ts_grouped;
   struct TsEnc {                               // operands of the fused two-stage encoder (ops_ts_enc.cu, bf16 mode)
-    std::vector<uint32_t> sw, sb;              // stem weights / shifts as fp16 pairs: kernel parameters (host memory)
+    std::vector<uint32_t> sw, sb;              // stem weights / shifts as fp16 pairs (host copies)
+    const uint32_t* sw_dev = nullptr;          // the same on the device: every stem warp keeps its share in registers
+    const uint32_t* sb_dev = nullptr;
     const void* W2 = nullptr;                  // second convolutions, fp16, packed
     const float* shift2 = nullptr;             // [128]
     bool ready = false;

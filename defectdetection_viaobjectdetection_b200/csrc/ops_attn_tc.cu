@@ -68,7 +68,9 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// parity wait with a dead-lock guard: a protocol error traps instead of hanging the GPU
+// Parity wait that does not burn issue slots (a failed probe puts the warp to sleep before the next one: a spinning
+// warp takes the issue slots of the working warps on its scheduler), with a dead-lock guard: a protocol error traps
+// instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0;; ++spin) {
@@ -83,8 +85,14 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (spin > (1u << 24)) __trap();
+    asm volatile("nanosleep.u32 %0;" ::"r"(40));
+    if (spin > (1u << 22)) __trap();
   }
+}
+// one arrival per warp: every lane has executed its fences, lane 0 arrives for the warp
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -107,7 +115,7 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
   // MMA -> threads (count 1, tcgen05.commit):  bar_a, bar_q, s_full, pv_done, bar_y
-  // threads -> MMA (count 256):                bar_x, bar_free, bar_qs, p_full, bar_os
+  // threads -> MMA (one arrival per warp):     bar_x, bar_free, bar_qs, p_full, bar_os
   __shared__ __align__(8) uint64_t bar_x, bar_a, bar_free, bar_q, bar_qs, s_full, p_full, pv_done, bar_os, bar_y;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[192], bo_s[64], g_s[64], b_s[64];
@@ -131,8 +139,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&bar_a, 1); mbar_init(&bar_q, 1); mbar_init(&s_full, 1); mbar_init(&pv_done, 1); mbar_init(&bar_y, 1);
-    mbar_init(&bar_x, AT_COMPUTE); mbar_init(&bar_free, AT_COMPUTE); mbar_init(&bar_qs, AT_COMPUTE);
-    mbar_init(&p_full, AT_COMPUTE); mbar_init(&bar_os, AT_COMPUTE);
+    mbar_init(&bar_x, AT_COMPUTE / 32); mbar_init(&bar_free, AT_COMPUTE / 32); mbar_init(&bar_qs, AT_COMPUTE / 32);
+    mbar_init(&p_full, AT_COMPUTE / 32); mbar_init(&bar_os, AT_COMPUTE / 32);
     fence_mbar_init();
   }
   for (int i = tid; i < AT_WQK / 16; i += AT_THREADS) reinterpret_cast<uint4*>(WQK)[i] = __ldg(reinterpret_cast<const uint4*>(p.Wqk) + i);
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
         }
       }
       fence_async_smem();
-      mbar_arrive(&bar_x);
+      warp_arrive(&bar_x, lane);
       {  // next set's x -> L2 while this set is being processed
         const long long nxt = set + gridDim.x;
         if (nxt < p.B) {
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar_free);                                        // phase A accumulators drained, K / V^T stored
+      warp_arrive(&bar_free, lane);                                        // phase A accumulators drained, K / V^T stored
 
       for (int t = 0; t < tiles; ++t) {
         const int r0 = 128 * t;
@@ -345,14 +353,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
         }
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(&bar_qs);
+        warp_arrive(&bar_qs, lane);
 
+        // a warp whose 32 rows are all beyond the set (last tile) skips the softmax work: its rows of P, O and Y are
+        // garbage that is never stored (an MMA output row depends on its own A row only)
+        const int ncol_t = r0 + 32 * q < N ? ncol : 0;
         for (int h = 0; h < AT_NH; ++h) {
           // ---- pass 1: row maximum over this warp's key columns
           mbar_wait_g(&s_full, n_s++ & 1);
           tc_fence_after();
           float mx = -INFINITY;
-          for (int c0 = 0; c0 < ncol; c0 += 32) {
+          for (int c0 = 0; c0 < ncol_t; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tmem + t_lane + TC_S + col0 + c0, r);
             const int kbase = col0 + c0;
@@ -384,7 +395,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
             }
           }
           // ---- pass 2: P = exp2(S - max) as packed fp16 pairs -> tensor memory (A operand of the P V product)
-          for (int c0 = 0; c0 < ncol; c0 += 32) {
+          for (int c0 = 0; c0 < ncol_t; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tmem + t_lane + TC_S + col0 + c0, r);
             const int kbase = col0 + c0;
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
-          mbar_arrive(&p_full);
+          warp_arrive(&p_full, lane);
         }
         // ---- O of the last head, then the out-projection's operand is complete
         mbar_wait_g(&pv_done, n_pv++ & 1);
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
         }
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(&bar_os);
+        warp_arrive(&bar_os, lane);
         // ---- final epilogue: y = O Wo^T + bo + x -> LayerNorm -> out   (warp group 0: one thread per row)
         mbar_wait_g(&bar_y, n_y++ & 1);
         tc_fence_after();
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_msc_attn_tc(const AttnTcArgs 
           }
         }
         tc_fence_before();
-        mbar_arrive(&bar_free);                                      // Y drained: the next Q projection / set may start
+        warp_arrive(&bar_free, lane);                                      // Y drained: the next Q projection / set may start
       }
     }
   }

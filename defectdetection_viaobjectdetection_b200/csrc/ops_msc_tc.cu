@@ -92,6 +92,9 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 }
 
 // mbarrier wait / arrive on a precomputed shared-memory address (keeps the hot loop free of address arithmetic)
+// (A nanosleep between failed probes was tried per role -- issuer / loader / edge / compute warps, 0-100 ns -- and
+// changed nothing but the cost of the extra instruction: 1.80 -> 2.00 ms per 1 M A-scans, profiles/r02/h_enc_sleep_sweep.log.
+// The waits of this kernel are short and the spinning warps are few: spinning is not what limits it.)
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
   asm volatile(
       "{\n"

@@ -43,14 +43,16 @@ using namespace tc;
 
 namespace {
 
-constexpr int TE_MMA_WARP = 4, TE_TMA_WARP = 5;   // warps 0-3 epilogue, 6-7 idle
-constexpr int TE_STEM_WARP0 = 8;
-constexpr int TE_GROUP_WARPS = 5;                 // 160 threads per stem group
-constexpr int TE_GROUP = TE_GROUP_WARPS * 32;
-constexpr int TE_THREADS = (TE_STEM_WARP0 + 2 * TE_GROUP_WARPS) * 32;   // 576
+constexpr int TE_EPI_WARPS = 8;                   // warps 0-7: warp w = TMEM lane quarter w % 4, column half w / 4
+constexpr int TE_EPI = TE_EPI_WARPS * 32;
+constexpr int TE_MMA_WARP = 8, TE_TMA_WARP = 9;
+constexpr int TE_STEM_WARP0 = 10;
+constexpr int TE_STEM_WARPS = 8;                  // stem warp sw: chunk sw % 4 (8 channels) of branches {3, 0} (sw < 4) or {2, 1}
+constexpr int TE_STEM = TE_STEM_WARPS * 32;
+constexpr int TE_THREADS = (TE_STEM_WARP0 + TE_STEM_WARPS) * 32;   // 576
 constexpr int TE_PAD = 5;                         // k = 11
 constexpr int TE_ROWS = 128 + 2 * TE_PAD;         // 138 input rows per tile
-constexpr int TE_BROWS = 144;                     // rows per chunk of a stage buffer
+constexpr int TE_BROWS = 160;                     // rows per chunk of a stage buffer (5 row blocks of 32)
 constexpr int TE_STAGES = 3;
 constexpr int TE_BLOCK_A = 16;
 constexpr int TE_HALO = 8;
@@ -61,8 +63,8 @@ constexpr int TE_W2_BYTES = TE_NTAPS * 2048;      // [26][4 chunks][32 rows][16 
 constexpr int TE_XPAD = 64;                       // zero elements in front of / behind the x staging area
 
 struct TsEncArgs {
-  uint32_t sw[TE_NTAPS * 16];     // stem weights (BN scale folded) as fp16 pairs: [(branch, tap)][j] = channels (2j, 2j+1)
-  uint32_t sb[4 * 16];            // stem shift (folded bias) as fp16 pairs
+  const uint32_t* sw;             // stem weights (BN scale folded) as fp16 pairs: [(branch, tap)][j] = channels (2j, 2j+1)
+  const uint32_t* sb;             // stem shift (folded bias) as fp16 pairs [4][16]
   const __half* W2;               // second convolutions, BN scale folded, fp16 [26][4][32][8]
   const float* shift2;            // [128]
   float* feat;                    // [A][128] mean over the signal length
@@ -74,13 +76,18 @@ struct TsEncArgs {
   int xs_buf_bytes;               // one staging buffer
   int rows_per_ascan;             // rows of the [rows, W] tensor-map view one A-scan occupies (S / W)
   float invS;
+  unsigned long long* dbg;        // optional cycle probe (PAUT_TS_DEBUG=1): role timings of CTA 0
 };
 
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// parity wait with a dead-lock guard: a protocol error traps instead of hanging the GPU
+// Parity wait that does not burn issue slots: a failed probe puts the warp to sleep (nanosleep) before the next one
+// -- a spinning warp issues ~0.6 instructions per cycle and takes them from the working warps of its scheduler (ncu
+// of the first version: 37 % of all issued instructions were wait loops).  With a dead-lock guard: a protocol error
+// traps instead of hanging the GPU.
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0;; ++spin) {
@@ -95,7 +102,8 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (spin > (1u << 24)) __trap();
+    asm volatile("nanosleep.u32 %0;" ::"r"(SLEEP_NS));
+    if (spin > (1u << 22)) __trap();
   }
 }
 
@@ -111,42 +119,133 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-// Stem convolution of one branch at one row: 32 channels = 16 fp16 pairs in 4 chunks of 8 channels; xh[i] = sample
-// l - 5 + i of the A-scan (both halves).  The last tap carries the ReLU (fma.rn.relu).  vmask zeroes rows that are
-// not signal rows (bitwise: garbage inputs cannot leak).
-template <int K, int WOFF, int B>
-__device__ __forceinline__ void stem_branch(const TsEncArgs& p, const __half2 (&xh)[11], uint32_t dst, uint32_t vmask) {
+// TMEM -> registers, 16 lanes x 32 columns: thread t holds rows t/4 and t/4 + 8 of the 16-lane window, columns
+// 8j + 2(t%4) + {0, 1}, j = 0..3:  r[4j + 0, 1] = row t/4, r[4j + 2, 3] = row t/4 + 8   (the mma C-fragment layout)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Stem convolution of one branch, one chunk of 8 channels (4 fp16 pairs), one row: K taps with the weights in
+// registers (w[t][j]); xh[i] = sample l - 5 + i of the A-scan in both halves.  The last tap carries the ReLU
+// (fma.rn.relu).  vmask zeroes rows that are not signal rows (bitwise: garbage inputs cannot leak).
+template <int K, bool MASK>
+__device__ __forceinline__ void stem_chunk(const __half2 (&w)[K][4], const __half2 (&sh)[4], const __half2 (&xh)[11],
+                                           uint32_t dst, uint32_t vmask) {
+  uint32_t o[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t o[4];
+  for (int j = 0; j < 4; ++j) {
+    __half2 acc = sh[j];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int jj = c * 4 + j;
-      __half2 acc = *reinterpret_cast<const __half2*>(&p.sb[B * 16 + jj]);
+    for (int t = 0; t < K - 1; ++t) acc = __hfma2(w[t][j], xh[TE_PAD - K / 2 + t], acc);
+    acc = __hfma2_relu(w[K - 1][j], xh[TE_PAD + K / 2], acc);
+    o[j] = *reinterpret_cast<const uint32_t*>(&acc);
+    if (MASK) o[j] &= vmask;
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+}
+
+template <int K>
+__device__ __forceinline__ void load_stem_weights(const TsEncArgs& p, int woff, int b, int c, __half2 (&w)[K][4], __half2 (&sh)[4]) {
 #pragma unroll
-      for (int t = 0; t < K - 1; ++t)
-        acc = __hfma2(*reinterpret_cast<const __half2*>(&p.sw[(WOFF + t) * 16 + jj]), xh[TE_PAD - K / 2 + t], acc);
-      acc = __hfma2_relu(*reinterpret_cast<const __half2*>(&p.sw[(WOFF + K - 1) * 16 + jj]), xh[TE_PAD + K / 2], acc);
-      o[j] = *reinterpret_cast<const uint32_t*>(&acc) & vmask;
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t s = __ldg(p.sb + b * 16 + c * 4 + j);
+    sh[j] = *reinterpret_cast<const __half2*>(&s);
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      const uint32_t v = __ldg(p.sw + (woff + t) * 16 + c * 4 + j);
+      w[t][j] = *reinterpret_cast<const __half2*>(&v);
     }
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((B * 4 + c) * TE_LBO_A)), "r"(o[0]),
-                 "r"(o[1]), "r"(o[2]), "r"(o[3])
-                 : "memory");
   }
 }
 
-// Sum over the 32 lanes of 32 per-lane values, transposing: on return v[0] of lane L is the sum over all lanes of
-// their v[L].  Fixed reduction tree (deterministic).
-__device__ __forceinline__ void colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const bool hi = (lane & m) != 0;
-#pragma unroll
-    for (int i = 0; i < m; ++i) {
-      const float keep = hi ? v[m + i] : v[i];
-      const float send = hi ? v[i] : v[m + i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+// One stem warp: chunk c of branches (KA taps at weight offset WA, branch BA) and (KB, WB, BB), weights in registers
+// for the whole kernel.  Lane = row of a 32-row block of the tile's 138-row window.
+template <int KA, int WA, int BA, int KB, int WB, int BB>
+__device__ __forceinline__ void stem_loop(const TsEncArgs& p, int c, int lane, int nt_local, uint32_t xs_base, uint32_t abuf_base,
+                                          uint64_t* full, uint64_t* empty, uint64_t* x_full, uint64_t* x_empty, unsigned long long* dbg) {
+  __half2 wa[KA][4], sa[4], wb[KB][4], sbb[4];
+  load_stem_weights<KA>(p, WA, BA, c, wa, sa);
+  load_stem_weights<KB>(p, WB, BB, c, wb, sbb);
+  const int S = p.S, Lp = p.Lp, tpb = p.tpb;
+  int cur_blk = -1;
+  unsigned long long pt0 = 0, pt1 = 0, pt2 = 0;
+  for (int g = 0; g < nt_local; ++g) {
+    const int i_blk = g / tpb, T = g - i_blk * tpb;
+    const int stage = g % TE_STAGES;
+    const uint32_t use = (uint32_t)(g / TE_STAGES);
+    const long long s0 = dbg ? clock64() : 0;
+    if (i_blk != cur_blk) {
+      if (cur_blk >= 0) {                                              // this warp has read the last x of the block
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x_empty[cur_blk & 1]);
+      }
+      cur_blk = i_blk;
+      mbar_wait_g<200>(&x_full[i_blk & 1], (i_blk >> 1) & 1);
+      // bf16 -> fp16 in place, once per block (16 x S samples over the 256 stem threads), so that the per-row loads
+      // below need no conversion; the zero padding between the A-scans is the same bit pattern in both formats
+      {
+        const uint32_t xb0 = xs_base + (uint32_t)(i_blk & 1) * p.xs_buf_bytes + TE_XPAD * 2;
+        const int st = (int)(threadIdx.x) - TE_STEM_WARP0 * 32;
+        const int wpa = S / 2;                                           // 32-bit words per A-scan
+        for (int i = st; i < TE_BLOCK_A * wpa; i += TE_STEM) {
+          const int a = i / wpa, w = i - a * wpa;
+          const uint32_t addr = xb0 + (uint32_t)(a * p.xs_stride * 2 + w * 4);
+          uint32_t v;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+          const __half2 h = __floats2half2_rn(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
+        }
+        named_sync(2, TE_STEM);
+      }
     }
+    if (use > 0) mbar_wait_g<100>(&empty[stage], (use - 1) & 1);            // the MMAs that read this buffer are done
+    const long long s1 = dbg ? clock64() : 0;
+    // first row of the window: flat row 128 T - 5 of the block -> A-scan a0 (may be -1), position l0
+    const int fa = 128 * T - TE_PAD + Lp;                              // >= 0
+    const int a1 = (int)((unsigned)fa / (unsigned)Lp);
+    const int a0 = a1 - 1, l0 = fa - a1 * Lp;
+    const long long a_blk = ((long long)blockIdx.x + (long long)i_blk * gridDim.x) * TE_BLOCK_A;
+    const uint32_t xb = xs_base + (uint32_t)(i_blk & 1) * p.xs_buf_bytes;
+    const uint32_t sbuf = abuf_base + (uint32_t)stage * TE_STAGE_BYTES;
+#pragma unroll 1
+    for (int rb = 0; rb < (TE_ROWS + 31) / 32; ++rb) {
+      const int i = rb * 32 + lane;                                    // row of the window
+      int a_loc = a0, l = l0 + i;
+      while (l >= Lp) { l -= Lp; ++a_loc; }
+      const bool valid = i < TE_ROWS && a_loc >= 0 && a_loc < TE_BLOCK_A && l < S && a_blk + a_loc < p.A;
+      const int aa = valid ? a_loc : 0, ll = valid ? l : 0;
+      const uint32_t xa = xb + (uint32_t)(TE_XPAD + aa * p.xs_stride + ll - TE_PAD) * 2;
+      __half2 xh[11];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        uint16_t h;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(xa + 2 * k) : "memory");
+        xh[k] = __half2half2(__ushort_as_half(h));
+      }
+      const uint32_t dst = sbuf + (uint32_t)i * 16;
+      if (__all_sync(0xffffffffu, valid)) {                            // the common case: no masking instructions
+        stem_chunk<KA, false>(wa, sa, xh, dst + (uint32_t)((BA * 4 + c) * TE_LBO_A), 0xffffffffu);
+        stem_chunk<KB, false>(wb, sbb, xh, dst + (uint32_t)((BB * 4 + c) * TE_LBO_A), 0xffffffffu);
+      } else {
+        const uint32_t vmask = valid ? 0xffffffffu : 0u;
+        stem_chunk<KA, true>(wa, sa, xh, dst + (uint32_t)((BA * 4 + c) * TE_LBO_A), vmask);
+        stem_chunk<KB, true>(wb, sbb, xh, dst + (uint32_t)((BB * 4 + c) * TE_LBO_A), vmask);
+      }
+    }
+    fence_async_smem();                                                // generic-proxy stores -> tensor-core operand reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[stage]);
+    if (dbg) { pt0 += s1 - s0; pt1 += clock64() - s1; pt2 += 1; }
+  }
+  if (dbg) { dbg[0] = pt0; dbg[1] = pt1; dbg[2] = pt2; }
+  if (cur_blk >= 0) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&x_empty[cur_blk & 1]);
   }
 }
 
@@ -155,7 +254,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[TE_STAGES], empty[TE_STAGES], acc_full[2], acc_empty[2], x_full[2], x_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float shift_s[128];
   __shared__ __align__(16) float pool_s[2][128];          // running sums of the (at most two) open A-scans
   __shared__ __align__(16) float part_s[2][4][2][128];    // [tile parity][lane quarter][segment][column]
 
@@ -171,23 +269,25 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
   // ---- one-time setup
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
-    for (int s = 0; s < TE_STAGES; ++s) { mbar_init(&full[s], TE_GROUP); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TE_STAGES; ++s) { mbar_init(&full[s], TE_STEM_WARPS); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128);
-      mbar_init(&x_full[a], 1); mbar_init(&x_empty[a], 2 * TE_GROUP_WARPS);
+      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TE_EPI_WARPS);
+      mbar_init(&x_full[a], 1); mbar_init(&x_empty[a], TE_STEM_WARPS);
     }
     fence_mbar_init();
   }
   for (int i = tid; i < TE_W2_BYTES / 16; i += TE_THREADS)
     reinterpret_cast<uint4*>(W2S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2) + i);
   for (int i = tid; i < 2 * p.xs_buf_bytes / 16; i += TE_THREADS) reinterpret_cast<uint4*>(XS)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (tid < 128) { shift_s[tid] = __ldg(p.shift2 + tid); pool_s[0][tid] = 0.f; pool_s[1][tid] = 0.f; }
+  if (tid < 128) { pool_s[0][tid] = 0.f; pool_s[1][tid] = 0.f; }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t xs_base = smem_u32(XS), abuf_base = smem_u32(ABUF);
+  const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+  unsigned long long pt[4] = {0, 0, 0, 0};
 
   if (warp == TE_TMA_WARP) {
     // ================= TMA producer: x of block i -> staging buffer i & 1 =================
@@ -195,7 +295,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
       for (int i = 0; i < nb_local; ++i) {
         const int xb = i & 1;
-        if (i >= 2) mbar_wait_g(&x_empty[xb], ((i >> 1) - 1) & 1);       // every stem warp is done with block i - 2
+        if (i >= 2) mbar_wait_g<1000>(&x_empty[xb], ((i >> 1) - 1) & 1);       // every stem warp is done with block i - 2
         mbar_expect_tx(&x_full[xb], (uint32_t)(TE_BLOCK_A * S * 2));
         const long long a0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TE_BLOCK_A;
         const uint32_t dst0 = xs_base + (uint32_t)xb * p.xs_buf_bytes + TE_XPAD * 2;
@@ -214,8 +314,11 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
     for (int g = 0; g < nt_local; ++g) {
       const int stage = g % TE_STAGES, acc = g & 1;
       const uint32_t use = (uint32_t)(g / TE_STAGES);
-      if (g >= 2) mbar_wait_g(&acc_empty[acc], ((g >> 1) - 1) & 1);      // the epilogue drained this accumulator
-      mbar_wait_g(&full[stage], use & 1);                                // the stem rows of the tile are stored
+      const long long q0 = probe ? clock64() : 0;
+      if (g >= 2) mbar_wait_g<40>(&acc_empty[acc], ((g >> 1) - 1) & 1);      // the epilogue drained this accumulator
+      const long long q1 = probe ? clock64() : 0;
+      mbar_wait_g<40>(&full[stage], use & 1);                                // the stem rows of the tile are stored
+      const long long q2 = probe ? clock64() : 0;
       if (leader) {
         tc_fence_after();
         const uint32_t a_u = (abuf_base + (uint32_t)stage * TE_STAGE_BYTES) >> 4;
@@ -243,60 +346,31 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         mma_commit(&acc_full[acc]);
       }
       __syncwarp();
+      if (probe) { const long long q3 = clock64(); pt[0] += q1 - q0; pt[1] += q2 - q1; pt[2] += q3 - q2; pt[3] += 1; }
     }
+    if (probe) { p.dbg[0] = pt[0]; p.dbg[1] = pt[1]; p.dbg[2] = pt[2]; p.dbg[3] = pt[3]; }
   } else if (warp >= TE_STEM_WARP0) {
     // ================= stem warps =================
-    const int grp = (warp - TE_STEM_WARP0) / TE_GROUP_WARPS;
-    const int gi = tid - (TE_STEM_WARP0 + grp * TE_GROUP_WARPS) * 32;    // row of the tile's window, 0..159
-    const bool row_thread = gi < TE_ROWS;
-    int cur_blk = -1;
-    for (int g = grp; g < nt_local; g += 2) {
-      const int i_blk = g / tpb, T = g - i_blk * tpb;
-      const int stage = g % TE_STAGES;
-      const uint32_t use = (uint32_t)(g / TE_STAGES);
-      if (i_blk != cur_blk) {
-        if (cur_blk >= 0) {                                              // this warp has read the last x of the block
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&x_empty[cur_blk & 1]);
-        }
-        cur_blk = i_blk;
-        mbar_wait_g(&x_full[i_blk & 1], (i_blk >> 1) & 1);
-      }
-      if (use > 0) mbar_wait_g(&empty[stage], (use - 1) & 1);            // the MMAs that read this buffer are done
-      if (row_thread) {
-        // flat row of the block: f = 128 T - 5 + gi -> A-scan a_loc, position l (l >= S: zero rows)
-        const int fa = 128 * T - TE_PAD + gi + Lp;                       // >= 0
-        const int a1 = (int)((unsigned)fa / (unsigned)Lp);
-        const int a_loc = a1 - 1, l = fa - a1 * Lp;
-        const long long ga = ((long long)blockIdx.x + (long long)i_blk * gridDim.x) * TE_BLOCK_A + a_loc;
-        const bool valid = a_loc >= 0 && a_loc < TE_BLOCK_A && l < S && ga < p.A;
-        const uint32_t vmask = valid ? 0xffffffffu : 0u;
-        const int aa = valid ? a_loc : 0, ll = valid ? l : 0;
-        const uint32_t xa = xs_base + (uint32_t)(i_blk & 1) * p.xs_buf_bytes +
-                            (uint32_t)(TE_XPAD + aa * p.xs_stride + ll - TE_PAD) * 2;
-        __half2 xh[11];
+    const int sw = warp - TE_STEM_WARP0, c = sw & 3;
+    unsigned long long* sd = probe && (sw == 0 || sw == 4) ? p.dbg + 16 + 2 * sw : nullptr;
+    if (sw < 4) stem_loop<11, 15, 3, 3, 0, 0>(p, c, lane, nt_local, xs_base, abuf_base, full, empty, x_full, x_empty, sd);
+    else stem_loop<7, 8, 2, 5, 3, 1>(p, c, lane, nt_local, xs_base, abuf_base, full, empty, x_full, x_empty, sd);
+  } else {
+    // ================= epilogue: warp = (TMEM lane quarter q, column half hf) =================
+    // A thread holds 4 rows x 8 columns of every 32-column chunk (16x256b loads): + BN shift, ReLU, the 4 rows are
+    // added locally, then a 3-level transposing butterfly over the 8 lanes that hold the same columns leaves ONE
+    // column sum of the warp's 32 rows in every lane (column 8 (i / 2) + 2 (lane % 4) + i % 2 with i = lane / 4).
+    const int q = warp & 3, hf = warp >> 2;
+    const int t4 = lane & 3, i8 = lane >> 2;
+    float shv[2][8];                                   // BN shift of this thread's columns (fixed for the kernel)
 #pragma unroll
-        for (int i = 0; i < 11; ++i) {
-          uint16_t h;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(xa + 2 * i));
-          xh[i] = __float2half2_rn(__uint_as_float((uint32_t)h << 16));
-        }
-        const uint32_t dst = abuf_base + (uint32_t)stage * TE_STAGE_BYTES + (uint32_t)gi * 16;
-        stem_branch<3, 0, 0>(p, xh, dst, vmask);
-        stem_branch<5, 3, 1>(p, xh, dst, vmask);
-        stem_branch<7, 8, 2>(p, xh, dst, vmask);
-        stem_branch<11, 15, 3>(p, xh, dst, vmask);
+    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        shv[cc][2 * j] = __ldg(p.shift2 + 64 * hf + 32 * cc + 8 * j + 2 * t4);
+        shv[cc][2 * j + 1] = __ldg(p.shift2 + 64 * hf + 32 * cc + 8 * j + 2 * t4 + 1);
       }
-      fence_async_smem();                                                // generic-proxy stores -> tensor-core operand reads
-      mbar_arrive(&full[stage]);
-    }
-    if (cur_blk >= 0) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&x_empty[cur_blk & 1]);
-    }
-  } else if (warp < 4) {
-    // ================= epilogue: warp q owns TMEM lanes 32q .. 32q+31 = rows of the tile =================
-    const int q = warp;
+    const int my_col = 8 * (i8 >> 1) + 2 * t4 + (i8 & 1);
     for (int g = 0; g < nt_local; ++g) {
       const int i_blk = g / tpb, T = g - i_blk * tpb;
       const int acc = g & 1;
@@ -304,63 +378,95 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
       // geometry of the tile: first A-scan, its position at the tile's first row; a second A-scan starts at row Lp - l0
       const int t0 = 128 * T;
       const int a_first = (int)((unsigned)t0 / (unsigned)Lp), l0 = t0 - a_first * Lp;
-      const int lr = l0 + q * 32 + lane;
-      const int seg = lr >= Lp ? 1 : 0, l = lr - seg * Lp;
-      const bool valid = l < S && a_blk + a_first + seg < p.A;
-      const bool m0 = valid && seg == 0, m1 = valid && seg == 1;
-      const bool uni0 = __all_sync(0xffffffffu, m0);
-      mbar_wait_g(&acc_full[acc], (g >> 1) & 1);
+      // the warp's 32 rows are all signal rows of the first A-scan (warp-uniform, the common case)
+      const bool uni0 = l0 + 32 * q + 31 < S && a_blk + a_first < p.A;
+      bool m0[4], m1[4];                               // rows i8 + 8k of the quarter: valid row of segment 0 / 1
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int lr = l0 + 32 * q + i8 + 8 * k;
+        const int seg = lr >= Lp ? 1 : 0, l = lr - seg * Lp;
+        const bool valid = l < S && a_blk + a_first + seg < p.A;
+        m0[k] = valid && seg == 0;
+        m1[k] = valid && seg == 1;
+      }
+      const long long e0 = probe ? clock64() : 0;
+      mbar_wait_g<60>(&acc_full[acc], (g >> 1) & 1);
+      const long long e1 = probe ? clock64() : 0;
       tc_fence_after();
-      float* pq = &part_s[acc][q][0][0];
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + cc * 32), r);
-        if (cc == 3) {                                                   // accumulator drained: tile g + 2 may start
+      float* pq = &part_s[acc][q][0][64 * hf];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t ra[16], rb[16];
+        const uint32_t col = (uint32_t)(acc * 128 + 64 * hf + 32 * cc);
+        tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32) << 16) + col, ra);          // rows i8, i8 + 8
+        tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32 + 16) << 16) + col, rb);     // rows i8 + 16, i8 + 24
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cc == 1) {                                                   // accumulator drained: tile g + 2 may start
           tc_fence_before();
-          mbar_arrive(&acc_empty[acc]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
-        float v[32];
+        float s0[8], s1[8];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 sh = *reinterpret_cast<const float4*>(&shift_s[cc * 32 + 4 * j4]);
-          v[4 * j4 + 0] = fmaxf(__uint_as_float(r[4 * j4 + 0]) + sh.x, 0.f);
-          v[4 * j4 + 1] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + sh.y, 0.f);
-          v[4 * j4 + 2] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + sh.z, 0.f);
-          v[4 * j4 + 3] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + sh.w, 0.f);
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float sh = shv[cc][2 * j + e];
+            const float v0 = fmaxf(__uint_as_float(ra[4 * j + e]) + sh, 0.f), v1 = fmaxf(__uint_as_float(ra[4 * j + 2 + e]) + sh, 0.f);
+            const float v2 = fmaxf(__uint_as_float(rb[4 * j + e]) + sh, 0.f), v3 = fmaxf(__uint_as_float(rb[4 * j + 2 + e]) + sh, 0.f);
+            if (uni0) {
+              s0[2 * j + e] = (v0 + v1) + (v2 + v3);
+              s1[2 * j + e] = 0.f;
+            } else {
+              s0[2 * j + e] = ((m0[0] ? v0 : 0.f) + (m0[1] ? v1 : 0.f)) + ((m0[2] ? v2 : 0.f) + (m0[3] ? v3 : 0.f));
+              s1[2 * j + e] = ((m1[0] ? v0 : 0.f) + (m1[1] ? v1 : 0.f)) + ((m1[2] ? v2 : 0.f) + (m1[3] ? v3 : 0.f));
+            }
+          }
+        // transposing butterfly over the lanes with equal lane % 4 (xor 16, 8, 4): 8 values -> 1
+        auto bfly = [&](float (&v)[8]) {
+#pragma unroll
+          for (int m = 4; m >= 1; m >>= 1) {
+            const bool hi = (lane & (4 * m)) != 0;
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+              const float keep = hi ? v[m + i] : v[i];
+              const float send = hi ? v[i] : v[m + i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4 * m);
+            }
+          }
+        };
+        bfly(s0);
+        pq[32 * cc + my_col] = s0[0];
         if (uni0) {
-          colsum32(v, lane);
-          pq[cc * 32 + lane] = v[0];
-          pq[128 + cc * 32 + lane] = 0.f;
+          pq[128 + 32 * cc + my_col] = 0.f;
         } else {
-          float w[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { w[j] = m1 ? v[j] : 0.f; v[j] = m0 ? v[j] : 0.f; }
-          colsum32(v, lane);
-          colsum32(w, lane);
-          pq[cc * 32 + lane] = v[0];
-          pq[128 + cc * 32 + lane] = w[0];
+          bfly(s1);
+          pq[128 + 32 * cc + my_col] = s1[0];
         }
       }
-      named_sync(1, 128);
-      // ---- combine the four lane quarters (fixed order) and accumulate per A-scan: thread = column
+      named_sync(1, TE_EPI);
+      // ---- combine the four lane quarters (fixed order) and accumulate per A-scan: threads 0..127 = the columns of the
+      // tile's first A-scan, threads 128..255 = the columns of a second A-scan that starts in this tile
       {
-        const int c = tid;
-        const float s0 = ((part_s[acc][0][0][c] + part_s[acc][1][0][c]) + part_s[acc][2][0][c]) + part_s[acc][3][0][c];
-        const float s1 = ((part_s[acc][0][1][c] + part_s[acc][1][1][c]) + part_s[acc][2][1][c]) + part_s[acc][3][1][c];
+        const int c = tid & 127, sg = tid >> 7;
+        const float s = ((part_s[acc][0][sg][c] + part_s[acc][1][sg][c]) + part_s[acc][2][sg][c]) + part_s[acc][3][sg][c];
         const int par0 = a_first & 1;
-        const float sum0 = pool_s[par0][c] + s0;
-        const bool flush0 = l0 < S && S - 1 - l0 <= 127;                 // the first A-scan's last row is in this tile
-        if (flush0) {
-          if (a_blk + a_first < p.A) p.feat[(a_blk + a_first) * 128 + c] = sum0 * p.invS;
-          pool_s[par0][c] = 0.f;
-        } else {
-          pool_s[par0][c] = sum0;
+        if (sg == 0) {
+          const float sum0 = pool_s[par0][c] + s;
+          const bool flush0 = l0 < S && S - 1 - l0 <= 127;               // the first A-scan's last row is in this tile
+          if (flush0) {
+            if (a_blk + a_first < p.A) p.feat[(a_blk + a_first) * 128 + c] = sum0 * p.invS;
+            pool_s[par0][c] = 0.f;
+          } else {
+            pool_s[par0][c] = sum0;
+          }
+        } else if (l0 + 127 >= Lp) {
+          pool_s[par0 ^ 1][c] += s;                                      // (S >= 128: a second A-scan cannot end here)
         }
-        if (l0 + 127 >= Lp) pool_s[par0 ^ 1][c] += s1;                   // a second A-scan starts in this tile (S >= 128:
-      }                                                                  // it cannot end here)
+      }
+      if (probe) { pt[0] += e1 - e0; pt[1] += clock64() - e1; pt[2] += 1; }
     }
+    if (probe && warp == 0) { p.dbg[8] = pt[0]; p.dbg[9] = pt[1]; p.dbg[10] = pt[2]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -419,14 +525,13 @@ void ts_encoder_pack(const float* const* w1, const float* const* sh1, const floa
   }
 }
 
-void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t* sw_host, const uint32_t* sb_host,
+void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t* sw_dev, const uint32_t* sb_dev,
                    const void* W2, const float* shift2, float* feat) {
   if (c.dry) return;
   PAUT_CHECK(ts_encoder_supported(S, 128), PAUT_ERR_UNSUPPORTED, "two-stage encoder: unsupported signal length");
   PAUT_CHECK((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, PAUT_ERR_INVALID, "two-stage encoder: x must be 16-byte aligned");
   TsEncArgs p;
-  memcpy(p.sw, sw_host, sizeof(p.sw));
-  memcpy(p.sb, sb_host, sizeof(p.sb));
+  p.sw = sw_dev; p.sb = sb_dev;
   p.W2 = static_cast<const __half*>(W2); p.shift2 = shift2; p.feat = feat;
   p.A = A; p.nblk = (A + TE_BLOCK_A - 1) / TE_BLOCK_A;
   p.S = S; p.Lp = S + TE_HALO; p.tpb = TE_BLOCK_A * p.Lp / 128;
@@ -453,7 +558,20 @@ void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t*
   PAUT_CUDA(cudaFuncGetAttributes(&fa, k_ts_encoder));
   PAUT_CHECK(smem + fa.sharedSizeBytes <= (size_t)c.smem_optin, PAUT_ERR_UNSUPPORTED, "two-stage encoder: shared memory budget exceeded");
   const long long grid = p.nblk < c.num_sms ? p.nblk : c.num_sms;     // persistent: one CTA per SM
+  static const bool debug = std::getenv("PAUT_TS_DEBUG") != nullptr;
+  p.dbg = nullptr;
+  if (debug) { PAUT_CUDA(cudaMalloc(&p.dbg, 32 * sizeof(unsigned long long))); PAUT_CUDA(cudaMemset(p.dbg, 0, 32 * 8)); }
   k_ts_encoder<<<(unsigned)grid, TE_THREADS, smem, c.stream>>>(tmap, p);
+  if (debug) {
+    unsigned long long h[32];
+    PAUT_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    auto per = [](unsigned long long v, unsigned long long n) { return n ? v / n : 0ull; };
+    fprintf(stderr, "[ts probe] per tile (CTA 0, %llu tiles) | mma: wait_acc_empty %llu wait_full %llu issue %llu | "
+                    "epilogue w0: wait_acc_full %llu work %llu | stem w0 (k11+k3): wait %llu work %llu | stem w4 (k7+k5): wait %llu work %llu\n",
+            h[3], per(h[0], h[3]), per(h[1], h[3]), per(h[2], h[3]), per(h[8], h[10]), per(h[9], h[10]), per(h[16], h[18]),
+            per(h[17], h[18]), per(h[24], h[26]), per(h[25], h[26]));
+  }
   c.launched("ts_encoder");
 }
 
