@@ -202,12 +202,11 @@ void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const fl
 // bf16 flat rows [R, C] -> dense fp32 [A, L, C]
 void op_unflatten(Ctx& c, const void* flat, int64_t A, int L, int halo, int C, float* out);
 // Fused encoder of TwoStageDefectDetector (ops_ts_enc.cu, bf16 mode): x [A,S] bf16 -> feat [A,128] (mean over the signal
-// length of the four conv branches), TMA input staging + stem on HFMA2 + tcgen05 second convolutions + pooled epilogue
+// length of the four conv branches), TMA input staging, stem and second convolutions on tcgen05, pooled epilogue
 bool ts_encoder_supported(int S, int d_model);
-void ts_encoder_pack(const float* const* w1, const float* const* sh1, const float* const* w2, std::vector<uint32_t>& sw,
-                     std::vector<uint32_t>& sb, std::vector<uint16_t>& W2);
-void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t* sw_dev, const uint32_t* sb_dev,
-                   const void* W2, const float* shift2, float* feat);
+void ts_encoder_pack(const float* const* w1, const float* const* sh1, const float* const* w2, std::vector<uint16_t>& Wst,
+                     std::vector<uint16_t>& W2);
+void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const void* Wst, const void* W2, const float* shift2, float* feat);
 // Fused per-set stage of MSC / MSC_N (ops_set_tc.cu, bf16 mode): attention block and FFN + head
 bool msc_set_tc_supported(int N, int d, int heads, int ff);
 void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bqkv, const void* Wo, const float* bo,

@@ -767,22 +767,18 @@ void Model::finalize() {
           ++i;
         }
         if (ok) {
-          std::vector<uint16_t> W2h;
-          ts_encoder_pack(w1p, s1p, w2p, ts_enc.sw, ts_enc.sb, W2h);
+          std::vector<uint16_t> W2h, Wsth;
+          ts_encoder_pack(w1p, s1p, w2p, Wsth, W2h);
           void* dptr = nullptr;
           PAUT_CUDA(cudaMalloc(&dptr, W2h.size() * sizeof(uint16_t)));
           dev_allocs.push_back(dptr);
           PAUT_CUDA(cudaMemcpy(dptr, W2h.data(), W2h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
           ts_enc.W2 = dptr;
-          auto up32 = [&](const std::vector<uint32_t>& v) {
-            void* q = nullptr;
-            PAUT_CUDA(cudaMalloc(&q, v.size() * sizeof(uint32_t)));
-            dev_allocs.push_back(q);
-            PAUT_CUDA(cudaMemcpy(q, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            return static_cast<const uint32_t*>(q);
-          };
-          ts_enc.sw_dev = up32(ts_enc.sw);
-          ts_enc.sb_dev = up32(ts_enc.sb);
+          void* wq = nullptr;
+          PAUT_CUDA(cudaMalloc(&wq, Wsth.size() * sizeof(uint16_t)));
+          dev_allocs.push_back(wq);
+          PAUT_CUDA(cudaMemcpy(wq, Wsth.data(), Wsth.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          ts_enc.Wst = wq;
           ts_enc.shift2 = upload(shift2);
           ts_enc.ready = true;
         }
@@ -989,8 +985,10 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
     const std::string te = "transformer_encoder.";
     const MHAW& sa = mha["self"];
     float* x1 = c.allocf((size_t)A * D);
-    static const bool attn_mma = std::getenv("PAUT_ATTN_MMA") != nullptr;      // A/B switch: the mma.sync attention block
-    const bool attn_tc = !attn_mma && msc_attn_tc_supported(N, D, cfg.num_heads) && set_tc.tc_w[0][0] != nullptr;
+    // A/B switch between the two attention blocks: PAUT_ATTN=tc | mma (default below)
+    static const char* attn_env = std::getenv("PAUT_ATTN");
+    static const bool attn_want_tc = attn_env ? std::string(attn_env) == "tc" : false;
+    const bool attn_tc = attn_want_tc && msc_attn_tc_supported(N, D, cfg.num_heads) && set_tc.tc_w[0][0] != nullptr;
     if (attn_tc)
       op_msc_attn_tc(c, h, set_tc.tc_w[0][0], set_tc.tc_w[0][1], set_tc.tc_w[0][2], sa.in_proj.b, sa.out_proj.b,
                      ln[te + "norm1"].g, ln[te + "norm1"].b, x1, B, N, false);
@@ -1147,7 +1145,7 @@ void Model::fwd_two_stage(XIn& x, int64_t B, int N, int S, const paut_outputs& o
   if (g.bf16 && ts_enc.ready && ts_encoder_supported(S, d) && !no_fused) {
     // one persistent kernel: TMA input staging, stems on HFMA2, the four second convolutions on tcgen05, BN shift +
     // ReLU + mean over the signal length in the epilogue (two_stage_model.py:102-118); no activation touches HBM
-    op_ts_encoder(c, x.as_bf16(c), A, S, ts_enc.sw_dev, ts_enc.sb_dev, ts_enc.W2, ts_enc.shift2, feat);
+    op_ts_encoder(c, x.as_bf16(c), A, S, ts_enc.Wst, ts_enc.W2, ts_enc.shift2, feat);
   } else if (tcc && ts_grouped.ready) {
     // all four stems write one [rows, 4q] buffer; the four second convolutions + BN + ReLU + mean run as one
     // grouped tcgen05 launch whose pooled output is the concatenated feature vector (two_stage_model.py:102-118)
@@ -1610,7 +1608,7 @@ void Model::debug_stage(int stage, const void* x, int x_dtype, int64_t B, int64_
   if (stage == 1) {
     PAUT_CHECK(kind == PAUT_MODEL_TWO_STAGE && ts_enc.ready && ts_encoder_supported((int)S, cfg.d_model), PAUT_ERR_UNSUPPORTED,
                "debug_stage 1: the fused two-stage encoder is not available for this model / precision / length");
-    op_ts_encoder(c, xin.as_bf16(c), A, (int)S, ts_enc.sw_dev, ts_enc.sb_dev, ts_enc.W2, ts_enc.shift2, out_dev);
+    op_ts_encoder(c, xin.as_bf16(c), A, (int)S, ts_enc.Wst, ts_enc.W2, ts_enc.shift2, out_dev);
   } else if (stage >= 2 && stage <= 5) {
     // MSC attention block on an fp32 [B, N, 64] input: stage 2 / 3 = tcgen05 kernel (self / shifted keys and values),
     // stage 4 / 5 = the mma.sync kernel

@@ -105,9 +105,7 @@ struct Model {
     bool ready = false;
   } ts_grouped;
   struct TsEnc {                               // operands of the fused two-stage encoder (ops_ts_enc.cu, bf16 mode)
-    std::vector<uint32_t> sw, sb;              // stem weights / shifts as fp16 pairs (host copies)
-    const uint32_t* sw_dev = nullptr;          // the same on the device: every stem warp keeps its share in registers
-    const uint32_t* sb_dev = nullptr;
+    const void* Wst = nullptr;                 // the four stems + folded BN shift as one [128 x 16] bf16 operand
     const void* W2 = nullptr;                  // second convolutions, fp16, packed
     const float* shift2 = nullptr;             // [128]
     bool ready = false;

@@ -542,7 +542,9 @@ __global__ void __launch_bounds__(256, 2) k_stem_flat_t(const void* __restrict__
     for (int i = 0; i < K + STEM_RPT - 1; ++i) {
       const int li = l - K / 2 + i;
       xw[i] = 0.f;
-      if (scan_ok && li >= 0 && li < S) xw[i] = x_dtype == PAUT_BF16 ? __bfloat162float(xb[base + li]) : __ldg(xf + base + li);
+      if (scan_ok && li >= 0 && li < S)
+        xw[i] = x_dtype == PAUT_BF16 ? __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(xb) + base + li) << 16)
+                                     : __ldg(xf + base + li);
     }
 #pragma unroll
     for (int j = 0; j < STEM_RPT; ++j) {
@@ -575,7 +577,9 @@ __global__ void __launch_bounds__(256, 2) k_stem_flat_t(const void* __restrict__
           for (int t = 0; t < K; ++t) {
             const int li = l2 + t - K / 2;
             float xv = 0.f;
-            if (li >= 0 && li < S) xv = x_dtype == PAUT_BF16 ? __bfloat162float(xb[b2 + li]) : __ldg(xf + b2 + li);
+            if (li >= 0 && li < S)
+              xv = x_dtype == PAUT_BF16 ? __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(xb) + b2 + li) << 16)
+                                        : __ldg(xf + b2 + li);
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[c] = fmaf(xv, wr[t][c], acc[c]);
           }

@@ -6,27 +6,39 @@
 //
 // Work units.  A CTA walks blocks of 16 A-scans.  Inside a block the A-scans are laid on a flat row axis with period
 // Lp = S + 8 (S signal rows followed by 8 zero rows, the padding of every convolution); 16 * Lp is a multiple of 128,
-// so a block is a whole number of 128-row M tiles (41 for S = 320) and a tile touches at most two A-scans.
+// so a block is a whole number of 128-row M tiles (41 for S = 320), a tile touches at most two A-scans, and the
+// tiles of consecutive blocks form one continuous row stream.
 //
-// Warp roles (18 warps):
-//   TMA warp    : x of the NEXT block -> shared memory (cp.async.bulk.tensor.2d, one box per A-scan, mbarrier
-//                 complete_tx), double buffered.
-//   stem warps  : two groups of 5 warps, group g takes every other tile.  A thread owns one of the 138 input rows
-//                 of the tile's window (128 rows + 5 on each side), runs the four C_in = 1 stem convolutions in packed
-//                 fp16 (HFMA2, weights and folded BN shift in the constant bank = kernel parameters) and stores the
-//                 fp16 row [128 channels] into the stage buffer in the canonical K-major operand layout
-//                 [branch][4 chunks][144 rows][16 B].  Rows outside an A-scan are stored as zeros.
-//   MMA warp    : per tile 52 tcgen05.mma 128x32x16 (SS form, fp16 x fp16 -> fp32): branch b, tap t, K step ks reads
-//                 the SAME stage buffer through a descriptor advanced by (5 - k/2 + t) rows -- no im2col copy --
-//                 against the resident folded weights; 4 x 32 accumulator columns, two accumulator buffers in TMEM.
-//   epilogue    : 4 warps: TMEM -> registers, + BN shift, ReLU, and the pooled sum over the tile's rows with a
-//                 transposing butterfly (31 shuffles per 32 columns); per-tile partial sums of the four lane quarters
-//                 are combined in a fixed order and accumulated per A-scan in shared memory; the finished mean is
-//                 written once per A-scan.  The summation order depends only on the A-scan's index modulo 16.
+// BOTH convolutions run on the tensor cores:
+//   stem (C_in = 1): the 11-sample window of a row is an im2col row of K = 16 (taps 0..10 = x[l-5 .. l+5], taps 11, 12
+//          = 1.0 carrying the folded BN shift as a bf16 hi + lo pair, rest 0).  ONE tcgen05.mma 128 x 128 x 16 per
+//          tile computes all four branches (smaller kernels are zero-padded, centred); rows outside an A-scan are
+//          all-zero im2col rows, so their outputs are exactly zero -- the zero padding of the second convolution.
+//          Its accumulator is read back once: cvt.rn.relu.f16x2 (ReLU + fp16 in one instruction) -> the fp16
+//          activation rows [128 channels] in a shared-memory RING of 4 tiles (+ 8 mirrored rows at each end), in
+//          the canonical K-major operand layout [branch][4 chunks][rows][16 B].
+//   second convolutions: per tile 52 tcgen05.mma 128x32x16 (SS form, fp16 x fp16 -> fp32): branch b, tap t, K step
+//          ks reads the ring through a descriptor advanced by (t - k/2) rows -- no im2col copy, no recomputed halo
+//          -- against the resident folded weights; 4 x 32 accumulator columns, two accumulator buffers.
+// Measured on the way here (profiles/r02): a version with the stems on HFMA2 (register-resident weights) issued 14.7 k
+// warp instructions per tile and was bound by instruction issue at 3.3 IPC (4360 cycles per tile against 2224 for the
+// MMAs); as an MMA the stem costs 64 tensor-pipe cycles and ~600 instructions per tile.
+//
+// Warp roles (16 warps):
+//   TMA warp      : x of the next block -> shared memory (cp.async.bulk.tensor.2d, one box per A-scan, mbarrier
+//                   complete_tx).
+//   stem warps    : 4 warps, thread = row of the tile: build the im2col row (11 ld.shared.u16, 2 st.shared.v4), and
+//                   one tile later turn the stem accumulator into ring rows.
+//   MMA warp      : stem MMA of tile g, second-convolution MMAs of tile g - 2 (it needs the first rows of tile g - 1).
+//   epilogue      : 8 warps (lane quarter x column half): TMEM -> registers (16x256b loads: a thread holds 4 rows x 8
+//                   columns), + BN shift, ReLU, the 4 rows are added locally, a 3-level transposing butterfly leaves
+//                   one column sum per lane; per-tile partial sums of the four lane quarters are combined in a fixed
+//                   order and accumulated per A-scan in shared memory; the finished mean is written once per
+//                   A-scan.  The summation order depends only on the A-scan's index modulo 16.
 //
 // Roofline: 17.0 MFLOP per A-scan on the tensor pipe; an SS-form 128x32x16 MMA is paced by the 4 KB A-tile fetch
-// from shared memory (measured 40 cycles against the 16 of the pipe), which bounds this kernel at ~0.4 of the MMA
-// rate at the clock it runs at.
+// from shared memory (measured 40 cycles against the 16 of the pipe, tools/mma_probe2.py), which bounds this kernel
+// at ~0.4 of the MMA rate at the clock it runs at.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -45,26 +57,27 @@ namespace {
 
 constexpr int TE_EPI_WARPS = 8;                   // warps 0-7: warp w = TMEM lane quarter w % 4, column half w / 4
 constexpr int TE_EPI = TE_EPI_WARPS * 32;
-constexpr int TE_MMA_WARP = 8, TE_TMA_WARP = 9;
-constexpr int TE_STEM_WARP0 = 10;
-constexpr int TE_STEM_WARPS = 8;                  // stem warp sw: chunk sw % 4 (8 channels) of branches {3, 0} (sw < 4) or {2, 1}
-constexpr int TE_STEM = TE_STEM_WARPS * 32;
-constexpr int TE_THREADS = (TE_STEM_WARP0 + TE_STEM_WARPS) * 32;   // 576
+constexpr int TE_MMA_WARP = 8, TE_TMA_WARP = 9;   // warps 10, 11 idle
+constexpr int TE_STEM_WARP0 = 12;                 // warps 12-15: stem group, warp = TMEM lane quarter
+constexpr int TE_STEM_WARPS = 4;
+constexpr int TE_THREADS = (TE_STEM_WARP0 + TE_STEM_WARPS) * 32;   // 512
 constexpr int TE_PAD = 5;                         // k = 11
-constexpr int TE_ROWS = 128 + 2 * TE_PAD;         // 138 input rows per tile
-constexpr int TE_BROWS = 160;                     // rows per chunk of a stage buffer (5 row blocks of 32)
-constexpr int TE_STAGES = 3;
+constexpr int TE_SLOTS = 4;                       // ring of 4 tiles
+constexpr int TE_MIRROR = 8;                      // mirrored rows at each end of the ring
+constexpr int TE_RROWS = TE_MIRROR + TE_SLOTS * 128 + TE_MIRROR;   // 528
+constexpr int TE_LBO_R = TE_RROWS * 16;           // chunk stride of the ring (bytes)
+constexpr int TE_RING_BYTES = 16 * TE_LBO_R;      // 4 branches x 4 chunks
 constexpr int TE_BLOCK_A = 16;
 constexpr int TE_HALO = 8;
-constexpr int TE_LBO_A = TE_BROWS * 16;           // chunk stride of the A operand (bytes)
-constexpr int TE_STAGE_BYTES = 16 * TE_LBO_A;     // 4 branches x 4 chunks
 constexpr int TE_NTAPS = 3 + 5 + 7 + 11;          // 26 (branch, tap) pairs
 constexpr int TE_W2_BYTES = TE_NTAPS * 2048;      // [26][4 chunks][32 rows][16 B]
+constexpr int TE_WST_BYTES = 2 * 128 * 16;        // stem weights [2 chunks][128 rows][16 B], bf16
+constexpr int TE_XA_BYTES = 2 * 128 * 16;         // one im2col tile [2 chunks][128 rows][16 B], bf16
 constexpr int TE_XPAD = 64;                       // zero elements in front of / behind the x staging area
+constexpr int TC_ACC = 0, TC_STEM = 256;          // TMEM columns: 2 x 128 second-convolution, 2 x 128 stem accumulators
 
 struct TsEncArgs {
-  const uint32_t* sw;             // stem weights (BN scale folded) as fp16 pairs: [(branch, tap)][j] = channels (2j, 2j+1)
-  const uint32_t* sb;             // stem shift (folded bias) as fp16 pairs [4][16]
+  const __nv_bfloat16* Wst;       // stem weights + BN shift as a [128 x 16] bf16 B operand, K-major chunks
   const __half* W2;               // second convolutions, BN scale folded, fp16 [26][4][32][8]
   const float* shift2;            // [128]
   float* feat;                    // [A][128] mean over the signal length
@@ -73,7 +86,7 @@ struct TsEncArgs {
   int S, Lp;                      // signal length, row period S + 8
   int tpb;                        // tiles per block = 16 * Lp / 128
   int xs_stride;                  // elements between A-scans in the x staging buffer (multiple of 64)
-  int xs_buf_bytes;               // one staging buffer
+  int xs_buf_bytes;               // the staging buffer
   int rows_per_ascan;             // rows of the [rows, W] tensor-map view one A-scan occupies (S / W)
   float invS;
   unsigned long long* dbg;        // optional cycle probe (PAUT_TS_DEBUG=1): role timings of CTA 0
@@ -83,10 +96,8 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Parity wait that does not burn issue slots: a failed probe puts the warp to sleep (nanosleep) before the next one
-// -- a spinning warp issues ~0.6 instructions per cycle and takes them from the working warps of its scheduler (ncu
-// of the first version: 37 % of all issued instructions were wait loops).  With a dead-lock guard: a protocol error
-// traps instead of hanging the GPU.
+// Parity wait; a failed probe puts the warp to sleep (nanosleep) before the next one, with a dead-lock guard: a
+// protocol error traps instead of hanging the GPU.
 template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -102,9 +113,14 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    asm volatile("nanosleep.u32 %0;" ::"r"(SLEEP_NS));
+    if (SLEEP_NS > 0) asm volatile("nanosleep.u32 %0;" ::"r"(SLEEP_NS));
     if (spin > (1u << 22)) __trap();
   }
+}
+// one arrival per warp: every lane has executed its fences, lane 0 arrives for the warp
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -130,232 +146,226 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-// Stem convolution of one branch, one chunk of 8 channels (4 fp16 pairs), one row: K taps with the weights in
-// registers (w[t][j]); xh[i] = sample l - 5 + i of the A-scan in both halves.  The last tap carries the ReLU
-// (fma.rn.relu).  vmask zeroes rows that are not signal rows (bitwise: garbage inputs cannot leak).
-template <int K, bool MASK>
-__device__ __forceinline__ void stem_chunk(const __half2 (&w)[K][4], const __half2 (&sh)[4], const __half2 (&xh)[11],
-                                           uint32_t dst, uint32_t vmask) {
-  uint32_t o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __half2 acc = sh[j];
-#pragma unroll
-    for (int t = 0; t < K - 1; ++t) acc = __hfma2(w[t][j], xh[TE_PAD - K / 2 + t], acc);
-    acc = __hfma2_relu(w[K - 1][j], xh[TE_PAD + K / 2], acc);
-    o[j] = *reinterpret_cast<const uint32_t*>(&acc);
-    if (MASK) o[j] &= vmask;
-  }
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int K>
-__device__ __forceinline__ void load_stem_weights(const TsEncArgs& p, int woff, int b, int c, __half2 (&w)[K][4], __half2 (&sh)[4]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t s = __ldg(p.sb + b * 16 + c * 4 + j);
-    sh[j] = *reinterpret_cast<const __half2*>(&s);
-#pragma unroll
-    for (int t = 0; t < K; ++t) {
-      const uint32_t v = __ldg(p.sw + (woff + t) * 16 + c * 4 + j);
-      w[t][j] = *reinterpret_cast<const __half2*>(&v);
-    }
-  }
-}
-
-// One stem warp: chunk c of branches (KA taps at weight offset WA, branch BA) and (KB, WB, BB), weights in registers
-// for the whole kernel.  Lane = row of a 32-row block of the tile's 138-row window.
-template <int KA, int WA, int BA, int KB, int WB, int BB>
-__device__ __forceinline__ void stem_loop(const TsEncArgs& p, int c, int lane, int nt_local, uint32_t xs_base, uint32_t abuf_base,
-                                          uint64_t* full, uint64_t* empty, uint64_t* x_full, uint64_t* x_empty, unsigned long long* dbg) {
-  __half2 wa[KA][4], sa[4], wb[KB][4], sbb[4];
-  load_stem_weights<KA>(p, WA, BA, c, wa, sa);
-  load_stem_weights<KB>(p, WB, BB, c, wb, sbb);
-  const int S = p.S, Lp = p.Lp, tpb = p.tpb;
-  int cur_blk = -1;
-  unsigned long long pt0 = 0, pt1 = 0, pt2 = 0;
-  for (int g = 0; g < nt_local; ++g) {
-    const int i_blk = g / tpb, T = g - i_blk * tpb;
-    const int stage = g % TE_STAGES;
-    const uint32_t use = (uint32_t)(g / TE_STAGES);
-    const long long s0 = dbg ? clock64() : 0;
-    if (i_blk != cur_blk) {
-      if (cur_blk >= 0) {                                              // this warp has read the last x of the block
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&x_empty[cur_blk & 1]);
-      }
-      cur_blk = i_blk;
-      mbar_wait_g<200>(&x_full[i_blk & 1], (i_blk >> 1) & 1);
-      // bf16 -> fp16 in place, once per block (16 x S samples over the 256 stem threads), so that the per-row loads
-      // below need no conversion; the zero padding between the A-scans is the same bit pattern in both formats
-      {
-        const uint32_t xb0 = xs_base + (uint32_t)(i_blk & 1) * p.xs_buf_bytes + TE_XPAD * 2;
-        const int st = (int)(threadIdx.x) - TE_STEM_WARP0 * 32;
-        const int wpa = S / 2;                                           // 32-bit words per A-scan
-        for (int i = st; i < TE_BLOCK_A * wpa; i += TE_STEM) {
-          const int a = i / wpa, w = i - a * wpa;
-          const uint32_t addr = xb0 + (uint32_t)(a * p.xs_stride * 2 + w * 4);
-          uint32_t v;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-          const __half2 h = __floats2half2_rn(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
-        }
-        named_sync(2, TE_STEM);
-      }
-    }
-    if (use > 0) mbar_wait_g<100>(&empty[stage], (use - 1) & 1);            // the MMAs that read this buffer are done
-    const long long s1 = dbg ? clock64() : 0;
-    // first row of the window: flat row 128 T - 5 of the block -> A-scan a0 (may be -1), position l0
-    const int fa = 128 * T - TE_PAD + Lp;                              // >= 0
-    const int a1 = (int)((unsigned)fa / (unsigned)Lp);
-    const int a0 = a1 - 1, l0 = fa - a1 * Lp;
-    const long long a_blk = ((long long)blockIdx.x + (long long)i_blk * gridDim.x) * TE_BLOCK_A;
-    const uint32_t xb = xs_base + (uint32_t)(i_blk & 1) * p.xs_buf_bytes;
-    const uint32_t sbuf = abuf_base + (uint32_t)stage * TE_STAGE_BYTES;
-#pragma unroll 1
-    for (int rb = 0; rb < (TE_ROWS + 31) / 32; ++rb) {
-      const int i = rb * 32 + lane;                                    // row of the window
-      int a_loc = a0, l = l0 + i;
-      while (l >= Lp) { l -= Lp; ++a_loc; }
-      const bool valid = i < TE_ROWS && a_loc >= 0 && a_loc < TE_BLOCK_A && l < S && a_blk + a_loc < p.A;
-      const int aa = valid ? a_loc : 0, ll = valid ? l : 0;
-      const uint32_t xa = xb + (uint32_t)(TE_XPAD + aa * p.xs_stride + ll - TE_PAD) * 2;
-      __half2 xh[11];
-#pragma unroll
-      for (int k = 0; k < 11; ++k) {
-        uint16_t h;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(xa + 2 * k) : "memory");
-        xh[k] = __half2half2(__ushort_as_half(h));
-      }
-      const uint32_t dst = sbuf + (uint32_t)i * 16;
-      if (__all_sync(0xffffffffu, valid)) {                            // the common case: no masking instructions
-        stem_chunk<KA, false>(wa, sa, xh, dst + (uint32_t)((BA * 4 + c) * TE_LBO_A), 0xffffffffu);
-        stem_chunk<KB, false>(wb, sbb, xh, dst + (uint32_t)((BB * 4 + c) * TE_LBO_A), 0xffffffffu);
-      } else {
-        const uint32_t vmask = valid ? 0xffffffffu : 0u;
-        stem_chunk<KA, true>(wa, sa, xh, dst + (uint32_t)((BA * 4 + c) * TE_LBO_A), vmask);
-        stem_chunk<KB, true>(wb, sbb, xh, dst + (uint32_t)((BB * 4 + c) * TE_LBO_A), vmask);
-      }
-    }
-    fence_async_smem();                                                // generic-proxy stores -> tensor-core operand reads
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&full[stage]);
-    if (dbg) { pt0 += s1 - s0; pt1 += clock64() - s1; pt2 += 1; }
-  }
-  if (dbg) { dbg[0] = pt0; dbg[1] = pt1; dbg[2] = pt2; }
-  if (cur_blk >= 0) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&x_empty[cur_blk & 1]);
-  }
+// relu + fp32 -> fp16 of two values in one instruction: lo in the low half
+__device__ __forceinline__ uint32_t relu_pack_f16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 __global__ void __launch_bounds__(TE_THREADS, 1)
     k_ts_encoder(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TsEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[TE_STAGES], empty[TE_STAGES], acc_full[2], acc_empty[2], x_full[2], x_empty[2];
+  __shared__ __align__(8) uint64_t x_full, x_empty, xa_full[2], xa_empty[2], sacc_full[2], sacc_empty[2], ring_full[TE_SLOTS],
+      ring_empty[TE_SLOTS], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float pool_s[2][128];          // running sums of the (at most two) open A-scans
   __shared__ __align__(16) float part_s[2][4][2][128];    // [tile parity][lane quarter][segment][column]
 
   unsigned char* W2S = smem;                              // resident weights of the second convolutions
-  unsigned char* ABUF = W2S + TE_W2_BYTES;                // [TE_STAGES] stage buffers
-  unsigned char* XS = ABUF + TE_STAGES * TE_STAGE_BYTES;  // [2] x staging buffers (bf16)
+  unsigned char* WST = W2S + TE_W2_BYTES;                 // stem weights (B operand)
+  unsigned char* RING = WST + TE_WST_BYTES;               // fp16 activation rows of 4 tiles (+ mirrors)
+  unsigned char* XA = RING + TE_RING_BYTES;               // [2] im2col tiles of the stem
+  unsigned char* XS = XA + 2 * TE_XA_BYTES;               // x staging buffer (bf16)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
   const int S = p.S, Lp = p.Lp, tpb = p.tpb;
   const int nb_local = (int)((p.nblk - blockIdx.x + gridDim.x - 1) / gridDim.x);
-  const int nt_local = nb_local * tpb;
+  const int nt = nb_local * tpb;                          // tiles of this CTA; the stem side runs one more (all zero)
 
   // ---- one-time setup
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
-    for (int s = 0; s < TE_STAGES; ++s) { mbar_init(&full[s], TE_STEM_WARPS); mbar_init(&empty[s], 1); }
+    mbar_init(&x_full, 1); mbar_init(&x_empty, TE_STEM_WARPS);
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&xa_full[a], TE_STEM_WARPS); mbar_init(&xa_empty[a], 1);
+      mbar_init(&sacc_full[a], 1); mbar_init(&sacc_empty[a], TE_STEM_WARPS);
       mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TE_EPI_WARPS);
-      mbar_init(&x_full[a], 1); mbar_init(&x_empty[a], TE_STEM_WARPS);
     }
+    for (int s = 0; s < TE_SLOTS; ++s) { mbar_init(&ring_full[s], TE_STEM_WARPS); mbar_init(&ring_empty[s], 1); }
     fence_mbar_init();
   }
   for (int i = tid; i < TE_W2_BYTES / 16; i += TE_THREADS)
     reinterpret_cast<uint4*>(W2S)[i] = __ldg(reinterpret_cast<const uint4*>(p.W2) + i);
-  for (int i = tid; i < 2 * p.xs_buf_bytes / 16; i += TE_THREADS) reinterpret_cast<uint4*>(XS)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < TE_WST_BYTES / 16; i += TE_THREADS)
+    reinterpret_cast<uint4*>(WST)[i] = __ldg(reinterpret_cast<const uint4*>(p.Wst) + i);
+  // ring (the rows in front of the first tile are the zero rows before the first A-scan), im2col tiles, x staging pads
+  for (int i = tid; i < (TE_RING_BYTES + 2 * TE_XA_BYTES + p.xs_buf_bytes) / 16; i += TE_THREADS)
+    reinterpret_cast<uint4*>(RING)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 128) { pool_s[0][tid] = 0.f; pool_s[1][tid] = 0.f; }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t xs_base = smem_u32(XS), abuf_base = smem_u32(ABUF);
+  const uint32_t xs_base = smem_u32(XS), ring_base = smem_u32(RING), xa_base = smem_u32(XA);
   const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
   unsigned long long pt[4] = {0, 0, 0, 0};
 
   if (warp == TE_TMA_WARP) {
-    // ================= TMA producer: x of block i -> staging buffer i & 1 =================
+    // ================= TMA producer: x of block i -> the staging buffer =================
     if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
       for (int i = 0; i < nb_local; ++i) {
-        const int xb = i & 1;
-        if (i >= 2) mbar_wait_g<1000>(&x_empty[xb], ((i >> 1) - 1) & 1);       // every stem warp is done with block i - 2
-        mbar_expect_tx(&x_full[xb], (uint32_t)(TE_BLOCK_A * S * 2));
+        if (i >= 1) mbar_wait_g<500>(&x_empty, (i - 1) & 1);            // the im2col rows of block i - 1 are built
+        mbar_expect_tx(&x_full, (uint32_t)(TE_BLOCK_A * S * 2));
         const long long a0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TE_BLOCK_A;
-        const uint32_t dst0 = xs_base + (uint32_t)xb * p.xs_buf_bytes + TE_XPAD * 2;
+        const uint32_t dst0 = xs_base + TE_XPAD * 2;
 #pragma unroll 1
         for (int j = 0; j < TE_BLOCK_A; ++j)     // rows beyond the volume are zero-filled by the TMA unit
-          tma_load_2d(dst0 + (uint32_t)(j * p.xs_stride * 2), &tmap, 0, (int)((a0 + j) * p.rows_per_ascan), &x_full[xb]);
+          tma_load_2d(dst0 + (uint32_t)(j * p.xs_stride * 2), &tmap, 0, (int)((a0 + j) * p.rows_per_ascan), &x_full);
       }
     }
     __syncwarp();
   } else if (warp == TE_MMA_WARP) {
     // ================= MMA issuer =================
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(128, 32);
+    const uint32_t idesc2 = make_idesc_f16(128, 32), idesc_st = make_idesc_bf16(128, 128);
     const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
-    const uint32_t w_u = smem_u32(W2S) >> 4;                             // 16-byte units
-    for (int g = 0; g < nt_local; ++g) {
-      const int stage = g % TE_STAGES, acc = g & 1;
-      const uint32_t use = (uint32_t)(g / TE_STAGES);
-      const long long q0 = probe ? clock64() : 0;
-      if (g >= 2) mbar_wait_g<40>(&acc_empty[acc], ((g >> 1) - 1) & 1);      // the epilogue drained this accumulator
-      const long long q1 = probe ? clock64() : 0;
-      mbar_wait_g<40>(&full[stage], use & 1);                                // the stem rows of the tile are stored
-      const long long q2 = probe ? clock64() : 0;
-      if (leader) {
-        tc_fence_after();
-        const uint32_t a_u = (abuf_base + (uint32_t)stage * TE_STAGE_BYTES) >> 4;
-        auto branch = [&](int b, int K, int woff) {
-          const uint32_t d = tmem + (uint32_t)(acc * 128 + b * 32);
-          uint32_t accum = 0u;
-#pragma unroll
-          for (int t = 0; t < K; ++t) {
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              // A: rows (5 - K/2 + t) .. +127 of chunks (2ks, 2ks+1) of branch b;  B: [32 x 16] block of tap t
-              const uint32_t ad = ((a_u + (uint32_t)((b * 4 + ks * 2) * TE_BROWS + TE_PAD - K / 2 + t)) & 0x3FFFu) |
-                                  ((uint32_t)TE_BROWS << 16);
-              const uint32_t bd = ((w_u + (uint32_t)((woff + t) * 128 + ks * 64)) & 0x3FFFu) | (32u << 16);
-              mma_bf16_ss2(d, ad, desc_hi, bd, desc_hi, idesc, accum);
-              accum = 1u;
-            }
-          }
-        };
-        branch(0, 3, 0);
-        branch(1, 5, 3);
-        branch(2, 7, 8);
-        branch(3, 11, 15);
-        mma_commit(&empty[stage]);
-        mma_commit(&acc_full[acc]);
+    const uint32_t w_u = smem_u32(W2S) >> 4, wst_u = smem_u32(WST) >> 4, r_u = ring_base >> 4, xa_u = xa_base >> 4;   // 16-byte units
+    for (int g = 0; g <= nt + 1; ++g) {
+      if (g <= nt) {
+        // ---- stem MMA of tile g: [128 rows x 16 taps] x [16 taps x 128 channels]
+        const int b = g & 1;
+        mbar_wait_g<0>(&xa_full[b], (g >> 1) & 1);
+        if (g >= 2) mbar_wait_g<0>(&sacc_empty[b], ((g >> 1) - 1) & 1);
+        if (leader) {
+          tc_fence_after();
+          mma_bf16_ss2(tmem + (uint32_t)(TC_STEM + 128 * b), ((xa_u + (uint32_t)(b * (TE_XA_BYTES / 16))) & 0x3FFFu) | (128u << 16), desc_hi,
+                       (wst_u & 0x3FFFu) | (128u << 16), desc_hi, idesc_st, 0u);
+          mma_commit(&xa_empty[b]);
+          mma_commit(&sacc_full[b]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      if (probe) { const long long q3 = clock64(); pt[0] += q1 - q0; pt[1] += q2 - q1; pt[2] += q3 - q2; pt[3] += 1; }
+      if (g >= 2) {
+        // ---- second convolutions of tile u: its window reaches 5 rows into tiles u - 1 and u + 1
+        const int u = g - 2, slot = u & (TE_SLOTS - 1), acc = u & 1;
+        const long long q0 = probe ? clock64() : 0;
+        mbar_wait_g<0>(&ring_full[(u + 1) & (TE_SLOTS - 1)], ((u + 1) >> 2) & 1);
+        const long long q1 = probe ? clock64() : 0;
+        if (u >= 2) mbar_wait_g<0>(&acc_empty[acc], ((u >> 1) - 1) & 1);    // the epilogue drained this accumulator
+        const long long q2 = probe ? clock64() : 0;
+        if (leader) {
+          tc_fence_after();
+          const uint32_t a_u = r_u + (uint32_t)(TE_MIRROR + 128 * slot);       // ring row of the tile's first output row
+          auto branch = [&](int b, int K, int woff) {
+            const uint32_t d = tmem + (uint32_t)(TC_ACC + acc * 128 + b * 32);
+            uint32_t accum = 0u;
+#pragma unroll
+            for (int t = 0; t < K; ++t) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                // A: rows (t - K/2) .. +127 of chunks (2ks, 2ks+1) of branch b;  B: [32 x 16] block of tap t
+                const uint32_t ad = ((a_u + (uint32_t)((b * 4 + ks * 2) * TE_RROWS + t - K / 2)) & 0x3FFFu) | ((uint32_t)TE_RROWS << 16);
+                const uint32_t bd = ((w_u + (uint32_t)((woff + t) * 128 + ks * 64)) & 0x3FFFu) | (32u << 16);
+                mma_bf16_ss2(d, ad, desc_hi, bd, desc_hi, idesc2, accum);
+                accum = 1u;
+              }
+            }
+          };
+          branch(0, 3, 0);
+          branch(1, 5, 3);
+          branch(2, 7, 8);
+          branch(3, 11, 15);
+          mma_commit(&acc_full[acc]);
+          mma_commit(&ring_empty[(u + TE_SLOTS - 1) & (TE_SLOTS - 1)]);        // tile u - 1 has no reader left
+        }
+        __syncwarp();
+        if (probe) { const long long q3 = clock64(); pt[0] += q1 - q0; pt[1] += q2 - q1; pt[2] += q3 - q2; pt[3] += 1; }
+      }
     }
     if (probe) { p.dbg[0] = pt[0]; p.dbg[1] = pt[1]; p.dbg[2] = pt[2]; p.dbg[3] = pt[3]; }
   } else if (warp >= TE_STEM_WARP0) {
-    // ================= stem warps =================
-    const int sw = warp - TE_STEM_WARP0, c = sw & 3;
-    unsigned long long* sd = probe && (sw == 0 || sw == 4) ? p.dbg + 16 + 2 * sw : nullptr;
-    if (sw < 4) stem_loop<11, 15, 3, 3, 0, 0>(p, c, lane, nt_local, xs_base, abuf_base, full, empty, x_full, x_empty, sd);
-    else stem_loop<7, 8, 2, 5, 3, 1>(p, c, lane, nt_local, xs_base, abuf_base, full, empty, x_full, x_empty, sd);
-  } else {
+    // ================= stem group: thread = row i of the tile =================
+    const int qw = warp - TE_STEM_WARP0;
+    const int i = qw * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(qw * 32) << 16;
+    // stem accumulator of tile u -> relu -> fp16 rows of ring slot u % 4 (+ the mirrored rows at the ring's ends)
+    auto stem_epilogue = [&](int u) {
+      const int b = u & 1, slot = u & (TE_SLOTS - 1), lap = u >> 2;
+      const long long s0 = probe ? clock64() : 0;
+      mbar_wait_g<40>(&sacc_full[b], (u >> 1) & 1);
+      // the slot's previous tile (u - 4) was last read by the MMAs of tile u - 3; slot 3 also owns the mirrored rows
+      // in front of the ring, which tile 0 reads as its zero rows: ring_empty[3] carries an extra first phase
+      if (slot == TE_SLOTS - 1) mbar_wait_g<100>(&ring_empty[slot], lap & 1);
+      else if (lap >= 1) mbar_wait_g<100>(&ring_empty[slot], (lap - 1) & 1);
+      const long long s1 = probe ? clock64() : 0;
+      tc_fence_after();
+      const uint32_t row = ring_base + (uint32_t)(TE_MIRROR + 128 * slot + i) * 16;
+      const bool mir_hi = slot == 0 && i < TE_MIRROR;                      // first rows of the ring -> behind its end
+      const bool mir_lo = slot == TE_SLOTS - 1 && i >= 128 - TE_MIRROR;    // last rows of the ring -> in front of it
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tmem + t_lane + (uint32_t)(TC_STEM + 128 * b + 32 * cc), r);
+        if (cc == 3) {                                                     // accumulator drained
+          tc_fence_before();
+          warp_arrive(&sacc_empty[b], lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = relu_pack_f16(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1]));
+          const uint32_t a = row + (uint32_t)((4 * cc + j) * TE_LBO_R);
+          st_shared_v4(a, w[0], w[1], w[2], w[3]);
+          if (mir_hi) st_shared_v4(a + TE_SLOTS * 128 * 16, w[0], w[1], w[2], w[3]);
+          if (mir_lo) st_shared_v4(a - TE_SLOTS * 128 * 16, w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_async_smem();                                                  // generic-proxy stores -> tensor-core operand reads
+      warp_arrive(&ring_full[slot], lane);
+      if (probe && qw == 0) { pt[0] += s1 - s0; pt[1] += clock64() - s1; pt[2] += 1; }
+    };
+    int a_loc = 0, l = i;                                                  // row i of tile T of the block: A-scan, position
+    int cur_blk = -1;
+    for (int t = 0; t <= nt; ++t) {
+      const int i_blk = t / tpb, T = t - i_blk * tpb;
+      const int b = t & 1;
+      bool valid = false;
+      uint32_t xa = 0;
+      if (t < nt) {
+        if (i_blk != cur_blk) {
+          cur_blk = i_blk;
+          a_loc = 0; l = i;                                                // (Lp >= 136: the first 128 rows are A-scan 0)
+          mbar_wait_g<200>(&x_full, i_blk & 1);
+        }
+        const long long a_blk = ((long long)blockIdx.x + (long long)i_blk * gridDim.x) * TE_BLOCK_A;
+        valid = l < S && a_blk + a_loc < p.A;
+        xa = xs_base + (uint32_t)(TE_XPAD + a_loc * p.xs_stride + l - TE_PAD) * 2;
+      }
+      // ---- im2col row: taps 0..10 = x[l-5 .. l+5] (bf16 as stored), taps 11, 12 = 1.0 (BN shift hi + lo), rest 0
+      uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (valid) {
+        uint16_t h[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h[k]) : "r"(xa + 2 * k) : "memory");
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k] = (uint32_t)h[2 * k] | ((uint32_t)h[2 * k + 1] << 16);
+        w[5] = (uint32_t)h[10] | 0x3F800000u;
+        w[6] = 0x00003F80u;
+      }
+      if (t >= 2) mbar_wait_g<40>(&xa_empty[b], ((t >> 1) - 1) & 1);        // the stem MMA of tile t - 2 has read the buffer
+      const uint32_t dst = xa_base + (uint32_t)(b * TE_XA_BYTES + i * 16);
+      st_shared_v4(dst, w[0], w[1], w[2], w[3]);
+      st_shared_v4(dst + 128 * 16, w[4], w[5], w[6], w[7]);
+      fence_async_smem();
+      warp_arrive(&xa_full[b], lane);
+      if (t < nt) {
+        if (T == tpb - 1) warp_arrive(&x_empty, lane);                     // the block's x has been read
+        l += 128;                                                          // the same row of the next tile
+        if (l >= Lp) { l -= Lp; ++a_loc; }
+      }
+      if (t >= 1) stem_epilogue(t - 1);
+    }
+    stem_epilogue(nt);
+    if (probe && qw == 0) { p.dbg[16] = pt[0]; p.dbg[17] = pt[1]; p.dbg[18] = pt[2]; }
+  } else if (warp < TE_EPI_WARPS) {
     // ================= epilogue: warp = (TMEM lane quarter q, column half hf) =================
     // A thread holds 4 rows x 8 columns of every 32-column chunk (16x256b loads): + BN shift, ReLU, the 4 rows are
     // added locally, then a 3-level transposing butterfly over the 8 lanes that hold the same columns leaves ONE
@@ -371,24 +381,28 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         shv[cc][2 * j + 1] = __ldg(p.shift2 + 64 * hf + 32 * cc + 8 * j + 2 * t4 + 1);
       }
     const int my_col = 8 * (i8 >> 1) + 2 * t4 + (i8 & 1);
-    for (int g = 0; g < nt_local; ++g) {
+    // transposing butterfly over the lanes with equal lane % 4 (xor 16, 8, 4): 8 values -> 1
+    auto bfly = [&](float (&v)[8]) {
+#pragma unroll
+      for (int m = 4; m >= 1; m >>= 1) {
+        const bool hi = (lane & (4 * m)) != 0;
+#pragma unroll
+        for (int k = 0; k < m; ++k) {
+          const float keep = hi ? v[m + k] : v[k];
+          const float send = hi ? v[k] : v[m + k];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4 * m);
+        }
+      }
+    };
+    int a_first = 0, l0 = 0;                           // geometry of the tile: first A-scan, its position at the first row
+    for (int g = 0; g < nt; ++g) {
       const int i_blk = g / tpb, T = g - i_blk * tpb;
       const int acc = g & 1;
+      if (T == 0) { a_first = 0; l0 = 0; }
       const long long a_blk = ((long long)blockIdx.x + (long long)i_blk * gridDim.x) * TE_BLOCK_A;
-      // geometry of the tile: first A-scan, its position at the tile's first row; a second A-scan starts at row Lp - l0
-      const int t0 = 128 * T;
-      const int a_first = (int)((unsigned)t0 / (unsigned)Lp), l0 = t0 - a_first * Lp;
       // the warp's 32 rows are all signal rows of the first A-scan (warp-uniform, the common case)
       const bool uni0 = l0 + 32 * q + 31 < S && a_blk + a_first < p.A;
-      bool m0[4], m1[4];                               // rows i8 + 8k of the quarter: valid row of segment 0 / 1
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int lr = l0 + 32 * q + i8 + 8 * k;
-        const int seg = lr >= Lp ? 1 : 0, l = lr - seg * Lp;
-        const bool valid = l < S && a_blk + a_first + seg < p.A;
-        m0[k] = valid && seg == 0;
-        m1[k] = valid && seg == 1;
-      }
+      const bool uni1 = l0 + 32 * q >= Lp && l0 + 32 * q + 31 - Lp < S && a_blk + a_first + 1 < p.A;   // ... of the second one
       const long long e0 = probe ? clock64() : 0;
       mbar_wait_g<60>(&acc_full[acc], (g >> 1) & 1);
       const long long e1 = probe ? clock64() : 0;
@@ -397,50 +411,52 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t ra[16], rb[16];
-        const uint32_t col = (uint32_t)(acc * 128 + 64 * hf + 32 * cc);
+        const uint32_t col = (uint32_t)(TC_ACC + acc * 128 + 64 * hf + 32 * cc);
         tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32) << 16) + col, ra);          // rows i8, i8 + 8
         tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32 + 16) << 16) + col, rb);     // rows i8 + 16, i8 + 24
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (cc == 1) {                                                   // accumulator drained: tile g + 2 may start
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          warp_arrive(&acc_empty[acc], lane);
         }
-        float s0[8], s1[8];
+        float s0[8];
+        if (uni0 || uni1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float sh = shv[cc][2 * j + e];
-            const float v0 = fmaxf(__uint_as_float(ra[4 * j + e]) + sh, 0.f), v1 = fmaxf(__uint_as_float(ra[4 * j + 2 + e]) + sh, 0.f);
-            const float v2 = fmaxf(__uint_as_float(rb[4 * j + e]) + sh, 0.f), v3 = fmaxf(__uint_as_float(rb[4 * j + 2 + e]) + sh, 0.f);
-            if (uni0) {
-              s0[2 * j + e] = (v0 + v1) + (v2 + v3);
-              s1[2 * j + e] = 0.f;
-            } else {
-              s0[2 * j + e] = ((m0[0] ? v0 : 0.f) + (m0[1] ? v1 : 0.f)) + ((m0[2] ? v2 : 0.f) + (m0[3] ? v3 : 0.f));
-              s1[2 * j + e] = ((m1[0] ? v0 : 0.f) + (m1[1] ? v1 : 0.f)) + ((m1[2] ? v2 : 0.f) + (m1[3] ? v3 : 0.f));
+            for (int e = 0; e < 2; ++e) {
+              const float sh = shv[cc][2 * j + e];
+              s0[2 * j + e] = (fmaxf(__uint_as_float(ra[4 * j + e]) + sh, 0.f) + fmaxf(__uint_as_float(ra[4 * j + 2 + e]) + sh, 0.f)) +
+                              (fmaxf(__uint_as_float(rb[4 * j + e]) + sh, 0.f) + fmaxf(__uint_as_float(rb[4 * j + 2 + e]) + sh, 0.f));
             }
-          }
-        // transposing butterfly over the lanes with equal lane % 4 (xor 16, 8, 4): 8 values -> 1
-        auto bfly = [&](float (&v)[8]) {
-#pragma unroll
-          for (int m = 4; m >= 1; m >>= 1) {
-            const bool hi = (lane & (4 * m)) != 0;
-#pragma unroll
-            for (int i = 0; i < m; ++i) {
-              const float keep = hi ? v[m + i] : v[i];
-              const float send = hi ? v[i] : v[m + i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4 * m);
-            }
-          }
-        };
-        bfly(s0);
-        pq[32 * cc + my_col] = s0[0];
-        if (uni0) {
-          pq[128 + 32 * cc + my_col] = 0.f;
+          bfly(s0);
+          pq[32 * cc + my_col] = uni0 ? s0[0] : 0.f;
+          pq[128 + 32 * cc + my_col] = uni0 ? 0.f : s0[0];
         } else {
+          // rows i8 + 8k of the quarter: valid row of the first / of a second A-scan (or a zero row between them)
+          float f0[4], f1[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int lr = l0 + 32 * q + i8 + 8 * k;
+            const int seg = lr >= Lp ? 1 : 0, l = lr - seg * Lp;
+            const bool valid = l < S && a_blk + a_first + seg < p.A;
+            f0[k] = valid && seg == 0 ? 1.f : 0.f;
+            f1[k] = valid && seg == 1 ? 1.f : 0.f;
+          }
+          float s1[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float sh = shv[cc][2 * j + e];
+              const float v0 = fmaxf(__uint_as_float(ra[4 * j + e]) + sh, 0.f), v1 = fmaxf(__uint_as_float(ra[4 * j + 2 + e]) + sh, 0.f);
+              const float v2 = fmaxf(__uint_as_float(rb[4 * j + e]) + sh, 0.f), v3 = fmaxf(__uint_as_float(rb[4 * j + 2 + e]) + sh, 0.f);
+              s0[2 * j + e] = (f0[0] * v0 + f0[1] * v1) + (f0[2] * v2 + f0[3] * v3);
+              s1[2 * j + e] = (f1[0] * v0 + f1[1] * v1) + (f1[2] * v2 + f1[3] * v3);
+            }
+          bfly(s0);
           bfly(s1);
+          pq[32 * cc + my_col] = s0[0];
           pq[128 + 32 * cc + my_col] = s1[0];
         }
       }
@@ -464,13 +480,15 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
           pool_s[par0 ^ 1][c] += s;                                      // (S >= 128: a second A-scan cannot end here)
         }
       }
+      l0 += 128;                                                         // next tile (Lp >= 136: at most one A-scan further)
+      if (l0 >= Lp) { l0 -= Lp; ++a_first; }
       if (probe) { pt[0] += e1 - e0; pt[1] += clock64() - e1; pt[2] += 1; }
     }
     if (probe && warp == 0) { p.dbg[8] = pt[0]; p.dbg[9] = pt[1]; p.dbg[10] = pt[2]; }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 uint16_t f2h_bits(float f) {
@@ -499,23 +517,38 @@ EncodeTiledFn encode_tiled() {
 
 }  // namespace
 
-bool ts_encoder_supported(int S, int d_model) { return d_model == 128 && S % 16 == 0 && S >= 128 && S <= 512; }
+bool ts_encoder_supported(int S, int d_model) { return d_model == 128 && S % 16 == 0 && S >= 128 && S <= 448; }
+
+uint16_t f2bf_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+float bf2f_bits(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 
 // Host-side packing (BatchNorm already folded by the caller):
-//   w1[b]: [k_b][32] stem weights, sh1[b]: [32];  w2[b]: [k_b][32 in][32 out], sh2: [128]
-void ts_encoder_pack(const float* const* w1, const float* const* sh1, const float* const* w2, std::vector<uint32_t>& sw,
-                     std::vector<uint32_t>& sb, std::vector<uint16_t>& W2) {
+//   w1[b]: [k_b][32] stem weights, sh1[b]: [32];  w2[b]: [k_b][32 in][32 out]
+//   Wst: the stem as a [128 x 16] bf16 B operand ([2 chunks][128 rows][8]): row 32 b + co, K index = window tap
+//        (branch b's k_b taps centred in the 11-tap window), taps 11 / 12 = hi / lo halves of the folded shift
+//   W2 : fp16 [26 (branch, tap)][4 chunks][32 rows (co)][8 (ci)]
+void ts_encoder_pack(const float* const* w1, const float* const* sh1, const float* const* w2, std::vector<uint16_t>& Wst,
+                     std::vector<uint16_t>& W2) {
   const int taps[4] = {3, 5, 7, 11};
-  sw.assign(TE_NTAPS * 16, 0);
-  sb.assign(4 * 16, 0);
+  Wst.assign((size_t)2 * 128 * 8, 0);
   W2.assign((size_t)TE_NTAPS * 4 * 32 * 8, 0);
+  auto st = [&](int n, int k) -> uint16_t& { return Wst[((size_t)(k >> 3) * 128 + n) * 8 + (k & 7)]; };
   int woff = 0;
   for (int b = 0; b < 4; ++b) {
-    for (int j = 0; j < 16; ++j) {
-      sb[b * 16 + j] = (uint32_t)f2h_bits(sh1[b][2 * j]) | ((uint32_t)f2h_bits(sh1[b][2 * j + 1]) << 16);
-      for (int t = 0; t < taps[b]; ++t)
-        sw[(woff + t) * 16 + j] =
-            (uint32_t)f2h_bits(w1[b][t * 32 + 2 * j]) | ((uint32_t)f2h_bits(w1[b][t * 32 + 2 * j + 1]) << 16);
+    for (int co = 0; co < 32; ++co) {
+      for (int t = 0; t < taps[b]; ++t) st(32 * b + co, TE_PAD - taps[b] / 2 + t) = f2bf_bits(w1[b][t * 32 + co]);
+      const uint16_t hi = f2bf_bits(sh1[b][co]);
+      st(32 * b + co, 11) = hi;
+      st(32 * b + co, 12) = f2bf_bits(sh1[b][co] - bf2f_bits(hi));
     }
     for (int t = 0; t < taps[b]; ++t)
       for (int ci = 0; ci < 32; ++ci)
@@ -525,13 +558,12 @@ void ts_encoder_pack(const float* const* w1, const float* const* sh1, const floa
   }
 }
 
-void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t* sw_dev, const uint32_t* sb_dev,
-                   const void* W2, const float* shift2, float* feat) {
+void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const void* Wst, const void* W2, const float* shift2, float* feat) {
   if (c.dry) return;
   PAUT_CHECK(ts_encoder_supported(S, 128), PAUT_ERR_UNSUPPORTED, "two-stage encoder: unsupported signal length");
   PAUT_CHECK((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, PAUT_ERR_INVALID, "two-stage encoder: x must be 16-byte aligned");
   TsEncArgs p;
-  p.sw = sw_dev; p.sb = sb_dev;
+  p.Wst = static_cast<const __nv_bfloat16*>(Wst);
   p.W2 = static_cast<const __half*>(W2); p.shift2 = shift2; p.feat = feat;
   p.A = A; p.nblk = (A + TE_BLOCK_A - 1) / TE_BLOCK_A;
   p.S = S; p.Lp = S + TE_HALO; p.tpb = TE_BLOCK_A * p.Lp / 128;
@@ -552,7 +584,7 @@ void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t*
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PAUT_CHECK(r == CUDA_SUCCESS, PAUT_ERR_CUDA, "cuTensorMapEncodeTiled failed (two-stage encoder input)");
-  const size_t smem = (size_t)TE_W2_BYTES + (size_t)TE_STAGES * TE_STAGE_BYTES + 2 * (size_t)p.xs_buf_bytes;
+  const size_t smem = (size_t)TE_W2_BYTES + TE_WST_BYTES + TE_RING_BYTES + 2 * TE_XA_BYTES + (size_t)p.xs_buf_bytes;
   smem_optin(c, k_ts_encoder);
   cudaFuncAttributes fa;
   PAUT_CUDA(cudaFuncGetAttributes(&fa, k_ts_encoder));
@@ -567,10 +599,10 @@ void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const uint32_t*
     PAUT_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
     auto per = [](unsigned long long v, unsigned long long n) { return n ? v / n : 0ull; };
-    fprintf(stderr, "[ts probe] per tile (CTA 0, %llu tiles) | mma: wait_acc_empty %llu wait_full %llu issue %llu | "
-                    "epilogue w0: wait_acc_full %llu work %llu | stem w0 (k11+k3): wait %llu work %llu | stem w4 (k7+k5): wait %llu work %llu\n",
+    fprintf(stderr, "[ts probe] per tile (CTA 0, %llu tiles) | mma: wait_ring_full %llu wait_acc_empty %llu issue %llu | "
+                    "epilogue w0: wait_acc_full %llu work %llu | stem group w0, stem epilogue: wait %llu work %llu\n",
             h[3], per(h[0], h[3]), per(h[1], h[3]), per(h[2], h[3]), per(h[8], h[10]), per(h[9], h[10]), per(h[16], h[18]),
-            per(h[17], h[18]), per(h[24], h[26]), per(h[25], h[26]));
+            per(h[17], h[18]));
   }
   c.launched("ts_encoder");
 }

@@ -29,7 +29,7 @@ def two_stage_features(sd, x):
 
 
 @pytest.mark.parametrize("B,N,S", [(1, 1, 320), (1, 16, 320), (1, 17, 320), (3, 50, 320), (7, 37, 320), (40, 50, 320),
-                                   (2, 50, 128), (2, 33, 256), (1, 40, 512), (2, 50, 336)])
+                                   (2, 50, 128), (2, 33, 256), (1, 40, 448), (2, 50, 336)])
 def test_two_stage_fused_encoder_features(B, N, S):
     """k_ts_encoder (TMA staging, HFMA2 stems, tcgen05 second convolutions, pooled epilogue) against fp64.
     fp16 stems and fp16 operands of the second convolution: the pooled means agree to ~1e-3 relative."""
