@@ -169,3 +169,96 @@ def sequence_targets(sequences):
                     pos[w, i] = (a["bbox"][2], a["bbox"][3])
                     break
     return signals, label, pos, label_map, [s["file_name"] for s in sequences], [s["scan_key"] for s in sequences]
+
+
+# ------------------------------------------------------------------------------------------------ f1: training-side preparation
+def json_scan_annotations(path):
+    """The annotation half of SignalSequencePreparation.get_datafile_sequences (SignalSequenceDetection/
+    dataset_preparation.py:53-116): per scan key the list of defects {"bbox": [beam_first, beam_last, start, end],
+    "label"}, where a defect seen in consecutive beams with the same (start, end) extends the last entry instead of
+    opening a new one (:85-91), 'Health' scans only create an empty list (:71-73) and a key whose range does not
+    parse is reported and skipped (:99-101).  Returns (OrderedDict sorted by int(scan_key), (beam_start, beam_end))."""
+    from collections import OrderedDict
+    beams = load_json_volume(path, with_keys=True)
+    order = sorted(range(len(beams)), key=lambda i: float(beams[i]["key"].split("_")[1]))
+    beam_start = float(beams[order[0]]["key"].split("_")[1])
+    beam_end = float(beams[order[-1]]["key"].split("_")[1])
+    ann = {}
+    for b in order:
+        beam_idx = float(beams[b]["key"].split("_")[1])
+        for scan_file in beams[b]["scan_keys"]:
+            parts = scan_file.split("_")
+            scan_key = parts[0]
+            if parts[1] == "Health":
+                ann.setdefault(scan_key, [])
+                continue
+            try:
+                rng = parts[-1].split("-")
+                d0, d1 = float(rng[0]), float(rng[1])
+            except Exception as ex:                                  # noqa: BLE001 -- the reference catches everything here
+                print(f"Error: {ex} in {os.path.splitext(os.path.basename(path))[0]}, {beams[b]['key']}, {scan_file}")
+                continue
+            cur = ann.get(scan_key)
+            if not cur:
+                ann[scan_key] = [{"bbox": [beam_idx, beam_idx, d0, d1], "label": parts[1]}]
+            else:
+                last = cur[-1]["bbox"]
+                if last[2] == d0 and last[3] == d1 and last[1] == beam_idx - 1:
+                    last[1] += 1
+                else:
+                    cur.append({"bbox": [beam_idx, beam_idx, d0, d1], "label": parts[1]})
+    return OrderedDict(sorted(ann.items(), key=lambda kv: int(kv[0]))), (beam_start, beam_end)
+
+
+def normalize_annotations(annotations, beam_lims):
+    """dataset_preparation.py:118-152: beam positions -> [0, 1] over the file's beam range, defect range unchanged."""
+    b0, b1 = beam_lims
+    span = b1 - b0
+    return {k: [{"bbox": [(d["bbox"][0] - b0) / span, (d["bbox"][1] - b0) / span, d["bbox"][2], d["bbox"][3]],
+                 "label": d["label"]} for d in v] for k, v in annotations.items()}
+
+
+def window_has_objects(annotations, start_idx, end_idx, num_signals):
+    """The defect-only window filter of create_beam_sequences (dataset_preparation.py:255-268, :283-296): a window is
+    kept iff for some defect some signal position i / num_signals of the window lies in its beam range.  Closed
+    form of the reference's double loop (same float arithmetic: i / num_signals in fp64, inclusive bounds)."""
+    for d in annotations:
+        lo, hi = d["bbox"][0], d["bbox"][1]
+        for i in range(start_idx, end_idx):
+            if lo <= i / num_signals <= hi:
+                return True
+    return False
+
+
+def prepare_beam_sequences(all_sequences, all_annotations, seq_length=50):
+    """SignalSequencePreparation.create_beam_sequences (dataset_preparation.py:188-313) on host index arithmetic:
+    all_sequences {file: {scan_key: float [n, S]}}, all_annotations {file: {scan_key: [defect]}} (normalised) ->
+    the reference's list of sequence dicts (same keys, same order).  All-zero runs and runs without defects are
+    skipped, short runs are zero-padded (``original_length``), long runs are cut with the overlapping-window rule
+    (``runtime.window_table('ssd', n, seq_length)``) and only windows that contain a defect are kept."""
+    from .runtime import window_table
+    out = []
+    for file_name, sequences in all_sequences.items():
+        for scan_key, signals in sequences.items():
+            signals = np.asarray(signals)
+            if np.all(signals == 0):
+                continue
+            annotations = all_annotations[file_name].get(scan_key, [])
+            if len(annotations) == 0:
+                continue
+            n = len(signals)
+            if n < seq_length:
+                padded = np.zeros((seq_length, signals.shape[1]), dtype=signals.dtype)
+                padded[:n] = signals
+                out.append({"file_name": file_name, "scan_key": scan_key, "signals": padded, "annotations": annotations,
+                            "original_length": n, "has_objects": True})
+            elif n == seq_length:
+                out.append({"file_name": file_name, "scan_key": scan_key, "signals": signals, "annotations": annotations,
+                            "has_objects": True})
+            else:
+                for start, _ in window_table("ssd", n, seq_length):
+                    if window_has_objects(annotations, start, start + seq_length, n):
+                        out.append({"file_name": file_name, "scan_key": scan_key, "signals": signals[start:start + seq_length],
+                                    "annotations": annotations, "start_idx": start, "end_idx": start + seq_length,
+                                    "has_objects": True})
+    return out

@@ -2,6 +2,7 @@
 
     python tests/golden/make_golden.py            # needs /root/reference
     python tests/golden/make_golden.py --only msc_legacy,improved,hybrid,complex   # add kinds, keep the rest
+    python tests/golden/make_golden.py --bf16     # tests/golden/bf16/: the reference classes on bf16-rounded weights / inputs
 
 For every hot-path model it imports the reference class from /root/reference,
 loads the synthetic weights of oracle/synth.py with a strict load_state_dict,
@@ -297,9 +298,124 @@ def metrics_vectors():
     print("wrote metrics_vectors.npz", out["rule0_counts"].tolist(), out["rule1_counts"].tolist(), conf, healthy)
 
 
+# bf16-mode goldens: the REFERENCE classes (fp32 arithmetic) on bf16-rounded inputs and matrix weights -- the target the
+# library's bf16 mode is held to at 1e-2.  One case per kind, plus a 100 k-decision MSC case for the
+# defect-flag agreement rate.
+BF16_CASES = [
+    ("msc", "p4x300", dict(), dict(gen="paut", B=4, N=300, S=320, seed=21)),
+    ("msc", "p334x300", dict(), dict(gen="paut", B=334, N=300, S=320, seed=22)),
+    ("msc_n", "p3x170", dict(), dict(gen="paut", B=3, N=170, S=320, seed=23)),
+    ("conv1d_msc", "p2x300", dict(), dict(gen="paut", B=2, N=300, S=320, seed=24, transpose=True)),
+    ("ssd", "p6x50", dict(), dict(gen="paut", B=6, N=50, S=320, seed=25)),
+    ("enhanced", "p3x50", dict(), dict(gen="paut", B=3, N=50, S=320, seed=26)),
+    ("two_stage", "p8x50", dict(), dict(gen="paut", B=8, N=50, S=320, seed=27)),
+    ("two_stage", "p3x37", dict(), dict(gen="paut", B=3, N=37, S=320, seed=28)),
+    ("msc_legacy", "p3x298", dict(), dict(gen="paut", B=3, N=298, S=320, seed=29)),
+    ("improved", "p3x300", dict(), dict(gen="paut", B=3, N=300, S=320, seed=30)),
+    ("hybrid", "p3x300", dict(), dict(gen="paut", B=3, N=300, S=320, seed=31)),
+    ("complex", "p3x300", dict(), dict(gen="paut", B=3, N=300, S=320, seed=32)),
+]
+
+
+def bf16_round_state_dict(sd):
+    """The rounding rule of the bf16 mode (oracle/models.py:_prep): every floating-point tensor with >= 2 dimensions
+    except the positional tables is a matrix operand and is rounded to bf16; vectors (biases, norms, BN) stay fp32."""
+    return {k: (v.to(torch.bfloat16).float() if (v.is_floating_point() and v.dim() >= 2 and not k.endswith(".pe")
+                                                 and "encoding" not in k) else v) for k, v in sd.items()}
+
+
+def bf16_goldens():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    classes = reference_classes()
+    out_dir = os.path.join(HERE, "bf16")
+    os.makedirs(out_dir, exist_ok=True)
+    for kind, case, cfg, spec in BF16_CASES:
+        model = classes[kind](**cfg)
+        sd = bf16_round_state_dict(synth.synth_state_dict(kind, seed=0))
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        x_np = make_input(spec)
+        x = torch.from_numpy(x_np).to(torch.bfloat16).float()
+        outs = []
+        with torch.no_grad():
+            for b0 in range(0, x.shape[0], 16):                       # chunks bound the conv activations
+                outs.append(flatten_outputs(kind, model(x[b0:b0 + 16])))
+        flat = {}
+        for k in outs[0]:
+            dim = 1 if k == "attention_weights" else 0                # [layers, B, N, N] stacks along B = dim 1
+            flat[k] = torch.cat([o[k] for o in outs], dim=dim).numpy().astype(np.float32)
+        meta = dict(kind=kind, case=case, cfg=cfg, input=spec, input_sha256=hashlib.sha256(x_np.tobytes()).hexdigest(),
+                    rounding="inputs and matrix weights rounded to bf16, reference class in fp32", torch=torch.__version__)
+        save = {"out__" + k: v for k, v in flat.items()}
+        save["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        path = os.path.join(out_dir, f"{kind}__{case}.npz")
+        np.savez_compressed(path, **save)
+        print(f"wrote {path}: {[(k, v.shape) for k, v in flat.items()]}")
+
+
+def prep_vectors():
+    """f1: the reference's own SignalSequencePreparation (get_datafile_sequences -> normalize_annotations ->
+    create_beam_sequences, matplotlib / tqdm stubbed) on a synthetic multi-beam JSON volume with defects that span
+    consecutive beams, change range, reappear after a gap, an unparsable range and an all-zero run."""
+    import tempfile
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+    sys.modules.setdefault("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot"))
+    sys.path.insert(0, os.path.join(REF, "SignalSequenceDetection"))
+    from dataset_preparation import SignalSequencePreparation
+    rng = np.random.default_rng(99)
+    nb, S = 140, 6
+    data = {}
+    for b in range(nb):
+        scans = {}
+        for scan in range(5):
+            sig = [float(np.float32(v)) for v in rng.random(S)]
+            if scan == 0:
+                key = f"{scan}_Health"                                              # never a defect
+            elif scan == 1:
+                key = f"{scan}_Crack_0.25-0.5" if 30 <= b < 60 else f"{scan}_Health"    # one defect over consecutive beams
+            elif scan == 2:
+                # same beams, the range changes at beam 50 (new defect), reappears after a gap at 100..104
+                key = (f"{scan}_Pore_0.125-0.375" if 40 <= b < 50 else f"{scan}_Pore_0.5-0.75" if 50 <= b < 58
+                       else f"{scan}_Pore_0.5-0.75" if 100 <= b < 105 else f"{scan}_Health")
+            elif scan == 3:
+                key = f"{scan}_Crack_bad-range" if b == 7 else (f"{scan}_Crack_0.0-1.0" if b in (8, 9, 11) else f"{scan}_Health")
+                if b >= 20:
+                    continue                                                         # a short run (20 beams): zero-padded
+            else:
+                sig = [0.0] * S                                                      # all-zero run with a defect label: dropped
+                key = f"{scan}_Crack_0.25-0.5"
+            scans[key] = sig
+        data[f"Beam_{b}"] = scans
+    out_dir = os.path.join(HERE, "prep_volume")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "weld.json"), "w") as f:
+        json.dump(data, f)
+    with tempfile.TemporaryDirectory() as tmp:
+        prep = SignalSequencePreparation(out_dir, tmp, seq_length=50)
+        seq, ann, blims = prep.get_datafile_sequences("weld.json")
+        ann_n = prep.normalize_annotations(ann, blims)
+        prep.all_sequences["weld"] = seq
+        prep.all_annotations["weld"] = ann_n
+        seqs = prep.create_beam_sequences()
+    expected = {"annotations": {k: v for k, v in ann.items()}, "beam_lims": list(blims), "normalized": ann_n,
+                "sequences": [{"scan_key": s["scan_key"], "start_idx": s.get("start_idx"), "end_idx": s.get("end_idx"),
+                               "original_length": s.get("original_length"),
+                               "sha256": hashlib.sha256(np.ascontiguousarray(s["signals"], dtype=np.float64).tobytes()).hexdigest()}
+                              for s in seqs]}
+    with open(os.path.join(out_dir, "expected.json"), "w") as f:
+        json.dump(expected, f, indent=0, sort_keys=True)
+    print("wrote prep_volume:", {k: len(v) for k, v in ann.items()}, len(seqs), "sequences")
+
+
 def main():
     if "--metrics" in sys.argv:
         metrics_vectors()
+        return
+    if "--prep" in sys.argv:
+        prep_vectors()
+        return
+    if "--bf16" in sys.argv:
+        bf16_goldens()
         return
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))

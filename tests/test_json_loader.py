@@ -138,3 +138,33 @@ def test_sequence_targets_match_reference_dataset():
     assert [f"{k}={v}" for k, v in label_map.items()] == [str(s) for s in z["label_map"]]
     assert label_map["Health"] == len(label_map) - 1 and (label[3] == label_map["Health"]).all()
     assert keys == [str(i) for i in range(7)] and files[:2] == ["f0", "f1"]
+
+
+def test_annotation_merging_and_defect_only_windows_match_reference():
+    """f1 remainder: json_scan_annotations / normalize_annotations / prepare_beam_sequences against the reference's
+    SignalSequencePreparation run on the same file (tests/golden/make_golden.py --prep; dataset_preparation.py:70-100,
+    118-152, 188-313)."""
+    import hashlib
+    pdir = os.path.join(GOLDEN_DIR, "prep_volume")
+    with open(os.path.join(pdir, "expected.json")) as f:
+        exp = json.load(f)
+    path = os.path.join(pdir, "weld.json")
+    ann, lims = dataio.json_scan_annotations(path)
+    assert list(ann.keys()) == sorted(exp["annotations"], key=int)
+    assert {k: v for k, v in ann.items()} == exp["annotations"]              # merged ranges, labels, order
+    assert list(lims) == exp["beam_lims"]
+    norm = dataio.normalize_annotations(ann, lims)
+    assert norm == exp["normalized"]                                          # same fp64 arithmetic: exact
+    seqs = dataio.json_scan_sequences(path)
+    got = dataio.prepare_beam_sequences({"weld": seqs}, {"weld": norm}, seq_length=50)
+    assert len(got) == len(exp["sequences"])
+    for g, e in zip(got, exp["sequences"]):
+        assert g["scan_key"] == e["scan_key"]
+        assert g.get("start_idx") == e["start_idx"] and g.get("end_idx") == e["end_idx"]
+        assert g.get("original_length") == e["original_length"]
+        # the reference holds float64 rows (json floats); ours are float32(float64(text)) -- the fixture's samples are
+        # float32-representable, so the float64 views are identical
+        assert hashlib.sha256(np.ascontiguousarray(g["signals"], dtype=np.float64).tobytes()).hexdigest() == e["sha256"]
+    # the filter really filters: the long runs have more windows than were kept
+    from defectdetection_viaobjectdetection_b200.runtime import window_table
+    assert sum(1 for s in got if s["scan_key"] == "1") < len(window_table("ssd", 140, 50))

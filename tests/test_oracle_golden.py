@@ -99,3 +99,28 @@ def test_sample_index_is_float32_product():
     assert (i32 != i64).any()
     ref = np.array([int(np.float32(v) * 320) for v in x[:5000]], dtype=np.int32)
     np.testing.assert_array_equal(i32[:5000], ref)
+
+
+BF16_FILES = sorted(__import__("glob").glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bf16", "*__*.npz")))
+
+
+@pytest.mark.parametrize("path", [f for f in BF16_FILES if "p334" not in f], ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_bf16_emulation_matches_reference_on_rounded_operands(path):
+    """oracle precision='bf16' (fp32 math on bf16-rounded inputs and matrix weights) against what the REFERENCE
+    classes produce on the same rounded operands (make_golden.py --bf16): the emulation is pinned, not assumed."""
+    import hashlib
+    import json
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    spec = meta["input"]
+    x = synth.synth_paut_sets(spec["B"], spec["N"], spec["S"], seed=spec["seed"], defect_frac=0.2)
+    if spec.get("transpose"):
+        x = np.ascontiguousarray(x.transpose(0, 2, 1))
+    assert hashlib.sha256(x.tobytes()).hexdigest() == meta["input_sha256"]
+    kind = meta["kind"]
+    sd = synth.synth_state_dict(kind, seed=0)
+    with torch.no_grad():
+        got = flatten(kind, om.FORWARD[kind](sd, torch.from_numpy(x), precision="bf16"))
+    for k in got:
+        ref = z["out__" + k]
+        assert np.abs(got[k] - ref).max() <= 5e-5, (kind, k, np.abs(got[k] - ref).max())

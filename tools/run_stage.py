@@ -12,7 +12,7 @@ ap.add_argument("--stage", type=int, default=1)
 ap.add_argument("--sets", type=int, default=400)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
-kind, N, S, width = ("two_stage", 50, 320, 128) if a.stage == 1 else ("msc", 300, 320, 64)
+kind, N, S, width = ("two_stage", 50, 320, 128) if a.stage == 1 else ("msc", 300, 320, 64)  # stages 2-5: attention blocks
 m = FACTORIES[kind](dict(signal_length=S))
 m.load_state_dict(synth.synth_state_dict(kind, seed=0), strict=True)
 m = m.cuda().eval()
