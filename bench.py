@@ -164,16 +164,47 @@ def oracle_forward(kind, sd, x, threshold=0.5):
     return opp.postprocess(kind, out, threshold, S)
 
 
+_REF_MODELS = {}
+
+
+def reference_forward(kind, sd, x, threshold=0.5):
+    """The reference's own class (oracle/_ref, see oracle/build_ref.py) on the CPU: forward + its predict() loop
+    (SSD family) or the callers' threshold loop (model_pred.py:82-85).  None when oracle/_ref is absent."""
+    if kind not in _REF_MODELS:
+        from oracle import ref_models
+        m = ref_models.reference_model(kind, S)
+        if m is not None:
+            m.load_state_dict(sd, strict=True)
+            m.eval()
+        _REF_MODELS[kind] = m
+    m = _REF_MODELS[kind]
+    if m is None:
+        return None
+    with torch.no_grad():
+        if hasattr(m, "predict"):
+            return m.predict(x, threshold=threshold)
+        out = m(x)
+        prob = out[0] if isinstance(out, tuple) else out
+        return [[i for i, p in enumerate(row) if p > threshold] for row in prob.tolist()]
+
+
+def cpu_kind(kind, sd):
+    return "reference" if reference_forward(kind, sd, torch.zeros(1, 4, S) if kind != "conv1d_msc" else torch.zeros(1, S, 4)) is not None else "port"
+
+
 def cpu_reference_rate(kind, sd, x_host_f32, budget_s, n_per_set):
-    """Oracle (the CPU port of the reference path, torch fp32 on all host threads) on a bounded sample."""
+    """The reference classes (oracle/_ref) or, without them, the oracle port, in torch fp32 on all host threads, on a
+    bounded sample."""
     torch.set_num_threads(os.cpu_count() or 1)
     chunk = 8
     n_sets = x_host_f32.shape[0]
-    oracle_forward(kind, sd, x_host_f32[:chunk])                       # warm-up
+    use_ref = cpu_kind(kind, sd) == "reference"
+    fwd = (lambda xs: reference_forward(kind, sd, xs)) if use_ref else (lambda xs: oracle_forward(kind, sd, xs))
+    fwd(x_host_f32[:chunk])                                            # warm-up
     done, t0, i = 0, time.perf_counter(), 0
     while True:
         lo = (i * chunk) % max(n_sets - chunk, 1)
-        oracle_forward(kind, sd, x_host_f32[lo:lo + chunk])
+        fwd(x_host_f32[lo:lo + chunk])
         done += chunk * n_per_set
         i += 1
         el = time.perf_counter() - t0
@@ -324,9 +355,11 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "l2": "sample larger than L2 is not relevant on the CPU arm"},
-            "cpu_baseline": {"value": rate, "unit": "A-scans/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": rate, "unit": "A-scans/s", "cores": cores, "kind": cpu_kind(kind, sd),
                              "sample": f"{sample_sets} sets x {n_per} A-scans cycled for {per_step:.0f} s per step, "
-                                       "oracle port of the reference forward + predict post-processing, fp32"},
+                                       + ("the reference's own class (oracle/_ref) forward + its predict / threshold loop, fp32"
+                                          if cpu_kind(kind, sd) == "reference" else
+                                          "oracle port of the reference forward + predict post-processing, fp32")},
             "e2e": {"value": rate, "unit": "A-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -519,9 +552,12 @@ def main():
         if world == 1 and args.cpu_seconds > 0:
             x_cpu = x_host[:64].float()
             rate, done, el = cpu_reference_rate(kind, sd, x_cpu, args.cpu_seconds, n_per)
-            line["cpu_baseline"] = {"value": rate, "unit": "A-scans/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{done} A-scans (64 sets cycled) in {el:.1f} s, oracle port of the "
-                                              "reference forward + predict post-processing, fp32, all host threads"}
+            ck = cpu_kind(kind, sd)
+            line["cpu_baseline"] = {"value": rate, "unit": "A-scans/s", "cores": torch.get_num_threads(), "kind": ck,
+                                    "sample": f"{done} A-scans (64 sets cycled) in {el:.1f} s, "
+                                              + ("the reference's own class (oracle/_ref) forward + threshold loop"
+                                                 if ck == "reference" else "oracle port of the reference forward + predict post-processing")
+                                              + ", fp32, all host threads"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
