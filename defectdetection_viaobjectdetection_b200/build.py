@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libpaut.so")
-SOURCES = ["api.cu", "model.cu", "ops_f32.cu", "ops_post.cu", "ops_attn.cu", "ops_tc.cu", "ops_msc_tc.cu", "ops_conv_tc.cu", "ops_set_tc.cu", "ops_ts_enc.cu", "ops_attn_tc.cu", "ops_debug.cu", "ops_next.cu", "host_json.cu"]
+SOURCES = ["api.cu", "model.cu", "ops_f32.cu", "ops_post.cu", "ops_attn.cu", "ops_tc.cu", "ops_msc_tc.cu", "ops_conv_tc.cu", "ops_set_tc.cu", "ops_ts_enc.cu", "ops_attn_tc.cu", "ops_mscn_front.cu", "ops_debug.cu", "ops_next.cu", "host_json.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",

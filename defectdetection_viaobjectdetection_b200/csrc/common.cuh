@@ -201,6 +201,11 @@ void op_stem_flat(Ctx& c, const void* x, int x_dtype, int64_t A, int S, const fl
                   int Cout, bool relu, void* out, int ldc, int coff, int halo);
 // bf16 flat rows [R, C] -> dense fp32 [A, L, C]
 void op_unflatten(Ctx& c, const void* flat, int64_t A, int L, int halo, int C, float* out);
+// Fused front end of MultiSignalClassifier_N (ops_mscn_front.cu, bf16 mode): x [A,S] bf16 -> f [A,S] fp32 (conv1, conv2 and
+// the background-subtraction + channel-mean stencil as three chained tcgen05 stages over two shared-memory rings)
+bool mscn_front_supported(int S);
+void mscn_front_pack(const float* w1, const float* b1, const float* w2, const float* wbg, std::vector<uint16_t>& W);
+void op_mscn_front(Ctx& c, const void* x_bf16, int64_t A, int S, const void* W, const float* b2_host, float f_const, float* f);
 // Fused encoder of TwoStageDefectDetector (ops_ts_enc.cu, bf16 mode): x [A,S] bf16 -> feat [A,128] (mean over the signal
 // length of the four conv branches), TMA input staging, stem and second convolutions on tcgen05, pooled epilogue
 bool ts_encoder_supported(int S, int d_model);

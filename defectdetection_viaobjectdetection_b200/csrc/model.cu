@@ -526,6 +526,24 @@ void Model::finalize() {
         enc_tc.W2p = up16(packed);
         enc_tc.ready = true;
       }
+      mscn = MscnFront{};
+      if (cfg.precision == PAUT_PRECISION_BF16 && kind == PAUT_MODEL_MSC_N && mscn_front_supported(cfg.signal_length)) {
+        std::vector<uint16_t> packed;
+        mscn_front_pack(H("conv1d.0.weight").data.data(), H("conv1d.0.bias").data.data(), H("conv1d.2.weight").data.data(),
+                        H("background_extractor.weight").data.data(), packed);
+        void* p = nullptr;
+        PAUT_CUDA(cudaMalloc(&p, packed.size() * sizeof(uint16_t)));
+        dev_allocs.push_back(p);
+        PAUT_CUDA(cudaMemcpy(p, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        mscn.W = p;
+        double fc = 0.0;
+        for (int c2 = 0; c2 < 16; ++c2) {
+          mscn.b2[c2] = H("conv1d.2.bias").data[c2];
+          fc += (double)H("background_extractor.bias").data[c2];
+        }
+        mscn.f_const = (float)(fc / 16.0);
+        mscn.ready = true;
+      }
       mha["self"] = pack_mha("transformer_encoder.self_attn", cfg.num_heads);
       if (kind == PAUT_MODEL_MSC) mha["cross"] = pack_mha("transformer_encoder.cross_attn", cfg.num_heads);
       L("transformer_encoder.ffn.0"); L("transformer_encoder.ffn.2");
@@ -966,6 +984,18 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
     }
     op_msc_encoder_tc(c, xin, x_dtype, A, S, N, H("conv1d.0.weight").data.data(), H("conv1d.0.bias").data.data(), enc_tc.Bc, enc_tc.W1p,
                       lin["shared_layer.0"].b, enc_tc.W2p, l2.b, raw["position_encoding.encoding"], h);
+  } else if (mscn.ready && isn && std::getenv("PAUT_MSCN_SIMT") == nullptr) {
+    // bf16 mode, MSC_N: conv1 -> conv2 -> background subtraction -> channel mean in one tcgen05 kernel (TMA input),
+    // then the two shared layers on the tcgen05 GEMM
+    if (x_dtype != PAUT_BF16) {
+      void* xb = c.alloc((size_t)A * S * sizeof(__nv_bfloat16));
+      op_to_bf16(c, static_cast<const float*>(xin), xb, A * S);
+      xin = xb;
+    }
+    float* f = c.allocf((size_t)A * S);
+    op_mscn_front(c, xin, A, S, mscn.W, mscn.b2, mscn.f_const, f);
+    float* h0 = g.linear(f, S, lin["shared_layer.0"], A, ACT_RELU);
+    h = g.linear(h0, l2.K, l2, A, ACT_RELU, nullptr, 0, nullptr, 0, 0, 0.f, raw["position_encoding.encoding"], N);
   } else {
     const float* x = static_cast<const float*>(xin);
     if (x_dtype != PAUT_F32) {
@@ -1609,6 +1639,10 @@ void Model::debug_stage(int stage, const void* x, int x_dtype, int64_t B, int64_
     PAUT_CHECK(kind == PAUT_MODEL_TWO_STAGE && ts_enc.ready && ts_encoder_supported((int)S, cfg.d_model), PAUT_ERR_UNSUPPORTED,
                "debug_stage 1: the fused two-stage encoder is not available for this model / precision / length");
     op_ts_encoder(c, xin.as_bf16(c), A, (int)S, ts_enc.Wst, ts_enc.W2, ts_enc.shift2, out_dev);
+  } else if (stage == 6) {
+    PAUT_CHECK(kind == PAUT_MODEL_MSC_N && mscn.ready && mscn_front_supported((int)S), PAUT_ERR_UNSUPPORTED,
+               "debug_stage 6: the fused MSC_N front end is not available for this model / precision / length");
+    op_mscn_front(c, xin.as_bf16(c), A, (int)S, mscn.W, mscn.b2, mscn.f_const, out_dev);
   } else if (stage >= 2 && stage <= 5) {
     // MSC attention block on an fp32 [B, N, 64] input: stage 2 / 3 = tcgen05 kernel (self / shifted keys and values),
     // stage 4 / 5 = the mma.sync kernel

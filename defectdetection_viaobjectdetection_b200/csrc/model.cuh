@@ -104,6 +104,12 @@ struct Model {
     int taps[4] = {0, 0, 0, 0}, goff[4] = {0, 0, 0, 0};
     bool ready = false;
   } ts_grouped;
+  struct MscnFront {                           // operands of the fused MSC_N front end (ops_mscn_front.cu, bf16 mode)
+    const void* W = nullptr;
+    float b2[16] = {0};
+    float f_const = 0.f;
+    bool ready = false;
+  } mscn;
   struct TsEnc {                               // operands of the fused two-stage encoder (ops_ts_enc.cu, bf16 mode)
     const void* Wst = nullptr;                 // the four stems + folded BN shift as one [128 x 16] bf16 operand
     const void* W2 = nullptr;                  // second convolutions, fp16, packed

@@ -255,7 +255,9 @@ int paut_debug_mma(paut_ctx* ctx, int mode, int N, int reps, int lbo, int alt, f
 
 /* Intermediate tensor of one fused kernel, for kernel-level parity tests (tests/test_gpu_fused.py); x as in
  * paut_forward, one resident chunk, synchronises.  stage 1: pooled encoder features of the two-stage model
- * (MultiScaleSignalEncoder before the projection, two_stage_model.py:102-115), out_dev fp32 [B*N, 128]. */
+ * (MultiScaleSignalEncoder before the projection, two_stage_model.py:102-115), out_dev fp32 [B*N, 128];
+ * stages 2-5: the MSC attention block (tcgen05 / mma.sync, self / shifted keys) on an fp32 [B, N, 64] input, out_dev
+ * [B*N, 64]; stage 6: the fused MSC_N front end (NN_models.py:227-234), out_dev fp32 [B*N, S]. */
 int paut_debug_stage(paut_model* model, int stage, const void* x_dev, int x_dtype, int64_t B, int64_t N, int64_t S,
                      float* out_dev);
 

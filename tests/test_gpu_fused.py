@@ -121,3 +121,35 @@ def test_msc_attention_block_tcgen05(B, N, cross):
         per_head_cols = [float(err[:, 16 * h:16 * h + 16].max()) for h in range(4)]
         pytest.fail(f"max abs err {err.max():.3e} (mma.sync block: {err_old.max():.3e}); per 16 columns {per_head_cols}; "
                     f"{len(rows)} bad rows, first {rows[:16]}, row mod N: {sorted(set(r % N for r in rows))[:24]}")
+
+
+def mscn_front_ref(sd, x):
+    """NN_models.py:227-234 in fp64: conv1 + ReLU, conv2 + ReLU, minus the depthwise k11 background, channel mean."""
+    A, S = x.shape
+    h = x.double().view(A, 1, S)
+    h = F.relu(F.conv1d(h, sd["conv1d.0.weight"].double(), sd["conv1d.0.bias"].double(), padding=1))
+    h = F.relu(F.conv1d(h, sd["conv1d.2.weight"].double(), sd["conv1d.2.bias"].double(), padding=1))
+    bg = F.conv1d(h, sd["background_extractor.weight"].double(), sd["background_extractor.bias"].double(), padding=5, groups=16)
+    return (h - bg).mean(dim=1).float()
+
+
+@pytest.mark.parametrize("B,N,S", [(1, 1, 320), (1, 16, 320), (1, 17, 320), (3, 170, 320), (2, 300, 320), (40, 300, 320),
+                                   (2, 50, 128), (2, 33, 256), (1, 40, 512)])
+def test_msc_n_fused_front_end(B, N, S):
+    """k_mscn_front (TMA staging, conv1 / conv2 / background stencil as chained tcgen05 stages) against fp64: bf16
+    inputs and conv1 weights, fp16 activations and conv2 / stencil weights."""
+    sd = synth.synth_state_dict("msc_n", seed=0, signal_length=S)
+    x = torch.from_numpy(synth.synth_paut_sets(B, N, S, seed=9 + B + N, defect_frac=0.2)).to(torch.bfloat16)
+    ref = mscn_front_ref(sd, x.float().view(B * N, S))
+    m = build("msc_n", dict(signal_length=S), precision="bf16")
+    native = m._native_for(x.cuda())
+    got = native.debug_stage(6, x.cuda(), S).cpu()
+    assert torch.isfinite(got).all(), "non-finite values (unwritten rows?)"
+    err = (got - ref).abs()
+    scale = max(ref.abs().max().item(), 1e-3)
+    if err.max() > 4e-3 * max(scale, 1.0):
+        bad = torch.nonzero(err > 4e-3 * max(scale, 1.0))
+        rows = sorted(set(bad[:, 0].tolist()))
+        cols = sorted(set(bad[:, 1].tolist()))
+        pytest.fail(f"max abs err {err.max():.3e} (scale {scale:.3f}); {len(rows)} bad A-scans, first {rows[:12]} (mod 16: "
+                    f"{sorted(set(r % 16 for r in rows))}); bad positions first {cols[:16]} last {cols[-8:]}")
