@@ -441,8 +441,9 @@ def main():
 
     # ---- end to end through the public API with host buffers: H2D + forward + post-process + D2H records
     # (VolumeScanner: resident chunks on a few streams, H2D / kernels / D2H of kept records overlapped)
-    scan_chunk = int(os.environ.get("PAUT_BENCH_CHUNK_ASCANS", "38400" if world < 4 else "76800"))
-    lanes = int(os.environ.get("PAUT_BENCH_LANES", "4" if world < 4 else "2"))
+    # 4 lanes x 128-set chunks at every N (measured at 4 GPUs: 274 M A-scans/s against 243 M with 2 lanes x 256 sets)
+    scan_chunk = int(os.environ.get("PAUT_BENCH_CHUNK_ASCANS", "38400"))
+    lanes = int(os.environ.get("PAUT_BENCH_LANES", "4"))
     scanner = VolumeScanner(model, chunk_sets=max(1, (scan_chunk // n_per)), lanes=lanes, reuse_output=True)
 
     def time_e2e(xh, steps):
@@ -472,9 +473,14 @@ def main():
             del x32
         ceil = h2d_ceiling(dev, 640 << 20, 5, barrier)
         t = torch.tensor([ceil], device=dev, dtype=torch.float64)
+        tmin = t.clone()
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         e2e_extra["h2d_ceiling_gbs"] = float(t[0])
+        # every rank streams the same number of bytes and the step ends with the slowest rank: with equal shards the
+        # ceiling of the box is N x the slowest rank's rate (at 8 GPUs this pool gives 4 ranks 23 GB/s and 4 ranks 35 GB/s)
+        e2e_extra["h2d_ceiling_equal_shards_gbs"] = world * float(tmin[0])
         e2e_extra["h2d_achieved_gbs"] = world * h2d_b * args.steps / e2e_s / 1e9
         e2e_extra["host_cores_per_rank"] = cores_per_rank
 

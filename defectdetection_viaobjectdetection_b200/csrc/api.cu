@@ -27,7 +27,12 @@ void Ctx::reserve(size_t bytes) {
 void* Ctx::alloc(size_t bytes) {
   const size_t off = (ws_off + 255) & ~size_t(255);
   ws_off = off + bytes;
-  if (!dry && ws_off > ws_cap) throw Error(PAUT_ERR_STATE, "internal: activation workspace overflow");
+  if (!dry && ws_off > ws_cap)
+    throw Error(PAUT_ERR_STATE, "internal: activation workspace overflow (request " + std::to_string(bytes) + " B at offset " +
+                                    std::to_string(off) + ", capacity " + std::to_string(ws_cap) + ", limit " + std::to_string(ws_limit) + ")");
+  // a dry run on a fresh context has no workspace yet: hand out addresses from a fake, well-aligned, non-null base so
+  // that "is this optional buffer present" tests in the model code take the same branch as the real run
+  if (dry && !ws) return reinterpret_cast<char*>(uintptr_t(1) << 40) + off;
   return ws + off;
 }
 

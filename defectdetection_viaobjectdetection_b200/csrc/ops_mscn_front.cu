@@ -434,7 +434,8 @@ void op_mscn_front(Ctx& c, const void* x_bf16, int64_t A, int S, const void* W, 
   PAUT_CHECK(r == CUDA_SUCCESS, PAUT_ERR_CUDA, "cuTensorMapEncodeTiled failed (msc_n front end input)");
   const size_t smem = (size_t)MF_W_BYTES + MF_R1_BYTES + MF_R2_BYTES + 2 * MF_XA_BYTES + (size_t)p.xs_buf_bytes;
   smem_optin(c, k_mscn_front);
-  long long grid = (long long)c.num_sms * 4;           // four CTAs per SM (shared memory ~50 KB, 128 TMEM columns each)
+  static const int ctas_per_sm = [] { const char* e = std::getenv("PAUT_MSCN_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
+  long long grid = (long long)c.num_sms * ctas_per_sm;  // four CTAs per SM (shared memory ~50 KB, 128 TMEM columns each)
   if (grid > p.nblk) grid = p.nblk;
   k_mscn_front<<<(unsigned)grid, MF_THREADS, smem, c.stream>>>(tmap, p);
   c.launched("mscn_front");

@@ -12,12 +12,12 @@ ap.add_argument("--stage", type=int, default=1)
 ap.add_argument("--sets", type=int, default=400)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
-kind, N, S, width = ("two_stage", 50, 320, 128) if a.stage == 1 else ("msc", 300, 320, 64)  # stages 2-5: attention blocks
+kind, N, S, width = {1: ("two_stage", 50, 320, 128), 6: ("msc_n", 300, 320, 320)}.get(a.stage, ("msc", 300, 320, 64))  # stages 2-5: attention blocks
 m = FACTORIES[kind](dict(signal_length=S))
 m.load_state_dict(synth.synth_state_dict(kind, seed=0), strict=True)
 m = m.cuda().eval()
 m.precision = "bf16"
-if a.stage == 1:
+if a.stage in (1, 6):
     x = torch.from_numpy(synth.synth_paut_sets(a.sets, N, S, seed=1, defect_frac=0.01)).to(torch.bfloat16).cuda()
     native = m._native_for(x)
 else:
