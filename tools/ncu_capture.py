@@ -19,9 +19,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sets", type=int, default=4000)
     ap.add_argument("--kinds", default="msc,msc_n,two_stage,ssd")
+    ap.add_argument("--n", type=int, default=50, help="A-scans per set")
     args = ap.parse_args()
     for kind in args.kinds.split(","):
-        n = 50
+        n = args.n
         m = FACTORIES[kind](dict(signal_length=320))
         m.load_state_dict(synth.synth_state_dict(kind, seed=0), strict=True)
         m = m.cuda().eval()

@@ -40,6 +40,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
     ap.add_argument("--ascans", type=int, required=True, help="A-scans per forward in the capture")
+    ap.add_argument("--passes", default="", help="name=count,...: for kernels whose forward was chunked in the capture, the number "
+                    "of launches that together cover all A-scans once per layer (conv_tc=2: two layers), default = launches")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     out = subprocess.run(["ncu", "-i", args.rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -65,8 +67,10 @@ def main():
         e["launches"] += 1
         e["duration_us"] += dur_us
         order.append((fn, rd, wr, dur_us))
+    passes = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in args.passes.split(",") if kv)
     for name, e in res.items():
-        e["bytes_per_ascan"] = (e["read"] + e["write"]) / args.ascans / e["launches"]   # per launch, as bench.py's roofline
+        e["passes"] = passes.get(name, e["launches"])
+        e["bytes_per_ascan"] = (e["read"] + e["write"]) / args.ascans / e["passes"]    # per launch, as bench.py's roofline
         e["source"] = f"ncu --set full, {os.path.basename(args.rep)}, {args.ascans} A-scans per forward, " \
                       f"dram__bytes_read.sum + dram__bytes_write.sum"
     for fn, rd, wr, d in order:
