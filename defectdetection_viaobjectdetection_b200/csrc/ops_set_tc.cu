@@ -11,6 +11,10 @@
 // statistics) stays in registers as mma.sync fragments.  The products are warp-level mma.sync m16n8k16
 // (bf16 -> fp32): the stage is bound by the exp of the softmax (MUFU) and by shared-memory fragment loads,
 // not by the tensor pipe, so the accumulators are better off in registers than in TMEM.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "mma_common.cuh"
 
@@ -101,6 +105,36 @@ __device__ __forceinline__ void layer_norm_tile(float (&y)[8][4], const float* _
     y[nt][1] = (y[nt][1] - m0) * r0 * g1 + b1;
     y[nt][2] = (y[nt][2] - m1) * r1 * g0 + b0;
     y[nt][3] = (y[nt][3] - m1) * r1 * g1 + b1;
+  }
+}
+
+// same with the affine parameters loaded as pairs
+__device__ __forceinline__ void layer_norm_tile2(float (&y)[8][4], const float* __restrict__ gam,
+                                                 const float* __restrict__ bet, int t) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { s0 += y[nt][0] + y[nt][1]; s1 += y[nt][2] + y[nt][3]; }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float m0 = s0 * (1.f / DM), m1 = s1 * (1.f / DM);
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float a = y[nt][0] - m0, b = y[nt][1] - m0, c = y[nt][2] - m1, d = y[nt][3] - m1;
+    q0 += a * a + b * b;
+    q1 += c * c + d * d;
+  }
+  q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  const float r0 = rsqrtf(q0 * (1.f / DM) + 1e-5f), r1 = rsqrtf(q1 * (1.f / DM) + 1e-5f);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + nt * 8 + 2 * t));
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(bet + nt * 8 + 2 * t));
+    y[nt][0] = (y[nt][0] - m0) * r0 * gg.x + bb.x;
+    y[nt][1] = (y[nt][1] - m0) * r0 * gg.y + bb.y;
+    y[nt][2] = (y[nt][2] - m1) * r1 * gg.x + bb.x;
+    y[nt][3] = (y[nt][3] - m1) * r1 * gg.y + bb.y;
   }
 }
 
@@ -282,6 +316,327 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block(AttnBlockAr
   }
 }
 
+// ------------------------------------------------------------------------------------------ persistent attention block
+// Second generation of the attention block (the first, above, stays as the fallback for sets whose K / V do not fit).
+// ncu of the first at 300 A-scans per set (profiles/r02/r_ncu_msc_n300_summary.txt): 60 k cycles per set, issue slots
+// 56 % busy, special-function pipe 44 %, legacy tensor pipe 33 %; timing variants of a first persistent version
+// (profiles/r02/t_attn_variants.log) showed that HALF of the time is outside the softmax loop -- the K / V projection
+// with its per-element slot arithmetic for the shifted sequence (1250 SASS instructions per row tile), the
+// out-projection / LayerNorm epilogue (800) and their global-load latencies, which all 20 warps of a CTA go through in
+// lock step.  This version:
+//   * persistent CTA per SM, projection weights staged once; the 20 warps form TWO TEAMS of ten that work on different
+//     sets with their own K / V buffer and their own named barrier, so that one team's latency-bound phases (x loads,
+//     projections, LayerNorm, stores) overlap the other team's softmax loops;
+//   * shifted keys / values (cross block) without any slot arithmetic: softmax attention is invariant under a
+//     permutation of the keys, and the shifted sequence [x_1 .. x_{N-1}, x_{N-1}] is the set's own rows with row 0
+//     replaced by a second copy of row N-1 -- rows go to their own slot, the owner of row 0 skips its store and the
+//     owner of row N-1 also writes slot 0;
+//   * V stays row-major like K (plain 32-bit stores of the accumulator fragments) and is read through ldmatrix.trans;
+//   * 221 -> ~100 instructions per (head, 64 keys): B fragments through ldmatrix.x4, the running maximum enters the
+//     QK^T product as its C operand (no subtraction), fp32 ex2 + one packing conversion per pair (ex2.approx.f16x2
+//     compiles to two MUFU and a PRMT), and the reference maximum is only raised when a score exceeds it by more than
+//     2^8 (warp vote; probabilities stay below 2^8 in fp16, the denominators are sums of the same rounded values),
+//     which takes the rescaling of the partial outputs out of the common path; 32-key blocks keep the scores in 16
+//     registers; the last block runs only the 16-key steps that hold real keys.
+// 1.52 -> 1.29 ms per 1 M A-scans for the two calls (profiles/r02/u_bench_msc_attn_p.log).  Tried on top of it and dropped,
+// all within +-3 % or slower (profiles/r02/t_attn_variants.log): the next block's Q K^T issued before this block's
+// exponentials (ping-pong score registers), two heads interleaved per warp, 16 / 48 / 64-key blocks, and a quarter or
+// three eighths of the exponentials as a cubic on the FMA pipe -- which made it SLOWER, so the special-function unit
+// (50 % busy) is not the limiter, and neither is any other pipe: issue slots 40 %, legacy tensor pipe 41 %.  Removing the
+// exponentials, the P V products, the Q K^T products or the vote saves 10 / 7 / 21 / 9 %, and removing the whole softmax
+// loop still leaves 45 % of the time in the projections, LayerNorm and barriers at five warps per scheduler.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// D = A * B + C with C in its own registers
+__device__ __forceinline__ void mma_bf16_16816_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1,
+                                                 const float (&c)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};\n"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// one 8-column output tile of X[16 x 64] * W[rows n0..n0+7]^T + bias; w_addr = this lane's ldmatrix row address of the tile
+__device__ __forceinline__ void proj_tile_lm(const uint32_t (&xa)[4][4], uint32_t w_addr, const float* __restrict__ bias,
+                                             int n0, int t, float (&c)[4]) {
+  const float2 b = __ldg(reinterpret_cast<const float2*>(bias + n0 + 2 * t));
+  c[0] = b.x; c[1] = b.y; c[2] = b.x; c[3] = b.y;
+  uint32_t w[8];
+  ldsm4(w_addr, w[0], w[1], w[2], w[3]);
+  ldsm4(w_addr + 64, w[4], w[5], w[6], w[7]);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) mma_bf16_16816(c, xa[ks], w[2 * ks], w[2 * ks + 1]);
+}
+
+constexpr int TEAMS = 2, TW = AB_WARPS / TEAMS;   // two teams of ten warps
+constexpr int PB = 2;                  // 16-key steps per softmax block of the persistent kernel
+constexpr float LAZY_MAX = 8.f;        // the reference maximum of a row is raised when a score exceeds it by more than this
+
+// VAR != 0: timing experiments only (wrong results): 1 no exponentials, 2 no P V / row-sum products, 3 no Q K^T products,
+// 4 no K / V projection, 5 no maximum check after the first block, 6 no softmax loop at all
+template <int VAR>
+__global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block_p(AttnBlockArgs p, int nsets, int Np) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int N = p.N;
+  const uint32_t voff = (uint32_t)(Np * WS * 2);                          // V [Np][WS] fp16 follows K [Np][WS] bf16
+  const uint32_t kv_bytes = 2 * voff;
+  __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(smraw);           // [192][WS]
+  __nv_bfloat16* Wo = Wq + (size_t)3 * DM * WS;                          // [64][WS]
+  unsigned char* KV = reinterpret_cast<unsigned char*>(Wo + (size_t)DM * WS);   // one K | V buffer per team
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- once per CTA: weights -> shared memory (rows padded to WS), K / V buffers zeroed (the padding keys stay zero)
+  for (int i = tid; i < 3 * DM * (DM / 8); i += AB_WARPS * 32) {
+    const int r = i / (DM / 8), c8 = i - r * (DM / 8);
+    *reinterpret_cast<uint4*>(Wq + (size_t)r * WS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.Wqkv + (size_t)r * DM + c8 * 8));
+  }
+  for (int i = tid; i < DM * (DM / 8); i += AB_WARPS * 32) {
+    const int r = i / (DM / 8), c8 = i - r * (DM / 8);
+    *reinterpret_cast<uint4*>(Wo + (size_t)r * WS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.Wo + (size_t)r * DM + c8 * 8));
+  }
+  for (uint32_t i = tid; i < TEAMS * kv_bytes / 16; i += AB_WARPS * 32) reinterpret_cast<uint4*>(KV)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  const int team = warp / TW, wt = warp - team * TW;
+  const int tiles = (N + 15) / 16;
+  // ldmatrix row addresses of this lane: matrix i = lane / 8, row r = lane % 8
+  const int lm_i = lane >> 3, lm_r = lane & 7;
+  const uint32_t wq_lane = smem_u32(Wq) + (uint32_t)(lm_r * WS * 2 + (lm_i >> 1) * 32 + (lm_i & 1) * 16);
+  const uint32_t wo_lane = smem_u32(Wo) + (uint32_t)(lm_r * WS * 2 + (lm_i >> 1) * 32 + (lm_i & 1) * 16);
+  const uint32_t kbuf = smem_u32(KV) + (uint32_t)team * kv_bytes;
+  // K: matrices (key tile j, dims lo), (j, dims hi), (j+1, lo), (j+1, hi)
+  const uint32_t k_lane = kbuf + (uint32_t)(((lm_i >> 1) * 8 + lm_r) * WS * 2 + (lm_i & 1) * 16);
+  // V through .trans: (keys lo, dims lo), (keys hi, dims lo), (keys lo, dims hi), (keys hi, dims hi)
+  const uint32_t v_lane = kbuf + voff + (uint32_t)(((lm_i & 1) * 8 + lm_r) * WS * 2 + (lm_i >> 1) * 16);
+  const float qscale = 0.25f * 1.4426950408889634f;          // 1/sqrt(16) * log2(e)
+  const uint32_t ones_b = g == 0 ? 0x3C003C00u : 0u;
+  const int bar_id = 1 + team;
+
+  // the teams start half a set apart and, doing the same work at the same speed, stay apart
+  if (team == 1) __nanosleep(12000);
+
+  for (int set = (int)blockIdx.x * TEAMS + team; set < nsets; set += (int)gridDim.x * TEAMS) {
+    const float* xs = p.x + (size_t)set * N * DM;
+    float* outs = p.out + (size_t)set * N * DM;
+
+    // ---- phase 1: K and V of the team's set (rows 64..191 of the packed projection) -> the team's buffer
+    if (VAR != 4) {
+      for (int rt = wt; rt < tiles; rt += TW) {
+        const int r0 = rt * 16;
+        uint32_t xa[4][4];
+        load_x_frags(xs, r0, N, g, t, xa);
+        const int row_lo = r0 + g, row_hi = row_lo + 8;
+        // shifted sequence: row 0 is dropped and row N-1 counts twice (slot 0 takes the second copy)
+        const bool p_lo = row_lo < N && !(p.kv_shift && row_lo == 0), p_hi = row_hi < N;
+        const bool d_lo = p.kv_shift && row_lo == N - 1, d_hi = p.kv_shift && row_hi == N - 1;
+        const bool has_dup = p.kv_shift && N - 1 >= r0 && N - 1 < r0 + 16;     // warp-uniform
+        const uint32_t st = kbuf + (uint32_t)(row_lo * WS * 2 + 4 * t), st0 = kbuf + (uint32_t)(4 * t);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          float kc[4], vc[4];
+          proj_tile_lm(xa, wq_lane + (uint32_t)((DM + nt * 8) * WS * 2), p.bqkv, DM + nt * 8, t, kc);
+          proj_tile_lm(xa, wq_lane + (uint32_t)((2 * DM + nt * 8) * WS * 2), p.bqkv, 2 * DM + nt * 8, t, vc);
+          const uint32_t k_lo = pack_bf16(kc[0], kc[1]), k_hi = pack_bf16(kc[2], kc[3]);
+          const uint32_t v_lo = pack_f16(vc[0], vc[1]), v_hi = pack_f16(vc[2], vc[3]);
+          if (p_lo) { sts32(st + nt * 16, k_lo); sts32(st + voff + nt * 16, v_lo); }
+          if (p_hi) { sts32(st + 8 * WS * 2 + nt * 16, k_hi); sts32(st + voff + 8 * WS * 2 + nt * 16, v_hi); }
+          if (has_dup) {
+            if (d_lo) { sts32(st0 + nt * 16, k_lo); sts32(st0 + voff + nt * 16, v_lo); }
+            if (d_hi) { sts32(st0 + nt * 16, k_hi); sts32(st0 + voff + nt * 16, v_hi); }
+          }
+        }
+      }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TW * 32) : "memory");
+
+    // ---- phase 2: per 16-row tile: Q, attention over all keys per head, out-projection, residual, LayerNorm
+    for (int rt = wt; rt < tiles; rt += TW) {
+      const int r0 = rt * 16;
+      const int row_lo = r0 + g, row_hi = row_lo + 8;
+      // Q of all four heads first (pre-scaled A fragments): x is dead afterwards, and head h's slot of `qo` is reused
+      // for its normalised output (= k-step h of the out-projection), so the two never add up
+      uint32_t qo[NH][4];
+      {
+        uint32_t xa[4][4];
+        load_x_frags(xs, r0, N, g, t, xa);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          float q0[4], q1[4];
+          proj_tile_lm(xa, wq_lane + (uint32_t)((h * HD) * WS * 2), p.bqkv, h * HD, t, q0);
+          proj_tile_lm(xa, wq_lane + (uint32_t)((h * HD + 8) * WS * 2), p.bqkv, h * HD + 8, t, q1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { q0[i] *= qscale; q1[i] *= qscale; }
+          c_to_a(q0, q1, qo[h]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        uint32_t qa[4] = {qo[h][0], qo[h][1], qo[h][2], qo[h][3]};
+        float negm[4] = {0.f, 0.f, 0.f, 0.f};                 // minus the reference maximum of rows g (0, 1) and g + 8 (2, 3)
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float osum[4] = {0.f, 0.f, 0.f, 0.f};                 // P x [1 0 .. 0]: column 0 = row sums of the rounded probabilities
+        const uint32_t ka = k_lane + (uint32_t)(h * HD * 2), va = v_lane + (uint32_t)(h * HD * 2);
+        // scores of one block of `nks` <= PB 16-key steps starting at key kb (reference maximum = C operand)
+        auto scores = [&](float (&s)[2 * PB][4], int kb, int nks, bool last) {
+#pragma unroll
+          for (int jp = 0; jp < PB; ++jp) {
+            if (last && jp >= nks) break;
+            if (VAR == 3) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { s[2 * jp][i] = negm[i] + __uint_as_float(qa[i]) * 1e-30f; s[2 * jp + 1][i] = negm[i]; }
+              continue;
+            }
+            uint32_t k0, k1, k2, k3;
+            ldsm4(ka + (uint32_t)((kb + jp * 16) * WS * 2), k0, k1, k2, k3);
+            mma_bf16_16816_c(s[2 * jp], qa, k0, k1, negm);
+            mma_bf16_16816_c(s[2 * jp + 1], qa, k2, k3, negm);
+          }
+          if (last) {
+#pragma unroll
+            for (int j = 0; j < 2 * PB; ++j) {
+              if (j >= 2 * nks) break;
+              const int c0 = kb + j * 8 + 2 * t;
+              if (c0 >= N) s[j][0] = s[j][2] = -INFINITY;
+              if (c0 + 1 >= N) s[j][1] = s[j][3] = -INFINITY;
+            }
+          }
+        };
+        // softmax numerators and P V of a block whose scores are in s.  Blocks are short (32 keys): without a rescale per
+        // block their only overhead is the vote, and 16 score registers keep the loop free of spills
+        auto consume = [&](float (&s)[2 * PB][4], int kb, int nks, bool last) {
+          float lm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 2 * PB; ++j) {
+            if (last && j >= 2 * nks) break;
+            lm = fmaxf(lm, fmaxf(fmaxf(s[j][0], s[j][1]), fmaxf(s[j][2], s[j][3])));
+          }
+          // does any score exceed its row's reference by more than 2^LAZY_MAX (always true for the first block, whose
+          // reference is still zero)?
+          const bool first = kb == 0;
+          if (first || (VAR != 5 && __any_sync(0xffffffffu, lm > LAZY_MAX))) {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 2 * PB; ++j) {
+              if (last && j >= 2 * nks) break;
+              mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+              mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            // first block: the reference becomes the block maximum (nothing accumulated yet); later: raise, never lower
+            const float d0 = first ? mx0 : fmaxf(mx0, 0.f), d1 = first ? mx1 : fmaxf(mx1, 0.f);
+            const float c0 = first ? 1.f : fast_exp2(-d0), c1 = first ? 1.f : fast_exp2(-d1);
+            negm[0] -= d0; negm[1] -= d0; negm[2] -= d1; negm[3] -= d1;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) { o[d][0] *= c0; o[d][1] *= c0; o[d][2] *= c1; o[d][3] *= c1; }
+            osum[0] *= c0; osum[1] *= c0; osum[2] *= c1; osum[3] *= c1;
+#pragma unroll
+            for (int j = 0; j < 2 * PB; ++j) {
+              if (last && j >= 2 * nks) break;
+              s[j][0] -= d0; s[j][1] -= d0; s[j][2] -= d1; s[j][3] -= d1;
+            }
+          }
+#pragma unroll
+          for (int ks = 0; ks < PB; ++ks) {
+            if (last && ks >= nks) break;
+            uint32_t pa[4];
+            if (VAR == 1) {
+              pa[0] = pack_f16(s[2 * ks][0], s[2 * ks][1]);
+              pa[1] = pack_f16(s[2 * ks][2], s[2 * ks][3]);
+              pa[2] = pack_f16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+              pa[3] = pack_f16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+            } else {
+              pa[0] = pack_f16(fast_exp2(s[2 * ks][0]), fast_exp2(s[2 * ks][1]));
+              pa[1] = pack_f16(fast_exp2(s[2 * ks][2]), fast_exp2(s[2 * ks][3]));
+              pa[2] = pack_f16(fast_exp2(s[2 * ks + 1][0]), fast_exp2(s[2 * ks + 1][1]));
+              pa[3] = pack_f16(fast_exp2(s[2 * ks + 1][2]), fast_exp2(s[2 * ks + 1][3]));
+            }
+            if (VAR == 2) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[0][i] += __uint_as_float(pa[i]);
+              continue;
+            }
+            uint32_t v0, v1, v2, v3;
+            ldsm4t(va + (uint32_t)((kb + ks * 16) * WS * 2), v0, v1, v2, v3);
+            mma_f16_16816(o[0], pa, v0, v1);
+            mma_f16_16816(o[1], pa, v2, v3);
+            mma_f16_16816(osum, pa, ones_b, ones_b);
+          }
+        };
+        if (VAR != 6) {
+          const int nfull = N / (PB * 16), tail_ks = (N - nfull * PB * 16 + 15) >> 4;      // full blocks, 16-key steps of the tail
+          float sa[2 * PB][4];
+          for (int b = 0; b < nfull; ++b) {
+            scores(sa, b * PB * 16, PB, false);
+            consume(sa, b * PB * 16, PB, false);
+          }
+          if (tail_ks) {
+            scores(sa, nfull * PB * 16, tail_ks, true);
+            consume(sa, nfull * PB * 16, tail_ks, true);
+          }
+        } else {
+          o[0][0] = __uint_as_float(qa[0]); osum[0] = osum[2] = 1.f;
+        }
+        // column 0 of the sum tile lives in the lanes with t == 0: rows g (osum[0]) and g + 8 (osum[2])
+        const float l0 = __shfl_sync(0xffffffffu, osum[0], lane & ~3), l1 = __shfl_sync(0xffffffffu, osum[2], lane & ~3);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) { o[d][0] *= i0; o[d][1] *= i0; o[d][2] *= i1; o[d][3] *= i1; }
+        c_to_a(o[0], o[1], qo[h]);       // head h = k-step h of the out-projection
+      }
+      // out-projection + bias + residual + LayerNorm
+      const bool p_lo = row_lo < N, p_hi = row_hi < N;
+      const float* x_lo = xs + (size_t)(p_lo ? row_lo : 0) * DM + 2 * t;     // rows beyond the set read row 0 and are not stored
+      const float* x_hi = xs + (size_t)(p_hi ? row_hi : 0) * DM + 2 * t;
+      float y[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 bo = __ldg(reinterpret_cast<const float2*>(p.bo + nt * 8 + 2 * t));
+        const float2 rl = __ldg(reinterpret_cast<const float2*>(x_lo + nt * 8));
+        const float2 rh = __ldg(reinterpret_cast<const float2*>(x_hi + nt * 8));
+        y[nt][0] = bo.x + rl.x; y[nt][1] = bo.y + rl.y; y[nt][2] = bo.x + rh.x; y[nt][3] = bo.y + rh.y;
+        uint32_t w[8];
+        ldsm4(wo_lane + (uint32_t)(nt * 8 * WS * 2), w[0], w[1], w[2], w[3]);
+        ldsm4(wo_lane + (uint32_t)(nt * 8 * WS * 2) + 64, w[4], w[5], w[6], w[7]);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_bf16_16816(y[nt], qo[ks], w[2 * ks], w[2 * ks + 1]);
+      }
+      layer_norm_tile2(y, p.ln_g, p.ln_b, t);
+      float* o_lo = outs + (size_t)row_lo * DM + 2 * t;
+      float* o_hi = outs + (size_t)row_hi * DM + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        if (p_lo) *reinterpret_cast<float2*>(o_lo + nt * 8) = make_float2(y[nt][0], y[nt][1]);
+        if (p_hi) *reinterpret_cast<float2*>(o_hi + nt * 8) = make_float2(y[nt][2], y[nt][3]);
+      }
+    }
+    // the team's next set overwrites the buffer: every warp of the team must be out of its softmax loops
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TW * 32) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ FFN + LayerNorm + head
 struct FfnHeadArgs {
   const float* x;                      // [M, 64]
@@ -408,8 +763,32 @@ void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bq
   const int Np = (N + KBLK - 1) / KBLK * KBLK;
   const size_t smem = sizeof(__nv_bfloat16) * ((size_t)Np * WS + (size_t)DM * (Np + 8) + (size_t)4 * DM * WS);
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "attn block: set too long for shared memory");
-  smem_optin(c, k_msc_attn_block);
   PAUT_CHECK(B < (int64_t(1) << 31), PAUT_ERR_INVALID, "attn block: too many sets");
+  // persistent kernel: one CTA per SM, two teams of ten warps with a K / V buffer each (PAUT_ATTN=v1 keeps the
+  // one-CTA-per-set kernel for A/B runs)
+  static const bool force_v1 = [] { const char* e = std::getenv("PAUT_ATTN"); return e && std::strcmp(e, "v1") == 0; }();
+  const int Np16 = (N + 15) / 16 * 16;
+  const size_t smem_p = sizeof(__nv_bfloat16) * ((size_t)TEAMS * 2 * Np16 * WS + (size_t)4 * DM * WS);
+  if (!force_v1 && (int)smem_p <= c.smem_optin && (N + 15) / 16 <= 2 * TW) {
+    const unsigned grid = (unsigned)std::min<int64_t>((B + TEAMS - 1) / TEAMS, c.num_sms);
+    static const int var = [] { const char* e = std::getenv("PAUT_ATTN_VARIANT"); return e ? std::atoi(e) : 0; }();
+    auto launch = [&](auto kern) {
+      smem_optin(c, kern);
+      kern<<<grid, AB_WARPS * 32, smem_p, c.stream>>>(p, (int)B, Np16);
+    };
+    switch (var) {                                   // timing experiments (tools/r2t.sh); 0 = the product kernel
+      case 1: launch(k_msc_attn_block_p<1>); break;
+      case 2: launch(k_msc_attn_block_p<2>); break;
+      case 3: launch(k_msc_attn_block_p<3>); break;
+      case 4: launch(k_msc_attn_block_p<4>); break;
+      case 5: launch(k_msc_attn_block_p<5>); break;
+      case 6: launch(k_msc_attn_block_p<6>); break;
+      default: launch(k_msc_attn_block_p<0>); break;
+    }
+    c.launched("msc_attn_block");
+    return;
+  }
+  smem_optin(c, k_msc_attn_block);
   k_msc_attn_block<<<(unsigned)B, AB_WARPS * 32, smem, c.stream>>>(p);
   c.launched("msc_attn_block");
 }
