@@ -108,6 +108,9 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// (Probing a barrier early with mbarrier.test_wait -- the x / edge barrier of the next group at the end of a pass, the MMA
+// barrier of the previous group at its top -- so that the blocking wait is skipped when the answer is already "complete"
+// cost more than it hid: 1.715 -> 1.769 ms per 1 M A-scans, profiles/r02/z_bench_msc_early_probes.log.)
 __device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
@@ -138,9 +141,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int b = 0; b < 2; ++b)
-      for (int t = 0; t < MAX_TILES; ++t) { mbar_init(&bar_conv[b][t], 1); mbar_init(&bar_full[b][t], 1); }
-    // an x slot is released by every team (one arrival each) once its conv1 of the group is done
-    for (int i = 0; i < XS_SLOTS; ++i) { mbar_init(&bar_x[i], 32); mbar_init(&bar_xe[i], tiles); mbar_init(&bar_e[i], 1); }
+      for (int t = 0; t < MAX_TILES; ++t) { mbar_init(&bar_conv[b][t], 1); mbar_init(&bar_full[b][t], 4); }   // 4 warps hand a tile over
+    // an x slot is released by every compute warp (one arrival each) once its conv1 of the group is done
+    for (int i = 0; i < XS_SLOTS; ++i) { mbar_init(&bar_x[i], 32); mbar_init(&bar_xe[i], tiles * 4); mbar_init(&bar_e[i], 1); }
     mbar_init(&bar_l1, 1);
     mbar_init(&bar_l2, 1);
     fence_mbar_init();
@@ -192,31 +195,36 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     const uint64_t bd0 = make_desc(smem_u32(BC), 512, 128);
     const uint64_t bd1 = bd0 + (uint64_t)((2 * 512) >> 4);
     const bool leader = elect_one();
-    uint32_t G = 0;
-    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-      for (int g = 0; g < ngroups; ++g, ++G) {
-        const uint32_t buf = G & 1;
-        const long long i0 = probe ? clock64() : 0;
-        const uint32_t a0t = tmem + buf * tbuf, d0 = a0t + tiles * 16;
-        // every M tile is handed over by its own team of four compute warps and committed to its own barrier:
-        // the teams drift apart instead of meeting at a 640-thread barrier once per group
+    const long long i0 = probe ? clock64() : 0;
+    // Every M tile is handed over by its own four compute warps and committed to its own barrier; the tiles are served in
+    // index order, blocking on each tile's barrier.  (Serving them in whatever order they become ready -- a round robin of
+    // non-blocking mbarrier.test_wait probes -- was tried: the probing warp's shared-memory traffic slowed the compute warps
+    // down, 1.72 -> 2.16 ms per 1 M A-scans, profiles/r02/z_bench_msc_issuer_ab.log.)
+    {
+      uint32_t G = 0;
+      // (Rotating the first tile served with the group, so that no team is always last, was tried too: 1.72 -> 1.81 ms.)
+      for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        for (int g = 0; g < ngroups; ++g, ++G) {
+          const uint32_t buf = G & 1;
+          const uint32_t a0t = tmem + buf * tbuf, d0 = a0t + tiles * 16;
 #pragma unroll
-        for (int T = 0; T < MAX_TILES; ++T) {
-          if (T < tiles) {
-            mbar_wait_a(a_bar_full + (buf * MAX_TILES + T) * 8, (G >> 1) & 1);  // operand rows of tile T are in tensor memory
-            if (leader) {
-              tc_fence_after();
-              mma_f16_ts(d0 + T * 32, a0t + T * 16, bd0, idesc_conv, 0u);
-              mma_f16_ts(d0 + T * 32, a0t + T * 16 + 8, bd1, idesc_conv, 1u);
-              mma_commit(&bar_conv[buf][T]);
+          for (int T = 0; T < MAX_TILES; ++T) {
+            if (T < tiles) {
+              mbar_wait_a(a_bar_full + (buf * MAX_TILES + T) * 8, (G >> 1) & 1);
+              if (leader) {
+                tc_fence_after();
+                mma_f16_ts(d0 + T * 32, a0t + T * 16, bd0, idesc_conv, 0u);
+                mma_f16_ts(d0 + T * 32, a0t + T * 16 + 8, bd1, idesc_conv, 1u);
+                mma_commit(&bar_conv[buf][T]);
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
         }
-        if (probe) tsum[0] += clock64() - i0;    // waiting for the operands + MMA issue
       }
     }
     if (probe) {
+      tsum[0] = clock64() - i0;    // whole issue loop
 #pragma unroll
       for (int i = 0; i < 5; ++i) p.dbg[warp * 8 + i] = tsum[i];
     }
@@ -330,11 +338,16 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
     auto epi_finish = [&](int g, uint32_t (&r)[18]) {
       if (c_active) {
         tmem_wait18(r);
-        // two independent accumulation chains (|.| is a free source modifier)
-        float f0 = __uint_as_float(r[16]), f1 = __uint_as_float(r[17]);
+        // four independent accumulation chains (|.| is a free source modifier): depth 6 instead of 10 dependent FADDs
+        float f0 = __uint_as_float(r[16]) + fabsf(__uint_as_float(r[0])), f1 = __uint_as_float(r[17]) + fabsf(__uint_as_float(r[1]));
+        float f2 = fabsf(__uint_as_float(r[2])) + fabsf(__uint_as_float(r[3])), f3 = fabsf(__uint_as_float(r[4])) + fabsf(__uint_as_float(r[5]));
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) { f0 += fabsf(__uint_as_float(r[c])); f1 += fabsf(__uint_as_float(r[c + 1])); }
-        const __nv_bfloat16 fb = __float2bfloat16_rn(f0 + f1);
+        for (int c = 6; c < 16; c += 4) {
+          f0 += fabsf(__uint_as_float(r[c]));
+          f1 += fabsf(__uint_as_float(r[c + 1]));
+          if (c + 2 < 16) { f2 += fabsf(__uint_as_float(r[c + 2])); f3 += fabsf(__uint_as_float(r[c + 3])); }
+        }
+        const __nv_bfloat16 fb = __float2bfloat16_rn((f0 + f1) + (f2 + f3));
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(a2_base + e_off + (uint32_t)g * 32), "h"(*reinterpret_cast<const uint16_t*>(&fb)) : "memory");
       }
     };
@@ -392,10 +405,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_msc_encoder_tc(MscEncArgs p)
         const long long c1 = probe ? clock64() : 0;
         tc_fence_before();
         const long long c1b = probe ? clock64() : 0;
-        named_sync(1 + T, 128);                             // the team's four warps: operand rows of tile T stored
-        if ((tid & 127) == 0) {
-          mbar_arrive_a(bar_full_t + buf * (MAX_TILES * 8));   // hand the tile to the issuer warp
-          mbar_arrive_a(a_bar_xe + slot * 8);               // and the team's share of the x slot back to the loader warp
+        // every warp hands its 32 operand rows over by itself (the tile's barrier counts four arrivals): no warp waits
+        // for its team mates (ncu: the 128-thread named barrier that used to sit here was 9 % of the compute warps' time)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_a(bar_full_t + buf * (MAX_TILES * 8));   // operand rows of this quarter of tile T are in tensor memory
+          mbar_arrive_a(a_bar_xe + slot * 8);               // and this warp's share of the x slot goes back to the loader warp
         }
         const long long c2 = probe ? clock64() : 0;
         if (g > 0) epi_finish(g - 1, er);
