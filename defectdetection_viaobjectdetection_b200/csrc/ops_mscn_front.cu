@@ -19,6 +19,16 @@
 //            used; an SS-form MMA costs the same 39 cycles for N = 16 as for N = 32: it is paced by the A-tile fetch).
 //            Epilogue: column 0 -> f (fp32) -> HBM.
 //
+// (Round 2 also tried the contraction the other way round -- channel mix G[l][t] = sum_c y_c[l] M[c][t] as ONE MMA, then the
+// diagonal gather f[l] = sum_t G[l + t - 5][t] by the worker threads from a transposed fp16 ring: 4 MMAs per tile instead of
+// 14, parity-green, and SLOWER, 9.4 against 7.5 ms per 1 M A-scans.  The in-kernel probe explains both versions
+// (profiles/r02/3_mscn_front_v2_experiment.log): a worker warp runs ~700 instructions per pass at ~9 cycles each -- one
+// thread per row, one warp per scheduler and CTA -- so the kernel is bound by the worker warps' instruction latency, not by
+// the tensor pipe (546 cycles per tile here, 156 there), not by sleeping waits (spinning changes nothing) and not by the
+// number of hand-overs per pass (merging the five stages of a pass into one TMEM round trip + one fence changed nothing).
+// What it needs is the instruction diet the MSC encoder got in round 1 -- constant ring indices through unrolling, no
+// 64-bit index arithmetic or wait-loop bookkeeping in the pass -- before the 4-MMA formulation can pay off.)
+//
 // One CTA = 4 worker warps (thread = row of the tile: im2col rows and the three epilogues), one MMA warp, one TMA
 // warp; ~50 KB of shared memory and 128 TMEM columns, so FOUR CTAs share an SM and hide each other's hand-over
 // latencies (the chain of one tile is seven steps long).

@@ -15,8 +15,12 @@ import torch.distributed as dist
 from ._lib import DETECTION
 
 
-def shard_range(n_sets, world_size, rank, align=1):
+def shard_range(n_sets, world_size, rank, align=1, weights=None):
     """Contiguous, near-equal blocks in scan order: the first ranks get one more unit.
+
+    ``weights`` (one positive number per rank): shard sizes proportional to them instead of equal -- for boxes whose
+    GPUs do not share the host-to-device bandwidth equally (tools/h2d_ceiling.py: four of eight GPUs at 23 GB/s, four at
+    35 GB/s), where equal shards leave the faster root complex idle in an end-to-end scan.
 
     ``align`` (sets): shard boundaries fall on multiples of it (the last shard takes the remainder).  The bf16
     convolution models pool per 128-row tile of their flat activation layout, whose period is 64 A-scans:
@@ -25,6 +29,13 @@ def shard_range(n_sets, world_size, rank, align=1):
         raise ValueError("rank out of range")
     align = max(1, int(align))
     units = -(-int(n_sets) // align)                     # blocks of `align` sets (the last one may be short)
+    if weights is not None:
+        w = [float(x) for x in weights]
+        if len(w) != int(world_size) or min(w) <= 0:
+            raise ValueError("weights: one positive number per rank")
+        cum = np.concatenate([[0.0], np.cumsum(w)]) / sum(w)
+        edges = np.rint(cum * units).astype(np.int64)    # monotone, edges[0] = 0, edges[-1] = units
+        return min(int(edges[rank]) * align, int(n_sets)), min(int(edges[rank + 1]) * align, int(n_sets))
     base, extra = divmod(units, int(world_size))
     start = rank * base + min(rank, extra)
     stop = start + base + (1 if rank < extra else 0)

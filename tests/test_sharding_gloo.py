@@ -61,6 +61,20 @@ def test_shard_range_alignment():
             assert all(lo % 32 == 0 for lo, _ in spans if lo < n)
 
 
+def test_shard_range_weights_partition_in_proportion():
+    w = [23.3] * 4 + [35.5] * 4
+    for n in (0, 1, 7, 3334, 26667):
+        spans = [sharding.shard_range(n, 8, r, weights=w) for r in range(8)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    spans = [sharding.shard_range(26667, 8, r, align=32, weights=w) for r in range(8)]
+    sizes = [hi - lo for lo, hi in spans]
+    assert all(lo % 32 == 0 for lo, _ in spans)
+    assert abs(sizes[4] / sizes[0] - 35.5 / 23.3) < 0.02
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 2, 0, weights=[1.0])
+
+
 def test_shard_range_partitions_exactly():
     for n in (0, 1, 7, 8, 9, 3334, 160000):
         for w in (1, 2, 4, 8):
