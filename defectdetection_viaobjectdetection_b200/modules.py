@@ -110,6 +110,14 @@ class PautModule(nn.Module):
             self._fingerprint[key] = fp
         return native
 
+    def release(self, device_index=None, stream_handle=None):
+        """Close the packed native copies of this module made for one (device, stream) -- or all of them -- so that their
+        context can be destroyed (``runtime.release_context``); the next call on that stream packs the weights again."""
+        for key in list(self._native):
+            if (device_index is None or key[0] == device_index) and (stream_handle is None or key[1] == stream_handle):
+                self._native.pop(key).close()
+                self._fingerprint.pop(key, None)
+
     def _run(self, x, wanted=None):
         native = self._native_for(x)
         nl = int(self._cfg.get("num_layers") or 6)

@@ -90,6 +90,18 @@ def get_context(device=None):
     return ctx
 
 
+def release_context(device_index, stream_handle):
+    """Destroy the context cached for (device, raw stream handle) and give its workspace back to the driver.  Call it
+    when the stream goes away (``VolumeScanner.close`` does for its lanes): contexts are keyed by the raw handle, and a
+    handle that CUDA reuses for a new stream would otherwise pick up the stale context and its grown workspace.
+    The models created on the context must be closed first (``PautModule.release``)."""
+    with _contexts_lock:
+        ctx = _contexts.pop((int(device_index), int(stream_handle)), None)
+    if ctx is not None:
+        ctx.close()
+    return ctx is not None
+
+
 def total_launches():
     return sum(c.launch_count for c in _contexts.values())
 

@@ -51,10 +51,40 @@ class VolumeScanner:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def close(self):
+        """Release what the scanner's lanes own outside torch's allocator: the module's packed weights for the lane
+        streams and the lanes' library contexts with their workspaces (they are cached by raw stream handle, which
+        CUDA may hand out again once the lane's Stream object is gone).  The scanner can be used again afterwards."""
+        from .runtime import release_context
+        if self._lanes:
+            index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            for lane in self._lanes:
+                lane.stream.synchronize()
+                self.model.release(index, lane.stream.cuda_stream)
+                release_context(index, lane.stream.cuda_stream)
+        self._lanes, self._key = None, None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        import sys
+        if sys.is_finalizing():                # interpreter shutdown: the driver reclaims everything, handles may be gone
+            return
+        try:
+            self.close()
+        except Exception:                      # noqa: BLE001 -- interpreter shutdown: the driver reclaims everything
+            pass
+
     def _ensure_lanes(self, x_host):
         shape = (self.chunk_sets,) + tuple(x_host.shape[1:])
         key = (shape, x_host.dtype)
         if self._key != key:
+            self.close()                       # lanes of the previous shape: their contexts go with them
             n_per = x_host.shape[2] if self.model._kind == "conv1d_msc" else x_host.shape[1]
             self._lanes = [_Lane(self.device, shape, x_host.dtype, self.chunk_sets * n_per)
                            for _ in range(self.num_lanes)]

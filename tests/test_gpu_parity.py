@@ -220,6 +220,47 @@ def test_volume_scanner_equals_resident_run(kind, precision):
     assert scanner.h2d_bytes == x.numel() * x.element_size()
     preds = to_predictions(got, B)
     assert sum(len(p) for p in preds) == len(got)
+    # lifetime: close() destroys the lanes' contexts (workspaces outside torch's allocator) and the packed weights made
+    # for them; the scanner works again afterwards
+    before = len(runtime._contexts)
+    natives = len(m._native)
+    scanner.close()
+    assert len(runtime._contexts) == before - scanner.num_lanes
+    assert len(m._native) == natives - scanner.num_lanes
+    with scanner:
+        again2 = scanner.scan(x.pin_memory(), threshold=thr)
+        for f in whole.dtype.names:
+            np.testing.assert_array_equal(again2[f], whole[f], err_msg=f)
+    assert len(runtime._contexts) == before - scanner.num_lanes
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_shapes_alternate_across_streams(precision):
+    """The opt-in to more than 48 KB of dynamic shared memory is a property of (device, kernel), not of a context
+    (round-1 advice): a large-shape model on the default stream, a small-shape model on a second stream (its own
+    context and workspace), the large shape again -- every launch must succeed and reproduce its first result."""
+    big = build("msc", dict(signal_length=320), precision=precision)
+    small = build("two_stage", dict(signal_length=320), precision=precision)
+    xb = torch.from_numpy(synth.synth_paut_sets(3, 300, 320, seed=5, defect_frac=0.1)).cuda()
+    xs = torch.from_numpy(synth.synth_paut_sets(2, 50, 320, seed=6, defect_frac=0.1)).cuda()
+    if precision == "bf16":
+        xb, xs = xb.to(torch.bfloat16), xs.to(torch.bfloat16)
+    first_big = run_flat(big, "msc", xb)
+    first_small = run_flat(small, "two_stage", xs)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for _ in range(2):
+        with torch.cuda.stream(side):
+            on_side_small = run_flat(small, "two_stage", xs)
+            on_side_big = run_flat(big, "msc", xb[:1])
+        again_big = run_flat(big, "msc", xb)
+        again_small = run_flat(small, "two_stage", xs)
+        for k in first_big:
+            np.testing.assert_array_equal(again_big[k], first_big[k], err_msg=k)
+            np.testing.assert_array_equal(on_side_big[k], first_big[k][:1], err_msg=k)
+        for k in first_small:
+            np.testing.assert_array_equal(again_small[k], first_small[k], err_msg=k)
+            np.testing.assert_array_equal(on_side_small[k], first_small[k], err_msg=k)
 
 
 @pytest.mark.parametrize("n_sets,kind", [(3334, "msc"), (26667, "msc"), (20000, "two_stage")])

@@ -19,7 +19,7 @@ import sys
 # kernel function name -> Ctx::launched() name
 NAMES = {
     "k_msc_encoder_tc": "msc_encoder_tc", "k_msc_attn_block": "msc_attn_block", "k_msc_ffn_head": "msc_ffn_head",
-    "k_msc_attn_tc": "msc_attn_tc", "k_ts_encoder": "ts_encoder", "k_mscn_front": "mscn_front", "k_conv_tc": "conv_tc",
+    "k_msc_attn_tc": "msc_attn_tc", "k_msc_attn_block_p": "msc_attn_block", "k_ts_encoder": "ts_encoder", "k_mscn_front": "mscn_front", "k_conv_tc": "conv_tc",
     "k_stem_flat_t": "stem_flat", "k_stem_flat": "stem_flat", "k_linear_tc": "linear_tc", "k_two_stage_final": "two_stage_final",
 }
 
@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--passes", default="", help="name=count,...: for kernels whose forward was chunked in the capture, the number "
                     "of launches that together cover all A-scans once per layer (conv_tc=2: two layers), default = launches")
     ap.add_argument("--out", default="")
+    ap.add_argument("--merge", action="store_true", help="keep the entries of --out for kernels that are not in this report")
     args = ap.parse_args()
     out = subprocess.run(["ncu", "-i", args.rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -77,6 +78,10 @@ def main():
         print(f"{fn:22s} read {rd / 1e6:10.2f} MB  write {wr / 1e6:10.2f} MB  {d:10.1f} us  "
               f"{(rd + wr) / args.ascans:9.1f} B/A-scan")
     if args.out:
+        if args.merge and os.path.exists(args.out):
+            old = json.load(open(args.out))
+            old.update(res)
+            res = old
         with open(args.out, "w") as f:
             json.dump(res, f, indent=1, sort_keys=True)
         print("wrote", args.out)
