@@ -1245,53 +1245,79 @@ void Model::fwd_enhanced(XIn& x, int64_t B, int N, int S, const paut_outputs& ou
   float* feat = c.allocf((size_t)A * 640);
   int L1 = 0, L2 = 0;
   if (g.tc_convs(S)) {
-    // bf16 mode: every stride-1 conv of the encoder is a tcgen05 implicit GEMM on flat bf16 rows
-    __nv_bfloat16* s0 = g.alloc_flat(A, S, 64);
-    g.stem_flat(x, A, S, ci, s0, 64, 0);
-    __nv_bfloat16* bufA = g.alloc_flat(A, S, 128);
-    __nv_bfloat16* bufB = g.alloc_flat(A, S, 128);
-    __nv_bfloat16* bufC = g.alloc_flat(A, S, 128);
-    if (enh_branches.ready) {
-      // the four dilated branches read the same 64 channels: one launch, one staged window (dilation 8 wide),
-      // one 128-column accumulator = the concatenated output (enhanced_model.py:82-89)
-      ConvTcLaunch a;
-      a.in = s0; a.A = A; a.L = S; a.Cin = 64; a.Cout = 128; a.Wp = enh_branches.Wp; a.shift = enh_branches.shift;
-      a.NT = 128; a.CB = 64; a.groups = 4; a.shared_input = true;
-      for (int b = 0; b < 4; ++b) { a.gtaps[b] = 3; a.goff[b] = enh_branches.goff[b]; a.gdil[b] = 1 << b; }
-      a.taps = 3; a.dil = 8; a.pad = 1; a.relu = false; a.out = bufA; a.ldc = 128; a.coff = 0;
-      op_conv_tc(c, a);
-    } else {
-      for (int b = 0; b < 4; ++b)
-        g.convtc(s0, A, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, false, nullptr, 0, bufA, 128, 32 * b,
-                 nullptr, 0, 0);
-    }
-    g.convtc(bufA, A, S, conv[e + "multi_scale.combine.0"], 1, true, nullptr, 0, bufB, 128, 0, nullptr, 0, 0);
-    __nv_bfloat16* h = bufB;
-    __nv_bfloat16* spare = bufC;
-    for (int r = 0; r < 3; ++r) {
-      const int dil = 1 << r;
-      const std::string qn = e + "res_blocks." + istr(r) + ".conv_block.";
-      g.convtc(h, A, S, conv[qn + "0"], dil, true, nullptr, 0, bufA, 128, 0, nullptr, 0, 0);
-      g.convtc(bufA, A, S, conv[qn + "3"], dil, true, h, 128, spare, 128, 0, r == 2 ? feat : nullptr, 640, 0);
-      std::swap(h, spare);
-    }
+    // bf16 mode: every stride-1 conv of the encoder is a tcgen05 implicit GEMM on flat bf16 rows.
+    // The conv stack walks the resident chunk in SUB-CHUNKS of 16 384 A-scans with its own, smaller set of flat-row
+    // buffers (378 KB per A-scan): the buffers no longer dictate the size of the resident chunk, which grows 4x for
+    // everything behind the encoder (recurrences 52 -> 27 ms, linears 88 -> 70 ms per 1 M A-scans: fuller grids).
+    // Sub-chunks start on multiples of the layout period (64 A-scans), so the pooled sums are the same tiles in the same
+    // order as in one launch over the whole chunk.  L2-sized sub-chunks (256-1024 A-scans: a 128-channel layer moves 96 KB
+    // per 128-row tile against 12.6 MFLOP and is HBM-bound at 2.9x its tensor time when it streams from HBM) were the
+    // idea and are SLOWER, 1164 / 950 / 869 ms at 256 / 512 / 1024 against 816: every k_conv_tc launch stages its resident
+    // weights and sets up its rings again, ~10 us per launch (profiles/r02/3c_enhanced_subchunk_sweep.log); on-chip reuse
+    // needs the layers fused into one persistent kernel, not smaller launches.
+    static const int64_t sub_env = [] { const char* e2 = std::getenv("PAUT_CONV_SUBCHUNK"); return e2 ? (int64_t)atoll(e2) : (int64_t)16384; }();
+    const int64_t Asub = sub_env > 0 ? std::min<int64_t>(A, (sub_env + 63) / 64 * 64) : A;
+    __nv_bfloat16* s0 = g.alloc_flat(Asub, S, 64);
+    __nv_bfloat16* bufA = g.alloc_flat(Asub, S, 128);
+    __nv_bfloat16* bufB = g.alloc_flat(Asub, S, 128);
+    __nv_bfloat16* bufC = g.alloc_flat(Asub, S, 128);
     const int Lp0 = S + CONV_HALO;
     const ConvW& p1 = conv[e + "pyramid_1"];
     const ConvW& p2 = conv[e + "pyramid_2"];
-    if (p1.Wp_s2 && p2.Wp_s2 && S % 4 == 0 && Lp0 % 4 == 0 && Lp0 / 4 >= 64) {
-      // stride-2 pyramid on the tensor cores through the space-to-depth view of the flat rows
-      L1 = S / 2; L2 = S / 4;
-      __nv_bfloat16* x1 = static_cast<__nv_bfloat16*>(
-          c.alloc(((size_t)CONV_HALO / 2 + (size_t)A * (Lp0 / 2)) * 256 * sizeof(__nv_bfloat16)));
-      g.convtc_s2(h, A, S, Lp0, CONV_HALO, p1, x1, feat, 640, 128);
-      g.convtc_s2(x1, A, L1, Lp0 / 2, CONV_HALO / 2, p2, nullptr, feat, 640, 384);
+    const bool tc_pyramid = p1.Wp_s2 && p2.Wp_s2 && S % 4 == 0 && Lp0 % 4 == 0 && Lp0 / 4 >= 64;
+    __nv_bfloat16* x1 = nullptr;
+    float* hd = nullptr;
+    float* x1f = nullptr;
+    if (tc_pyramid) {
+      x1 = static_cast<__nv_bfloat16*>(c.alloc(((size_t)CONV_HALO / 2 + (size_t)Asub * (Lp0 / 2)) * 256 * sizeof(__nv_bfloat16)));
     } else {
-      // short signals: the two stride-2 pyramid convs run on the fp32 CUDA-core kernel
-      float* hd = c.allocf((size_t)A * S * 128);
-      op_unflatten(c, h, A, S, CONV_HALO, 128, hd);
-      float* x1 = c.allocf((size_t)A * ((S + 1) / 2) * 256);
-      g.conv(hd, A, S, p1, 1, 2, 1, true, nullptr, x1, 256, 0, feat, 640, 128, &L1);
-      g.conv(x1, A, L1, p2, 1, 2, 1, true, nullptr, nullptr, 0, 0, feat, 640, 384, &L2);
+      hd = c.allocf((size_t)Asub * S * 128);
+      x1f = c.allocf((size_t)Asub * ((S + 1) / 2) * 256);
+    }
+    const size_t esz = x.dtype == PAUT_BF16 ? 2 : 4;
+    const size_t ws_mark = c.ws_off;                       // per-sub-chunk scratch (pooled partial sums) is released every pass
+    for (int64_t a0 = 0; a0 < A; a0 += Asub) {
+      const int64_t na = std::min<int64_t>(Asub, A - a0);
+      c.ws_off = ws_mark;
+      XIn xs;
+      xs.p = static_cast<const char*>(x.p) + (size_t)a0 * S * esz; xs.dtype = x.dtype; xs.n = na * S;
+      float* feat_s = feat + (size_t)a0 * 640;
+      g.stem_flat(xs, na, S, ci, s0, 64, 0);
+      if (enh_branches.ready) {
+        // the four dilated branches read the same 64 channels: one launch, one staged window (dilation 8 wide),
+        // one 128-column accumulator = the concatenated output (enhanced_model.py:82-89)
+        ConvTcLaunch a;
+        a.in = s0; a.A = na; a.L = S; a.Cin = 64; a.Cout = 128; a.Wp = enh_branches.Wp; a.shift = enh_branches.shift;
+        a.NT = 128; a.CB = 64; a.groups = 4; a.shared_input = true;
+        for (int b = 0; b < 4; ++b) { a.gtaps[b] = 3; a.goff[b] = enh_branches.goff[b]; a.gdil[b] = 1 << b; }
+        a.taps = 3; a.dil = 8; a.pad = 1; a.relu = false; a.out = bufA; a.ldc = 128; a.coff = 0;
+        op_conv_tc(c, a);
+      } else {
+        for (int b = 0; b < 4; ++b)
+          g.convtc(s0, na, S, conv[e + "multi_scale.branch" + istr(b + 1)], 1 << b, false, nullptr, 0, bufA, 128, 32 * b,
+                   nullptr, 0, 0);
+      }
+      g.convtc(bufA, na, S, conv[e + "multi_scale.combine.0"], 1, true, nullptr, 0, bufB, 128, 0, nullptr, 0, 0);
+      __nv_bfloat16* h = bufB;
+      __nv_bfloat16* spare = bufC;
+      for (int r = 0; r < 3; ++r) {
+        const int dil = 1 << r;
+        const std::string qn = e + "res_blocks." + istr(r) + ".conv_block.";
+        g.convtc(h, na, S, conv[qn + "0"], dil, true, nullptr, 0, bufA, 128, 0, nullptr, 0, 0);
+        g.convtc(bufA, na, S, conv[qn + "3"], dil, true, h, 128, spare, 128, 0, r == 2 ? feat_s : nullptr, 640, 0);
+        std::swap(h, spare);
+      }
+      if (tc_pyramid) {
+        // stride-2 pyramid on the tensor cores through the space-to-depth view of the flat rows
+        L1 = S / 2; L2 = S / 4;
+        g.convtc_s2(h, na, S, Lp0, CONV_HALO, p1, x1, feat_s, 640, 128);
+        g.convtc_s2(x1, na, L1, Lp0 / 2, CONV_HALO / 2, p2, nullptr, feat_s, 640, 384);
+      } else {
+        // short signals: the two stride-2 pyramid convs run on the fp32 CUDA-core kernel
+        op_unflatten(c, h, na, S, CONV_HALO, 128, hd);
+        g.conv(hd, na, S, p1, 1, 2, 1, true, nullptr, x1f, 256, 0, feat_s, 640, 128, &L1);
+        g.conv(x1f, na, L1, p2, 1, 2, 1, true, nullptr, nullptr, 0, 0, feat_s, 640, 384, &L2);
+      }
     }
   } else {
     float* s0 = c.allocf((size_t)A * S * 64);

@@ -181,6 +181,25 @@ def test_bf16_chunked_matches_unchunked(kind):
             assert np.abs(full[k] - tiny[k]).max() <= BF16_ATOL, (k, np.abs(full[k] - tiny[k]).max())
 
 
+def test_enhanced_conv_stack_subchunks_reproduce_a_block():
+    """The enhanced model's conv stack walks a resident chunk in sub-chunks of 16 384 A-scans (model.cu): a volume made
+    of one 64-set block (3200 A-scans = 50 layout periods) repeated six times spans two sub-chunks, and every repetition
+    must reproduce the block's outputs bit for bit -- which also pins the block itself against a stand-alone run."""
+    block = torch.from_numpy(synth.synth_paut_sets(64, 50, 320, seed=21, defect_frac=0.1)).to(torch.bfloat16)
+    m = build("enhanced", dict(signal_length=320), precision="bf16")
+    alone = run_flat(m, "enhanced", block.cuda())
+    whole = run_flat(m, "enhanced", block.repeat(6, 1, 1).cuda())
+    for k, ref in alone.items():
+        if k == "attention_weights":                       # [layers, sets, N, N]
+            got = whole[k].reshape(whole[k].shape[0], 6, 64, *whole[k].shape[2:])
+            for r in range(6):
+                assert np.array_equal(got[:, r], ref), (k, r)
+            continue
+        got = whole[k].reshape(6, 64, *whole[k].shape[1:])
+        for r in range(6):
+            assert np.array_equal(got[r], ref), (k, r)
+
+
 @pytest.mark.parametrize("M,K,N", [(100, 2048, 128), (777, 1024, 256), (33, 640, 256)])
 def test_tcgen05_linear_streamed_weights(M, K, N):
     """Shapes whose weights cannot stay resident at the full N tile take the streamed-weights mode of the GEMM
