@@ -38,6 +38,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -58,6 +59,8 @@ constexpr int MF_R2_BYTES = 2 * MF_RROWS * 16;     // ring 2: two chunks (16 cha
 constexpr int MF_XA_BYTES = 2 * 128 * 16;          // im2col tile [2 chunks][128 rows][16 B]
 constexpr int MF_W_BYTES = (1 + 2 + 11) * 512;     // B operands: conv1, conv2 (2), stencil taps (11): [2 chunks][16 rows][16 B]
 constexpr int MF_BLOCK_A = 16, MF_HALO = 8, MF_XPAD = 64;
+// barrier indices
+constexpr int X_FULL = 0, X_EMPTY = 1, XA_FULL = 2, XA_EMPTY = 4, D_FULL = 6, D_EMPTY = 12, R_FULL = 18, R_EMPTY = 26, MF_NBAR = 34;
 constexpr int TC_D1 = 0, TC_D2 = 32, TC_D3 = 64;   // TMEM columns: 2 x 16 per stage
 
 struct MscnArgs {
@@ -70,8 +73,7 @@ struct MscnArgs {
 };
 
 template <int SLEEP_NS>
-__device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait_g(uint32_t addr, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {
     uint32_t done;
     asm volatile(
@@ -88,18 +90,18 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 22)) __trap();               // dead-lock guard: a protocol error traps instead of hanging
   }
 }
-__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -123,22 +125,12 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   return r;
 }
 
-// position of a thread's row in the flat row stream: A-scan of the block, sample index, tile of the block
-struct RowCursor {
-  int a_loc, l, T, blk;
-  __device__ void init(int row) { a_loc = 0; l = row; T = 0; blk = 0; }
-  __device__ void advance(int row, int Lp, int tpb) {          // the same row of the next tile
-    if (++T == tpb) { T = 0; ++blk; a_loc = 0; l = row; return; }
-    l += 128;
-    if (l >= Lp) { l -= Lp; ++a_loc; }                         // Lp >= 136: at most one A-scan further
-  }
-};
-
 __global__ void __launch_bounds__(MF_THREADS, 4)
     k_mscn_front(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ MscnArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t x_full, x_empty, xa_full[2], xa_empty[2], d_full[3][2], d_empty[3][2], r_full[2][MF_SLOTS],
-      r_empty[2][MF_SLOTS];
+  // all mbarriers in ONE array: their shared-window addresses are then one pinned register + compile-time offsets (as
+  // separate variables every use re-derived its address with S2R + LEA, ~5 instructions and an S2R latency each)
+  __shared__ __align__(8) uint64_t bars[MF_NBAR];
   __shared__ uint32_t tmem_slot;
 
   unsigned char* WS = smem;                               // B operands
@@ -154,13 +146,13 @@ __global__ void __launch_bounds__(MF_THREADS, 4)
 
   if (warp == 0) tmem_alloc(&tmem_slot, 128);
   if (tid == 0) {
-    mbar_init(&x_full, 1); mbar_init(&x_empty, MF_WORKERS);
+    mbar_init(&bars[X_FULL], 1); mbar_init(&bars[X_EMPTY], MF_WORKERS);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&xa_full[a], MF_WORKERS); mbar_init(&xa_empty[a], 1);
-      for (int s = 0; s < 3; ++s) { mbar_init(&d_full[s][a], 1); mbar_init(&d_empty[s][a], MF_WORKERS); }
+      mbar_init(&bars[XA_FULL + a], MF_WORKERS); mbar_init(&bars[XA_EMPTY + a], 1);
+      for (int s = 0; s < 3; ++s) { mbar_init(&bars[D_FULL + 2 * s + a], 1); mbar_init(&bars[D_EMPTY + 2 * s + a], MF_WORKERS); }
     }
     for (int r = 0; r < 2; ++r)
-      for (int s = 0; s < MF_SLOTS; ++s) { mbar_init(&r_full[r][s], MF_WORKERS); mbar_init(&r_empty[r][s], 1); }
+      for (int s = 0; s < MF_SLOTS; ++s) { mbar_init(&bars[R_FULL + 4 * r + s], MF_WORKERS); mbar_init(&bars[R_EMPTY + 4 * r + s], 1); }
     fence_mbar_init();
   }
   for (int i = tid; i < MF_W_BYTES / 16; i += MF_THREADS) reinterpret_cast<uint4*>(WS)[i] = __ldg(reinterpret_cast<const uint4*>(p.W) + i);
@@ -171,6 +163,9 @@ __global__ void __launch_bounds__(MF_THREADS, 4)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  uint32_t bar_u = smem_u32(bars);
+  asm volatile("" : "+r"(bar_u));                     // opaque: keeps the address in a register instead of re-deriving it
+  auto BA = [&](int idx) { return bar_u + (uint32_t)idx * 8u; };
   const uint32_t xs_base = smem_u32(XS), r1_base = smem_u32(R1), r2_base = smem_u32(R2), xa_base = smem_u32(XA);
 
   if (warp == MF_TMA_WARP) {
@@ -178,12 +173,12 @@ __global__ void __launch_bounds__(MF_THREADS, 4)
     if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
       for (int i = 0; i < nb_local; ++i) {
-        if (i >= 1) mbar_wait_g<500>(&x_empty, (i - 1) & 1);
-        mbar_expect_tx(&x_full, (uint32_t)(MF_BLOCK_A * S * 2));
+        if (i >= 1) mbar_wait_g<500>(BA(X_EMPTY), (i - 1) & 1);
+        mbar_expect_tx(BA(X_FULL), (uint32_t)(MF_BLOCK_A * S * 2));
         const long long a0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * MF_BLOCK_A;
 #pragma unroll 1
         for (int j = 0; j < MF_BLOCK_A; ++j)
-          tma_load_2d(xs_base + (uint32_t)((MF_XPAD + j * p.xs_stride) * 2), &tmap, 0, (int)((a0 + j) * p.rows_per_ascan), &x_full);
+          tma_load_2d(xs_base + (uint32_t)((MF_XPAD + j * p.xs_stride) * 2), &tmap, 0, (int)((a0 + j) * p.rows_per_ascan), BA(X_FULL));
       }
     }
     __syncwarp();
@@ -197,37 +192,37 @@ __global__ void __launch_bounds__(MF_THREADS, 4)
     for (int g = 0; g < nt + 5; ++g) {
       if (g < nt) {
         const int b = g & 1;
-        mbar_wait_g<0>(&xa_full[b], (g >> 1) & 1);
-        if (g >= 2) mbar_wait_g<0>(&d_empty[0][b], ((g >> 1) - 1) & 1);
+        mbar_wait_g<0>(BA(XA_FULL + (b)), (g >> 1) & 1);
+        if (g >= 2) mbar_wait_g<0>(BA(D_EMPTY + 2 * (0) + (b)), ((g >> 1) - 1) & 1);
         if (leader) {
           tc_fence_after();
           mma_bf16_ss2(tmem + (uint32_t)(TC_D1 + 16 * b), lo(xa_u + (uint32_t)(b * (MF_XA_BYTES / 16)), 128), hi, lo(w_u, 16), hi, id_bf16, 0u);
-          mma_commit(&xa_empty[b]);
-          mma_commit(&d_full[0][b]);
+          commit_a(BA(XA_EMPTY + (b)));
+          commit_a(BA(D_FULL + 2 * (0) + (b)));
         }
         __syncwarp();
       }
       const int u = g - 2;
       if (u >= 0 && u < nt) {
         const int b = u & 1, slot = u & (MF_SLOTS - 1);
-        mbar_wait_g<0>(&r_full[0][(u + 1) & (MF_SLOTS - 1)], ((u + 1) >> 2) & 1);
-        if (u >= 2) mbar_wait_g<0>(&d_empty[1][b], ((u >> 1) - 1) & 1);
+        mbar_wait_g<0>(BA(R_FULL + 4 * (0) + ((u + 1) & (MF_SLOTS - 1))), ((u + 1) >> 2) & 1);
+        if (u >= 2) mbar_wait_g<0>(BA(D_EMPTY + 2 * (1) + (b)), ((u >> 1) - 1) & 1);
         if (leader) {
           tc_fence_after();
           const uint32_t row0 = r1_u + (uint32_t)(MF_MIRROR + 128 * slot);
           // K chunk 1 of a row = the next row (LBO = 16 B): (tap 0 | tap 1) starts one row early, (tap 2 | 0) one row late
           mma_bf16_ss2(tmem + (uint32_t)(TC_D2 + 16 * b), lo(row0 - 1, 1), hi, lo(w_u + 32, 16), hi, id_f16, 0u);
           mma_bf16_ss2(tmem + (uint32_t)(TC_D2 + 16 * b), lo(row0 + 1, 1), hi, lo(w_u + 64, 16), hi, id_f16, 1u);
-          mma_commit(&d_full[1][b]);
-          mma_commit(&r_empty[0][(u + MF_SLOTS - 1) & (MF_SLOTS - 1)]);   // ring 1 tile u - 1 has no reader left
+          commit_a(BA(D_FULL + 2 * (1) + (b)));
+          commit_a(BA(R_EMPTY + 4 * (0) + ((u + MF_SLOTS - 1) & (MF_SLOTS - 1))));   // ring 1 tile u - 1 has no reader left
         }
         __syncwarp();
       }
       const int v = g - 5;
       if (v >= 0 && v < nt) {
         const int b = v & 1, slot = v & (MF_SLOTS - 1);
-        mbar_wait_g<0>(&r_full[1][(v + 1) & (MF_SLOTS - 1)], ((v + 1) >> 2) & 1);
-        if (v >= 2) mbar_wait_g<0>(&d_empty[2][b], ((v >> 1) - 1) & 1);
+        mbar_wait_g<0>(BA(R_FULL + 4 * (1) + ((v + 1) & (MF_SLOTS - 1))), ((v + 1) >> 2) & 1);
+        if (v >= 2) mbar_wait_g<0>(BA(D_EMPTY + 2 * (2) + (b)), ((v >> 1) - 1) & 1);
         if (leader) {
           tc_fence_after();
           const uint32_t row0 = r2_u + (uint32_t)(MF_MIRROR + 128 * slot);
@@ -235,8 +230,8 @@ __global__ void __launch_bounds__(MF_THREADS, 4)
           for (int t = 0; t < 11; ++t)
             mma_bf16_ss2(tmem + (uint32_t)(TC_D3 + 16 * b), lo(row0 + (uint32_t)(t - 5), MF_RROWS), hi, lo(w_u + 96 + 32 * t, 16), hi, id_f16,
                          t ? 1u : 0u);
-          mma_commit(&d_full[2][b]);
-          mma_commit(&r_empty[1][(v + MF_SLOTS - 1) & (MF_SLOTS - 1)]);
+          commit_a(BA(D_FULL + 2 * (2) + (b)));
+          commit_a(BA(R_EMPTY + 4 * (1) + ((v + MF_SLOTS - 1) & (MF_SLOTS - 1))));
         }
         __syncwarp();
       }
@@ -245,28 +240,50 @@ __global__ void __launch_bounds__(MF_THREADS, 4)
     // ================= worker warps: thread = row i of the tile =================
     const int i = warp * 32 + lane;
     const uint32_t t_lane = (uint32_t)(warp * 32) << 16;
+    // The pass loop is unrolled by four: with g = 4k + J every ring slot, double-buffer index and most barrier parities of
+    // the four stages of a pass (im2col of tile g, epilogue 1 of g - 1, epilogue 2 of g - 3, epilogue 3 of g - 6) are
+    // compile-time constants of J; only the lap parity (k & 1) stays in a register.  The probe of round 2 showed the
+    // kernel bound by the worker warps' instruction stream (~9 cycles per instruction at one worker warp per scheduler and
+    // CTA), so what is removed here -- index arithmetic on the uniform datapath, 64-bit A-scan indices, guarded wait loops
+    // with a sleep and a spin counter, per-lane tests for the mirrored ring rows -- is time.
     // ring rule: the previous tile of a slot (tile - 4) was last read by the MMAs of tile - 3; slot 3 also owns the
     // mirrored rows in front of the ring (tile 0 reads them as zero rows): r_empty[.][3] carries an extra first phase
-    auto wait_ring = [&](int r, int tile) {
-      const int slot = tile & (MF_SLOTS - 1), lap = tile >> 2;
-      if (slot == MF_SLOTS - 1) mbar_wait_g<100>(&r_empty[r][slot], lap & 1);
-      else if (lap >= 1) mbar_wait_g<100>(&r_empty[r][slot], (lap - 1) & 1);
+    auto spin = [](uint32_t bar, uint32_t parity) {                     // lean parity wait: probe + branch
+      asm volatile(
+          "{\n"
+          ".reg .pred P1;\n"
+          "W_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+          "@!P1 bra W_%=;\n"
+          "}\n" ::"r"(bar),
+          "r"(parity)
+          : "memory");
     };
-    RowCursor c0, c2, c3;                            // rows of the tiles handled by prep / epilogue 2 / epilogue 3
-    c0.init(i); c2.init(i); c3.init(i);
-    int cur_blk = -1;
-    for (int g = 0; g < nt + 7; ++g) {
+    // row cursors: (A-scan, sample) of this thread's row in the tiles handled by im2col / epilogue 2 / epilogue 3
+    struct Cur { int a, l, T, a_blk; };
+    const int a_first = (int)blockIdx.x * MF_BLOCK_A, a_step = (int)gridDim.x * MF_BLOCK_A, nA = (int)p.A;
+    auto cur_advance = [&](Cur& q) {
+      if (++q.T == tpb) { q.T = 0; q.a_blk += a_step; q.a = q.a_blk; q.l = i; return; }
+      q.l += 128;
+      if (q.l >= Lp) { q.l -= Lp; ++q.a; }                            // Lp >= 136: at most one A-scan further
+    };
+    Cur c0{a_first, i, 0, a_first}, c2 = c0, c3 = c0;
+    int x_blk = -1, blk0 = 0;                                            // block whose x is staged / block of the im2col cursor
+    const bool first_rows = warp == 0, last_rows = warp == MF_WORKERS - 1;   // warps that own mirrored ring rows
+    auto pass = [&](auto Jc, int k) {
+      constexpr int J = decltype(Jc)::value;
+      const int g = 4 * k + J;
+      const uint32_t kp = (uint32_t)k & 1u;
       // ---- im2col row of tile g
       if (g < nt) {
-        const int b = g & 1;
-        if (c0.blk != cur_blk) {
-          cur_blk = c0.blk;
-          mbar_wait_g<200>(&x_full, cur_blk & 1);
+        constexpr int b = J & 1;
+        if (blk0 != x_blk) {
+          x_blk = blk0;
+          spin(BA(X_FULL), (uint32_t)x_blk & 1u);
         }
-        const long long a_blk = ((long long)blockIdx.x + (long long)c0.blk * gridDim.x) * MF_BLOCK_A;
         uint32_t w0 = 0u, w1 = 0u, w2 = 0u;
-        if (c0.l < S && a_blk + c0.a_loc < p.A) {
-          const uint32_t xa = xs_base + (uint32_t)(MF_XPAD + c0.a_loc * p.xs_stride + c0.l - 1) * 2;
+        if (c0.l < S && c0.a < nA) {
+          const uint32_t xa = xs_base + (uint32_t)(MF_XPAD + (c0.a - c0.a_blk) * p.xs_stride + c0.l - 1) * 2;
           uint16_t h0, h1, h2;
           asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h0) : "r"(xa) : "memory");
           asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h1) : "r"(xa + 2) : "memory");
@@ -275,83 +292,109 @@ __global__ void __launch_bounds__(MF_THREADS, 4)
           w1 = (uint32_t)h2 | 0x3F800000u;           // tap 3 = 1.0 (bias hi)
           w2 = 0x00003F80u;                          // tap 4 = 1.0 (bias lo)
         }
-        if (g >= 2) mbar_wait_g<40>(&xa_empty[b], ((g >> 1) - 1) & 1);
-        const uint32_t dst = xa_base + (uint32_t)(b * MF_XA_BYTES + i * 16);
+        if (g >= 2) spin(BA(XA_EMPTY + (b)), (uint32_t)(((J >> 1) + 1) & 1));   // ((g >> 1) - 1) & 1
+        const uint32_t dst = xa_base + (uint32_t)(b * MF_XA_BYTES) + (uint32_t)i * 16;
         st_shared_v4(dst, w0, w1, w2, 0u);
         st_shared_v4(dst + 128 * 16, 0u, 0u, 0u, 0u);
         fence_async_smem();
-        warp_arrive(&xa_full[b], lane);
-        if (c0.T == tpb - 1) warp_arrive(&x_empty, lane);   // the block's x has been read
-        c0.advance(i, Lp, tpb);
-      }
-      // ---- epilogue 1 of tile u: relu(conv1) -> ring 1 (tiles >= nt: zero rows, the stream ends)
-      const int u = g - 1;
-      if (u >= 0 && u <= nt) {
-        const int b = u & 1, slot = u & (MF_SLOTS - 1);
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (u < nt) {
-          mbar_wait_g<40>(&d_full[0][b], (u >> 1) & 1);
-          tc_fence_after();
-          uint32_t r[8];
-          tmem_ld8(tmem + t_lane + (uint32_t)(TC_D1 + 16 * b), r);
-          tc_fence_before();
-          warp_arrive(&d_empty[0][b], lane);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = relu_pack_f16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+        __syncwarp();
+        if (lane == 0) {
+          arrive_a(BA(XA_FULL + (b)));
+          if (c0.T == tpb - 1) arrive_a(BA(X_EMPTY));                   // the block's x has been read
         }
-        wait_ring(0, u);
-        const uint32_t a = r1_base + (uint32_t)(MF_MIRROR + 128 * slot + i) * 16;
-        st_shared_v4(a, w[0], w[1], w[2], w[3]);
-        if (slot == 0 && i < MF_MIRROR) st_shared_v4(a + MF_SLOTS * 128 * 16, w[0], w[1], w[2], w[3]);
-        if (slot == MF_SLOTS - 1 && i >= 128 - MF_MIRROR) st_shared_v4(a - MF_SLOTS * 128 * 16, w[0], w[1], w[2], w[3]);
-        fence_async_smem();
-        warp_arrive(&r_full[0][slot], lane);
+        if (c0.T == tpb - 1) ++blk0;
+        cur_advance(c0);
       }
-      // ---- epilogue 2 of tile v: relu(conv2 + bias), zero outside the A-scans -> ring 2
-      const int v = g - 3;
-      if (v >= 0 && v <= nt) {
-        const int b = v & 1, slot = v & (MF_SLOTS - 1);
-        uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        if (v < nt) {
-          mbar_wait_g<40>(&d_full[1][b], (v >> 1) & 1);
-          tc_fence_after();
-          float y[16];
-          tmem_ld16(tmem + t_lane + (uint32_t)(TC_D2 + 16 * b), y);
-          tc_fence_before();
-          warp_arrive(&d_empty[1][b], lane);
-          const long long a_blk = ((long long)blockIdx.x + (long long)c2.blk * gridDim.x) * MF_BLOCK_A;
-          if (c2.l < S && a_blk + c2.a_loc < p.A) {
+      // ---- epilogue 1 of tile u = g - 1: relu(conv1) -> ring 1 (tile nt: zero rows, the stream ends)
+      {
+        constexpr int uJ = (J + 3) & 3, b = uJ & 1;
+        const int u = g - 1;
+        const uint32_t lap_p = J >= 1 ? kp : kp ^ 1u;                    // parity of the tile's lap (u >> 2)
+        if (u >= 0 && u <= nt) {
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
+          if (u < nt) {
+            spin(BA(D_FULL + 2 * (0) + (b)), (uint32_t)((uJ >> 1) & 1));
+            tc_fence_after();
+            uint32_t r[8];
+            tmem_ld8(tmem + t_lane + (uint32_t)(TC_D1 + 16 * b), r);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_a(BA(D_EMPTY + 2 * (0) + (b)));
 #pragma unroll
-            for (int e = 0; e < 8; ++e) w[e] = relu_pack_f16(y[2 * e] + p.b2[2 * e], y[2 * e + 1] + p.b2[2 * e + 1]);
+            for (int e = 0; e < 4; ++e) w[e] = relu_pack_f16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
           }
-          c2.advance(i, Lp, tpb);
+          if (uJ == MF_SLOTS - 1) spin(BA(R_EMPTY + 4 * (0) + (uJ)), lap_p);
+          else if (u >= MF_SLOTS) spin(BA(R_EMPTY + 4 * (0) + (uJ)), lap_p ^ 1u);
+          const uint32_t a = r1_base + (uint32_t)(MF_MIRROR + 128 * uJ) * 16 + (uint32_t)i * 16;
+          st_shared_v4(a, w[0], w[1], w[2], w[3]);
+          if (uJ == 0 && first_rows) { if (lane < MF_MIRROR) st_shared_v4(a + MF_SLOTS * 128 * 16, w[0], w[1], w[2], w[3]); }
+          if (uJ == MF_SLOTS - 1 && last_rows) { if (lane >= 32 - MF_MIRROR) st_shared_v4(a - MF_SLOTS * 128 * 16, w[0], w[1], w[2], w[3]); }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) arrive_a(BA(R_FULL + 4 * (0) + (uJ)));
         }
-        wait_ring(1, v);
-        const uint32_t a = r2_base + (uint32_t)(MF_MIRROR + 128 * slot + i) * 16;
+      }
+      // ---- epilogue 2 of tile v = g - 3: relu(conv2 + bias), zero outside the A-scans -> ring 2
+      {
+        constexpr int vJ = (J + 1) & 3, b = vJ & 1;
+        const int v = g - 3;
+        const uint32_t lap_p = J >= 3 ? kp : kp ^ 1u;
+        if (v >= 0 && v <= nt) {
+          uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (v < nt) {
+            spin(BA(D_FULL + 2 * (1) + (b)), (uint32_t)((vJ >> 1) & 1));
+            tc_fence_after();
+            float y[16];
+            tmem_ld16(tmem + t_lane + (uint32_t)(TC_D2 + 16 * b), y);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_a(BA(D_EMPTY + 2 * (1) + (b)));
+            if (c2.l < S && c2.a < nA) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const uint32_t ac = a + (uint32_t)(ch * MF_RROWS * 16);
-          st_shared_v4(ac, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-          if (slot == 0 && i < MF_MIRROR) st_shared_v4(ac + MF_SLOTS * 128 * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-          if (slot == MF_SLOTS - 1 && i >= 128 - MF_MIRROR)
-            st_shared_v4(ac - MF_SLOTS * 128 * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+              for (int e = 0; e < 8; ++e) w[e] = relu_pack_f16(y[2 * e] + p.b2[2 * e], y[2 * e + 1] + p.b2[2 * e + 1]);
+            }
+            cur_advance(c2);
+          }
+          if (vJ == MF_SLOTS - 1) spin(BA(R_EMPTY + 4 * (1) + (vJ)), lap_p);
+          else if (v >= MF_SLOTS) spin(BA(R_EMPTY + 4 * (1) + (vJ)), lap_p ^ 1u);
+          const uint32_t a = r2_base + (uint32_t)(MF_MIRROR + 128 * vJ) * 16 + (uint32_t)i * 16;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const uint32_t ac = a + (uint32_t)(ch * MF_RROWS * 16);
+            st_shared_v4(ac, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+            if (vJ == 0 && first_rows) {
+              if (lane < MF_MIRROR) st_shared_v4(ac + MF_SLOTS * 128 * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+            }
+            if (vJ == MF_SLOTS - 1 && last_rows) {
+              if (lane >= 32 - MF_MIRROR) st_shared_v4(ac - MF_SLOTS * 128 * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) arrive_a(BA(R_FULL + 4 * (1) + (vJ)));
         }
-        fence_async_smem();
-        warp_arrive(&r_full[1][slot], lane);
       }
-      // ---- epilogue 3 of tile w: f = column 0 of the stencil accumulator - mean(b_bg)
-      const int wv = g - 6;
-      if (wv >= 0 && wv < nt) {
-        const int b = wv & 1;
-        mbar_wait_g<40>(&d_full[2][b], (wv >> 1) & 1);
-        tc_fence_after();
-        const float fv = __uint_as_float(tmem_ld1(tmem + t_lane + (uint32_t)(TC_D3 + 16 * b))) - p.f_const;
-        tc_fence_before();
-        warp_arrive(&d_empty[2][b], lane);
-        const long long a_glob = ((long long)blockIdx.x + (long long)c3.blk * gridDim.x) * MF_BLOCK_A + c3.a_loc;
-        if (c3.l < S && a_glob < p.A) p.f[a_glob * S + c3.l] = fv;
-        c3.advance(i, Lp, tpb);
+      // ---- epilogue 3 of tile w = g - 6: f = column 0 of the stencil accumulator - mean(b_bg)
+      {
+        constexpr int wJ = (J + 2) & 3, b = wJ & 1;
+        const int wv = g - 6;
+        if (wv >= 0 && wv < nt) {
+          spin(BA(D_FULL + 2 * (2) + (b)), (uint32_t)((wJ >> 1) & 1));
+          tc_fence_after();
+          const float fv = __uint_as_float(tmem_ld1(tmem + t_lane + (uint32_t)(TC_D3 + 16 * b))) - p.f_const;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_a(BA(D_EMPTY + 2 * (2) + (b)));
+          if (c3.l < S && c3.a < nA) p.f[(size_t)c3.a * S + c3.l] = fv;
+          cur_advance(c3);
+        }
       }
+    };
+    for (int k = 0; 4 * k < nt + 7; ++k) {
+      pass(std::integral_constant<int, 0>{}, k);
+      pass(std::integral_constant<int, 1>{}, k);
+      pass(std::integral_constant<int, 2>{}, k);
+      pass(std::integral_constant<int, 3>{}, k);
     }
   }
   tc_fence_before();
