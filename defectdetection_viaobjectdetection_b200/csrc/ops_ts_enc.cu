@@ -63,6 +63,8 @@ constexpr int TE_STEM_WARPS = 4;
 constexpr int TE_THREADS = (TE_STEM_WARP0 + TE_STEM_WARPS) * 32;   // 512
 constexpr int TE_PAD = 5;                         // k = 11
 constexpr int TE_SLOTS = 4;                       // ring of 4 tiles
+constexpr int X_FULL = 0, X_EMPTY = 1, XA_FULL = 2, XA_EMPTY = 4, SACC_FULL = 6, SACC_EMPTY = 8, ACC_FULL = 10, ACC_EMPTY = 12,
+              RING_FULL = 14, RING_EMPTY = 14 + TE_SLOTS, TE_NBAR = 14 + 2 * TE_SLOTS;     // barrier indices
 constexpr int TE_MIRROR = 8;                      // mirrored rows at each end of the ring
 constexpr int TE_RROWS = TE_MIRROR + TE_SLOTS * 128 + TE_MIRROR;   // 528
 constexpr int TE_LBO_R = TE_RROWS * 16;           // chunk stride of the ring (bytes)
@@ -99,8 +101,7 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 // Parity wait; a failed probe puts the warp to sleep (nanosleep) before the next one, with a dead-lock guard: a
 // protocol error traps instead of hanging the GPU.
 template <int SLEEP_NS>
-__device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait_g(uint32_t addr, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {
     uint32_t done;
     asm volatile(
@@ -118,20 +119,22 @@ __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
   }
 }
 // one arrival per warp: every lane has executed its fences, lane 0 arrives for the warp
-__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
 // one box of the 2-D tensor map -> shared memory, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
 
@@ -160,8 +163,9 @@ __device__ __forceinline__ uint32_t relu_pack_f16(float lo, float hi) {
 __global__ void __launch_bounds__(TE_THREADS, 1)
     k_ts_encoder(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TsEncArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t x_full, x_empty, xa_full[2], xa_empty[2], sacc_full[2], sacc_empty[2], ring_full[TE_SLOTS],
-      ring_empty[TE_SLOTS], acc_full[2], acc_empty[2];
+  // all mbarriers in ONE array: their shared-window addresses are one pinned register + compile-time offsets (as separate
+  // variables every use re-derived its address with S2R + LEA)
+  __shared__ __align__(8) uint64_t bars[TE_NBAR];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float pool_s[2][128];          // running sums of the (at most two) open A-scans
   __shared__ __align__(16) float part_s[2][4][2][128];    // [tile parity][lane quarter][segment][column]
@@ -180,13 +184,13 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
   // ---- one-time setup
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
-    mbar_init(&x_full, 1); mbar_init(&x_empty, TE_STEM_WARPS);
+    mbar_init(&bars[X_FULL], 1); mbar_init(&bars[X_EMPTY], TE_STEM_WARPS);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&xa_full[a], TE_STEM_WARPS); mbar_init(&xa_empty[a], 1);
-      mbar_init(&sacc_full[a], 1); mbar_init(&sacc_empty[a], TE_STEM_WARPS);
-      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TE_EPI_WARPS);
+      mbar_init(&bars[XA_FULL + a], TE_STEM_WARPS); mbar_init(&bars[XA_EMPTY + a], 1);
+      mbar_init(&bars[SACC_FULL + a], 1); mbar_init(&bars[SACC_EMPTY + a], TE_STEM_WARPS);
+      mbar_init(&bars[ACC_FULL + a], 1); mbar_init(&bars[ACC_EMPTY + a], TE_EPI_WARPS);
     }
-    for (int s = 0; s < TE_SLOTS; ++s) { mbar_init(&ring_full[s], TE_STEM_WARPS); mbar_init(&ring_empty[s], 1); }
+    for (int s = 0; s < TE_SLOTS; ++s) { mbar_init(&bars[RING_FULL + s], TE_STEM_WARPS); mbar_init(&bars[RING_EMPTY + s], 1); }
     fence_mbar_init();
   }
   for (int i = tid; i < TE_W2_BYTES / 16; i += TE_THREADS)
@@ -202,6 +206,9 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  uint32_t bar_u = smem_u32(bars);
+  asm volatile("" : "+r"(bar_u));                     // opaque: keeps the address in a register instead of re-deriving it
+  auto BA = [&](int idx) { return bar_u + (uint32_t)idx * 8u; };
   const uint32_t xs_base = smem_u32(XS), ring_base = smem_u32(RING), xa_base = smem_u32(XA);
   const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
   unsigned long long pt[4] = {0, 0, 0, 0};
@@ -211,13 +218,13 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
     if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
       for (int i = 0; i < nb_local; ++i) {
-        if (i >= 1) mbar_wait_g<500>(&x_empty, (i - 1) & 1);            // the im2col rows of block i - 1 are built
-        mbar_expect_tx(&x_full, (uint32_t)(TE_BLOCK_A * S * 2));
+        if (i >= 1) mbar_wait_g<500>(BA(X_EMPTY), (i - 1) & 1);            // the im2col rows of block i - 1 are built
+        mbar_expect_tx(BA(X_FULL), (uint32_t)(TE_BLOCK_A * S * 2));
         const long long a0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TE_BLOCK_A;
         const uint32_t dst0 = xs_base + TE_XPAD * 2;
 #pragma unroll 1
         for (int j = 0; j < TE_BLOCK_A; ++j)     // rows beyond the volume are zero-filled by the TMA unit
-          tma_load_2d(dst0 + (uint32_t)(j * p.xs_stride * 2), &tmap, 0, (int)((a0 + j) * p.rows_per_ascan), &x_full);
+          tma_load_2d(dst0 + (uint32_t)(j * p.xs_stride * 2), &tmap, 0, (int)((a0 + j) * p.rows_per_ascan), BA(X_FULL));
       }
     }
     __syncwarp();
@@ -231,14 +238,14 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
       if (g <= nt) {
         // ---- stem MMA of tile g: [128 rows x 16 taps] x [16 taps x 128 channels]
         const int b = g & 1;
-        mbar_wait_g<0>(&xa_full[b], (g >> 1) & 1);
-        if (g >= 2) mbar_wait_g<0>(&sacc_empty[b], ((g >> 1) - 1) & 1);
+        mbar_wait_g<0>(BA(XA_FULL + (b)), (g >> 1) & 1);
+        if (g >= 2) mbar_wait_g<0>(BA(SACC_EMPTY + (b)), ((g >> 1) - 1) & 1);
         if (leader) {
           tc_fence_after();
           mma_bf16_ss2(tmem + (uint32_t)(TC_STEM + 128 * b), ((xa_u + (uint32_t)(b * (TE_XA_BYTES / 16))) & 0x3FFFu) | (128u << 16), desc_hi,
                        (wst_u & 0x3FFFu) | (128u << 16), desc_hi, idesc_st, 0u);
-          mma_commit(&xa_empty[b]);
-          mma_commit(&sacc_full[b]);
+          commit_a(BA(XA_EMPTY + (b)));
+          commit_a(BA(SACC_FULL + (b)));
         }
         __syncwarp();
       }
@@ -246,9 +253,9 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         // ---- second convolutions of tile u: its window reaches 5 rows into tiles u - 1 and u + 1
         const int u = g - 2, slot = u & (TE_SLOTS - 1), acc = u & 1;
         const long long q0 = probe ? clock64() : 0;
-        mbar_wait_g<0>(&ring_full[(u + 1) & (TE_SLOTS - 1)], ((u + 1) >> 2) & 1);
+        mbar_wait_g<0>(BA(RING_FULL + ((u + 1) & (TE_SLOTS - 1))), ((u + 1) >> 2) & 1);
         const long long q1 = probe ? clock64() : 0;
-        if (u >= 2) mbar_wait_g<0>(&acc_empty[acc], ((u >> 1) - 1) & 1);    // the epilogue drained this accumulator
+        if (u >= 2) mbar_wait_g<0>(BA(ACC_EMPTY + (acc)), ((u >> 1) - 1) & 1);    // the epilogue drained this accumulator
         const long long q2 = probe ? clock64() : 0;
         if (leader) {
           tc_fence_after();
@@ -272,8 +279,8 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
           branch(1, 5, 3);
           branch(2, 7, 8);
           branch(3, 11, 15);
-          mma_commit(&acc_full[acc]);
-          mma_commit(&ring_empty[(u + TE_SLOTS - 1) & (TE_SLOTS - 1)]);        // tile u - 1 has no reader left
+          commit_a(BA(ACC_FULL + (acc)));
+          commit_a(BA(RING_EMPTY + ((u + TE_SLOTS - 1) & (TE_SLOTS - 1))));        // tile u - 1 has no reader left
         }
         __syncwarp();
         if (probe) { const long long q3 = clock64(); pt[0] += q1 - q0; pt[1] += q2 - q1; pt[2] += q3 - q2; pt[3] += 1; }
@@ -289,11 +296,11 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
     auto stem_epilogue = [&](int u) {
       const int b = u & 1, slot = u & (TE_SLOTS - 1), lap = u >> 2;
       const long long s0 = probe ? clock64() : 0;
-      mbar_wait_g<40>(&sacc_full[b], (u >> 1) & 1);
+      mbar_wait_g<40>(BA(SACC_FULL + (b)), (u >> 1) & 1);
       // the slot's previous tile (u - 4) was last read by the MMAs of tile u - 3; slot 3 also owns the mirrored rows
       // in front of the ring, which tile 0 reads as its zero rows: ring_empty[3] carries an extra first phase
-      if (slot == TE_SLOTS - 1) mbar_wait_g<100>(&ring_empty[slot], lap & 1);
-      else if (lap >= 1) mbar_wait_g<100>(&ring_empty[slot], (lap - 1) & 1);
+      if (slot == TE_SLOTS - 1) mbar_wait_g<100>(BA(RING_EMPTY + (slot)), lap & 1);
+      else if (lap >= 1) mbar_wait_g<100>(BA(RING_EMPTY + (slot)), (lap - 1) & 1);
       const long long s1 = probe ? clock64() : 0;
       tc_fence_after();
       const uint32_t row = ring_base + (uint32_t)(TE_MIRROR + 128 * slot + i) * 16;
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         tmem_ld32(tmem + t_lane + (uint32_t)(TC_STEM + 128 * b + 32 * cc), r);
         if (cc == 3) {                                                     // accumulator drained
           tc_fence_before();
-          warp_arrive(&sacc_empty[b], lane);
+          warp_arrive(BA(SACC_EMPTY + (b)), lane);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         }
       }
       fence_async_smem();                                                  // generic-proxy stores -> tensor-core operand reads
-      warp_arrive(&ring_full[slot], lane);
+      warp_arrive(BA(RING_FULL + (slot)), lane);
       if (probe && qw == 0) { pt[0] += s1 - s0; pt[1] += clock64() - s1; pt[2] += 1; }
     };
     int a_loc = 0, l = i;                                                  // row i of tile T of the block: A-scan, position
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         if (i_blk != cur_blk) {
           cur_blk = i_blk;
           a_loc = 0; l = i;                                                // (Lp >= 136: the first 128 rows are A-scan 0)
-          mbar_wait_g<200>(&x_full, i_blk & 1);
+          mbar_wait_g<200>(BA(X_FULL), i_blk & 1);
         }
         const long long a_blk = ((long long)blockIdx.x + (long long)i_blk * gridDim.x) * TE_BLOCK_A;
         valid = l < S && a_blk + a_loc < p.A;
@@ -350,14 +357,14 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         w[5] = (uint32_t)h[10] | 0x3F800000u;
         w[6] = 0x00003F80u;
       }
-      if (t >= 2) mbar_wait_g<40>(&xa_empty[b], ((t >> 1) - 1) & 1);        // the stem MMA of tile t - 2 has read the buffer
+      if (t >= 2) mbar_wait_g<40>(BA(XA_EMPTY + (b)), ((t >> 1) - 1) & 1);        // the stem MMA of tile t - 2 has read the buffer
       const uint32_t dst = xa_base + (uint32_t)(b * TE_XA_BYTES + i * 16);
       st_shared_v4(dst, w[0], w[1], w[2], w[3]);
       st_shared_v4(dst + 128 * 16, w[4], w[5], w[6], w[7]);
       fence_async_smem();
-      warp_arrive(&xa_full[b], lane);
+      warp_arrive(BA(XA_FULL + (b)), lane);
       if (t < nt) {
-        if (T == tpb - 1) warp_arrive(&x_empty, lane);                     // the block's x has been read
+        if (T == tpb - 1) warp_arrive(BA(X_EMPTY), lane);                     // the block's x has been read
         l += 128;                                                          // the same row of the next tile
         if (l >= Lp) { l -= Lp; ++a_loc; }
       }
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
       const bool uni0 = l0 + 32 * q + 31 < S && a_blk + a_first < p.A;
       const bool uni1 = l0 + 32 * q >= Lp && l0 + 32 * q + 31 - Lp < S && a_blk + a_first + 1 < p.A;   // ... of the second one
       const long long e0 = probe ? clock64() : 0;
-      mbar_wait_g<60>(&acc_full[acc], (g >> 1) & 1);
+      mbar_wait_g<60>(BA(ACC_FULL + (acc)), (g >> 1) & 1);
       const long long e1 = probe ? clock64() : 0;
       tc_fence_after();
       float* pq = &part_s[acc][q][0][64 * hf];
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (cc == 1) {                                                   // accumulator drained: tile g + 2 may start
           tc_fence_before();
-          warp_arrive(&acc_empty[acc], lane);
+          warp_arrive(BA(ACC_EMPTY + (acc)), lane);
         }
         float s0[8];
         if (uni0 || uni1) {
