@@ -24,7 +24,7 @@ SYMBOLS = (
     "paut_ctx_profile_end", "paut_op_linear", "paut_debug_mma", "paut_debug_stage",
     "paut_difference_matrix", "paut_metrics_match", "paut_metrics_confusion",
     "paut_json_load_host", "paut_json_free", "paut_json_last_error", "paut_json_num_beams", "paut_json_beam_info",
-    "paut_json_beam_copy_host", "paut_json_scan_key", "paut_json_scan_copy_host", "paut_group_nonzero",
+    "paut_json_beam_copy_host", "paut_json_scan_key", "paut_json_scan_copy_host", "paut_json_beam_status", "paut_group_nonzero",
 )
 
 
@@ -109,6 +109,7 @@ def load():
         "paut_json_beam_copy_host": (i32, [vp, i32, vp, vp, vp, vp]),
         "paut_json_scan_key": (C.c_char_p, [vp, i32, i64]),
         "paut_json_scan_copy_host": (i64, [vp, i32, i64, vp, i64]),
+        "paut_json_beam_status": (i32, [vp, i32, C.POINTER(C.c_char_p)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

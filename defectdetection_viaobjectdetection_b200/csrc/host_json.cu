@@ -19,6 +19,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <fcntl.h>
@@ -38,12 +39,15 @@ struct Scan {
   int32_t label = 0;
   float d0 = 0.f, d1 = 0.f;
   size_t off = 0, len = 0;     // samples in Beam::data
+  bool bad = false;            // an object without a 'signal' list: np.array(dict) raises, the reference skips the scan
 };
 struct Beam {
   std::string key;
   std::vector<Scan> scans;     // sorted
   std::vector<float> data;
   int64_t S = 0;               // common signal length, -1 if the scans differ
+  int status = 0;              // PAUT_JSON_BEAM_* bits: where the reference would raise out of its per-file try block
+  std::string status_msg;
 };
 
 struct Parser {
@@ -192,6 +196,7 @@ bool py_float(const std::string& raw, double* out) {
 
 // one beam's object "{ "<scan key>": [..] | {"signal": [..]}, ... }" -> sorted scans (json_dataset.py:44-81)
 void parse_beam(Parser& ps, Beam& beam) {
+  std::unordered_map<std::string, size_t> index;     // scan key -> position (duplicates)
   ps.expect('{');
   if (!ps.eat('}')) {
     do {
@@ -212,17 +217,27 @@ void parse_beam(Parser& ps, Beam& beam) {
           } while (ps.eat(','));
           ps.expect('}');
         }
-        if (!found) throw std::runtime_error("scan '" + sc.key + "' is an object without a 'signal' list");
+        if (!found) { beam.data.resize(sc.off); sc.bad = true; }   // caught per scan in the reference (json_dataset.py:108-126)
       } else {
         ps.numbers(beam.data);
       }
       sc.len = beam.data.size() - sc.off;
       // key parsing, json_dataset.py:48,69-79
       const std::vector<std::string> parts = split(sc.key, '_');
-      if (!py_int(parts[0], &sc.order))
-        throw std::runtime_error("scan key '" + sc.key + "': int(key.split('_')[0]) fails");
-      if (parts.size() < 2) throw std::runtime_error("scan key '" + sc.key + "' has no label field");
-      if (parts[1] == "Health") {
+      // The reference raises out of its per-file try block here -- at the sort for a key without an integer prefix (every
+      // beam, json_dataset.py:48), at the label for a key without a second field (only beams with at least seq_length
+      // scans, :51-52, :69) -- and keeps the sequences of the EARLIER beams of the file.  Recorded per beam; the caller
+      // stops at the first beam whose status applies.
+      if (!py_int(parts[0], &sc.order)) {
+        if (!(beam.status & PAUT_JSON_BEAM_BAD_ORDER_KEY)) beam.status_msg = "scan key '" + sc.key + "': int(key.split('_')[0]) fails";
+        beam.status |= PAUT_JSON_BEAM_BAD_ORDER_KEY;
+        sc.order = 0;
+      }
+      if (parts.size() < 2) {
+        if (!beam.status) beam.status_msg = "scan key '" + sc.key + "' has no label field";
+        beam.status |= PAUT_JSON_BEAM_NO_LABEL;
+        sc.label = 0;
+      } else if (parts[1] == "Health") {
         sc.label = 0;
       } else {
         sc.label = 1;
@@ -235,16 +250,25 @@ void parse_beam(Parser& ps, Beam& beam) {
         sc.d0 = ok ? (float)a : 0.f;
         sc.d1 = ok ? (float)b : 0.f;
       }
-      beam.scans.push_back(std::move(sc));
+      // a repeated key: Python's json keeps the LAST value at the position of the first occurrence
+      auto seen = index.find(sc.key);
+      if (seen != index.end()) {
+        Scan& old = beam.scans[seen->second];
+        old.off = sc.off; old.len = sc.len; old.bad = sc.bad;
+      } else {
+        index.emplace(sc.key, beam.scans.size());
+        beam.scans.push_back(std::move(sc));
+      }
     } while (ps.eat(','));
     ps.expect('}');
   }
   ps.ws();
   if (ps.p != ps.end) ps.fail("trailing data in beam object");
-  std::stable_sort(beam.scans.begin(), beam.scans.end(), [](const Scan& x, const Scan& y) { return x.order < y.order; });
+  if (!(beam.status & PAUT_JSON_BEAM_BAD_ORDER_KEY))
+    std::stable_sort(beam.scans.begin(), beam.scans.end(), [](const Scan& x, const Scan& y) { return x.order < y.order; });
   beam.S = beam.scans.empty() ? 0 : (int64_t)beam.scans[0].len;
   for (const Scan& s : beam.scans)
-    if ((int64_t)s.len != beam.S) beam.S = -1;
+    if ((int64_t)s.len != beam.S || s.bad) beam.S = -1;          // a skipped scan makes the beam take the per-scan path
 }
 
 }  // namespace
@@ -416,11 +440,19 @@ const char* paut_json_scan_key(const paut_json_volume* v, int beam, int64_t i) {
   return i >= 0 && i < (int64_t)b.scans.size() ? b.scans[i].key.c_str() : nullptr;
 }
 
+int paut_json_beam_status(const paut_json_volume* v, int beam, const char** message) {
+  if (!v || beam < 0 || beam >= (int)v->beams.size()) return PAUT_ERR_INVALID;
+  const Beam& b = v->beams[beam];
+  if (message) *message = b.status_msg.c_str();
+  return b.status;
+}
+
 int64_t paut_json_scan_copy_host(const paut_json_volume* v, int beam, int64_t i, float* out, int64_t cap) {
   if (!v || beam < 0 || beam >= (int)v->beams.size()) return PAUT_ERR_INVALID;
   const Beam& b = v->beams[beam];
   if (i < 0 || i >= (int64_t)b.scans.size()) return PAUT_ERR_INVALID;
   const Scan& s = b.scans[i];
+  if (s.bad) return PAUT_JSON_SCAN_SKIPPED;
   if (out && cap > 0) std::memcpy(out, b.data.data() + s.off, (size_t)std::min<int64_t>(cap, (int64_t)s.len) * sizeof(float));
   return (int64_t)s.len;
 }

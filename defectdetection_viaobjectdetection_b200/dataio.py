@@ -15,10 +15,18 @@ import numpy as np
 from . import _lib
 
 
-def load_json_volume(path, with_keys=False):
-    """One file -> list of beams in file order: dict(key, signals float32 [n,S] (None if the scans differ in length:
-    then ``ragged`` is the list of per-scan arrays), labels int32 [n], defects float32 [n,2], scan_order int64 [n],
-    scan_keys (the full key strings, only with ``with_keys=True``)) with the scans in the reference's sorted order.
+BEAM_BAD_ORDER_KEY, BEAM_NO_LABEL, SCAN_SKIPPED = 1, 2, -100          # include/paut.h: PAUT_JSON_BEAM_*, PAUT_JSON_SCAN_SKIPPED
+
+
+def load_json_volume(path, with_keys=False, strict=True):
+    """One file -> list of beams in file order: dict(key, signals float32 [n,S] (None if the scans differ in length or
+    one of them is skipped: then ``ragged`` is the list of per-scan arrays, None for a skipped scan), labels int32 [n],
+    defects float32 [n,2], scan_order int64 [n], scan_keys (the full key strings, only with ``with_keys=True``),
+    status / status_msg) with the scans in the reference's sorted order.  ``status`` holds the BEAM_* bits of a beam on
+    which JsonSignalDataset would raise out of its per-file try block (a key without an integer prefix: the sort of
+    every beam; a key without a label field: beams with at least seq_length scans); ``strict=True`` raises ValueError
+    for such a file like round 1 did, ``strict=False`` leaves the decision to the caller (json_signal_sets keeps the
+    earlier beams, as the reference does).  Repeated scan keys keep the last value, like Python's json.
     Beams are parsed on several threads (PAUT_JSON_THREADS, default: all cores up to 16) from a memory-mapped file."""
     lib = _lib.load()
     h = C.c_void_p()
@@ -26,9 +34,13 @@ def load_json_volume(path, with_keys=False):
         raise ValueError(lib.paut_json_last_error().decode())
     try:
         beams = []
-        key, n, S = C.c_char_p(), C.c_int64(), C.c_int64()
+        key, n, S, msg = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_char_p()
         for b in range(lib.paut_json_num_beams(h)):
             lib.paut_json_beam_info(h, b, C.byref(key), C.byref(n), C.byref(S))
+            status = lib.paut_json_beam_status(h, b, C.byref(msg))
+            status_msg = msg.value.decode() if status else ""
+            if strict and status:
+                raise ValueError(f"{path}: {status_msg}")
             labels = np.empty(n.value, np.int32)
             defects = np.empty((n.value, 2), np.float32)
             order = np.empty(n.value, np.int64)
@@ -42,12 +54,15 @@ def load_json_volume(path, with_keys=False):
                 ragged = []
                 for i in range(n.value):
                     ln = lib.paut_json_scan_copy_host(h, b, i, None, 0)
+                    if ln == SCAN_SKIPPED:                       # an object without "signal": the reference skips the scan
+                        ragged.append(None)
+                        continue
                     row = np.empty(ln, np.float32)
                     lib.paut_json_scan_copy_host(h, b, i, row.ctypes.data, ln)
                     ragged.append(row)
             keys = [lib.paut_json_scan_key(h, b, i).decode() for i in range(n.value)] if with_keys else None
             beams.append(dict(key=key.value.decode(), signals=signals, labels=labels, defects=defects, scan_order=order,
-                              scan_keys=keys, ragged=ragged))
+                              scan_keys=keys, ragged=ragged, status=status, status_msg=status_msg))
         return beams
     finally:
         lib.paut_json_free(h)
@@ -57,7 +72,10 @@ def json_signal_sets(json_dir_or_files, seq_length=50, device=None, dtype=None):
     """JsonSignalDataset(json_dir, seq_length) without the Python loops: returns (signal_sets [W, L, S],
     labels float32 [W, L], defect_positions float32 [W, L, 2]) in the dataset's order.  ``signal_sets`` is a CUDA
     tensor gathered on the device when ``device`` is a CUDA device (dtype fp32, or bf16 on request), else numpy.
-    Files that fail to parse are skipped, like the reference's per-file try/except (json_dataset.py:38,158)."""
+    Error granularity as in the reference (json_dataset.py:38-158): a file that is not valid JSON contributes nothing; a
+    key that breaks the sort of a beam (:48) or -- in a beam with at least seq_length scans -- the label lookup (:69) ends
+    the file there, and the sequences of the earlier beams stay; a scan that cannot be converted (:108-126) only drops the
+    windows that contain it."""
     import torch
     from .runtime import gather_windows, window_table
     if isinstance(json_dir_or_files, (str, os.PathLike)) and os.path.isdir(json_dir_or_files):
@@ -68,12 +86,15 @@ def json_signal_sets(json_dir_or_files, seq_length=50, device=None, dtype=None):
     sets, labels, defects = [], [], []
     for path in files:
         try:
-            beams = load_json_volume(path)
+            beams = load_json_volume(path, strict=False)
         except ValueError as e:
             print(f"Error loading {os.path.basename(path)}: {e}")
             continue
         for beam in beams:
             n = len(beam["labels"])
+            if beam["status"] & BEAM_BAD_ORDER_KEY or (beam["status"] & BEAM_NO_LABEL and n >= seq_length):
+                print(f"Error loading {os.path.basename(path)}: {beam['status_msg']}")
+                break                                               # the reference leaves its per-file try block here
             wins = window_table("msc", n, seq_length)               # json_dataset.py:51-52, 84-103
             if not wins:
                 continue                                            # fewer scans than seq_length
@@ -82,7 +103,7 @@ def json_signal_sets(json_dir_or_files, seq_length=50, device=None, dtype=None):
                 # (json_dataset.py:136-146); such beams are rare, so they take the host path
                 for s0, _ in wins:
                     rows = beam["ragged"][s0:s0 + seq_length]
-                    if any(len(r) != len(rows[0]) for r in rows):
+                    if any(r is None for r in rows) or any(len(r) != len(rows[0]) for r in rows):
                         continue
                     w = np.stack(rows)
                     sets.append(torch.from_numpy(w).to(device=device, dtype=dtype or torch.float32)[None] if on_gpu else w[None])

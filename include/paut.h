@@ -204,6 +204,18 @@ const char* paut_json_last_error(void);
 int paut_json_num_beams(const paut_json_volume* v);
 /* signal_length is -1 when the scans of the beam differ in length */
 int paut_json_beam_info(const paut_json_volume* v, int beam, const char** key, int64_t* n_scans, int64_t* signal_length);
+/* Where JsonSignalDataset would raise out of its per-file try block (keeping the sequences of the EARLIER beams of the
+ * file, json_dataset.py:38,158): a scan key without an integer prefix breaks the sort of every beam (:48); a key without a
+ * label field breaks only beams with at least seq_length scans (:51-52,:69).  Returns the PAUT_JSON_BEAM_* bits of the beam
+ * (0 = clean) or a negative paut_status; *message (may be NULL) describes the first problem.  A beam with
+ * PAUT_JSON_BEAM_BAD_ORDER_KEY is left in file order.  Repeated scan keys keep the last value at the first position, like
+ * Python's json. */
+#define PAUT_JSON_BEAM_BAD_ORDER_KEY 1
+#define PAUT_JSON_BEAM_NO_LABEL 2
+int paut_json_beam_status(const paut_json_volume* v, int beam, const char** message);
+/* returned by paut_json_scan_copy_host for a scan the reference skips (an object without a "signal" list: the window that
+ * contains it is dropped, json_dataset.py:108-131) */
+#define PAUT_JSON_SCAN_SKIPPED (-100)
 /* full key ("<scan>_<label>[_<start>-<end>]") of the i-th sorted scan of a beam; NULL when out of range */
 const char* paut_json_scan_key(const paut_json_volume* v, int beam, int64_t i);
 /* samples of the i-th sorted scan of a beam (for beams whose scans differ in length): copies min(cap, length)

@@ -39,19 +39,51 @@ def load_beams(path):
 
 
 def signal_sets(path, seq_length=50):
-    """(signal_sets, labels, defect_positions) of one file, json_dataset.py:51-52,84-160."""
+    """(signal_sets, labels, defect_positions) of one file, json_dataset.py:38-158 statement by statement, including where
+    its exceptions are caught: per scan (:108-126, the scan is skipped and its window dropped) and per file (:158, the
+    sequences appended before the exception stay)."""
     sets, labels, defects = [], [], []
-    for _, sig, lab, dfx in load_beams(path):
-        n = len(sig)
-        if n < seq_length:
-            continue
-        num = math.ceil(n / seq_length)
-        for i in range(num):
-            start = i * seq_length if i < num - 1 else n - seq_length
-            win = sig[start:start + seq_length]
-            if any(len(s) != len(win[0]) for s in win):
+    try:
+        with open(path, "r") as f:
+            data = json.load(f)
+        for beam_key in data.keys():
+            beam = data[beam_key]
+            keys = sorted(beam.keys(), key=lambda x: int(x.split('_')[0]))             # :48
+            if len(keys) < seq_length:                                                  # :51-52
                 continue
-            sets.append(np.array(win, dtype=np.float32))
-            labels.append(lab[start:start + seq_length].astype(np.float32))
-            defects.append(dfx[start:start + seq_length])
+            scans, lab, dfx = [], [], []
+            for k in keys:
+                scans.append(beam[k])
+                if k.split('_')[1] == "Health":                                         # :69-71
+                    lab.append(0)
+                    dfx.append([0.0, 0.0])
+                else:
+                    lab.append(1)
+                    try:                                                                # :74-79
+                        r = k.split('_')[2].split('-')
+                        dfx.append([float(r[0]), float(r[1])])
+                    except Exception:
+                        dfx.append([0.0, 0.0])
+            n = len(keys)
+            num = math.ceil(n / seq_length)
+            for i in range(num):
+                start = i * seq_length if i < num - 1 else n - seq_length
+                seq, l, d = [], [], []
+                for j in range(start, start + seq_length):
+                    try:                                                                # :108-126
+                        scan = scans[j]
+                        if isinstance(scan, dict) and 'signal' in scan:
+                            scan = scan['signal']
+                        seq.append(np.array(scan, dtype=np.float32))
+                        l.append(lab[j])
+                        d.append(dfx[j])
+                    except Exception:
+                        continue
+                if len(seq) != seq_length or any(len(x) != len(seq[0]) for x in seq):   # :129-146
+                    continue
+                sets.append(np.array(seq, dtype=np.float32))
+                labels.append(np.array(l, np.float32))
+                defects.append(np.array(d, np.float32).reshape(-1, 2))
+    except Exception:                                                                    # :158
+        pass
     return sets, labels, defects

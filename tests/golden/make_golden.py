@@ -407,7 +407,68 @@ def prep_vectors():
     print("wrote prep_volume:", {k: len(v) for k, v in ann.items()}, len(seqs), "sequences")
 
 
+def json_partial_vectors():
+    """f1, error granularity: the reference's own JsonSignalDataset on files that are only PARTLY usable -- a scan that
+    cannot be converted drops its window, a key that breaks the sort or the label lookup ends the file but keeps the
+    sequences of the earlier beams, a short beam with a label-less key is skipped before the lookup, repeated keys keep the
+    last value.  Writes tests/golden/json_volume/e_partial*.json + expected_partial.npz."""
+    import importlib.util
+    import shutil
+    import tempfile
+    spec = importlib.util.spec_from_file_location("ref_json_dataset", os.path.join(REF, "signals", "improved_multisignal", "json_dataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(7)
+    S = 6
+
+    def sig():
+        return [float(np.float32(v)) for v in rng.random(S)]
+
+    def beam(n, defect_every=4):
+        return {(f"{i}_Health" if i % defect_every else f"{i}_Defect_0.25-0.5"): sig() for i in rng.permutation(n)}
+
+    files = {}
+    # 1: a skipped scan in the middle of a beam (its window goes), then a clean beam
+    b0 = beam(13)
+    b0["6_Health"] = {"amplitude": 3}                      # an object without "signal": np.array(dict) raises, scan skipped
+    b1 = beam(11)
+    b1["4_Defect_0.25-0.5"] = {"signal": sig(), "note": "x"}
+    files["e_partial1.json"] = {"beam_0": b0, "beam_1": b1}
+    # 2: clean beam, SHORT beam with a label-less key (skipped before the label lookup), clean beam, a beam whose key
+    #    breaks the sort (the file ends there), a clean beam that is never reached
+    b_short = {"0_Health": sig(), "1": sig(), "2_Health": sig()}
+    b_bad = beam(7)
+    b_bad["x7_Health"] = sig()
+    files["e_partial2.json"] = {"beam_0": beam(10), "beam_1": b_short, "beam_2": beam(6), "beam_3": b_bad, "beam_4": beam(9)}
+    # 3: clean beam, then a LONG beam with a label-less key (raises at the label lookup), then an unreachable beam
+    b_nolabel = beam(8)
+    b_nolabel["3"] = sig()
+    files["e_partial3.json"] = {"beam_0": beam(5), "beam_1": b_nolabel, "beam_2": beam(12)}
+    out_dir = os.path.join(HERE, "json_volume")
+    save = {}
+    for name, data in files.items():
+        text = json.dumps(data)
+        if name == "e_partial1.json":                      # a repeated key: the last value wins, at the first position
+            dup = json.dumps({"2_Health": [9.0] * S})[1:-1]
+            text = text.replace('"beam_1": {', '"beam_1": {' + dup + ', ', 1).replace('}}', ', ' + json.dumps({"2_Health": [0.5] * S})[1:-1] + '}}', 1)
+        with open(os.path.join(out_dir, name), "w") as f:
+            f.write(text)
+        tmp = tempfile.mkdtemp()
+        shutil.copy(os.path.join(out_dir, name), tmp)
+        ds = mod.JsonSignalDataset(tmp, seq_length=5)
+        stem = name[:-5]
+        save[stem + "_sets"] = np.array(ds.signal_sets, np.float32).reshape(len(ds.signal_sets), 5, -1)
+        save[stem + "_labels"] = np.array(ds.labels, np.float32).reshape(len(ds.labels), 5)
+        save[stem + "_defects"] = np.array(ds.defect_positions, np.float32).reshape(len(ds.defect_positions), 5, 2)
+        shutil.rmtree(tmp)
+        print(name, "->", len(ds.signal_sets), "sequences")
+    np.savez_compressed(os.path.join(out_dir, "expected_partial.npz"), **save)
+
+
 def main():
+    if "--json-partial" in sys.argv:
+        json_partial_vectors()
+        return
     if "--metrics" in sys.argv:
         metrics_vectors()
         return

@@ -24,6 +24,21 @@ def test_oracle_loader_pinned_on_reference_fixtures(name, L):
     np.testing.assert_array_equal(np.array(defects, np.float32), z[name + "_defects"])
 
 
+@pytest.mark.parametrize("name", ["e_partial1", "e_partial2", "e_partial3"])
+def test_partly_usable_files_match_reference_dataset(name):
+    """Error granularity of JsonSignalDataset (fixtures made by the reference class, make_golden.py --json-partial): a scan
+    that cannot be converted drops its window; a key that breaks the sort or the label lookup ends the file and keeps the
+    earlier beams; a short beam is skipped before the label lookup; a repeated key keeps its last value.  Oracle and
+    native loader against the reference's arrays."""
+    z = np.load(os.path.join(JDIR, "expected_partial.npz"))
+    path = os.path.join(JDIR, name + ".json")
+    for sets, labels, defects in (jsonload.signal_sets(path, 5), dataio.json_signal_sets([path], seq_length=5)):
+        assert len(sets) == len(z[name + "_sets"]) > 0
+        np.testing.assert_array_equal(np.array(sets, np.float32), z[name + "_sets"])
+        np.testing.assert_array_equal(np.array(labels, np.float32), z[name + "_labels"])
+        np.testing.assert_array_equal(np.array(defects, np.float32), z[name + "_defects"])
+
+
 number = st.one_of(
     st.floats(allow_nan=False, allow_infinity=False, width=64),
     st.floats(min_value=0.0, max_value=1.0),
@@ -49,6 +64,53 @@ def volumes(draw):
             scans[key] = vals if draw(st.booleans()) else {"gain": 3, "signal": vals, "tags": ["a", {"b": None}]}
         beams[f"beam_{b}"] = scans
     return beams, draw(st.sampled_from([None, 1, 2])), draw(st.integers(min_value=1, max_value=4))
+
+
+@st.composite
+def broken_volumes(draw):
+    """volumes() with, somewhere, a scan that cannot be converted, a key without a label field, a key without an integer
+    prefix, or a repeated key."""
+    beams, indent, L = draw(volumes())
+    names = list(beams)
+    for _ in range(draw(st.integers(min_value=1, max_value=3))):
+        b = beams[draw(st.sampled_from(names))]
+        kind = draw(st.sampled_from(["skipped", "nolabel", "badint", "nothing"]))
+        pos = draw(st.integers(min_value=0, max_value=30))
+        if kind == "skipped":
+            b[f"{pos}_Health_s"] = {"amplitude": 1.5, "tags": [1, 2]}
+        elif kind == "nolabel":
+            b[f"{pos}"] = [0.5]
+        elif kind == "badint":
+            b[f"q{pos}_Health"] = [0.25]
+    return beams, indent, L
+
+
+@pytest.mark.filterwarnings("ignore:overflow encountered in cast")
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(broken_volumes(), st.booleans())
+def test_partly_usable_files_equal_oracle(tmp_path, case, repeat_key):
+    beams, indent, L = case
+    text = json.dumps(beams, indent=indent)
+    first = next(iter(beams.values()))
+    if repeat_key and first:                                         # the first beam's first key once more, with another value
+        k = next(iter(first))
+        again = json.dumps({k: [7.0]})[1:-1]
+        at = text.index("{", text.index("{") + 1) + 1                # just inside the first beam's object
+        text = text[:at] + again + ", " + text[at:]
+    p = tmp_path / "v.json"
+    p.write_text(text)
+    ws, wl, wd = jsonload.signal_sets(str(p), L)
+    lengths = {s.shape[-1] for s in ws}
+    if len(lengths) <= 1:
+        sets, labels, defects = dataio.json_signal_sets([str(p)], seq_length=L)
+        assert len(sets) == len(ws)
+        for i in range(len(ws)):
+            np.testing.assert_array_equal(sets[i], ws[i])
+            np.testing.assert_array_equal(labels[i], wl[i])
+            np.testing.assert_array_equal(defects[i], wd[i])
+    else:
+        with pytest.raises(ValueError):
+            dataio.json_signal_sets([str(p)], seq_length=L)
 
 
 @pytest.mark.filterwarnings("ignore:overflow encountered in cast")
