@@ -80,7 +80,10 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 template <bool OUT, bool POOL, bool RES>
 __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[CT_STAGES], empty[CT_STAGES], acc_full[2], acc_empty[2];
+  // all mbarriers in ONE array behind a pinned base address (as separate variables every use re-derived its shared-window
+  // address with S2R + LEA): full[CT_STAGES] | empty[CT_STAGES] | acc_full[2] | acc_empty[2]
+  __shared__ __align__(8) uint64_t bars[2 * CT_STAGES + 4];
+  constexpr int FULL = 0, EMPTY = CT_STAGES, ACC_FULL = 2 * CT_STAGES, ACC_EMPTY = 2 * CT_STAGES + 2;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float pool_s[4 * 2 * 128];                    // [TMEM quarter][segment][NT]; 4*nseg*NT <= 1024
   __shared__ __align__(128) float tsm[CT_EPI_WARPS][32 * 32];   // per-warp 32x32 fp32 transposition tile (swizzled)
@@ -98,8 +101,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
 
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 0) {
-    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&full[s], CT_LOADERS); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], CT_EPI); }
+    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&bars[FULL + s], CT_LOADERS); mbar_init(&bars[EMPTY + s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars[ACC_FULL + a], 1); mbar_init(&bars[ACC_EMPTY + a], CT_EPI); }
     fence_mbar_init();
   }
   {  // resident weights of this N tile: one contiguous block in the packed layout
@@ -113,6 +116,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  uint32_t bar_u = smem_u32(bars);
+  asm volatile("" : "+r"(bar_u));
+  auto BA = [&](int idx) { return bar_u + (uint32_t)idx * 8u; };
   const bool probe = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == CT_EPI_WARPS || warp == CT_EPI_WARPS + 1);
   unsigned long long pt[4] = {0, 0, 0, 0};
 
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
       const int64_t wr0 = tile * 128 - (int64_t)p.pad * p.dil;
       for (int cb = 0; cb < ncb; ++cb) {
         const long long q0 = probe ? clock64() : 0;
-        if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);        // MMAs that read this slot are done
+        if (use > 0) wait_a(BA(EMPTY + (stage)), (use - 1) & 1);        // MMAs that read this slot are done
         const long long q1 = probe ? clock64() : 0;
         if (ch < chunks) {
           uint32_t dst = a_ring + (uint32_t)stage * p.a_stage_bytes + (uint32_t)(ch * p.wrows + rsub) * 16;
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
         // coupling of the hand-over to the request of a later stage (a wait_group-based hand-over of stage j only
         // happens once stage j + LAG can be requested, i.e. after the MMAs of stage j - 1 have completed: that
         // serialised consecutive stages and left the tensor pipe idle between them)
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(BA(FULL + (stage))) : "memory");
         if (probe) { const long long q2 = clock64(); pt[0] += q1 - q0; pt[1] += q2 - q1; pt[2] += 1; }
         if (++stage == CT_STAGES) { stage = 0; ++use; }
       }
@@ -175,11 +181,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
     for (int64_t tile = tile0; tile < p.num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
       const long long m0 = probe ? clock64() : 0;
-      if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);         // epilogue drained this accumulator
+      if (it >= 2) wait_a(BA(ACC_EMPTY + (acc)), ((it >> 1) - 1) & 1);         // epilogue drained this accumulator
       if (probe) pt[0] += clock64() - m0;
       for (int cb = 0; cb < ncb; ++cb) {
         const long long m1 = probe ? clock64() : 0;
-        mbar_wait(&full[stage], use & 1);
+        wait_a(BA(FULL + (stage)), use & 1);
         const long long m2 = probe ? clock64() : 0;
         if (leader) {
           tc_fence_after();
@@ -253,8 +259,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
               ad_t += a_t;
             }
           }
-          mma_commit(&empty[stage]);
-          if (cb == ncb - 1) mma_commit(&acc_full[acc]);
+          commit_a(BA(EMPTY + (stage)));
+          if (cb == ncb - 1) commit_a(BA(ACC_FULL + (acc)));
         }
         __syncwarp();
         if (probe) { pt[1] += m2 - m1; pt[2] += clock64() - m2; pt[3] += 1; }
@@ -333,12 +339,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
         }
       }
       const long long e0 = probe ? clock64() : 0;
-      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      wait_a(BA(ACC_FULL + (acc)), (it >> 1) & 1);
       const long long e1 = probe ? clock64() : 0;
       tc_fence_after();
       if (npass == 0) {                                      // narrow N tile: this warp only keeps the barrier phases in step
         tc_fence_before();
-        mbar_arrive(&acc_empty[acc]);
+        arrive_a(BA(ACC_EMPTY + (acc)));
       }
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_tc(ConvTcArgs p) {
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * 128 + 32 * h + 64 * k, t32);
           if (k == npass - 1) {                              // accumulator drained: the MMAs of tile it+2 may start
             tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
+            arrive_a(BA(ACC_EMPTY + (acc)));
           }
 #pragma unroll
           for (int c = 0; c < 8; ++c)

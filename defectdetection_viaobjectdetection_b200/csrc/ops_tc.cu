@@ -70,7 +70,10 @@ struct GemmTcArgs {
 
 __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[GT_STAGES], empty[GT_STAGES], acc_full[2], acc_empty[2];
+  // all mbarriers in ONE array behind a pinned base address (as separate variables every use re-derived its shared-window
+  // address with S2R + LEA): full[GT_STAGES] | empty[GT_STAGES] | acc_full[2] | acc_empty[2]
+  __shared__ __align__(8) uint64_t bars[2 * GT_STAGES + 4];
+  constexpr int FULL = 0, EMPTY = GT_STAGES, ACC_FULL = 2 * GT_STAGES, ACC_EMPTY = 2 * GT_STAGES + 2;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[256];
 
@@ -91,8 +94,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
 
   if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
   if (tid == 0) {
-    for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&full[s], GT_LOAD_WARPS); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], GT_EPI_WARPS * 32); }
+    for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&bars[FULL + s], GT_LOAD_WARPS); mbar_init(&bars[EMPTY + s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars[ACC_FULL + a], 1); mbar_init(&bars[ACC_EMPTY + a], GT_EPI_WARPS * 32); }
     fence_mbar_init();
   }
   {  // resident weights of this N tile: one contiguous block of the packed layout
@@ -106,6 +109,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  uint32_t bar_u = smem_u32(bars);
+  asm volatile("" : "+r"(bar_u));
+  auto BA = [&](int idx) { return bar_u + (uint32_t)idx * 8u; };
 
   if (warp > GT_EPI_WARPS) {
     // ================= loaders =================
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
         // the next block's weights are requested now (its slot must be free), so that they land while this
         // block's activations are converted; this block's slot was waited for one iteration ago
         if (have_n) {
-          if (use_n > 0) mbar_wait(&empty[stage_n], (use_n - 1) & 1);
+          if (use_n > 0) wait_a(BA(EMPTY + (stage_n)), (use_n - 1) & 1);
           load_b(kb_n, stage_n);
           load(tile_n, kb_n, nxt);
         }
@@ -176,12 +182,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
       } else {
         if (have_n) load(tile_n, kb_n, nxt);                        // next block in flight while this one is stored
-        if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);       // MMAs that read this slot are done
+        if (use > 0) wait_a(BA(EMPTY + (stage)), (use - 1) & 1);       // MMAs that read this slot are done
         store(stage, cur);
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
+      if (lane == 0) arrive_a(BA(FULL + (stage)));
       stage = stage_n; use = use_n;
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
@@ -197,9 +203,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
     uint32_t use = 0;
     for (int64_t tile = tile0; tile < num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
-      if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
+      if (it >= 2) wait_a(BA(ACC_EMPTY + (acc)), ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[stage], use & 1);
+        wait_a(BA(FULL + (stage)), use & 1);
         if (leader) {
           tc_fence_after();
           const int nch = min(8, chunks_total - kb * 8);             // chunks of this block (even)
@@ -212,8 +218,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
             ad += a_ks;
             bd += b_ks;
           }
-          mma_commit(&empty[stage]);
-          if (kb == nkb - 1) mma_commit(&acc_full[acc]);
+          commit_a(BA(EMPTY + (stage)));
+          if (kb == nkb - 1) commit_a(BA(ACC_FULL + (acc)));
         }
         __syncwarp();
         if (++stage == GT_STAGES) { stage = 0; ++use; }
@@ -235,11 +241,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
     int it = 0;
     for (int64_t tile = tile0; tile < num_tiles; tile += tstep, ++it) {
       const int acc = it & 1;
-      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      wait_a(BA(ACC_FULL + (acc)), (it >> 1) & 1);
       tc_fence_after();
       if (npass == 0) {                                      // narrow N tile: only keep the barrier phases in step
         tc_fence_before();
-        mbar_arrive(&acc_empty[acc]);
+        arrive_a(BA(ACC_EMPTY + (acc)));
       }
       const int64_t m0 = tile * BM + q * 32 + rr;
       const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
         tmem_ld32(t_row + c0, t32);
         if (k == npass - 1) {                                // accumulator drained: the MMAs of tile it+2 may start
           tc_fence_before();
-          mbar_arrive(&acc_empty[acc]);
+          arrive_a(BA(ACC_EMPTY + (acc)));
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c)
