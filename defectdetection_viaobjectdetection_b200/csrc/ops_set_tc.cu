@@ -393,7 +393,7 @@ constexpr float LAZY_MAX = 8.f;        // the reference maximum of a row is rais
 // VAR != 0: timing experiments only (wrong results): 1 no exponentials, 2 no P V / row-sum products, 3 no Q K^T products,
 // 4 no K / V projection, 5 no maximum check after the first block, 6 no softmax loop at all
 template <int VAR>
-__global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block_p(AttnBlockArgs p, int nsets, int Np) {
+__global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block_p(AttnBlockArgs p, int nsets, int Np, unsigned skew_ns) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int N = p.N;
   const uint32_t voff = (uint32_t)(Np * WS * 2);                          // V [Np][WS] fp16 follows K [Np][WS] bf16
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block_p(AttnBlock
   const int bar_id = 1 + team;
 
   // the teams start half a set apart and, doing the same work at the same speed, stay apart
-  if (team == 1) __nanosleep(12000);
+  if (team == 1 && skew_ns) __nanosleep(skew_ns);
 
   for (int set = (int)blockIdx.x * TEAMS + team; set < nsets; set += (int)gridDim.x * TEAMS) {
     const float* xs = p.x + (size_t)set * N * DM;
@@ -772,9 +772,10 @@ void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bq
   if (!force_v1 && (int)smem_p <= c.smem_optin && (N + 15) / 16 <= 2 * TW) {
     const unsigned grid = (unsigned)std::min<int64_t>((B + TEAMS - 1) / TEAMS, c.num_sms);
     static const int var = [] { const char* e = std::getenv("PAUT_ATTN_VARIANT"); return e ? std::atoi(e) : 0; }();
+    static const unsigned skew = [] { const char* e = std::getenv("PAUT_ATTN_SKEW_NS"); return e ? (unsigned)std::atoi(e) : 12000u; }();
     auto launch = [&](auto kern) {
       smem_optin(c, kern);
-      kern<<<grid, AB_WARPS * 32, smem_p, c.stream>>>(p, (int)B, Np16);
+      kern<<<grid, AB_WARPS * 32, smem_p, c.stream>>>(p, (int)B, Np16, skew);
     };
     switch (var) {                                   // timing experiments (tools/r2t.sh); 0 = the product kernel
       case 1: launch(k_msc_attn_block_p<1>); break;
