@@ -221,6 +221,10 @@ bool msc_attn_tc_supported(int N, int d, int heads);
 void msc_attn_tc_pack(const float* W, int row0, int rows, std::vector<uint16_t>& out);
 void op_msc_attn_tc(Ctx& c, const float* x, const void* Wqk, const void* Wv, const void* Wo, const float* bqkv, const float* bo,
                     const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift);
+bool ts_heads_supported(int d, int hidden);
+void op_ts_heads(Ctx& c, const float* x, const float* ng, const float* nb, const void* const* W0, const float* const* b0,
+                 const float* const* lg, const float* const* lb, const float* const* W4, const float* const* b4, const int* act,
+                 const float* eps, float* const* out, int64_t M);
 void op_msc_ffn_head(Ctx& c, const float* x, const float* pre, const float* pre_g, const float* pre_b, const void* W1,
                      const float* b1, const void* W2, const float* b2, const float* ln_g, const float* ln_b,
                      const void* Wc, const float* bc, float* prob, float* start, float* end, int64_t M);

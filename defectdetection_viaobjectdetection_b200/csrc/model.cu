@@ -737,6 +737,26 @@ void Model::finalize() {
         ts_grouped.shift = upload(shift_all);
         ts_grouped.ready = true;
       }
+      ts_heads = TsHeads{};
+      if (cfg.precision == PAUT_PRECISION_BF16 && ts_heads_supported(d, 64)) {
+        const char* mods[4] = {"defect_classifier.classifier", "defect_classifier.uncertainty",
+                               "position_predictor.position_predictor", "position_predictor.uncertainty"};
+        for (int h = 0; h < 4; ++h) {
+          const std::vector<float>& w = H(std::string(mods[h]) + ".0.weight").data;       // [64][128]
+          std::vector<uint16_t> hb(w.size());
+          for (size_t i = 0; i < w.size(); ++i) {
+            uint32_t u;
+            memcpy(&u, &w[i], 4);
+            hb[i] = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+          }
+          void* dp = nullptr;
+          PAUT_CUDA(cudaMalloc(&dp, hb.size() * sizeof(uint16_t)));
+          dev_allocs.push_back(dp);
+          PAUT_CUDA(cudaMemcpy(dp, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+          ts_heads.W0[h] = dp;
+        }
+        ts_heads.ready = true;
+      }
       ts_enc = TsEnc{};
       if (cfg.precision == PAUT_PRECISION_BF16 && d == 128) {
         // operands of the fused encoder kernel: BatchNorm folded on the host in fp64, everything in fp16 (stem weights
@@ -1217,6 +1237,26 @@ void Model::fwd_two_stage(XIn& x, int64_t B, int N, int S, const paut_outputs& o
     seq = seq2;
   }
   for (const TELW& t : tel) seq = g.encoder_layer(seq, t, B, N, ACT_RELU);
+  static const bool heads_unfused = std::getenv("PAUT_TS_HEADS_UNFUSED") != nullptr;     // A/B switch
+  if (g.bf16 && ts_heads.ready && !heads_unfused) {
+    // final LayerNorm + the four heads in one kernel (two_stage_model.py:160-251): the rows are read once
+    const char* mods[4] = {"defect_classifier.classifier", "defect_classifier.uncertainty",
+                           "position_predictor.position_predictor", "position_predictor.uncertainty"};
+    const int acts[4] = {ACT_NONE, ACT_SOFTPLUS, ACT_SIGMOID, ACT_SOFTPLUS};
+    const float epss[4] = {0.f, 1e-6f, 0.f, 1e-6f};
+    float* logits = slot_at<float>(out, 0, b0 * N * 2);
+    if (!logits) logits = c.allocf((size_t)A * 2);
+    float* outs[4] = {logits, slot_at<float>(out, 2, b0 * N * 2), slot_at<float>(out, 3, b0 * N * 2), slot_at<float>(out, 4, b0 * N * 2)};
+    const float *b0s[4], *lgs[4], *lbs[4], *w4s[4], *b4s[4];
+    for (int h = 0; h < 4; ++h) {
+      const std::string m = mods[h];
+      b0s[h] = lin[m + ".0"].b; lgs[h] = ln[m + ".1"].g; lbs[h] = ln[m + ".1"].b; w4s[h] = lin[m + ".4"].W; b4s[h] = lin[m + ".4"].b;
+    }
+    const LNW& fn = ln["sequence_transformer.norm"];
+    op_ts_heads(c, seq, fn.g, fn.b, ts_heads.W0, b0s, lgs, lbs, w4s, b4s, acts, epss, outs, A);
+    op_two_stage_final(c, logits, slot_at<float>(out, 1, b0 * N * 2), outs[2], A);
+    return;
+  }
   seq = g.norm(seq, nullptr, ln["sequence_transformer.norm"], A);
   auto head = [&](const std::string& m, int act, float eps, float* dst) {
     float* h = g.linear(seq, d, lin[m + ".0"], A);

@@ -116,6 +116,10 @@ struct Model {
     const float* shift2 = nullptr;             // [128]
     bool ready = false;
   } ts_enc;
+  struct TsHeads {                             // first Linear of the four two-stage heads as plain bf16 [64][128] (ops_set_tc.cu)
+    const void* W0[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ready = false;
+  } ts_heads;
   struct BranchConv {                          // the enhanced encoder's four dilated branches as one launch
     const void* Wp = nullptr;
     const float* shift = nullptr;              // [128] (the conv biases)

@@ -750,6 +750,137 @@ __global__ void __launch_bounds__(256) k_msc_ffn_head(FfnHeadArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ two-stage heads
+// The four heads of TwoStageDefectDetector (defect classifier, its uncertainty, position predictor, its uncertainty:
+// two_stage_model.py:160-251) are each  Linear 128 -> 64, LayerNorm(64), ReLU, Linear 64 -> 2, activation  on the
+// transformer output after its final LayerNorm(128).  As separate launches that is 13 kernels and ~4.5 ms per 1 M A-scans
+// (four GEMMs that each re-read the 512-byte rows, four LayerNorms, four 64 -> 2 row kernels, the final norm); here a
+// warp takes 16 rows, normalises them in registers and runs the four heads on mma.sync fragments: the rows are read
+// once and 8 floats per head row are written.
+constexpr int HW = 128, HH = 64, HS = HW + 8;      // head input width, hidden width, bf16 row stride of the staged weights
+
+struct TsHeadsArgs {
+  const float* x;                      // [M, 128] transformer output before sequence_transformer.norm
+  const float* ng;                     // final norm
+  const float* nb;
+  const __nv_bfloat16* W0[4];          // [64][128]
+  const float* b0[4];
+  const float* lg[4];                  // LayerNorm(64)
+  const float* lb[4];
+  const float* W4[4];                  // [2][64] fp32
+  const float* b4[4];
+  int act[4];
+  float eps[4];
+  float* out[4];                       // [M, 2] (null: head not wanted)
+  int64_t M;
+};
+
+__device__ __forceinline__ float head_act(float v, int act) {
+  if (act == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  if (act == ACT_SOFTPLUS) return v > 20.f ? v : log1pf(expf(v));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_ts_heads(TsHeadsArgs p) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(hsm);            // [4][64][HS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < 4 * HH * (HW / 8); i += 256) {
+    const int h = i / (HH * (HW / 8)), r = (i / (HW / 8)) % HH, c8 = i % (HW / 8);
+    if (p.out[h])
+      *reinterpret_cast<uint4*>(Ws + ((size_t)h * HH + r) * HS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.W0[h] + (size_t)r * HW + c8 * 8));
+  }
+  __syncthreads();
+  const int lm_i = lane >> 3, lm_r = lane & 7;
+  const uint32_t w_lane = smem_u32(Ws) + (uint32_t)(lm_r * HS * 2 + (lm_i >> 1) * 32 + (lm_i & 1) * 16);
+
+  const int64_t tiles = (p.M + 15) / 16;
+  for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < tiles; tile += (int64_t)gridDim.x * 8) {
+    const int64_t row_lo = tile * 16 + g, row_hi = row_lo + 8;
+    const bool p_lo = row_lo < p.M, p_hi = row_hi < p.M;
+    const float* x_lo = p.x + (p_lo ? row_lo : 0) * HW + 2 * t;
+    const float* x_hi = p.x + (p_hi ? row_hi : 0) * HW + 2 * t;
+    // ---- the 16 x 128 tile in accumulator layout, final LayerNorm(128) in registers
+    float x[16][4];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(x_lo + nt * 8));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(x_hi + nt * 8));
+      x[nt][0] = a.x; x[nt][1] = a.y; x[nt][2] = b.x; x[nt][3] = b.y;
+      s0 += a.x + a.y; s1 += b.x + b.y;
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float m0 = s0 * (1.f / HW), m1 = s1 * (1.f / HW);
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float a = x[nt][0] - m0, b = x[nt][1] - m0, c = x[nt][2] - m1, d = x[nt][3] - m1;
+      q0 += a * a + b * b; q1 += c * c + d * d;
+    }
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    const float r0 = rsqrtf(q0 * (1.f / HW) + 1e-5f), r1 = rsqrtf(q1 * (1.f / HW) + 1e-5f);
+    uint32_t xa[8][4];                                     // A fragments of the normalised tile, 8 k-steps
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      float v[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int nt = 2 * ks + j;
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(p.ng + nt * 8 + 2 * t));
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(p.nb + nt * 8 + 2 * t));
+        v[j][0] = (x[nt][0] - m0) * r0 * gg.x + bb.x; v[j][1] = (x[nt][1] - m0) * r0 * gg.y + bb.y;
+        v[j][2] = (x[nt][2] - m1) * r1 * gg.x + bb.x; v[j][3] = (x[nt][3] - m1) * r1 * gg.y + bb.y;
+      }
+      c_to_a(v[0], v[1], xa[ks]);
+    }
+    // ---- the heads
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      if (!p.out[h]) continue;
+      float hc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 b = __ldg(reinterpret_cast<const float2*>(p.b0[h] + nt * 8 + 2 * t));
+        hc[nt][0] = b.x; hc[nt][1] = b.y; hc[nt][2] = b.x; hc[nt][3] = b.y;
+        const uint32_t wa = w_lane + (uint32_t)((h * HH + nt * 8) * HS * 2);
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {                   // four k-steps pairs: ldmatrix.x4 = two k-steps of one n-tile
+          uint32_t w0, w1, w2, w3;
+          ldsm4(wa + kq * 64, w0, w1, w2, w3);
+          mma_bf16_16816(hc[nt], xa[2 * kq], w0, w1);
+          mma_bf16_16816(hc[nt], xa[2 * kq + 1], w2, w3);
+        }
+      }
+      layer_norm_tile2(hc, p.lg[h], p.lb[h], t);
+      // ReLU, then Linear 64 -> 2 as per-lane partial dot products reduced over the quad
+      float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;     // [row lo / hi][output 0 / 1]
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 wA = __ldg(reinterpret_cast<const float2*>(p.W4[h] + nt * 8 + 2 * t));
+        const float2 wB = __ldg(reinterpret_cast<const float2*>(p.W4[h] + HH + nt * 8 + 2 * t));
+        const float a = fmaxf(hc[nt][0], 0.f), b = fmaxf(hc[nt][1], 0.f), c = fmaxf(hc[nt][2], 0.f), d = fmaxf(hc[nt][3], 0.f);
+        o00 += a * wA.x + b * wA.y; o01 += a * wB.x + b * wB.y;
+        o10 += c * wA.x + d * wA.y; o11 += c * wB.x + d * wB.y;
+      }
+      o00 += __shfl_xor_sync(0xffffffffu, o00, 1); o00 += __shfl_xor_sync(0xffffffffu, o00, 2);
+      o01 += __shfl_xor_sync(0xffffffffu, o01, 1); o01 += __shfl_xor_sync(0xffffffffu, o01, 2);
+      o10 += __shfl_xor_sync(0xffffffffu, o10, 1); o10 += __shfl_xor_sync(0xffffffffu, o10, 2);
+      o11 += __shfl_xor_sync(0xffffffffu, o11, 1); o11 += __shfl_xor_sync(0xffffffffu, o11, 2);
+      if (t == 0) {
+        const float bA = __ldg(p.b4[h]), bB = __ldg(p.b4[h] + 1);
+        const int act = p.act[h];
+        const float eps = p.eps[h];
+        if (p_lo) *reinterpret_cast<float2*>(p.out[h] + row_lo * 2) = make_float2(head_act(o00 + bA, act) + eps, head_act(o01 + bB, act) + eps);
+        if (p_hi) *reinterpret_cast<float2*>(p.out[h] + row_hi * 2) = make_float2(head_act(o10 + bA, act) + eps, head_act(o11 + bB, act) + eps);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 bool msc_set_tc_supported(int N, int d, int heads, int ff) { return d == DM && heads == NH && ff == FF && N >= 1 && N <= 320; }
@@ -807,6 +938,27 @@ void op_msc_ffn_head(Ctx& c, const float* x, const float* pre, const float* pre_
   if (blocks > c.num_sms * 8) blocks = c.num_sms * 8;
   k_msc_ffn_head<<<(unsigned)blocks, 256, 0, c.stream>>>(p);
   c.launched("msc_ffn_head");
+}
+
+bool ts_heads_supported(int d, int hidden) { return d == HW && hidden == HH; }
+
+void op_ts_heads(Ctx& c, const float* x, const float* ng, const float* nb, const void* const* W0, const float* const* b0,
+                 const float* const* lg, const float* const* lb, const float* const* W4, const float* const* b4, const int* act,
+                 const float* eps, float* const* out, int64_t M) {
+  if (c.dry) return;
+  TsHeadsArgs p;
+  p.x = x; p.ng = ng; p.nb = nb; p.M = M;
+  for (int h = 0; h < 4; ++h) {
+    p.W0[h] = static_cast<const __nv_bfloat16*>(W0[h]); p.b0[h] = b0[h]; p.lg[h] = lg[h]; p.lb[h] = lb[h];
+    p.W4[h] = W4[h]; p.b4[h] = b4[h]; p.act[h] = act[h]; p.eps[h] = eps[h]; p.out[h] = out[h];
+  }
+  const size_t smem = (size_t)4 * HH * HS * sizeof(__nv_bfloat16);
+  smem_optin(c, k_ts_heads);
+  const int64_t tiles = (M + 15) / 16;
+  int64_t blocks = (tiles + 7) / 8;
+  if (blocks > (int64_t)c.num_sms * 3) blocks = (int64_t)c.num_sms * 3;   // 70 KB of staged weights: three CTAs per SM
+  k_ts_heads<<<(unsigned)blocks, 256, smem, c.stream>>>(p);
+  c.launched("ts_heads");
 }
 
 }  // namespace paut
