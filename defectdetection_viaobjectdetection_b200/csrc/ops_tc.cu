@@ -251,6 +251,19 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
       const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
       for (int k = 0; k < npass; ++k) {
         const int c0 = 32 * half + 64 * k;
+        // the residual rows of this pass are requested FIRST: their latency then hides behind the TMEM load and the
+        // transposition (requested at the point of use, each of the eight adds waited for its own load -- ncu: 30 % of the
+        // kernel's stall samples on the 512 -> 128 + residual layer, profiles/r02/3j_ncu_gemm_tc_two_stage.txt)
+        float4 rres[8];
+        const bool has_res = p.res != nullptr && c0 + 4 * cg < NT;
+        if (has_res) {
+          const float* rp = p.res + (int64_t)(nt * NT + c0 + 4 * cg);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + 4 * i;
+            rres[i] = m < p.M ? __ldg(reinterpret_cast<const float4*>(rp + m * p.ldr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t t32[32];
         tmem_ld32(t_row + c0, t32);
         if (k == npass - 1) {                                // accumulator drained: the MMAs of tile it+2 may start
@@ -275,10 +288,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
             if (m < p.M) {
               t.x = tc_act(t.x + b4.x, p.act) + p.act_eps; t.y = tc_act(t.y + b4.y, p.act) + p.act_eps;
               t.z = tc_act(t.z + b4.z, p.act) + p.act_eps; t.w = tc_act(t.w + b4.w, p.act) + p.act_eps;
-              if (p.res) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + m * p.ldr + n));
-                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
-              }
+              if (has_res) { t.x += rres[i].x; t.y += rres[i].y; t.z += rres[i].z; t.w += rres[i].w; }
               if (p.table) {
                 const float4 r = __ldg(reinterpret_cast<const float4*>(p.table + (m % p.table_mod) * p.N + n));
                 t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
