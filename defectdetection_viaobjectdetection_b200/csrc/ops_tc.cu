@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs p) {
         if (have_n) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
       } else {
-        if (have_n) load(tile_n, kb_n, nxt);                        // next block in flight while this one is stored
+        // next block in flight while this one is stored.  (Two stages in flight per thread -- each register set refilled
+        // right after its stage is stored -- was measured in round 2: no change, 10.90 -> 10.86 ms on the two-stage model's
+        // linears; after the residual prefetch below the loaders are not what bounds this kernel.)
+        if (have_n) load(tile_n, kb_n, nxt);
         if (use > 0) wait_a(BA(EMPTY + (stage)), (use - 1) & 1);       // MMAs that read this slot are done
         store(stage, cur);
       }
