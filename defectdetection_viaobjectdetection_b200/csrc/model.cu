@@ -297,6 +297,19 @@ Lin Model::pack_lin_rows(const std::string& wkey, const std::string& bkey, int r
 // bf16 mode: additionally pack the weight for the tcgen05 GEMM (chunked K-major bf16)
 void Model::pack_tc(Lin& l, const std::vector<float>& W) {
   if (cfg.precision != PAUT_PRECISION_BF16) return;
+  if (lin_res_ln_supported(l.N, l.K, l.K)) {           // candidates for the fused Linear + residual + LayerNorm kernel
+    std::vector<uint16_t> hb(W.size());
+    for (size_t i = 0; i < W.size(); ++i) {
+      uint32_t u;
+      memcpy(&u, &W[i], 4);
+      hb[i] = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+    }
+    void* dp = nullptr;
+    PAUT_CUDA(cudaMalloc(&dp, hb.size() * sizeof(uint16_t)));
+    dev_allocs.push_back(dp);
+    PAUT_CUDA(cudaMemcpy(dp, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    l.Wrow = dp;
+  }
   const int nt = tc_pick_ntile(l.N, l.K, &l.stream_b);
   if (nt == 0) return;
   std::vector<uint16_t> packed;
@@ -916,6 +929,23 @@ struct G {
   // post-norm encoder layer (nn.TransformerEncoderLayer / SelfAttentionBlock)
   float* encoder_layer(const float* x, const TELW& t, int64_t B, int N, int act, float* avgw = nullptr) {
     const int64_t M = B * N;
+    static const bool unfused = std::getenv("PAUT_LRL_UNFUSED") != nullptr;          // A/B switch
+    const bool fuse = bf16 && !unfused && t.attn.D == 128 && t.n1.D == 128 && t.n2.D == 128 && t.attn.out_proj.Wrow && t.l2.Wrow &&
+                      lin_res_ln_supported(t.attn.out_proj.N, t.attn.out_proj.K, t.attn.Dp) &&
+                      lin_res_ln_supported(t.l2.N, t.l2.K, t.l1.N);
+    if (fuse) {
+      // out-projection + residual + LayerNorm and FFN layer 2 + residual + LayerNorm as one mma.sync kernel each
+      const MHAW& m = t.attn;
+      float* qkv = linear(x, m.D, m.in_proj, M);
+      float* att = c.allocf((size_t)M * m.Dp);
+      attention(qkv, 3 * m.Dp, qkv + m.Dp, 3 * m.Dp, qkv + 2 * m.Dp, 3 * m.Dp, att, m.Dp, B, N, N, m.H, m.hd, false, avgw);
+      float* x1 = c.allocf((size_t)M * 128);
+      op_lin_res_ln(c, att, m.Dp, m.out_proj.Wrow, m.out_proj.K, m.out_proj.b, x, t.n1.g, t.n1.b, x1, M);
+      float* h = linear(x1, m.D, t.l1, M, act);
+      float* out = c.allocf((size_t)M * 128);
+      op_lin_res_ln(c, h, t.l1.N, t.l2.Wrow, t.l2.K, t.l2.b, x1, t.n2.g, t.n2.b, out, M);
+      return out;
+    }
     float* y = self_attention(x, t.attn, B, N, x, false, avgw);
     float* x1 = norm(y, nullptr, t.n1, M);
     float* h = linear(x1, t.attn.D, t.l1, M, act);

@@ -20,6 +20,7 @@ struct Lin {
   const float* W = nullptr;   // [N][K]
   const float* b = nullptr;
   const void* Wp = nullptr;   // bf16 packed for tcgen05 (bf16 mode only)
+  const void* Wrow = nullptr; // plain bf16 [N][K] for the mma.sync Linear + residual + LayerNorm kernel (N = 128, bf16 mode)
   int NT = 0;
   int stream_b = 0;              // tcgen05 GEMM mode chosen with NT (weights resident or streamed)
   int K = 0, N = 0;

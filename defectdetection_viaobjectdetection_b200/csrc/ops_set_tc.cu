@@ -881,6 +881,118 @@ __global__ void __launch_bounds__(256) k_ts_heads(TsHeadsArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ Linear + residual + LayerNorm
+// out = LayerNorm(x W^T + b + res) for a 128-wide output: the attention out-projection and the second FFN layer of a
+// post-norm encoder layer with d_model 128 (two-stage model, SignalSequenceDetector).  As a tcgen05 GEMM followed by a
+// LayerNorm launch the sum made a round trip through HBM (512 B written + read per row) and the GEMM's epilogue was its
+// slowest part; here a warp owns 16 rows: A fragments straight from the fp32 activations, W (bf16, rows padded by 8)
+// resident in shared memory and read through ldmatrix, the 16 x 128 sum and its LayerNorm in registers.
+constexpr int LRL_N = 128;
+
+struct LinResLnArgs {
+  const float* x;                      // [M, lda] fp32
+  int lda, K;                          // K % 32 == 0
+  const __nv_bfloat16* W;              // [128][K]
+  const float* bias;
+  const float* res;                    // [M, 128]
+  const float* g;
+  const float* b;
+  float* out;                          // [M, 128]
+  int64_t M;
+};
+
+// THREADS = 256 with two CTAs per SM (weights <= ~100 KB) or 512 with one: 16 warps per SM either way at 128 registers
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) k_lin_res_ln(LinResLnArgs p) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(lsm);            // [128][K + 8]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int K = p.K, KS = K + 8;
+  for (int i = tid; i < LRL_N * (K / 8); i += THREADS) {
+    const int r = i / (K / 8), c8 = i - r * (K / 8);
+    *reinterpret_cast<uint4*>(Ws + (size_t)r * KS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.W + (size_t)r * K + c8 * 8));
+  }
+  __syncthreads();
+  const int lm_i = lane >> 3, lm_r = lane & 7;
+  const uint32_t w_lane = smem_u32(Ws) + (uint32_t)(lm_r * KS * 2 + (lm_i >> 1) * 32 + (lm_i & 1) * 16);
+  const uint32_t nt_stride = (uint32_t)(8 * KS * 2);
+
+  const int64_t tiles = (p.M + 15) / 16;
+  for (int64_t tile = (int64_t)blockIdx.x * (THREADS / 32) + warp; tile < tiles; tile += (int64_t)gridDim.x * (THREADS / 32)) {
+    const int64_t row_lo = tile * 16 + g, row_hi = row_lo + 8;
+    const bool p_lo = row_lo < p.M, p_hi = row_hi < p.M;
+    const float* x_lo = p.x + (p_lo ? row_lo : 0) * p.lda + 2 * t;
+    const float* x_hi = p.x + (p_hi ? row_hi : 0) * p.lda + 2 * t;
+    const float* r_lo = p.res + (p_lo ? row_lo : 0) * LRL_N + 2 * t;
+    const float* r_hi = p.res + (p_hi ? row_hi : 0) * LRL_N + 2 * t;
+    float y[16][4];
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + nt * 8 + 2 * t));
+      const float2 a = __ldg(reinterpret_cast<const float2*>(r_lo + nt * 8));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(r_hi + nt * 8));
+      y[nt][0] = bb.x + a.x; y[nt][1] = bb.y + a.y; y[nt][2] = bb.x + b.x; y[nt][3] = bb.y + b.y;
+    }
+    // K in steps of 32 (two MMA k-steps = one ldmatrix.x4 per 8 output columns); the activations of the next step are
+    // requested before this step's products
+    auto load_a = [&](int kq, float2 (&v)[8]) {
+      const int k = kq * 32;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        v[4 * j + 0] = __ldg(reinterpret_cast<const float2*>(x_lo + k + 16 * j));
+        v[4 * j + 1] = __ldg(reinterpret_cast<const float2*>(x_hi + k + 16 * j));
+        v[4 * j + 2] = __ldg(reinterpret_cast<const float2*>(x_lo + k + 16 * j + 8));
+        v[4 * j + 3] = __ldg(reinterpret_cast<const float2*>(x_hi + k + 16 * j + 8));
+      }
+    };
+    const int nkq = K / 32;
+    float2 cur[8], nxt[8];
+    load_a(0, cur);
+    for (int kq = 0; kq < nkq; ++kq) {
+      if (kq + 1 < nkq) load_a(kq + 1, nxt);
+      uint32_t a0[4], a1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a0[i] = pack_bf16(cur[i].x, cur[i].y); a1[i] = pack_bf16(cur[4 + i].x, cur[4 + i].y); }
+      const uint32_t wk = w_lane + (uint32_t)kq * 64;
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        uint32_t w0, w1, w2, w3;
+        ldsm4(wk + (uint32_t)nt * nt_stride, w0, w1, w2, w3);
+        mma_bf16_16816(y[nt], a0, w0, w1);
+        mma_bf16_16816(y[nt], a1, w2, w3);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
+    // LayerNorm(128) on the accumulator fragments
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) { s0 += y[nt][0] + y[nt][1]; s1 += y[nt][2] + y[nt][3]; }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float m0 = s0 * (1.f / LRL_N), m1 = s1 * (1.f / LRL_N);
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float a = y[nt][0] - m0, b = y[nt][1] - m0, c = y[nt][2] - m1, d = y[nt][3] - m1;
+      q0 += a * a + b * b; q1 += c * c + d * d;
+    }
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    const float r0 = rsqrtf(q0 * (1.f / LRL_N) + 1e-5f), r1 = rsqrtf(q1 * (1.f / LRL_N) + 1e-5f);
+    float* o_lo = p.out + row_lo * LRL_N + 2 * t;
+    float* o_hi = p.out + row_hi * LRL_N + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(p.g + nt * 8 + 2 * t));
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b + nt * 8 + 2 * t));
+      if (p_lo) *reinterpret_cast<float2*>(o_lo + nt * 8) = make_float2((y[nt][0] - m0) * r0 * gg.x + bb.x, (y[nt][1] - m0) * r0 * gg.y + bb.y);
+      if (p_hi) *reinterpret_cast<float2*>(o_hi + nt * 8) = make_float2((y[nt][2] - m1) * r1 * gg.x + bb.x, (y[nt][3] - m1) * r1 * gg.y + bb.y);
+    }
+  }
+}
+
 }  // namespace
 
 bool msc_set_tc_supported(int N, int d, int heads, int ff) { return d == DM && heads == NH && ff == FF && N >= 1 && N <= 320; }
@@ -959,6 +1071,31 @@ void op_ts_heads(Ctx& c, const float* x, const float* ng, const float* nb, const
   if (blocks > (int64_t)c.num_sms * 3) blocks = (int64_t)c.num_sms * 3;   // 70 KB of staged weights: three CTAs per SM
   k_ts_heads<<<(unsigned)blocks, 256, smem, c.stream>>>(p);
   c.launched("ts_heads");
+}
+
+bool lin_res_ln_supported(int N, int K, int lda) { return N == LRL_N && K % 32 == 0 && K >= 32 && K <= 512 && lda % 2 == 0; }
+
+void op_lin_res_ln(Ctx& c, const float* x, int lda, const void* Wrow, int K, const float* bias, const float* res, const float* g,
+                   const float* b, float* out, int64_t M) {
+  if (c.dry) return;
+  PAUT_CHECK(lin_res_ln_supported(LRL_N, K, lda), PAUT_ERR_UNSUPPORTED, "lin_res_ln: unsupported shape");
+  LinResLnArgs p;
+  p.x = x; p.lda = lda; p.K = K; p.W = static_cast<const __nv_bfloat16*>(Wrow); p.bias = bias; p.res = res; p.g = g; p.b = b;
+  p.out = out; p.M = M;
+  const size_t smem = (size_t)LRL_N * (K + 8) * sizeof(__nv_bfloat16);
+  const int64_t tiles = (M + 15) / 16;
+  if (smem > 100 * 1024) {                                 // one CTA of 16 warps per SM
+    smem_optin(c, k_lin_res_ln<512>);
+    int64_t blocks = (tiles + 15) / 16;
+    if (blocks > (int64_t)c.num_sms) blocks = c.num_sms;
+    k_lin_res_ln<512><<<(unsigned)blocks, 512, smem, c.stream>>>(p);
+  } else {                                                 // two CTAs of 8 warps per SM
+    smem_optin(c, k_lin_res_ln<256>);
+    int64_t blocks = (tiles + 7) / 8;
+    if (blocks > (int64_t)c.num_sms * 2) blocks = (int64_t)c.num_sms * 2;
+    k_lin_res_ln<256><<<(unsigned)blocks, 256, smem, c.stream>>>(p);
+  }
+  c.launched("lin_res_ln");
 }
 
 }  // namespace paut
