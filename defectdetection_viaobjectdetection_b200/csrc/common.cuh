@@ -223,7 +223,7 @@ void op_msc_attn_tc(Ctx& c, const float* x, const void* Wqk, const void* Wv, con
                     const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift);
 bool lin_res_ln_supported(int N, int K, int lda);
 void op_lin_res_ln(Ctx& c, const float* x, int lda, const void* Wrow, int K, const float* bias, const float* res, const float* g,
-                   const float* b, float* out, int64_t M);
+                   const float* b, float* out, int64_t M, const float* table = nullptr, int table_mod = 0);
 bool ts_heads_supported(int d, int hidden);
 void op_ts_heads(Ctx& c, const float* x, const float* ng, const float* nb, const void* const* W0, const float* const* b0,
                  const float* const* lg, const float* const* lb, const float* const* W4, const float* const* b4, const int* act,

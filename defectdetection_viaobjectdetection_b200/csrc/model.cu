@@ -1258,9 +1258,17 @@ void Model::fwd_two_stage(XIn& x, int64_t B, int N, int S, const paut_outputs& o
     }
   }
   }
-  float* pr = g.linear(feat, d, lin["signal_encoder.projection.0"], A);
-  float* seq = g.norm(pr, nullptr, ln["signal_encoder.projection.1"], A);
-  {
+  float* seq = nullptr;
+  const Lin& pj = lin["signal_encoder.projection.0"];
+  static const bool lrl_unfused = std::getenv("PAUT_LRL_UNFUSED") != nullptr;
+  if (g.bf16 && !lrl_unfused && pj.Wrow && d == 128 && lin_res_ln_supported(pj.N, pj.K, d)) {
+    // projection Linear + LayerNorm + positional encoding (two_stage_model.py:86-89,133) in one kernel
+    seq = c.allocf((size_t)A * d);
+    const LNW& pn = ln["signal_encoder.projection.1"];
+    op_lin_res_ln(c, feat, d, pj.Wrow, pj.K, pj.b, nullptr, pn.g, pn.b, seq, A, raw["sequence_transformer.pos_encoder.pe"], N);
+  } else {
+    float* pr = g.linear(feat, d, pj, A);
+    seq = g.norm(pr, nullptr, ln["signal_encoder.projection.1"], A);
     // + pe[:, :N]: reuse the row-table epilogue through an identity-free path
     float* seq2 = c.allocf((size_t)A * d);
     op_add_table(c, seq, raw["sequence_transformer.pos_encoder.pe"], N, seq2, A, d);

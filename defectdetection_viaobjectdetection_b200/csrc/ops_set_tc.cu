@@ -894,9 +894,11 @@ struct LinResLnArgs {
   int lda, K;                          // K % 32 == 0
   const __nv_bfloat16* W;              // [128][K]
   const float* bias;
-  const float* res;                    // [M, 128]
+  const float* res;                    // [M, 128] (may be null)
   const float* g;
   const float* b;
+  const float* table;                  // optional [table_mod, 128] added AFTER the LayerNorm to row (m % table_mod): positional encoding
+  int table_mod;
   float* out;                          // [M, 128]
   int64_t M;
 };
@@ -924,15 +926,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) k_lin_res_ln(
     const bool p_lo = row_lo < p.M, p_hi = row_hi < p.M;
     const float* x_lo = p.x + (p_lo ? row_lo : 0) * p.lda + 2 * t;
     const float* x_hi = p.x + (p_hi ? row_hi : 0) * p.lda + 2 * t;
-    const float* r_lo = p.res + (p_lo ? row_lo : 0) * LRL_N + 2 * t;
-    const float* r_hi = p.res + (p_hi ? row_hi : 0) * LRL_N + 2 * t;
     float y[16][4];
+    if (p.res) {
+      const float* r_lo = p.res + (p_lo ? row_lo : 0) * LRL_N + 2 * t;
+      const float* r_hi = p.res + (p_hi ? row_hi : 0) * LRL_N + 2 * t;
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-      const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + nt * 8 + 2 * t));
-      const float2 a = __ldg(reinterpret_cast<const float2*>(r_lo + nt * 8));
-      const float2 b = __ldg(reinterpret_cast<const float2*>(r_hi + nt * 8));
-      y[nt][0] = bb.x + a.x; y[nt][1] = bb.y + a.y; y[nt][2] = bb.x + b.x; y[nt][3] = bb.y + b.y;
+      for (int nt = 0; nt < 16; ++nt) {
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + nt * 8 + 2 * t));
+        const float2 a = __ldg(reinterpret_cast<const float2*>(r_lo + nt * 8));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(r_hi + nt * 8));
+        y[nt][0] = bb.x + a.x; y[nt][1] = bb.y + a.y; y[nt][2] = bb.x + b.x; y[nt][3] = bb.y + b.y;
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + nt * 8 + 2 * t));
+        y[nt][0] = bb.x; y[nt][1] = bb.y; y[nt][2] = bb.x; y[nt][3] = bb.y;
+      }
     }
     // K in steps of 32 (two MMA k-steps = one ldmatrix.x4 per 8 output columns); the activations of the next step are
     // requested before this step's products
@@ -983,12 +993,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) k_lin_res_ln(
     const float r0 = rsqrtf(q0 * (1.f / LRL_N) + 1e-5f), r1 = rsqrtf(q1 * (1.f / LRL_N) + 1e-5f);
     float* o_lo = p.out + row_lo * LRL_N + 2 * t;
     float* o_hi = p.out + row_hi * LRL_N + 2 * t;
+    const float* t_lo = p.table ? p.table + ((p_lo ? row_lo : 0) % p.table_mod) * LRL_N + 2 * t : nullptr;
+    const float* t_hi = p.table ? p.table + ((p_hi ? row_hi : 0) % p.table_mod) * LRL_N + 2 * t : nullptr;
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) {
       const float2 gg = __ldg(reinterpret_cast<const float2*>(p.g + nt * 8 + 2 * t));
       const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b + nt * 8 + 2 * t));
-      if (p_lo) *reinterpret_cast<float2*>(o_lo + nt * 8) = make_float2((y[nt][0] - m0) * r0 * gg.x + bb.x, (y[nt][1] - m0) * r0 * gg.y + bb.y);
-      if (p_hi) *reinterpret_cast<float2*>(o_hi + nt * 8) = make_float2((y[nt][2] - m1) * r1 * gg.x + bb.x, (y[nt][3] - m1) * r1 * gg.y + bb.y);
+      float2 ta = make_float2(0.f, 0.f), tb = ta;
+      if (p.table) { ta = __ldg(reinterpret_cast<const float2*>(t_lo + nt * 8)); tb = __ldg(reinterpret_cast<const float2*>(t_hi + nt * 8)); }
+      if (p_lo) *reinterpret_cast<float2*>(o_lo + nt * 8) = make_float2((y[nt][0] - m0) * r0 * gg.x + bb.x + ta.x, (y[nt][1] - m0) * r0 * gg.y + bb.y + ta.y);
+      if (p_hi) *reinterpret_cast<float2*>(o_hi + nt * 8) = make_float2((y[nt][2] - m1) * r1 * gg.x + bb.x + tb.x, (y[nt][3] - m1) * r1 * gg.y + bb.y + tb.y);
     }
   }
 }
@@ -1076,12 +1090,12 @@ void op_ts_heads(Ctx& c, const float* x, const float* ng, const float* nb, const
 bool lin_res_ln_supported(int N, int K, int lda) { return N == LRL_N && K % 32 == 0 && K >= 32 && K <= 512 && lda % 2 == 0; }
 
 void op_lin_res_ln(Ctx& c, const float* x, int lda, const void* Wrow, int K, const float* bias, const float* res, const float* g,
-                   const float* b, float* out, int64_t M) {
+                   const float* b, float* out, int64_t M, const float* table, int table_mod) {
   if (c.dry) return;
   PAUT_CHECK(lin_res_ln_supported(LRL_N, K, lda), PAUT_ERR_UNSUPPORTED, "lin_res_ln: unsupported shape");
   LinResLnArgs p;
   p.x = x; p.lda = lda; p.K = K; p.W = static_cast<const __nv_bfloat16*>(Wrow); p.bias = bias; p.res = res; p.g = g; p.b = b;
-  p.out = out; p.M = M;
+  p.out = out; p.M = M; p.table = table; p.table_mod = table_mod > 0 ? table_mod : 1;
   const size_t smem = (size_t)LRL_N * (K + 8) * sizeof(__nv_bfloat16);
   const int64_t tiles = (M + 15) / 16;
   if (smem > 100 * 1024) {                                 // one CTA of 16 warps per SM
