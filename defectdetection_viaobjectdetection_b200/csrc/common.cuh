@@ -214,8 +214,14 @@ void ts_encoder_pack(const float* const* w1, const float* const* sh1, const floa
 void op_ts_encoder(Ctx& c, const void* x_bf16, int64_t A, int S, const void* Wst, const void* W2, const float* shift2, float* feat);
 // Fused per-set stage of MSC / MSC_N (ops_set_tc.cu, bf16 mode): attention block and FFN + head
 bool msc_set_tc_supported(int N, int d, int heads, int ff);
+// optional tail of the second attention block of MultiSignalClassifier: FFN + LayerNorm + classifier in its epilogue
+struct MscTail {
+  const void* W1; const float* b1; const void* W2; const float* b2; const float* ln_g; const float* ln_b; const void* Wc; const float* bc;
+  float* prob; float* start; float* end;
+};
+bool msc_attn_tail_supported(const Ctx& c, int N);
 void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bqkv, const void* Wo, const float* bo,
-                       const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift);
+                       const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift, const MscTail* tail = nullptr);
 // the same attention block with every product on tcgen05 (ops_attn_tc.cu): S and P in tensor memory
 bool msc_attn_tc_supported(int N, int d, int heads);
 void msc_attn_tc_pack(const float* W, int row0, int rows, std::vector<uint16_t>& out);

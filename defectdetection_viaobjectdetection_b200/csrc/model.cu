@@ -1085,7 +1085,14 @@ void Model::fwd_msc(const void* xin, int x_dtype, int64_t B, int N, int S, const
       if (attn_tc)
         op_msc_attn_tc(c, x1, set_tc.tc_w[1][0], set_tc.tc_w[1][1], set_tc.tc_w[1][2], ca.in_proj.b, ca.out_proj.b,
                        ln[te + "norm2"].g, ln[te + "norm2"].b, x2, B, N, true);  // NN_models.py:35-37
-      else
+      else if (msc_attn_tail_supported(c, N)) {
+        // the FFN / LayerNorm / classifier tail rides in the epilogue of the second attention block: no [B, N, 64] round trip
+        MscTail tl{set_tc.W1, lin[te + "ffn.0"].b, set_tc.W2, lin[te + "ffn.2"].b, ln[te + "norm3"].g, ln[te + "norm3"].b, set_tc.Wc,
+                   lin["classifier"].b, slot_at<float>(out, 0, b0 * N), slot_at<float>(out, 1, b0 * N), slot_at<float>(out, 2, b0 * N)};
+        op_msc_attn_block(c, x1, set_tc.Wqkv_cross, ca.in_proj.b, set_tc.Wo_cross, ca.out_proj.b, ln[te + "norm2"].g,
+                          ln[te + "norm2"].b, x2, B, N, true, &tl);
+        return;
+      } else
         op_msc_attn_block(c, x1, set_tc.Wqkv_cross, ca.in_proj.b, set_tc.Wo_cross, ca.out_proj.b, ln[te + "norm2"].g,
                           ln[te + "norm2"].b, x2, B, N, true);
     } else {

@@ -40,6 +40,19 @@ struct AttnBlockArgs {
   float* out;                         // [B, N, 64]
   int N;
   int kv_shift;
+  // optional fused tail (persistent kernel only): FFN 64 -> 32 -> 64 + residual + LayerNorm + classifier 64 -> 3 on the
+  // block's output rows while they are still in registers (k_msc_ffn_head's arithmetic); `out` is then not written
+  const __nv_bfloat16* f_W1 = nullptr;   // [32][64]
+  const float* f_b1 = nullptr;
+  const __nv_bfloat16* f_W2 = nullptr;   // [64][32]
+  const float* f_b2 = nullptr;
+  const float* f_g = nullptr;
+  const float* f_b = nullptr;
+  const __nv_bfloat16* f_Wc = nullptr;   // [8][64] (rows 3..7 zero)
+  const float* f_bc = nullptr;
+  float* f_prob = nullptr;
+  float* f_start = nullptr;
+  float* f_end = nullptr;
 };
 
 // A fragments (4 k-steps) of the 16 x 64 fp32 tile starting at row r0 of one set; rows >= N are zero
@@ -400,7 +413,11 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block_p(AttnBlock
   const uint32_t kv_bytes = 2 * voff;
   __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(smraw);           // [192][WS]
   __nv_bfloat16* Wo = Wq + (size_t)3 * DM * WS;                          // [64][WS]
-  unsigned char* KV = reinterpret_cast<unsigned char*>(Wo + (size_t)DM * WS);   // one K | V buffer per team
+  __nv_bfloat16* W1f = Wo + (size_t)DM * WS;                            // fused tail: [32][WS], [64][FF + 8], [8][WS]
+  __nv_bfloat16* W2f = W1f + (size_t)FF * WS;
+  __nv_bfloat16* Wcf = W2f + (size_t)DM * (FF + 8);
+  const bool tail = p.f_W1 != nullptr;
+  unsigned char* KV = reinterpret_cast<unsigned char*>(tail ? Wcf + (size_t)8 * WS : W1f);   // one K | V buffer per team
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -415,6 +432,20 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block_p(AttnBlock
     *reinterpret_cast<uint4*>(Wo + (size_t)r * WS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.Wo + (size_t)r * DM + c8 * 8));
   }
   for (uint32_t i = tid; i < TEAMS * kv_bytes / 16; i += AB_WARPS * 32) reinterpret_cast<uint4*>(KV)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tail) {
+    for (int i = tid; i < FF * (DM / 8); i += AB_WARPS * 32) {
+      const int r = i / (DM / 8), c8 = i - r * (DM / 8);
+      *reinterpret_cast<uint4*>(W1f + r * WS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.f_W1 + r * DM + c8 * 8));
+    }
+    for (int i = tid; i < DM * (FF / 8); i += AB_WARPS * 32) {
+      const int r = i / (FF / 8), c8 = i - r * (FF / 8);
+      *reinterpret_cast<uint4*>(W2f + r * (FF + 8) + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.f_W2 + r * FF + c8 * 8));
+    }
+    for (int i = tid; i < 8 * (DM / 8); i += AB_WARPS * 32) {
+      const int r = i / (DM / 8), c8 = i - r * (DM / 8);
+      *reinterpret_cast<uint4*>(Wcf + r * WS + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(p.f_Wc + r * DM + c8 * 8));
+    }
+  }
   __syncthreads();
 
   const int team = warp / TW, wt = warp - team * TW;
@@ -624,12 +655,63 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) k_msc_attn_block_p(AttnBlock
         for (int ks = 0; ks < 4; ++ks) mma_bf16_16816(y[nt], qo[ks], w[2 * ks], w[2 * ks + 1]);
       }
       layer_norm_tile2(y, p.ln_g, p.ln_b, t);
-      float* o_lo = outs + (size_t)row_lo * DM + 2 * t;
-      float* o_hi = outs + (size_t)row_hi * DM + 2 * t;
+      if (tail) {
+        // FFN 64 -> 32 -> 64, residual, LayerNorm, classifier 64 -> 3, sigmoid / tanh (NN_models.py:39-41, :123-127) on the
+        // rows in registers: what k_msc_ffn_head does in a launch of its own, without the [B, N, 64] round trip
+        uint32_t xa[4][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        if (p_lo) *reinterpret_cast<float2*>(o_lo + nt * 8) = make_float2(y[nt][0], y[nt][1]);
-        if (p_hi) *reinterpret_cast<float2*>(o_hi + nt * 8) = make_float2(y[nt][2], y[nt][3]);
+        for (int ks = 0; ks < 4; ++ks) c_to_a(y[2 * ks], y[2 * ks + 1], xa[ks]);
+        float hc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          proj_tile(xa, W1f, nt * 8, p.f_b1, g, t, hc[nt]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hc[nt][i] = fmaxf(hc[nt][i], 0.f);
+        }
+        uint32_t ha[2][4];
+        c_to_a(hc[0], hc[1], ha[0]);
+        c_to_a(hc[2], hc[3], ha[1]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float b0 = __ldg(p.f_b2 + nt * 8 + 2 * t), b1 = __ldg(p.f_b2 + nt * 8 + 2 * t + 1);
+          y[nt][0] += b0; y[nt][1] += b1; y[nt][2] += b0; y[nt][3] += b1;           // residual = the block's output itself
+          const __nv_bfloat16* wr = W2f + (size_t)(nt * 8 + g) * (FF + 8) + 2 * t;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            mma_bf16_16816(y[nt], ha[ks], *reinterpret_cast<const uint32_t*>(wr + ks * 16),
+                           *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 8));
+        }
+        layer_norm_tile2(y, p.f_g, p.f_b, t);
+        uint32_t ya[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) c_to_a(y[2 * ks], y[2 * ks + 1], ya[ks]);
+        float oc[4];
+        proj_tile(ya, Wcf, 0, nullptr, g, t, oc);
+        const size_t base = (size_t)set * N;
+        // thread t = 0 holds columns 0, 1 (probability, start); t = 1 holds column 2 (end)
+        if (t == 0) {
+          const float bc0 = __ldg(p.f_bc), bc1 = __ldg(p.f_bc + 1);
+          if (p_lo) {
+            if (p.f_prob) p.f_prob[base + row_lo] = 1.f / (1.f + expf(-(oc[0] + bc0)));
+            if (p.f_start) p.f_start[base + row_lo] = tanhf(oc[1] + bc1) * 0.5f + 0.5f;
+          }
+          if (p_hi) {
+            if (p.f_prob) p.f_prob[base + row_hi] = 1.f / (1.f + expf(-(oc[2] + bc0)));
+            if (p.f_start) p.f_start[base + row_hi] = tanhf(oc[3] + bc1) * 0.5f + 0.5f;
+          }
+        } else if (t == 1) {
+          const float bc2 = __ldg(p.f_bc + 2);
+          if (p_lo && p.f_end) p.f_end[base + row_lo] = tanhf(oc[0] + bc2) * 0.5f + 0.5f;
+          if (p_hi && p.f_end) p.f_end[base + row_hi] = tanhf(oc[2] + bc2) * 0.5f + 0.5f;
+        }
+      } else {
+        float* o_lo = outs + (size_t)row_lo * DM + 2 * t;
+        float* o_hi = outs + (size_t)row_hi * DM + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          if (p_lo) *reinterpret_cast<float2*>(o_lo + nt * 8) = make_float2(y[nt][0], y[nt][1]);
+          if (p_hi) *reinterpret_cast<float2*>(o_hi + nt * 8) = make_float2(y[nt][2], y[nt][3]);
+        }
       }
     }
     // the team's next set overwrites the buffer: every warp of the team must be out of its softmax loops
@@ -1011,12 +1093,28 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) k_lin_res_ln(
 
 bool msc_set_tc_supported(int N, int d, int heads, int ff) { return d == DM && heads == NH && ff == FF && N >= 1 && N <= 320; }
 
+constexpr size_t TAIL_BYTES = sizeof(__nv_bfloat16) * ((size_t)FF * WS + (size_t)DM * (FF + 8) + (size_t)8 * WS);
+
+// can the FFN + head tail ride in the attention block's epilogue for sets of N tokens (persistent kernel, shared memory)?
+bool msc_attn_tail_supported(const Ctx& c, int N) {
+  static const bool off = [] { const char* e = std::getenv("PAUT_ATTN"); return e && (std::strcmp(e, "v1") == 0 || std::strcmp(e, "notail") == 0); }();
+  const int Np16 = (N + 15) / 16 * 16;
+  const size_t smem_p = sizeof(__nv_bfloat16) * ((size_t)TEAMS * 2 * Np16 * WS + (size_t)4 * DM * WS) + TAIL_BYTES;
+  return !off && (int)smem_p <= c.smem_optin - 64 && (N + 15) / 16 <= 2 * TW;
+}
+
 void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bqkv, const void* Wo, const float* bo,
-                       const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift) {
+                       const float* ln_g, const float* ln_b, float* out, int64_t B, int N, bool kv_shift, const MscTail* tail) {
   if (c.dry) return;
   AttnBlockArgs p;
   p.x = x; p.Wqkv = static_cast<const __nv_bfloat16*>(Wqkv); p.bqkv = bqkv; p.Wo = static_cast<const __nv_bfloat16*>(Wo);
   p.bo = bo; p.ln_g = ln_g; p.ln_b = ln_b; p.out = out; p.N = N; p.kv_shift = kv_shift ? 1 : 0;
+  if (tail) {
+    PAUT_CHECK(msc_attn_tail_supported(c, N), PAUT_ERR_UNSUPPORTED, "attn block: the fused tail does not fit for this set length");
+    p.f_W1 = static_cast<const __nv_bfloat16*>(tail->W1); p.f_b1 = tail->b1; p.f_W2 = static_cast<const __nv_bfloat16*>(tail->W2);
+    p.f_b2 = tail->b2; p.f_g = tail->ln_g; p.f_b = tail->ln_b; p.f_Wc = static_cast<const __nv_bfloat16*>(tail->Wc); p.f_bc = tail->bc;
+    p.f_prob = tail->prob; p.f_start = tail->start; p.f_end = tail->end;
+  }
   const int Np = (N + KBLK - 1) / KBLK * KBLK;
   const size_t smem = sizeof(__nv_bfloat16) * ((size_t)Np * WS + (size_t)DM * (Np + 8) + (size_t)4 * DM * WS);
   PAUT_CHECK((int)smem <= c.smem_optin, PAUT_ERR_UNSUPPORTED, "attn block: set too long for shared memory");
@@ -1025,8 +1123,8 @@ void op_msc_attn_block(Ctx& c, const float* x, const void* Wqkv, const float* bq
   // one-CTA-per-set kernel for A/B runs)
   static const bool force_v1 = [] { const char* e = std::getenv("PAUT_ATTN"); return e && std::strcmp(e, "v1") == 0; }();
   const int Np16 = (N + 15) / 16 * 16;
-  const size_t smem_p = sizeof(__nv_bfloat16) * ((size_t)TEAMS * 2 * Np16 * WS + (size_t)4 * DM * WS);
-  if (!force_v1 && (int)smem_p <= c.smem_optin && (N + 15) / 16 <= 2 * TW) {
+  const size_t smem_p = sizeof(__nv_bfloat16) * ((size_t)TEAMS * 2 * Np16 * WS + (size_t)4 * DM * WS) + (tail ? TAIL_BYTES : 0);
+  if ((tail || !force_v1) && (int)smem_p <= c.smem_optin && (N + 15) / 16 <= 2 * TW) {
     const unsigned grid = (unsigned)std::min<int64_t>((B + TEAMS - 1) / TEAMS, c.num_sms);
     static const int var = [] { const char* e = std::getenv("PAUT_ATTN_VARIANT"); return e ? std::atoi(e) : 0; }();
     static const unsigned skew = [] { const char* e = std::getenv("PAUT_ATTN_SKEW_NS"); return e ? (unsigned)std::atoi(e) : 12000u; }();
