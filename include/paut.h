@@ -32,6 +32,7 @@
 extern "C" {
 #endif
 
+/* bumped on incompatible changes only; entry points added since (paut_debug_stage, paut_json_beam_status) keep it at 1 */
 #define PAUT_ABI_VERSION 1
 
 typedef enum {
